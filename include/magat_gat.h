@@ -1,0 +1,156 @@
+/*
+ * magat_gat.h -- C ABI of the B200-native batched graph-attention layer.
+ *
+ * Drop-in boundary for ONE hot path of proroklab/magat_pathplanning:
+ *   utils/graphUtils/graphML.py:4506-4685  class GraphFilterBatchAttentional
+ *   utils/graphUtils/graphML.py:1724-1827  graphAttentionLSIGFBatch_{KeyQuery,modified}
+ *   utils/graphUtils/graphML.py:1180-1286  learnAttentionGSOBatch_KeyQuery
+ *   utils/graphUtils/graphML.py:713-823    learnAttentionGSOBatch (GAT_modified)
+ * The reference has no FFI of its own (pure PyTorch); the entry points below are what a
+ * ctypes/cffi binding for that path binds (see INTEGRATION.md for the stub).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing
+ *     synchronises unless stated;
+ *   - the library never allocates device memory: the caller passes every buffer;
+ *   - return value 0 = success, non-zero = error code (MAGAT_E_*), message through
+ *     magat_last_error(); nothing throws or exits across this boundary;
+ *   - E (edge features) is fixed to 1, the only value the planners use
+ *     (graphs/models/decentralplanner_GAT.py:179).
+ *
+ * Tensor layouts (fp32 unless noted; B batch, N nodes, G in-features, F out-features per
+ * head, K taps, P heads, D = ELL width >= max in/out degree over the batch, W = ceil(N/32)):
+ *   x        [B][N][G]   node-major rows (the planner's memory layout, decentralplanner_GAT.py:304);
+ *                        row stride x_sn >= G elements, batch stride x_sb, feature stride 1
+ *   S        [B][1][N][N] dense GSO as the reference passes it, fp32 or fp64; only
+ *                        |S| > 1e-9 is used (graphML.py:1274-1276)
+ *   y        element (b, n, c) at y[b*y_sb + n*y_sn + c*y_sc]; c = p*F+f when concatenating
+ *                        (graphML.py:4656-4662), c = f when averaging heads (:4665-4667)
+ *   rowbits  [B][N][W]   uint32, bit j%32 of word j/32 of row i set iff edge (i,j)
+ *   colbits  [B][N][W]   uint32, bit i%32 of word i/32 of row j set iff edge (i,j)
+ *   nbr_out  [B][N][D]   int32, receivers j of sender-row i, ascending, -1 padded
+ *   nbr_in   [B][N][D]   int32, senders i of column j, ascending, -1 padded
+ *   slot_in  [B][N][D]   int32, position of j inside nbr_out[b][i][:] for the same entry of nbr_in
+ *   att      [B][N][D][P] attention value A_p[i, nbr_out[i][s]] (row-softmax, graphML.py:1284)
+ *   taps     [B][N][P][K-1][G]  u_k = u_{k-1} A for k = 1..K-1 (graphML.py:1756-1759)
+ *   sproj    KeyQuery: [B][N][P][G], R_i^p = W_p^T x_i so that e_p[i,j] = R_i^p . x_j (:1257-1262);
+ *            GAT_modified: [B][N][P][2], {a1_p.z_n, a2_p.z_n} with z = W_p x + wb_p (:777-789)
+ */
+#ifndef MAGAT_GAT_H_
+#define MAGAT_GAT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAGAT_ABI_VERSION 2
+
+enum {
+  MAGAT_OK = 0,
+  MAGAT_E_BAD_ARG = 1,      /* shape / mode / null pointer; mirrors the reference's asserts */
+  MAGAT_E_UNSUPPORTED = 2,  /* e.g. KeyQuery with F != G (graphML.py:1728,1765), E != 1 */
+  MAGAT_E_ALIGN = 3,        /* pointer or stride not aligned as required */
+  MAGAT_E_CUDA = 4,         /* launch / runtime failure (cudaGetLastError) */
+  MAGAT_E_DEVICE = 5        /* not an sm_100 device */
+};
+
+enum { MAGAT_MODE_KEYQUERY = 0, MAGAT_MODE_GAT_MODIFIED = 1 };
+enum { MAGAT_DT_F32 = 0, MAGAT_DT_F64 = 1 };
+/* which implementation magat_gat_forward uses for the dense projections */
+enum { MAGAT_PATH_AUTO = 0, MAGAT_PATH_SIMT = 1, MAGAT_PATH_TCGEN05 = 2 };
+
+int magat_abi_version(void);
+const char* magat_last_error(void);
+
+/* Device check: 0 when the current device can run this library's sm_100a code. */
+int magat_device_check(void);
+
+/* ---- GSO -> adjacency (replaces graphML.py:1274-1278 / :808-812 mask construction) ----
+ * One pass over S.  stats[0] = max out-degree, stats[1] = max in-degree, stats[2] = total
+ * number of edges (saturating), stats[3] = 1 iff the mask is symmetric.  stats must be
+ * zero-initialised by the caller except stats[3] = 1. */
+int magat_gso_scan(const void* S, int s_dtype, int B, int N,
+                   uint32_t* rowbits, uint32_t* colbits, int32_t* stats, void* stream);
+
+/* Bit masks -> padded neighbour lists of width D (D >= max(stats[0], stats[1]), D >= 1). */
+int magat_gso_build_ell(const uint32_t* rowbits, const uint32_t* colbits, int B, int N, int D,
+                        int32_t* nbr_out, int32_t* nbr_in, int32_t* slot_in, void* stream);
+
+/* ---- forward (replaces GraphFilterBatchAttentional.forward, graphML.py:4636-4667) ---- */
+typedef struct magat_gat_fwd_args {
+  int32_t B, N, G, F, K, P, D;
+  int32_t mode;          /* MAGAT_MODE_* */
+  int32_t concat;        /* 1: activation then concat heads; 0: mean over heads then activation */
+  int32_t relu;          /* 1: fused ReLU (the reference default, graphML.py:4560); 0: identity */
+  int32_t path;          /* MAGAT_PATH_* */
+  int32_t reserved;
+  /* inputs */
+  const float* x; int64_t x_sb, x_sn;
+  const int32_t* nbr_out; const int32_t* nbr_in; const int32_t* slot_in;
+  /* parameters, in the reference's shapes (graphML.py:4579-4597) */
+  const float* weight;        /* KeyQuery [P][1][G][G]; GAT_modified [P][1][F][G] */
+  const float* mixer;         /* [P][1][2F] (GAT_modified only; may be NULL for KeyQuery) */
+  const float* weight_bias;   /* [P][1][F]  (GAT_modified only) */
+  const float* filterWeight;  /* [P][F][1][K][G] */
+  const float* bias;          /* [F][1] or NULL */
+  /* outputs */
+  float* y; int64_t y_sb, y_sn, y_sc;
+  float* att;                 /* [B][N][D][P] */
+  float* taps;                /* [B][N][P][K-1][G] (unused when K == 1) */
+  /* scratch (caller allocated) */
+  float* wprep;               /* magat_gat_wprep_floats(...) floats */
+  float* sproj;               /* KeyQuery: [B][N][P][G]; GAT_modified: [B][N][P][2] */
+} magat_gat_fwd_args;
+
+size_t magat_gat_wprep_floats(int G, int F, int K, int P, int mode);
+int magat_gat_forward(const magat_gat_fwd_args* a, void* stream);
+
+/* ---- backward (what autograd does over graphML.py:1180-1286,713-823,1724-1827) ---- */
+typedef struct magat_gat_bwd_args {
+  int32_t B, N, G, F, K, P, D;
+  int32_t mode, concat, relu, path;
+  int32_t need_dx, need_dweight, need_dfilter, need_dbias, need_dmixer;   /* requires_grad gating */
+  /* saved from forward */
+  const float* x; int64_t x_sb, x_sn;
+  const int32_t* nbr_out; const int32_t* nbr_in; const int32_t* slot_in;
+  const float* weight; const float* mixer; const float* weight_bias; const float* filterWeight;
+  const float* y; int64_t y_sb, y_sn, y_sc;   /* forward output (post activation) */
+  const float* att; const float* taps; const float* wprep; const float* sproj;
+  /* incoming gradient, same logical shape as y, own strides */
+  const float* dy; int64_t dy_sb, dy_sn, dy_sc;
+  /* outputs: written (not accumulated); any may be NULL when the matching need_* is 0 */
+  float* dx;                  /* [B][N][G] contiguous */
+  float* dweight; float* dmixer; float* dweight_bias; float* dfilterWeight; float* dbias;
+  /* scratch */
+  float* gz;                  /* [B][N][P][K][G] */
+  float* datt;                /* [B][N][D][P] */
+  float* rc;                  /* KeyQuery: [B][N][P][G]; GAT_modified: [B][N][P][2] */
+  float* partial;             /* magat_gat_bwd_partial_floats(...) floats */
+} magat_gat_bwd_args;
+
+size_t magat_gat_bwd_partial_floats(int B, int N, int G, int F, int K, int P, int mode);
+int magat_gat_backward(const magat_gat_bwd_args* a, void* stream);
+
+/* ---- lazy dense attention for returnAttentionGSO (graphML.py:4623-4634, :4650) ----
+ * Expands att into aij[B][P][1][N][N] (mean_heads == 0), or into the head-mean [B][1][N][N]
+ * that returnAttentionGSO returns.  `out` must be zero filled by the caller. */
+int magat_gat_attention_dense(const float* att, const int32_t* nbr_out, int B, int N, int D, int P,
+                              int mean_heads, float* out, void* stream);
+
+/* ---- launch accounting / measurement hooks (bench.py, tests) ----
+ * magat_launch_count: kernels launched by this library in this process so far.
+ * magat_profile_enable(1): from now on record a CUDA event behind every launch (and at every entry
+ * point) on the launching stream; magat_profile_collect synchronises those events and writes
+ * "kernel name,launches,total_ms" lines, aggregated per kernel, into buf (returns bytes needed). */
+long magat_launch_count(void);
+void magat_profile_enable(int on);
+long magat_profile_collect(char* buf, long cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAGAT_GAT_H_ */

@@ -1,0 +1,14 @@
+"""B200-native (sm_100a) batched graph-attention layer of proroklab/magat_pathplanning.
+
+Only the hot path is here: ``GraphFilterBatchAttentional`` and the functionals it calls
+(reference: utils/graphUtils/graphML.py:4506-4685, :1724-1827, :1180-1286, :713-823), behind the
+reference's own module interface.  See DESIGN.md / INTEGRATION.md.
+"""
+from .graphML import (GraphFilterBatchAttentional, graphAttentionLSIGFBatch_KeyQuery,  # noqa: F401
+                      graphAttentionLSIGFBatch_modified, learnAttentionGSOBatch_KeyQuery,
+                      learnAttentionGSOBatch, build_adjacency, gat_layer, attention_dense)
+from .integration import install_into_reference  # noqa: F401
+
+__all__ = ["GraphFilterBatchAttentional", "graphAttentionLSIGFBatch_KeyQuery",
+           "graphAttentionLSIGFBatch_modified", "learnAttentionGSOBatch_KeyQuery", "learnAttentionGSOBatch",
+           "build_adjacency", "gat_layer", "attention_dense", "install_into_reference"]

@@ -1,0 +1,408 @@
+// Backward of the batched graph-attention layer (fp32 SIMT; sparse parts are edge-wise).
+//
+// Given dY (same logical shape as y), with dP = dY * act'(y) (mean mode: / P, shared by heads):
+//   dH_{p,k} = dP_p^T u_k^p ;  dbias = sum dP ;  gU_k = dP_p H_{p,k}  (per node, [K][G])
+//   for k = K-1 .. 1:  dA_p[i,j] += u_{k-1}[i] . gU_k[j] ;  gU_{k-1}[i] += sum_j A_p[i,j] gU_k[j]
+//   dx += sum_p gU_0 ;  de = A * (dA - rowsum(A * dA))
+//   KeyQuery:     dR_i = sum_j de[i,j] x_j ; dx_j += sum_i de[i,j] R_i ; dx_i += W dR_i ; dW = sum_i x_i dR_i^T
+//   GAT_modified: ds = de * lrelu'(s) ; r_i = rowsum, c_j = colsum ; dx_n += c_n cvec_0 + r_n cvec_1 ;
+//                 dcvec_t = sum_n {c,r}_n x_n ; ddvec_t = sum_n {c,r}_n ; then the chain through
+//                 cvec_t = W^T a_t, dvec_t = a_t . wb  (gat_fwd.cu k_gm_prep)
+// mixer / weight_bias receive no gradient in KeyQuery mode (the reference leaves grad = None).
+#include "common.cuh"
+#include "simt_gemm.cuh"
+
+namespace magat {
+
+struct DPre {   // dP(m, p, f)
+  const float* y; long y_sb, y_sn, y_sc; const float* dy; long dy_sb, dy_sn, dy_sc;
+  int N, F, concat, relu; float scale;
+  __device__ __forceinline__ float operator()(long m, int p, int f) const {
+    const long b = m / N;
+    const long n = m - b * N;
+    const long c = concat ? (long)p * F + f : f;
+    const float g = __ldg(dy + b * dy_sb + n * dy_sn + c * dy_sc) * scale;
+    if (!relu) return g;
+    return __ldg(y + b * y_sb + n * y_sn + c * y_sc) > 0.f ? g : 0.f;
+  }
+};
+
+struct ZNode {   // u_k^p of node m, feature g
+  const float* x; long x_sb, x_sn; const float* taps; int N, G, K, P;
+  __device__ __forceinline__ float operator()(long m, int p, int k, int g) const {
+    if (k == 0) {
+      const long b = m / N;
+      return __ldg(x + b * x_sb + (m - b * N) * x_sn + g);
+    }
+    return __ldg(taps + (((size_t)m * P + p) * (K - 1) + (k - 1)) * G + g);
+  }
+};
+
+// gz[m][p][k][g] = sum_f dP(m,p,f) H[p][f][k][g]
+struct DPreA { DPre d; __device__ __forceinline__ float operator()(long m, int f, int z) const { return d(m, z, f); } };
+struct HtLoad {
+  const float* H; int KG;
+  __device__ __forceinline__ float operator()(int f, int n, int z) const {
+    return __ldg(H + ((size_t)z * gridF + f) * KG + n);
+  }
+  int gridF;
+};
+struct GzEpi {
+  float* gz; int P, KG;
+  __device__ __forceinline__ void operator()(long m, int n, int z, float v) const { gz[((size_t)m * P + z) * KG + n] = v; }
+};
+// dH[p][f][kg] = sum_m dP(m,p,f) Z(m,p,kg)
+struct DPreR { DPre d; __device__ __forceinline__ float operator()(long r, int f, int z) const { return d(r, z, f); } };
+struct ZRed {
+  ZNode zn; int G;
+  __device__ __forceinline__ float operator()(long r, int kg, int z) const {
+    const int k = kg / G;
+    return zn(r, z, k, kg - k * G);
+  }
+};
+// dbias[f] = sum_{m,p} dP(m,p,f)
+struct OneLoad { __device__ __forceinline__ float operator()(long, int, int) const { return 1.f; } };
+struct DPreSumP {
+  DPre d; int P;
+  __device__ __forceinline__ float operator()(long r, int f, int) const {
+    float s = 0.f;
+    for (int p = 0; p < P; ++p) s += d(r, p, f);
+    return s;
+  }
+};
+
+// ---- tap recursion backward, level k (k = K-1 .. 1) ---------------------------------------
+// warp per sender row i: dA[i,j] (+)= u_{k-1}[i] . gU_k[j];  gU_{k-1}[i] += sum_j A[i,j] gU_k[j].
+__global__ void __launch_bounds__(256) k_tap_bwd(ZNode zn, const float* __restrict__ att,
+                                                 const int32_t* __restrict__ nbr_out, long rows, int N, int G,
+                                                 int P, int K, int D, int k, int first,
+                                                 float* __restrict__ gz, float* __restrict__ datt) {
+  const int lane = threadIdx.x & 31;
+  const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  const long b = row / N;
+  const int32_t* nb = nbr_out + row * D;
+  for (int p = 0; p < P; ++p) {
+    float* gdst = gz + (((size_t)row * P + p) * K + (k - 1)) * G;
+    for (int s = 0; s < D; ++s) {
+      const int j = nb[s];
+      if (j < 0) break;
+      const float a = att[((size_t)row * D + s) * P + p];
+      const float* gsrc = gz + ((((size_t)(b * N + j)) * P + p) * K + k) * G;
+      float d = 0.f;
+      for (int g = lane; g < G; g += 32) {
+        const float gv = gsrc[g];
+        d = fmaf(zn(row, p, k - 1, g), gv, d);
+        gdst[g] = fmaf(a, gv, gdst[g]);
+      }
+      d = warp_sum(d);
+      if (lane == 0) {
+        float* da = datt + ((size_t)row * D + s) * P + p;
+        *da = first ? d : *da + d;
+      }
+    }
+  }
+}
+
+// ---- softmax backward per row + the row-side score gradients ---------------------------------
+// datt <- de (KeyQuery) or ds (GAT_modified), in place.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_softmax_bwd(const float* __restrict__ x, long x_sb, long x_sn,
+                                                     const float* __restrict__ sproj,
+                                                     const float* __restrict__ att,
+                                                     const int32_t* __restrict__ nbr_out, long rows, int N,
+                                                     int G, int P, int D, int has_datt,
+                                                     float* __restrict__ datt, float* __restrict__ rc) {
+  const int lane = threadIdx.x & 31;
+  const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  const long b = row / N;
+  const int32_t* nb = nbr_out + row * D;
+  const float* arow = att + row * (size_t)D * P;
+  float* drow = datt + row * (size_t)D * P;
+  for (int p = 0; p < P; ++p) {
+    float dot = 0.f;
+    int deg = 0;
+    for (int s0 = 0; s0 < D; s0 += 32) {
+      const int s = s0 + lane;
+      const bool v = s < D && nb[s] >= 0;
+      if (v) {
+        if (!has_datt) drow[(size_t)s * P + p] = 0.f;
+        dot = fmaf(arow[(size_t)s * P + p], drow[(size_t)s * P + p], dot);
+      }
+      deg += __popc(__ballot_sync(0xffffffffu, v));
+    }
+    dot = warp_sum(dot);
+    float rsum = 0.f;
+    const float si = (MODE == MAGAT_MODE_GAT_MODIFIED) ? sproj[((size_t)row * P + p) * 2 + 1] : 0.f;
+    for (int s = lane; s < deg; s += 32) {
+      float de = arow[(size_t)s * P + p] * (drow[(size_t)s * P + p] - dot);
+      if (MODE == MAGAT_MODE_GAT_MODIFIED) {
+        const float sr = si + sproj[((size_t)(b * N + nb[s]) * P + p) * 2 + 0];
+        de *= sr > 0.f ? 1.f : kLeaky;
+        rsum += de;
+      }
+      drow[(size_t)s * P + p] = de;
+    }
+    if (MODE == MAGAT_MODE_GAT_MODIFIED) {
+      rsum = warp_sum(rsum);
+      if (lane == 0) rc[((size_t)row * P + p) * 2 + 1] = rsum;
+    } else {
+      __syncwarp();
+      // dR_i^p = sum_j de[i,j] x_j
+      for (int g = lane; g < G; g += 32) {
+        float acc = 0.f;
+        for (int s = 0; s < deg; ++s)
+          acc = fmaf(drow[(size_t)s * P + p], x[b * x_sb + (long)nb[s] * x_sn + g], acc);
+        rc[((size_t)row * P + p) * G + g] = acc;
+      }
+    }
+  }
+}
+
+// ---- column side: dx_j = sum_p gU_0[j] + score terms gathered over the in-neighbours -----------
+template <int MODE>
+__global__ void __launch_bounds__(256) k_col_bwd(const float* __restrict__ gz, const float* __restrict__ datt,
+                                                 const float* __restrict__ sproj, const float* __restrict__ cvec,
+                                                 const int32_t* __restrict__ nbr_in,
+                                                 const int32_t* __restrict__ slot_in, long rows, int N, int G,
+                                                 int P, int K, int D, float* __restrict__ rc,
+                                                 float* __restrict__ dx) {
+  const int lane = threadIdx.x & 31;
+  const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  const long b = row / N;
+  const int32_t* nb = nbr_in + row * D;
+  const int32_t* sl = slot_in + row * D;
+  if (MODE == MAGAT_MODE_GAT_MODIFIED) {
+    for (int p = 0; p < P; ++p) {
+      float c = 0.f;
+      for (int s = lane; s < D; s += 32) {
+        const int i = nb[s];
+        if (i >= 0) c += datt[((size_t)(b * N + i) * D + sl[s]) * P + p];
+      }
+      c = warp_sum(c);
+      if (lane == 0) rc[((size_t)row * P + p) * 2 + 0] = c;
+    }
+    __syncwarp();
+  }
+  if (dx == nullptr) return;
+  for (int g = lane; g < G; g += 32) {
+    float acc = 0.f;
+    for (int p = 0; p < P; ++p) {
+      acc += gz[(((size_t)row * P + p) * K + 0) * G + g];
+      if (MODE == MAGAT_MODE_KEYQUERY) {
+        for (int s = 0; s < D; ++s) {
+          const int i = nb[s];
+          if (i < 0) break;
+          const long ri = b * N + i;
+          acc = fmaf(datt[((size_t)ri * D + sl[s]) * P + p], sproj[((size_t)ri * P + p) * G + g], acc);
+        }
+      } else {
+        acc = fmaf(rc[((size_t)row * P + p) * 2 + 0], cvec[((size_t)p * 2 + 0) * G + g], acc);
+        acc = fmaf(rc[((size_t)row * P + p) * 2 + 1], cvec[((size_t)p * 2 + 1) * G + g], acc);
+      }
+    }
+    dx[(size_t)row * G + g] = acc;
+  }
+}
+
+// KeyQuery: dx[m][g] += sum_{p,g'} W[p][g][g'] dR[m][p][g']
+struct RcLoad { const float* rc; int PG; __device__ __forceinline__ float operator()(long m, int k, int) const { return __ldg(rc + (size_t)m * PG + k); } };
+struct WtLoad {   // B(k = p*G+g', n = g) = W[p][g][g']
+  const float* W; int G;
+  __device__ __forceinline__ float operator()(int k, int n, int) const {
+    const int p = k / G;
+    return __ldg(W + ((size_t)p * G + n) * G + (k - p * G));
+  }
+};
+struct AccEpi { float* out; int ld; __device__ __forceinline__ void operator()(long m, int n, int, float v) const { out[m * ld + n] += v; } };
+// dW[p][g][g'] = sum_m x[m][g] dR[m][p][g']
+struct XRed {
+  const float* x; long x_sb, x_sn; int N;
+  __device__ __forceinline__ float operator()(long r, int g, int) const {
+    const long b = r / N;
+    return __ldg(x + b * x_sb + (r - b * N) * x_sn + g);
+  }
+};
+struct RcRed { const float* rc; int P, G; __device__ __forceinline__ float operator()(long r, int g, int z) const { return __ldg(rc + ((size_t)r * P + z) * G + g); } };
+// GAT_modified: dc[n = 2p+t][g] = sum_m rc[m][n] x[m][g], and column G carries sum_m rc[m][n]
+struct RcRed2 { const float* rc; int P2; __device__ __forceinline__ float operator()(long r, int n, int) const { return __ldg(rc + (size_t)r * P2 + n); } };
+struct XRed1 {
+  XRed xr; int G;
+  __device__ __forceinline__ float operator()(long r, int g, int z) const { return g < G ? xr(r, g, z) : 1.f; }
+};
+
+// chain through cvec = W^T a, dvec = a . wb  (dc: [P][2][G+1], last column = ddvec)
+__global__ void __launch_bounds__(128) k_gm_param_bwd(const float* __restrict__ W, const float* __restrict__ mixer,
+                                                      const float* __restrict__ wb, const float* __restrict__ dc,
+                                                      int G, int F, int P, float* __restrict__ dW,
+                                                      float* __restrict__ dmixer, float* __restrict__ dwb) {
+  const int p = blockIdx.x;
+  const float* dc0 = dc + ((size_t)p * 2 + 0) * (G + 1);
+  const float* dc1 = dc + ((size_t)p * 2 + 1) * (G + 1);
+  const float dd0 = dc0[G], dd1 = dc1[G];
+  const float* a1 = mixer + (size_t)p * 2 * F;
+  const float* a2 = a1 + F;
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    float m0 = dd0 * wb[(size_t)p * F + f], m1 = dd1 * wb[(size_t)p * F + f];
+    const float* w = W + ((size_t)p * F + f) * G;
+    for (int g = 0; g < G; ++g) {
+      m0 = fmaf(w[g], dc0[g], m0);
+      m1 = fmaf(w[g], dc1[g], m1);
+    }
+    if (dmixer) {
+      dmixer[(size_t)p * 2 * F + f] = m0;
+      dmixer[(size_t)p * 2 * F + F + f] = m1;
+    }
+    if (dwb) dwb[(size_t)p * F + f] = dd0 * a1[f] + dd1 * a2[f];
+    if (dW)
+      for (int g = 0; g < G; ++g) dW[((size_t)p * F + f) * G + g] = a1[f] * dc0[g] + a2[f] * dc1[g];
+  }
+}
+
+static int pick_splits(long R, int tiles) {
+  long s = (148l * 4 + tiles - 1) / tiles;
+  const long cap = (R + 255) / 256;
+  if (s > cap) s = cap;
+  if (s > 256) s = 256;
+  if (s < 1) s = 1;
+  return (int)s;
+}
+
+template <class ALoad, class BLoad>
+static int rowred(long R, int Mi, int Nj, int Z, ALoad A, BLoad Bm, float* partial, float* out, cudaStream_t st,
+                  const char* what) {
+  const int ti = cdiv(Mi, 64), tj = cdiv(Nj, 64);
+  const int splits = pick_splits(R, ti * tj * Z);
+  dim3 grid(ti, tj, Z * splits);
+  k_rowred_gemm<<<grid, 256, 0, st>>>(R, Mi, Nj, splits, A, Bm, partial);
+  int rc = check_launch(what, st);
+  if (rc) return rc;
+  const long per = (long)Mi * Nj, total = per * Z;
+  k_reduce_partials<<<cdiv(total, 256), 256, 0, st>>>(partial, splits, per, total, out);
+  return check_launch("k_reduce_partials", st);
+}
+
+}  // namespace magat
+
+using namespace magat;
+
+extern "C" size_t magat_gat_bwd_partial_floats(int B, int N, int G, int F, int K, int P, int mode) {
+  (void)B; (void)N;
+  // every row-reduction writes at most Z * splits * Mi * Nj floats with Z*splits*tiles <= ~148*4 + Z*tiles
+  auto need = [](long Mi, long Nj, long Z) {
+    const long tiles = ((Mi + 63) / 64) * ((Nj + 63) / 64) * Z;
+    long s = (148l * 4 + tiles - 1) / tiles;
+    if (s > 256) s = 256;
+    if (s < 1) s = 1;
+    return (size_t)(Z * s * Mi * Nj);
+  };
+  size_t m = need(F, (long)K * G, P);
+  m = max(m, need(1, F, 1));
+  if (mode == MAGAT_MODE_KEYQUERY) m = max(m, need(G, G, P));
+  else m = max(m, need(2l * P, G + 1, 1) + (size_t)2 * P * (G + 1));
+  return m;
+}
+
+extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
+  MAGAT_REQUIRE(a != nullptr, MAGAT_E_BAD_ARG, "magat_gat_backward: null args");
+  const int B = a->B, N = a->N, G = a->G, F = a->F, K = a->K, P = a->P, D = a->D;
+  MAGAT_REQUIRE(B >= 1 && N >= 1 && G >= 1 && F >= 1 && K >= 1 && P >= 1 && D >= 1, MAGAT_E_BAD_ARG,
+                "magat_gat_backward: bad shape");
+  MAGAT_REQUIRE(a->mode == MAGAT_MODE_KEYQUERY || a->mode == MAGAT_MODE_GAT_MODIFIED, MAGAT_E_BAD_ARG,
+                "magat_gat_backward: unknown mode %d", a->mode);
+  MAGAT_REQUIRE(a->mode != MAGAT_MODE_KEYQUERY || F == G, MAGAT_E_UNSUPPORTED, "KeyQuery needs F == G");
+  MAGAT_REQUIRE(a->x && a->nbr_out && a->nbr_in && a->slot_in && a->weight && a->filterWeight && a->y && a->att &&
+                    a->sproj && a->dy && a->gz && a->datt && a->rc && a->partial,
+                MAGAT_E_BAD_ARG, "magat_gat_backward: null pointer");
+  MAGAT_REQUIRE(K == 1 || a->taps, MAGAT_E_BAD_ARG, "magat_gat_backward: taps missing");
+  MAGAT_REQUIRE(!a->need_dx || a->dx, MAGAT_E_BAD_ARG, "magat_gat_backward: dx missing");
+  MAGAT_REQUIRE(!a->need_dfilter || a->dfilterWeight, MAGAT_E_BAD_ARG, "magat_gat_backward: dfilterWeight missing");
+  MAGAT_REQUIRE(!a->need_dbias || a->dbias, MAGAT_E_BAD_ARG, "magat_gat_backward: dbias missing");
+  MAGAT_REQUIRE(!a->need_dweight || a->dweight, MAGAT_E_BAD_ARG, "magat_gat_backward: dweight missing");
+  const bool gm = a->mode == MAGAT_MODE_GAT_MODIFIED;
+  MAGAT_REQUIRE(!(gm && a->need_dmixer) || (a->dmixer && a->dweight_bias), MAGAT_E_BAD_ARG,
+                "magat_gat_backward: dmixer / dweight_bias missing");
+  MAGAT_REQUIRE(!gm || (a->mixer && a->weight_bias && a->wprep), MAGAT_E_BAD_ARG,
+                "magat_gat_backward: GAT_modified needs mixer, weight_bias, wprep");
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin(st);
+  const long rows = (long)B * N;
+  const int row_blocks = cdiv(rows, 8);
+  const int KG = K * G;
+  int rc;
+  const DPre dp{a->y, a->y_sb, a->y_sn, a->y_sc, a->dy, a->dy_sb, a->dy_sn, a->dy_sc,
+                N, F, a->concat, a->relu, a->concat ? 1.f : 1.f / (float)P};
+  const ZNode zn{a->x, a->x_sb, a->x_sn, a->taps, N, G, K, P};
+  const bool need_scores = a->need_dx || a->need_dweight || (gm && a->need_dmixer);
+
+  if (a->need_dbias) {
+    if ((rc = rowred(rows, 1, F, 1, OneLoad{}, DPreSumP{dp, P}, a->partial, a->dbias, st, "k_rowred_gemm(dbias)")))
+      return rc;
+  }
+  if (a->need_dfilter) {
+    if ((rc = rowred(rows, F, KG, P, DPreR{dp}, ZRed{zn, G}, a->partial, a->dfilterWeight, st,
+                     "k_rowred_gemm(dfilterWeight)")))
+      return rc;
+  }
+  if (!need_scores) return MAGAT_OK;
+
+  {  // gz = dP H
+    dim3 grid(cdiv(rows, 64), cdiv(KG, 64), P);
+    HtLoad hl{a->filterWeight, KG, F};
+    k_node_gemm<<<grid, 256, 0, st>>>(rows, KG, F, DPreA{dp}, hl, GzEpi{a->gz, P, KG});
+    if ((rc = check_launch("k_node_gemm(gz)", st))) return rc;
+  }
+  for (int k = K - 1; k >= 1; --k) {
+    k_tap_bwd<<<row_blocks, 256, 0, st>>>(zn, a->att, a->nbr_out, rows, N, G, P, K, D, k, k == K - 1 ? 1 : 0,
+                                          a->gz, a->datt);
+    if ((rc = check_launch("k_tap_bwd", st))) return rc;
+  }
+  const int has_datt = K > 1 ? 1 : 0;
+  if (!gm) {
+    k_softmax_bwd<MAGAT_MODE_KEYQUERY><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj, a->att,
+                                                                    a->nbr_out, rows, N, G, P, D, has_datt,
+                                                                    a->datt, a->rc);
+    if ((rc = check_launch("k_softmax_bwd", st))) return rc;
+    k_col_bwd<MAGAT_MODE_KEYQUERY><<<row_blocks, 256, 0, st>>>(a->gz, a->datt, a->sproj, nullptr, a->nbr_in,
+                                                                a->slot_in, rows, N, G, P, K, D, a->rc,
+                                                                a->need_dx ? a->dx : nullptr);
+    if ((rc = check_launch("k_col_bwd", st))) return rc;
+    if (a->need_dx) {
+      dim3 grid(cdiv(rows, 64), cdiv(G, 64), 1);
+      k_node_gemm<<<grid, 256, 0, st>>>(rows, G, P * G, RcLoad{a->rc, P * G}, WtLoad{a->weight, G},
+                                        AccEpi{a->dx, G});
+      if ((rc = check_launch("k_node_gemm(dx += W dR)", st))) return rc;
+    }
+    if (a->need_dweight) {
+      if ((rc = rowred(rows, G, G, P, XRed{a->x, a->x_sb, a->x_sn, N}, RcRed{a->rc, P, G}, a->partial, a->dweight,
+                       st, "k_rowred_gemm(dweight)")))
+        return rc;
+    }
+  } else {
+    const float* cvec = a->wprep;
+    k_softmax_bwd<MAGAT_MODE_GAT_MODIFIED><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj, a->att,
+                                                                        a->nbr_out, rows, N, G, P, D, has_datt,
+                                                                        a->datt, a->rc);
+    if ((rc = check_launch("k_softmax_bwd", st))) return rc;
+    k_col_bwd<MAGAT_MODE_GAT_MODIFIED><<<row_blocks, 256, 0, st>>>(a->gz, a->datt, a->sproj, cvec, a->nbr_in,
+                                                                    a->slot_in, rows, N, G, P, K, D, a->rc,
+                                                                    a->need_dx ? a->dx : nullptr);
+    if ((rc = check_launch("k_col_bwd", st))) return rc;
+    if (a->need_dweight || a->need_dmixer) {
+      // dc [2P][G+1] lives at the tail of `partial`
+      const size_t head = (size_t)magat_gat_bwd_partial_floats(B, N, G, F, K, P, a->mode) - (size_t)2 * P * (G + 1);
+      float* dc = a->partial + head;
+      if ((rc = rowred(rows, 2 * P, G + 1, 1, RcRed2{a->rc, 2 * P}, XRed1{XRed{a->x, a->x_sb, a->x_sn, N}, G},
+                       a->partial, dc, st, "k_rowred_gemm(dcvec)")))
+        return rc;
+      k_gm_param_bwd<<<P, 128, 0, st>>>(a->weight, a->mixer, a->weight_bias, dc, G, F, P,
+                                        a->need_dweight ? a->dweight : nullptr,
+                                        a->need_dmixer ? a->dmixer : nullptr,
+                                        a->need_dmixer ? a->dweight_bias : nullptr);
+      if ((rc = check_launch("k_gm_param_bwd", st))) return rc;
+    }
+  }
+  return MAGAT_OK;
+}

@@ -1,0 +1,280 @@
+// Forward of the batched graph-attention layer -- generic fp32 SIMT path.
+//
+// Math (validated against the reference autograd):
+//   scores   KeyQuery      e_p[i,j] = x_i^T W_p x_j = R_i^p . x_j,  R_i^p = W_p^T x_i      (graphML.py:1246-1262)
+//            GAT_modified  e_p[i,j] = LeakyReLU_0.2(a2_p.z_i + a1_p.z_j), z = W_p x + wb_p  (graphML.py:777-796)
+//   A_p[i,:] = softmax of e_p[i,:] over the out-neighbours of i; empty row -> zeros      (graphML.py:1278-1286)
+//   u_0 = x, u_k[j] = sum_i A_p[i,j] u_{k-1}[i]                                          (graphML.py:1756-1759)
+//   Y_p[n] = sum_k H_{p,k} u_k^p[n] + bias; concat: relu(Y_p) at channel p*F+f; mean: relu(mean_p Y_p)
+//
+// Nothing N x N is ever materialised: the GSO arrives here already as padded neighbour lists
+// (gso_scan.cu).  This file is the path for every shape; the tcgen05 path (gat_tc.cu) replaces
+// the two dense projections for the shapes it covers.
+#include "common.cuh"
+#include "simt_gemm.cuh"
+
+namespace magat {
+
+// ---- GAT_modified parameter folding -------------------------------------------------------
+// a_t.z_n = a_t.(W x_n + wb) = (W^T a_t).x_n + a_t.wb, so per head two G-vectors and two scalars
+// replace the F x N projection:  cvec[p][t][g] = sum_f mixer[p][t*F+f] W[p][f][g],
+// dvec[p][t] = sum_f mixer[p][t*F+f] wb[p][f];  t = 0 is a1 (column/receiver term), t = 1 is a2.
+__global__ void __launch_bounds__(128) k_gm_prep(const float* __restrict__ W, const float* __restrict__ mixer,
+                                                 const float* __restrict__ wb, int G, int F, int P,
+                                                 float* __restrict__ cvec, float* __restrict__ dvec) {
+  const int pt = blockIdx.x;            // p*2 + t
+  const int p = pt >> 1, t = pt & 1;
+  const float* a = mixer + (size_t)p * 2 * F + (size_t)t * F;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float s = 0.f;
+    for (int f = 0; f < F; ++f) s = fmaf(a[f], W[((size_t)p * F + f) * G + g], s);
+    cvec[(size_t)pt * G + g] = s;
+  }
+  if (threadIdx.x < 32) {
+    float s = 0.f;
+    for (int f = threadIdx.x; f < F; f += 32) s = fmaf(a[f], wb[(size_t)p * F + f], s);
+    s = warp_sum(s);
+    if (threadIdx.x == 0) dvec[pt] = s;
+  }
+}
+
+// ---- row softmax over the neighbour list ---------------------------------------------------
+// One warp per sender row i.  Scores go through `att` (owned by this warp) so arbitrary degree
+// works; masked entries never enter the softmax, which is what softmax(e*M - 1e12(1-M))*M gives
+// in fp32 whenever the row has at least one edge, and an empty row stays all zero.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_attention(const float* __restrict__ x, long x_sb, long x_sn,
+                                                   const float* __restrict__ sproj,
+                                                   const int32_t* __restrict__ nbr_out, long rows, int N,
+                                                   int G, int P, int D, float* __restrict__ att) {
+  const int lane = threadIdx.x & 31;
+  const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  const long b = row / N;
+  const int32_t* nb = nbr_out + row * D;
+  float* arow = att + row * (size_t)D * P;
+  int deg = 0;
+  for (int s0 = 0; s0 < D; s0 += 32) {
+    const int s = s0 + lane;
+    deg += __popc(__ballot_sync(0xffffffffu, s < D && nb[s] >= 0));
+  }
+  for (int s = deg + lane; s < D; s += 32)
+    for (int p = 0; p < P; ++p) arow[(size_t)s * P + p] = 0.f;
+  if (deg == 0) return;
+  const float* xb = x + b * x_sb;
+  for (int p = 0; p < P; ++p) {
+    float mx = -INFINITY;
+    if (MODE == MAGAT_MODE_KEYQUERY) {
+      const float* r = sproj + ((size_t)row * P + p) * G;
+      for (int s = 0; s < deg; ++s) {
+        const float* xj = xb + (long)nb[s] * x_sn;
+        float d = 0.f;
+        for (int g = lane; g < G; g += 32) d = fmaf(r[g], xj[g], d);
+        d = warp_sum(d);
+        if (lane == 0) arow[(size_t)s * P + p] = d;
+        mx = fmaxf(mx, d);
+      }
+      __syncwarp();
+    } else {
+      const float si = sproj[((size_t)row * P + p) * 2 + 1];
+      for (int s = lane; s < deg; s += 32) {
+        const long j = b * N + nb[s];
+        float e = si + sproj[((size_t)j * P + p) * 2 + 0];
+        e = e > 0.f ? e : kLeaky * e;
+        arow[(size_t)s * P + p] = e;
+        mx = fmaxf(mx, e);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    float sum = 0.f;
+    for (int s = lane; s < deg; s += 32) {
+      const float ex = expf(arow[(size_t)s * P + p] - mx);
+      arow[(size_t)s * P + p] = ex;
+      sum += ex;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    for (int s = lane; s < deg; s += 32) arow[(size_t)s * P + p] *= inv;
+  }
+}
+
+// ---- one tap of the recursion: u_k[j] = sum_{i in in(j)} A_p[i,j] u_{k-1}[i] ----------------
+// One warp per receiver j; lanes sweep the feature axis.  k >= 1; u_0 = x.
+__global__ void __launch_bounds__(256) k_tap_gather(const float* __restrict__ x, long x_sb, long x_sn,
+                                                    const float* __restrict__ att,
+                                                    const int32_t* __restrict__ nbr_in,
+                                                    const int32_t* __restrict__ slot_in, long rows, int N,
+                                                    int G, int P, int K, int D, int k,
+                                                    float* __restrict__ taps) {
+  const int lane = threadIdx.x & 31;
+  const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  const long b = row / N;
+  const int32_t* nb = nbr_in + row * D;
+  const int32_t* sl = slot_in + row * D;
+  const int Km1 = K - 1;
+  for (int p = 0; p < P; ++p) {
+    for (int g0 = 0; g0 < G; g0 += 32) {
+      const int g = g0 + lane;
+      float acc = 0.f;
+      for (int s = 0; s < D; ++s) {
+        const int i = nb[s];
+        if (i < 0) break;
+        const long ri = b * N + i;
+        const float a = att[((size_t)ri * D + sl[s]) * P + p];
+        const float* src = (k == 1) ? (x + b * x_sb + (long)i * x_sn)
+                                    : (taps + (((size_t)ri * P + p) * Km1 + (k - 2)) * G);
+        if (g < G) acc = fmaf(a, src[g], acc);
+      }
+      if (g < G) taps[(((size_t)row * P + p) * Km1 + (k - 1)) * G + g] = acc;
+    }
+  }
+}
+
+// ---- functors for the tile GEMMs ----------------------------------------------------------
+struct XLoad {   // A(m, g): node features
+  const float* x; long x_sb, x_sn; int N;
+  __device__ __forceinline__ float operator()(long m, int g, int) const {
+    const long b = m / N;
+    return __ldg(x + b * x_sb + (m - b * N) * x_sn + g);
+  }
+};
+struct KqWLoad {   // B(g, n = p*G + g'): W[p][g][g']
+  const float* W; int G;
+  __device__ __forceinline__ float operator()(int g, int n, int) const {
+    const int p = n / G;
+    return __ldg(W + ((size_t)p * G + g) * G + (n - p * G));
+  }
+};
+struct StoreEpi {   // C[m][n]
+  float* out; int ld;
+  __device__ __forceinline__ void operator()(long m, int n, int, float v) const { out[m * ld + n] = v; }
+};
+struct GmCLoad {   // B(g, n = 2p+t): cvec[p][t][g]
+  const float* cvec; int G;
+  __device__ __forceinline__ float operator()(int g, int n, int) const { return __ldg(cvec + (size_t)n * G + g); }
+};
+struct GmEpi {   // sproj[m][n] = acc + dvec[n]
+  float* out; const float* dvec; int ld;
+  __device__ __forceinline__ void operator()(long m, int n, int, float v) const { out[m * ld + n] = v + dvec[n]; }
+};
+
+// Z(m, kk, z): the stacked taps [x | u_1^p | ... | u_{K-1}^p] of node m.
+// concat: z = p, kk in [0, K*G); mean: z = 0, kk in [0, P*K*G) with p = kk / (K*G).
+struct ZLoad {
+  const float* x; long x_sb, x_sn; const float* taps; int N, G, K, P, per_head;
+  __device__ __forceinline__ float operator()(long m, int kk, int z) const {
+    int p = z;
+    if (!per_head) { p = kk / (K * G); kk -= p * K * G; }
+    const int k = kk / G, g = kk - k * G;
+    if (k == 0) {
+      const long b = m / N;
+      return __ldg(x + b * x_sb + (m - b * N) * x_sn + g);
+    }
+    return __ldg(taps + (((size_t)m * P + p) * (K - 1) + (k - 1)) * G + g);
+  }
+};
+struct HLoad {   // B(kk, f, z): filterWeight[p][f][k][g]
+  const float* H; int G, K, F, per_head;
+  __device__ __forceinline__ float operator()(int kk, int f, int z) const {
+    int p = z;
+    if (!per_head) { p = kk / (K * G); kk -= p * K * G; }
+    return __ldg(H + ((size_t)p * F + f) * K * G + kk);
+  }
+};
+struct YEpi {
+  float* y; long y_sb, y_sn, y_sc; const float* bias; int N, F, relu; float scale;
+  __device__ __forceinline__ void operator()(long m, int f, int z, float v) const {
+    v = v * scale + (bias ? bias[f] : 0.f);
+    if (relu) v = fmaxf(v, 0.f);
+    const long b = m / N;
+    y[b * y_sb + (m - b * N) * y_sn + ((long)z * F + f) * y_sc] = v;
+  }
+};
+
+static int validate_common(int B, int N, int G, int F, int K, int P, int D, int mode) {
+  MAGAT_REQUIRE(B >= 1 && N >= 1 && G >= 1 && F >= 1 && K >= 1 && P >= 1 && D >= 1, MAGAT_E_BAD_ARG,
+                "bad shape B=%d N=%d G=%d F=%d K=%d P=%d D=%d", B, N, G, F, K, P, D);
+  MAGAT_REQUIRE(mode == MAGAT_MODE_KEYQUERY || mode == MAGAT_MODE_GAT_MODIFIED, MAGAT_E_BAD_ARG,
+                "unknown attention mode %d", mode);
+  MAGAT_REQUIRE(mode != MAGAT_MODE_KEYQUERY || F == G, MAGAT_E_UNSUPPORTED,
+                "KeyQuery needs F == G (got F=%d G=%d; graphML.py:1728,1765)", F, G);
+  MAGAT_REQUIRE(P <= 65535 && (long)P * K * G < (1l << 31), MAGAT_E_UNSUPPORTED, "P/K/G too large");
+  return MAGAT_OK;
+}
+
+int forward_tc(const magat_gat_fwd_args* a, cudaStream_t st);   // gat_tc.cu
+bool tc_supported(const magat_gat_fwd_args* a);
+
+int forward_simt(const magat_gat_fwd_args* a, cudaStream_t st) {
+  const int B = a->B, N = a->N, G = a->G, F = a->F, K = a->K, P = a->P, D = a->D;
+  const long rows = (long)B * N;
+  const int row_blocks = cdiv(rows, 8);
+  const XLoad xl{a->x, a->x_sb, a->x_sn, N};
+  int rc;
+  // 1. score projection
+  if (a->mode == MAGAT_MODE_KEYQUERY) {
+    dim3 grid(cdiv(rows, 64), cdiv((long)P * G, 64), 1);
+    k_node_gemm<<<grid, 256, 0, st>>>(rows, P * G, G, xl, KqWLoad{a->weight, G}, StoreEpi{a->sproj, P * G});
+    if ((rc = check_launch("k_node_gemm(score projection)", st))) return rc;
+    k_attention<MAGAT_MODE_KEYQUERY><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj, a->nbr_out,
+                                                                  rows, N, G, P, D, a->att);
+  } else {
+    float* cvec = a->wprep;
+    float* dvec = a->wprep + (size_t)P * 2 * G;
+    k_gm_prep<<<P * 2, 128, 0, st>>>(a->weight, a->mixer, a->weight_bias, G, F, P, cvec, dvec);
+    if ((rc = check_launch("k_gm_prep", st))) return rc;
+    dim3 grid(cdiv(rows, 64), cdiv(2l * P, 64), 1);
+    k_node_gemm<<<grid, 256, 0, st>>>(rows, 2 * P, G, xl, GmCLoad{cvec, G}, GmEpi{a->sproj, dvec, 2 * P});
+    if ((rc = check_launch("k_node_gemm(mixer projection)", st))) return rc;
+    k_attention<MAGAT_MODE_GAT_MODIFIED><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj,
+                                                                      a->nbr_out, rows, N, G, P, D, a->att);
+  }
+  if ((rc = check_launch("k_attention", st))) return rc;
+  // 2. taps
+  for (int k = 1; k < K; ++k) {
+    k_tap_gather<<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->att, a->nbr_in, a->slot_in, rows, N, G,
+                                             P, K, D, k, a->taps);
+    if ((rc = check_launch("k_tap_gather", st))) return rc;
+  }
+  // 3. per-(head, tap) projection + bias + activation + concat / head mean
+  const int per_head = a->concat ? 1 : 0;
+  const ZLoad zl{a->x, a->x_sb, a->x_sn, a->taps, N, G, K, P, per_head};
+  const HLoad hl{a->filterWeight, G, K, F, per_head};
+  const YEpi ye{a->y, a->y_sb, a->y_sn, a->y_sc, a->bias, N, F, a->relu, per_head ? 1.f : 1.f / (float)P};
+  dim3 grid(cdiv(rows, 64), cdiv(F, 64), per_head ? P : 1);
+  k_node_gemm<<<grid, 256, 0, st>>>(rows, F, per_head ? K * G : P * K * G, zl, hl, ye);
+  return check_launch("k_node_gemm(tap projection)", st);
+}
+
+}  // namespace magat
+
+using namespace magat;
+
+extern "C" size_t magat_gat_wprep_floats(int G, int F, int K, int P, int mode) {
+  (void)F; (void)K;
+  if (mode == MAGAT_MODE_GAT_MODIFIED) return (size_t)P * 2 * G + (size_t)P * 2;
+  return 4;
+}
+
+extern "C" int magat_gat_forward(const magat_gat_fwd_args* a, void* stream) {
+  MAGAT_REQUIRE(a != nullptr, MAGAT_E_BAD_ARG, "magat_gat_forward: null args");
+  int rc = validate_common(a->B, a->N, a->G, a->F, a->K, a->P, a->D, a->mode);
+  if (rc) return rc;
+  MAGAT_REQUIRE(a->x && a->nbr_out && a->nbr_in && a->slot_in && a->weight && a->filterWeight && a->y &&
+                    a->att && a->sproj && a->wprep,
+                MAGAT_E_BAD_ARG, "magat_gat_forward: null pointer");
+  MAGAT_REQUIRE(a->K == 1 || a->taps, MAGAT_E_BAD_ARG, "magat_gat_forward: taps buffer missing for K=%d", a->K);
+  MAGAT_REQUIRE(a->mode != MAGAT_MODE_GAT_MODIFIED || (a->mixer && a->weight_bias), MAGAT_E_BAD_ARG,
+                "magat_gat_forward: GAT_modified needs mixer and weight_bias");
+  MAGAT_REQUIRE(a->x_sn >= a->G, MAGAT_E_BAD_ARG, "magat_gat_forward: x row stride %ld < G", (long)a->x_sn);
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin(st);
+  if (a->path == MAGAT_PATH_TCGEN05) {
+    MAGAT_REQUIRE(tc_supported(a), MAGAT_E_UNSUPPORTED, "magat_gat_forward: shape not covered by the tcgen05 path");
+    return forward_tc(a, st);
+  }
+  if (a->path == MAGAT_PATH_AUTO && tc_supported(a)) return forward_tc(a, st);
+  return forward_simt(a, st);
+}

@@ -1,0 +1,418 @@
+"""Host-side mirror of the reference's operator interface for the batched graph-attention path.
+
+Same names, argument meaning and error behaviour as ``utils/graphUtils/graphML.py`` of
+proroklab/magat_pathplanning for:
+
+* ``GraphFilterBatchAttentional``            (graphML.py:4506-4685)  nn.Module: params, addGSO, forward, returnAttentionGSO
+* ``graphAttentionLSIGFBatch_KeyQuery``      (graphML.py:1724-1775)
+* ``graphAttentionLSIGFBatch_modified``      (graphML.py:1777-1827)
+* ``learnAttentionGSOBatch_KeyQuery``        (graphML.py:1180-1286)
+* ``learnAttentionGSOBatch``                 (graphML.py:713-823)
+
+All arithmetic happens in ``lib/libmagat_gat.so`` (hand-written sm_100a CUDA behind the C ABI of
+``include/magat_gat.h``); torch is used for device memory, streams and autograd bookkeeping only.
+There is no CPU path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _cabi
+
+zeroTolerance = 1e-9     # graphML.py:45
+infiniteNumber = 1e12    # graphML.py:46
+
+#: no host sync for the ELL width below this node count (width = N)
+_SMALL_N = 48
+
+_PATH = {"auto": _cabi.PATH_AUTO, "simt": _cabi.PATH_SIMT, "tcgen05": _cabi.PATH_TCGEN05}
+
+
+def _stream(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"magat_pathplanning_b200: {what} must be a CUDA tensor (sm_100a); "
+                           "this package has no CPU path")
+
+
+class Adjacency:
+    """Neighbour lists of one GSO batch (device tensors; layouts in include/magat_gat.h)."""
+
+    __slots__ = ("B", "N", "D", "nbr_out", "nbr_in", "slot_in", "symmetric_hint")
+
+    def __init__(self, B, N, D, nbr_out, nbr_in, slot_in):
+        self.B, self.N, self.D = B, N, D
+        self.nbr_out, self.nbr_in, self.slot_in = nbr_out, nbr_in, slot_in
+
+
+def build_adjacency(S: torch.Tensor) -> Adjacency:
+    """[B,1,N,N] dense GSO -> neighbour lists.  Only ``|S| > 1e-9`` matters (graphML.py:1274-1276):
+    NaN is "no edge", negative weights are edges.  S is read once, by one kernel."""
+    _require_cuda(S, "the GSO")
+    assert len(S.shape) == 4
+    B, E, N = S.shape[0], S.shape[1], S.shape[2]
+    assert S.shape[3] == N
+    if E != 1:
+        raise NotImplementedError("edge_features E != 1 is not supported (the planners use E = 1, "
+                                  "graphs/models/decentralplanner_GAT.py:179)")
+    S = S.detach()
+    if S.dtype not in (torch.float32, torch.float64):
+        S = S.to(torch.float32)
+    if not S.is_contiguous():
+        S = S.contiguous()
+    dev = S.device
+    L = _cabi.lib()
+    W = (N + 31) // 32
+    with torch.cuda.device(dev):
+        st = _stream(dev)
+        rowbits = torch.empty((B, N, W), dtype=torch.int32, device=dev)
+        colbits = torch.empty((B, N, W), dtype=torch.int32, device=dev)
+        stats = torch.zeros(4, dtype=torch.int32, device=dev)
+        stats[3] = 1
+        _cabi.check(L.magat_gso_scan(S.data_ptr(), _cabi.DT_F32 if S.dtype == torch.float32 else _cabi.DT_F64,
+                                     B, N, rowbits.data_ptr(), colbits.data_ptr(), stats.data_ptr(), st))
+        if N <= _SMALL_N:
+            D = N
+        else:
+            h = stats.cpu()
+            D = max(int(h[0]), int(h[1]), 1)
+        nbr_out = torch.empty((B, N, D), dtype=torch.int32, device=dev)
+        nbr_in = torch.empty((B, N, D), dtype=torch.int32, device=dev)
+        slot_in = torch.empty((B, N, D), dtype=torch.int32, device=dev)
+        _cabi.check(L.magat_gso_build_ell(rowbits.data_ptr(), colbits.data_ptr(), B, N, D, nbr_out.data_ptr(),
+                                          nbr_in.data_ptr(), slot_in.data_ptr(), st))
+    return Adjacency(B, N, D, nbr_out, nbr_in, slot_in)
+
+
+def _node_major(x: torch.Tensor):
+    """x is logically [B,G,N]; the kernels want node-major rows.  The planners hand over a permuted
+    view of contiguous [B,N,G] memory (decentralplanner_GAT.py:304) which is used in place."""
+    xt = x.permute(0, 2, 1)
+    G = xt.shape[2]
+    if xt.shape[2] > 1 and xt.stride(2) != 1:
+        xt = xt.contiguous()
+    elif xt.stride(1) < G or (xt.shape[0] > 1 and xt.stride(0) < 0):
+        xt = xt.contiguous()
+    return xt
+
+
+class _Meta:
+    __slots__ = ("mode", "concat", "relu", "path", "G", "F", "K", "P", "has_bias")
+
+
+class _GATFunction(torch.autograd.Function):
+    """x[B,G,N] -> y (concat: [B,P*F,N] view over [B,N,P*F]; mean: [B,F,N]) plus the sparse attention."""
+
+    @staticmethod
+    def forward(ctx, x, weight, mixer, weight_bias, filterWeight, bias, adj: Adjacency, meta: _Meta):
+        L = _cabi.lib()
+        dev = x.device
+        B, G, N = x.shape
+        F, K, P, D = meta.F, meta.K, meta.P, adj.D
+        xt = _node_major(x.detach())
+        weight_c = weight.detach().contiguous()
+        filt_c = filterWeight.detach().contiguous()
+        mixer_c = None if mixer is None else mixer.detach().contiguous()
+        wb_c = None if weight_bias is None else weight_bias.detach().contiguous()
+        bias_c = None if bias is None else bias.detach().contiguous()
+        C_out = P * F if meta.concat else F
+        with torch.cuda.device(dev):
+            if meta.concat:
+                y_mem = torch.empty((B, N, C_out), dtype=torch.float32, device=dev)
+                y = y_mem.permute(0, 2, 1)
+            else:
+                y_mem = torch.empty((B, C_out, N), dtype=torch.float32, device=dev)
+                y = y_mem
+            att = torch.empty((B, N, D, P), dtype=torch.float32, device=dev)
+            taps = torch.empty((B, N, P, max(K - 1, 1), G), dtype=torch.float32, device=dev) if K > 1 else None
+            wprep = torch.empty(L.magat_gat_wprep_floats(G, F, K, P, meta.mode), dtype=torch.float32, device=dev)
+            sproj = torch.empty((B, N, P, G if meta.mode == _cabi.MODE_KEYQUERY else 2), dtype=torch.float32,
+                                device=dev)
+            a = _cabi.FwdArgs(B=B, N=N, G=G, F=F, K=K, P=P, D=D, mode=meta.mode, concat=int(meta.concat),
+                              relu=int(meta.relu), path=meta.path, reserved=0,
+                              x=xt.data_ptr(), x_sb=xt.stride(0), x_sn=xt.stride(1),
+                              nbr_out=adj.nbr_out.data_ptr(), nbr_in=adj.nbr_in.data_ptr(),
+                              slot_in=adj.slot_in.data_ptr(),
+                              weight=weight_c.data_ptr(), mixer=_p(mixer_c), weight_bias=_p(wb_c),
+                              filterWeight=filt_c.data_ptr(), bias=_p(bias_c),
+                              y=y_mem.data_ptr(), y_sb=y.stride(0), y_sn=y.stride(2), y_sc=y.stride(1),
+                              att=att.data_ptr(), taps=_p(taps), wprep=wprep.data_ptr(), sproj=sproj.data_ptr())
+            _cabi.check(L.magat_gat_forward(a, _stream(dev)))
+        ctx.meta, ctx.adj = meta, adj
+        ctx.save_for_backward(xt, weight_c, mixer_c, wb_c, filt_c, y, att, taps, wprep, sproj)
+        ctx.mark_non_differentiable(att)
+        return y, att
+
+    @staticmethod
+    def backward(ctx, dy, _datt):
+        L = _cabi.lib()
+        meta, adj = ctx.meta, ctx.adj
+        xt, weight_c, mixer_c, wb_c, filt_c, y, att, taps, wprep, sproj = ctx.saved_tensors
+        dev = xt.device
+        B, N, G = xt.shape
+        F, K, P, D = meta.F, meta.K, meta.P, adj.D
+        gm = meta.mode == _cabi.MODE_GAT_MODIFIED
+        need = ctx.needs_input_grad
+        need_dx, need_dw = need[0], need[1]
+        need_dmix = gm and (need[2] or need[3])
+        need_df, need_db = need[4], (need[5] and meta.has_bias)
+        if dy.dtype != torch.float32:
+            dy = dy.float()
+        with torch.cuda.device(dev):
+            def buf(*shape):
+                return torch.empty(shape, dtype=torch.float32, device=dev)
+            dx = buf(B, N, G) if need_dx else None
+            dw = torch.empty_like(weight_c) if need_dw else None
+            dmix = torch.empty_like(mixer_c) if need_dmix else None
+            dwb = torch.empty_like(wb_c) if need_dmix else None
+            df = torch.empty_like(filt_c) if need_df else None
+            db = buf(F, 1) if need_db else None
+            gz = buf(B, N, P, K, G)
+            datt = buf(B, N, D, P)
+            rc = buf(B, N, P, 2 if gm else G)
+            partial = buf(L.magat_gat_bwd_partial_floats(B, N, G, F, K, P, meta.mode))
+            a = _cabi.BwdArgs(B=B, N=N, G=G, F=F, K=K, P=P, D=D, mode=meta.mode, concat=int(meta.concat),
+                              relu=int(meta.relu), path=meta.path,
+                              need_dx=int(need_dx), need_dweight=int(need_dw), need_dfilter=int(need_df),
+                              need_dbias=int(need_db), need_dmixer=int(need_dmix),
+                              x=xt.data_ptr(), x_sb=xt.stride(0), x_sn=xt.stride(1),
+                              nbr_out=adj.nbr_out.data_ptr(), nbr_in=adj.nbr_in.data_ptr(),
+                              slot_in=adj.slot_in.data_ptr(),
+                              weight=weight_c.data_ptr(), mixer=_p(mixer_c), weight_bias=_p(wb_c),
+                              filterWeight=filt_c.data_ptr(),
+                              y=y.data_ptr(), y_sb=y.stride(0), y_sn=y.stride(2), y_sc=y.stride(1),
+                              att=att.data_ptr(), taps=_p(taps), wprep=wprep.data_ptr(), sproj=sproj.data_ptr(),
+                              dy=dy.data_ptr(), dy_sb=dy.stride(0), dy_sn=dy.stride(2), dy_sc=dy.stride(1),
+                              dx=_p(dx), dweight=_p(dw), dmixer=_p(dmix), dweight_bias=_p(dwb),
+                              dfilterWeight=_p(df), dbias=_p(db),
+                              gz=gz.data_ptr(), datt=datt.data_ptr(), rc=rc.data_ptr(), partial=partial.data_ptr())
+            _cabi.check(L.magat_gat_backward(a, _stream(dev)))
+        gx = dx.permute(0, 2, 1) if need_dx else None
+        # KeyQuery never touches mixer / weight_bias: the reference leaves their grad = None
+        return (gx, dw, dmix if (need_dmix and need[2]) else None, dwb if (need_dmix and need[3]) else None,
+                df, db, None, None)
+
+
+def _mode_of(attentionMode: str) -> int:
+    if 'GAT_modified' in attentionMode:          # graphML.py:4588
+        return _cabi.MODE_GAT_MODIFIED
+    if attentionMode == 'KeyQuery':              # graphML.py:4594
+        return _cabi.MODE_KEYQUERY
+    raise ValueError(f"unsupported attentionMode {attentionMode!r}")
+
+
+def gat_layer(x, S, filterWeight, mixer, weight, weight_bias, bias, *, mode: int, concatenate: bool,
+              relu: bool = True, path: str = "auto", adjacency: Optional[Adjacency] = None):
+    """One call of the fused layer.  Returns ``(y, att, adjacency)``; ``att`` is the sparse attention
+    ([B,N,D,P], see include/magat_gat.h) that ``attention_dense`` expands on demand."""
+    _require_cuda(x, "x")
+    assert len(x.shape) == 3
+    P, F, E, K, G = filterWeight.shape
+    assert E == 1
+    assert x.shape[1] == G                       # graphML.py:1735
+    if x.dtype != torch.float32:
+        x = x.float()
+    adj = adjacency if adjacency is not None else build_adjacency(S)
+    assert adj.B == x.shape[0] and adj.N == x.shape[2]
+    if mode == _cabi.MODE_KEYQUERY:
+        assert tuple(weight.shape) == (P, E, G, G)
+        if F != G:
+            raise RuntimeError("KeyQuery attention needs out_features == in_features "
+                               "(the reference reshape at graphML.py:1765 fails otherwise)")
+    else:
+        assert tuple(weight.shape) == (P, E, F, G)
+        assert tuple(mixer.shape) == (P, E, 2 * F)
+    meta = _Meta()
+    meta.mode, meta.concat, meta.relu, meta.path = mode, bool(concatenate), bool(relu), _PATH[path]
+    meta.G, meta.F, meta.K, meta.P, meta.has_bias = G, F, K, P, bias is not None
+    if mode == _cabi.MODE_KEYQUERY:
+        mixer_in, wb_in = None, None             # unused by the math; grads stay None (graphML.py:1265-1266)
+    else:
+        mixer_in, wb_in = mixer, weight_bias
+    y, att = _GATFunction.apply(x, weight, mixer_in, wb_in, filterWeight, bias, adj, meta)
+    return y, att, adj
+
+
+def attention_dense(att: torch.Tensor, adj: Adjacency, mean_heads: bool = False) -> torch.Tensor:
+    """Sparse attention -> dense ``aij`` [B,P,1,N,N] (or its head mean [B,1,N,N])."""
+    L = _cabi.lib()
+    B, N, D, P = att.shape
+    dev = att.device
+    with torch.cuda.device(dev):
+        out = torch.zeros((B, 1, N, N) if mean_heads else (B, P, 1, N, N), dtype=torch.float32, device=dev)
+        _cabi.check(L.magat_gat_attention_dense(att.data_ptr(), adj.nbr_out.data_ptr(), B, N, D, P,
+                                                int(mean_heads), out.data_ptr(), _stream(dev)))
+    return out
+
+
+# ---- functionals with the reference's signatures -------------------------------------------------
+
+def _functional(h, x, a, W, W_b, S, b, mode):
+    P, F = h.shape[0], h.shape[1]
+    B, N = x.shape[0], x.shape[2]
+    y, att, adj = gat_layer(x, S, h, a, W, W_b, b, mode=mode, concatenate=True, relu=False)
+    y = y.permute(0, 2, 1).reshape(B, N, P, F).permute(0, 2, 3, 1)      # B x P x F x N
+    return y, attention_dense(att, adj)
+
+
+def graphAttentionLSIGFBatch_KeyQuery(h, x, a, W, W_b, S, b=None):
+    """graphML.py:1724-1775: returns (y [B,P,F,N] before the nonlinearity, aij [B,P,E,N,N])."""
+    return _functional(h, x, a, W, W_b, S, b, _cabi.MODE_KEYQUERY)
+
+
+def graphAttentionLSIGFBatch_modified(h, x, a, W, W_b, S, b=None):
+    """graphML.py:1777-1827."""
+    return _functional(h, x, a, W, W_b, S, b, _cabi.MODE_GAT_MODIFIED)
+
+
+def _attention_only(x, a, W, W_b, S, mode):
+    P, E, G = W.shape[0], W.shape[1], W.shape[3]
+    F = G if mode == _cabi.MODE_KEYQUERY else W.shape[2]
+    h = torch.zeros((P, F, E, 1, G), dtype=torch.float32, device=x.device)
+    with torch.no_grad():
+        _, att, adj = gat_layer(x, S, h, a, W, W_b, None, mode=mode, concatenate=True, relu=False)
+    return attention_dense(att, adj)
+
+
+def learnAttentionGSOBatch_KeyQuery(x, a, W, S, negative_slope=0.2):
+    """graphML.py:1180-1286 (the reference ignores ``a`` and ``negative_slope`` in this mode)."""
+    return _attention_only(x, a, W, None, S, _cabi.MODE_KEYQUERY)
+
+
+def learnAttentionGSOBatch(x, a, W, W_b, S, negative_slope=0.2):
+    """graphML.py:713-823."""
+    if negative_slope != 0.2:
+        raise NotImplementedError("only the reference's default negative_slope = 0.2 is built in")
+    return _attention_only(x, a, W, W_b, S, _cabi.MODE_GAT_MODIFIED)
+
+
+# ---- the module ------------------------------------------------------------------------------
+
+class GraphFilterBatchAttentional(nn.Module):
+    """Drop-in for ``utils.graphUtils.graphML.GraphFilterBatchAttentional`` (graphML.py:4506-4685).
+
+    Same constructor, parameter names / shapes / registration order (so reference checkpoints
+    ``GFL.{l}.*`` load), ``addGSO``, ``forward``, ``returnAttentionGSO`` and ``extra_repr``.
+    Differences, all invisible to the planners: the work runs in sm_100a CUDA kernels, and
+    ``self.aij`` (a dense numpy copy the reference makes on every forward, graphML.py:4650) is
+    materialised lazily on first access.
+    """
+
+    def __init__(self, G, F, K, P, E=1, bias=True, nonlinearity=nn.functional.relu, concatenate=True,
+                 attentionMode='GAT_modified'):
+        super().__init__()
+        self.G = G
+        self.F = F
+        self.K = K
+        self.P = P
+        self.E = E
+        self.S = None
+        self.nonlinearity = nonlinearity
+        self.concatenate = concatenate
+        self.attentionMode = attentionMode
+        self.path = "auto"
+        self._last = None
+        self._aij = None
+        if E != 1:
+            raise NotImplementedError("edge_features E != 1 is not supported")
+        self.mixer = nn.parameter.Parameter(torch.Tensor(P, E, 2 * F))
+        self.weight_bias = nn.parameter.Parameter(torch.Tensor(P, E, F))
+        self.filterWeight = nn.parameter.Parameter(torch.Tensor(P, F, E, K, G))
+        if bias:
+            self.bias = nn.parameter.Parameter(torch.Tensor(F, 1))
+        else:
+            self.register_parameter('bias', None)
+        if 'GAT_modified' in attentionMode:
+            self.weight = nn.parameter.Parameter(torch.Tensor(P, E, F, G))
+        elif attentionMode == 'KeyQuery':
+            self.weight = nn.parameter.Parameter(torch.Tensor(P, E, G, G))
+        self.reset_parameters()          # raises AttributeError for other modes, like the reference
+
+    def reset_parameters(self):
+        stdv = 1. / math.sqrt(self.G * self.P)
+        self.weight.data.uniform_(-stdv, stdv)
+        self.weight_bias.data.uniform_(0, 0)
+        self.mixer.data.uniform_(-stdv, stdv)
+        self.filterWeight.data.uniform_(-stdv, stdv)
+        if self.bias is not None:
+            self.bias.data.uniform_(-stdv, stdv)
+
+    def addGSO(self, S):
+        assert len(S.shape) == 4
+        assert S.shape[1] == self.E
+        self.N = S.shape[2]
+        assert S.shape[3] == self.N
+        self.S = S                       # borrowed, read at forward time like the reference
+
+    # ``aij`` is what graphML.py:4650 stores eagerly; here the dense copy is made on first use.
+    @property
+    def aij(self):
+        if self._aij is None and self._last is not None:
+            att, adj = self._last
+            self._aij = attention_dense(att, adj).cpu().numpy()
+        return self._aij
+
+    @aij.setter
+    def aij(self, value):
+        self._aij = value
+        self._last = None
+
+    def returnAttentionGSO(self):
+        if self._aij is None and self._last is not None:
+            att, adj = self._last
+            return attention_dense(att, adj, mean_heads=True).cpu().numpy()
+        aij = self.aij
+        assert len(aij.shape) == 5
+        assert aij.shape[2] == self.E
+        self.N = aij.shape[3]
+        return np.mean(aij, axis=1)
+
+    def forward(self, x):
+        B = x.shape[0]
+        F = x.shape[1]
+        Nin = x.shape[2]
+        if Nin < self.N:                 # graphML.py:4642-4646
+            x = torch.cat((x, torch.zeros(B, F, self.N - Nin).type(x.dtype).to(x.device)), dim=2)
+        fused_relu = self.nonlinearity in (nn.functional.relu, torch.relu)
+        y, att, adj = gat_layer(x, self.S, self.filterWeight, self.mixer, self.weight, self.weight_bias,
+                                self.bias, mode=_mode_of(self.attentionMode), concatenate=self.concatenate,
+                                relu=fused_relu, path=self.path)
+        self._last, self._aij = (att.detach(), adj), None
+        if not fused_relu:
+            y = self.nonlinearity(y)
+        if Nin < self.N:
+            y = torch.index_select(y, 2, torch.arange(Nin).to(y.device))
+        return y
+
+    def extra_repr(self):
+        reprString = "in_features=%d, " % self.G
+        reprString += "out_features=%d, " % self.F
+        reprString += "filter_taps=%d, " % self.K
+        reprString += "attention_heads=%d, " % self.P
+        reprString += "edge_features=%d, " % self.E
+        reprString += "bias=%s, " % (self.bias is not None)
+        reprString += "attentionMode=%s, " % (self.attentionMode)
+        if self.S is not None:
+            reprString += "GSO stored: number_nodes=%d" % (self.N)
+        else:
+            reprString += "no GSO stored"
+        return reprString
+
+    def __getstate__(self):
+        # picklable for torch.multiprocessing.spawn (agents/...GAT.py:720-728): no device scratch, no handles
+        state = self.__dict__.copy()
+        state["_last"] = None
+        state["_aij"] = None
+        return state

@@ -1,0 +1,92 @@
+"""The C-ABI library loads and exports every symbol include/magat_gat.h declares (no GPU needed),
+and the host-side mirror keeps the reference's module surface."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "magat_gat.h")
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+    g.build()
+    from magat_pathplanning_b200 import _cabi
+    return _cabi
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(magat_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(built):
+    names = declared_functions()
+    assert len(names) >= 10
+    L = ctypes.CDLL(built.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/magat_gat.h but not exported"
+    assert set(names) == set(built.EXPORTS)
+    assert L.magat_abi_version() == built.ABI_VERSION
+
+
+def test_struct_sizes_match_header(built):
+    # 12 x int32 + 19 x 8 bytes ; 16 x int32 + 32 x 8 bytes
+    assert ctypes.sizeof(built.FwdArgs) == 12 * 4 + 19 * 8
+    assert ctypes.sizeof(built.BwdArgs) == 16 * 4 + 32 * 8
+
+
+def test_sizes_helpers_need_no_gpu(built):
+    L = built.lib()
+    assert L.magat_gat_wprep_floats(128, 128, 3, 4, built.MODE_GAT_MODIFIED) == 4 * 2 * 128 + 8
+    assert L.magat_gat_bwd_partial_floats(512, 1000, 128, 128, 3, 4, built.MODE_KEYQUERY) > 0
+
+
+def test_bad_arguments_return_codes_not_crash(built):
+    L = built.lib()
+    a = built.FwdArgs(B=1, N=4, G=8, F=16, K=2, P=1, D=1, mode=built.MODE_KEYQUERY)
+    rc = L.magat_gat_forward(a, None)
+    assert rc == 2 and b"F == G" in L.magat_last_error()          # MAGAT_E_UNSUPPORTED
+    a = built.FwdArgs(B=0, N=4, G=8, F=8, K=2, P=1, D=1, mode=built.MODE_KEYQUERY)
+    assert L.magat_gat_forward(a, None) == 1                        # MAGAT_E_BAD_ARG
+    assert L.magat_gat_forward(None, None) == 1
+    assert L.magat_gso_scan(None, 0, 1, 4, None, None, None, None) == 1
+
+
+def test_module_surface_matches_reference():
+    from magat_pathplanning_b200 import GraphFilterBatchAttentional
+    m = GraphFilterBatchAttentional(16, 16, 3, 4, 1, True, concatenate=True, attentionMode="KeyQuery")
+    assert [k for k, _ in m.named_parameters()] == ["mixer", "weight_bias", "filterWeight", "bias", "weight"]
+    assert tuple(m.weight.shape) == (4, 1, 16, 16) and tuple(m.filterWeight.shape) == (4, 16, 1, 3, 16)
+    assert float(m.weight_bias.abs().max()) == 0.0
+    assert float(m.weight.abs().max()) <= 1.0 / (16 * 4) ** 0.5
+    m2 = GraphFilterBatchAttentional(16, 24, 2, 2, 1, False, attentionMode="GAT_modified")
+    assert "bias" not in m2.state_dict() and tuple(m2.weight.shape) == (2, 1, 24, 16)
+    assert "no GSO stored" in repr(m2)
+    with pytest.raises(AssertionError):
+        m.addGSO(torch.zeros(2, 5, 5))
+    m.addGSO(torch.zeros(2, 1, 5, 5))
+    assert m.N == 5 and "number_nodes=5" in repr(m)
+    assert m.aij is None
+    with pytest.raises(AttributeError):
+        GraphFilterBatchAttentional(8, 8, 2, 2, attentionMode="nonsense")
+
+
+def test_reference_state_dict_loads():
+    """Parameter names / shapes / order are API (checkpoints 'GFL.0.*'); load a reference layer's state."""
+    from oracle.ref_loader import load_reference_graphml, reference_available
+    if not reference_available():
+        pytest.skip("reference checkout not present")
+    gml = load_reference_graphml()
+    from magat_pathplanning_b200 import GraphFilterBatchAttentional
+    for mode in ("KeyQuery", "GAT_modified"):
+        ref = gml.GraphFilterBatchAttentional(16, 16, 3, 2, 1, True, concatenate=True, attentionMode=mode)
+        ours = GraphFilterBatchAttentional(16, 16, 3, 2, 1, True, concatenate=True, attentionMode=mode)
+        assert list(ref.state_dict()) == list(ours.state_dict())
+        ours.load_state_dict(ref.state_dict())
+        assert repr(ours) == repr(ref)

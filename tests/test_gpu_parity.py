@@ -1,0 +1,205 @@
+"""Parity of the CUDA path (through the C ABI) with the golden vectors of the unmodified reference
+and with the CPU oracle.  Tolerance: 1e-4 max-norm relative (BASELINE.json north_star) on outputs,
+attention and every gradient; the fp32 SIMT path is expected to sit near 1e-6."""
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_case_names
+from oracle import gat_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+PARAMS = ("mixer", "weight_bias", "filterWeight", "bias", "weight")
+
+
+def rel_err(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def make_layer(meta, d, dev, path="simt"):
+    from magat_pathplanning_b200 import GraphFilterBatchAttentional
+    layer = GraphFilterBatchAttentional(meta["G"], meta["F"], meta["K"], meta["P"], 1, meta.get("bias", True),
+                                        concatenate=meta["concat"], attentionMode=meta["mode"])
+    with torch.no_grad():
+        for k in PARAMS:
+            if ("param." + k) in d:
+                getattr(layer, k).copy_(d["param." + k])
+    layer.path = path
+    return layer.to(dev)
+
+
+@pytest.mark.parametrize("name", golden_case_names())
+def test_golden_forward_backward(golden, name):
+    d, meta = golden.case(name)
+    dev = torch.device("cuda:0")
+    layer = make_layer(meta, d, dev)
+    x = d["x"].to(dev).requires_grad_(True)
+    layer.addGSO(d["S"].to(dev))
+    y = layer(x)
+    assert y.shape == d["y"].shape
+    assert rel_err(y, d["y"]) < TOL
+    aij = layer.aij
+    assert isinstance(aij, np.ndarray) and aij.shape == tuple(d["aij"].shape)
+    assert np.abs(aij - d["aij"].numpy()).max() < TOL
+    ret = layer.returnAttentionGSO()
+    assert list(ret.shape) == meta["returnAttentionGSO_shape"]
+    assert np.abs(ret - d["aij"].numpy().mean(axis=1)).max() < TOL
+    y.backward(d["dy"].to(dev))
+    assert rel_err(x.grad, d["grad.x"]) < TOL
+    for k in PARAMS:
+        p = getattr(layer, k)
+        if p is None:
+            continue
+        if k in meta["none_grads"]:
+            assert p.grad is None, f"{k} must keep grad=None like the reference"
+        else:
+            assert rel_err(p.grad, d["grad." + k]) < TOL, k
+
+
+def test_output_layout_matches_reference(golden):
+    dev = torch.device("cuda:0")
+    for name in ("kq_concat_c2", "kq_mean_c1"):
+        d, meta = golden.case(name)
+        layer = make_layer(meta, d, dev)
+        layer.addGSO(d["S"].to(dev))
+        with torch.no_grad():
+            y = layer(d["x"].to(dev))
+        B, C, N = y.shape
+        if meta["concat"]:      # permuted view over [B,N,P*F] memory (graphML.py:4656-4662)
+            assert y.stride() == (N * C, 1, C)
+        else:                   # contiguous [B,F,N] (graphML.py:4665-4667)
+            assert y.is_contiguous()
+
+
+def test_x_layouts_and_gso_dtype(golden):
+    """x as the planners pass it (permuted view of [B,N,G]) and as a plain contiguous [B,G,N] tensor."""
+    dev = torch.device("cuda:0")
+    d, meta = golden.case("kq_concat_n10")
+    layer = make_layer(meta, d, dev)
+    layer.addGSO(d["S"].double().to(dev))               # simulator GSOs are float64 (new_simulator.py:317)
+    with torch.no_grad():
+        xa = d["x"].to(dev).contiguous()                # [B,G,N] contiguous
+        xb = d["x"].permute(0, 2, 1).contiguous().to(dev).permute(0, 2, 1)   # view of [B,N,G]
+        assert not xb.is_contiguous()
+        ya, yb = layer(xa), layer(xb)
+    assert rel_err(ya, d["y"]) < TOL and rel_err(yb, d["y"]) < TOL
+    assert torch.equal(ya, yb)
+
+
+def test_gso_scale_invariance_and_isolated_rows(golden):
+    dev = torch.device("cuda:0")
+    d, meta = golden.case("kq_concat_n10")
+    layer = make_layer(meta, d, dev)
+    x = d["x"].to(dev)
+    with torch.no_grad():
+        layer.addGSO(d["S"].to(dev))
+        y1 = layer(x)
+        a1 = layer.aij
+        layer.addGSO((d["S"] * 3.7).to(dev))
+        y2 = layer(x)
+    assert torch.equal(y1, y2)
+    mask = (d["S"].abs() > 1e-9)[:, 0].numpy()
+    assert np.all(a1[:, :, 0][np.broadcast_to(~mask[:, None], a1[:, :, 0].shape)] == 0.0)
+    iso = ~mask.any(-1)
+    rows = a1[:, :, 0].sum(-1)
+    assert np.all(rows[np.broadcast_to(iso[:, None], rows.shape)] == 0)
+
+
+def test_requires_grad_gating(golden):
+    dev = torch.device("cuda:0")
+    d, meta = golden.case("gm_concat_fneg")
+    layer = make_layer(meta, d, dev)
+    layer.filterWeight.requires_grad_(False)
+    layer.weight.requires_grad_(False)
+    layer.addGSO(d["S"].to(dev))
+    x = d["x"].to(dev)                                    # no grad on x either
+    y = layer(x)
+    y.backward(d["dy"].to(dev))
+    assert layer.filterWeight.grad is None and layer.weight.grad is None
+    assert rel_err(layer.mixer.grad, d["grad.mixer"]) < TOL
+    assert rel_err(layer.bias.grad, d["grad.bias"]) < TOL
+    assert rel_err(layer.weight_bias.grad, d["grad.weight_bias"]) < TOL
+
+
+def test_functional_surface(golden):
+    from magat_pathplanning_b200 import (graphAttentionLSIGFBatch_KeyQuery, graphAttentionLSIGFBatch_modified,
+                                         learnAttentionGSOBatch, learnAttentionGSOBatch_KeyQuery)
+    dev = torch.device("cuda:0")
+    for name, fn, att_fn in (("kq_concat_n10", graphAttentionLSIGFBatch_KeyQuery, learnAttentionGSOBatch_KeyQuery),
+                             ("gm_concat_fneg", graphAttentionLSIGFBatch_modified, learnAttentionGSOBatch)):
+        d, meta = golden.case(name)
+        p = {k: (d["param." + k].to(dev) if ("param." + k) in d else None) for k in PARAMS}
+        x, S = d["x"].to(dev), d["S"].to(dev)
+        y, aij = fn(p["filterWeight"], x, p["mixer"], p["weight"], p["weight_bias"], S, b=p["bias"])
+        _, aij_ref, pre = orc.gat_layer_forward(d["x"], d["S"], {k: d.get("param." + k) for k in PARAMS},
+                                                mode=meta["mode"], concatenate=True, return_pre=True)
+        assert y.shape == pre.shape and rel_err(y, pre) < TOL
+        assert aij.shape == aij_ref.shape and (aij.cpu() - aij_ref).abs().max() < TOL
+        if meta["mode"] == "KeyQuery":
+            a2 = att_fn(x, p["mixer"], p["weight"], S)
+        else:
+            a2 = att_fn(x, p["mixer"], p["weight"], p["weight_bias"], S)
+        assert (a2.cpu() - aij_ref).abs().max() < TOL
+
+
+def test_custom_nonlinearity_and_pickle(golden):
+    dev = torch.device("cuda:0")
+    d, meta = golden.case("kq_concat_n10")
+    layer = make_layer(meta, d, dev)
+    layer.nonlinearity = torch.tanh
+    layer.addGSO(d["S"].to(dev))
+    with torch.no_grad():
+        y = layer(d["x"].to(dev))
+    _, _, pre = orc.gat_layer_forward(d["x"], d["S"], {k: d.get("param." + k) for k in PARAMS},
+                                      mode="KeyQuery", concatenate=True, return_pre=True)
+    B, P, F, N = pre.shape
+    want = torch.tanh(pre).permute(0, 3, 1, 2).reshape(B, N, P * F).permute(0, 2, 1)
+    assert rel_err(y, want) < TOL
+    layer.nonlinearity = torch.nn.functional.relu
+    clone = pickle.loads(pickle.dumps(layer))            # mp.spawn pickles the model (agents/...GAT.py:720-728)
+    clone.addGSO(d["S"].to(dev))
+    with torch.no_grad():
+        assert rel_err(clone(d["x"].to(dev)), d["y"]) < TOL
+
+
+def test_cpu_tensors_raise(golden):
+    d, meta = golden.case("kq_concat_n10")
+    layer = make_layer(meta, d, torch.device("cpu"))
+    layer.addGSO(d["S"])
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        layer(d["x"])
+
+
+@pytest.mark.parametrize("mode,concat,G,F,K,P,B,N,gso", [
+    ("KeyQuery", True, 128, 128, 3, 4, 8, 200, "geometric"),
+    ("KeyQuery", False, 32, 32, 2, 4, 4, 100, "geometric"),
+    ("GAT_modified", True, 128, 128, 3, 4, 4, 100, "geometric"),
+    ("KeyQuery", True, 64, 64, 3, 2, 2, 70, "full"),
+    ("GAT_modified", False, 24, 40, 4, 3, 2, 65, "full"),
+])
+def test_oracle_parity_larger(mode, concat, G, F, K, P, B, N, gso):
+    """Sizes the oracle finishes in seconds, beyond the committed golden cases."""
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(1337 + N + G)
+    params = orc.init_params(G, F, K, P, mode=mode, generator=gen, weight_bias_std=0.1)
+    S = torch.ones(B, 1, N, N) if gso == "full" else orc.random_geometric_gso(B, N, generator=gen)
+    x = torch.relu(torch.randn(B, N, G, generator=gen)).permute(0, 2, 1)
+    dy = torch.randn(B, P * F if concat else F, N, generator=gen)
+    y_ref, aij_ref, g_ref = orc.gat_layer_fwd_bwd(x, S, params, dy, mode=mode, concatenate=concat)
+    meta = dict(G=G, F=F, K=K, P=P, concat=concat, mode=mode)
+    layer = make_layer(meta, {"param." + k: v for k, v in params.items() if v is not None}, dev)
+    xd = x.to(dev).requires_grad_(True)
+    layer.addGSO(S.to(dev))
+    y = layer(xd)
+    y.backward(dy.to(dev))
+    assert rel_err(y, y_ref) < TOL
+    assert (torch.from_numpy(layer.aij) - aij_ref).abs().max() < TOL
+    assert rel_err(xd.grad, g_ref["x"]) < TOL
+    for k in PARAMS:
+        if g_ref[k] is not None:
+            assert rel_err(getattr(layer, k).grad, g_ref[k]) < TOL, k
