@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""Benchmark of the batched graph-attention hot path (BASELINE.json metric: agent-steps/s, GAT fwd+bwd).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A step is one pass of the layer over one batch of synthetic planning instances: ``addGSO(S)`` (dense
+GSO -> neighbour lists on the device), ``forward(x)`` and ``backward(dy)`` (plus, for N > 1 ranks, the
+NCCL all-reduce of the parameter gradients).  ``value`` = agent-steps/s over all ranks with inputs
+resident in HBM; ``fwd`` holds the forward-only numbers; ``roofline`` is the forward path against the
+measured HBM peak (algorithmic bytes 4N^2 + 4GN + 4CN per instance); ``e2e``
+is the same step starting from pinned HOST buffers (S and x copied H2D every step, the scalar loss read
+back); ``cpu_baseline`` is the CPU oracle (a dense torch restatement of the reference's ATen sequence)
+on a bounded sample of the same workload on this box's host cores.
+
+Weak scaling: every rank owns B instances (independent graphs, no data-path collective).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: B per GPU, N, map width, G=F, K, P, concat, mode
+    "c4_n1000": dict(B=512, N=1000, width=200, G=128, K=3, P=4, concat=True, mode="KeyQuery"),
+    "c4_n200": dict(B=512, N=200, width=90, G=128, K=3, P=4, concat=True, mode="KeyQuery"),
+    "c4_n50": dict(B=512, N=50, width=45, G=128, K=3, P=4, concat=True, mode="KeyQuery"),
+    "c4_n10": dict(B=512, N=10, width=20, G=128, K=3, P=4, concat=True, mode="KeyQuery"),
+    "c3_n100": dict(B=256, N=100, width=50, G=128, K=3, P=4, concat=True, mode="KeyQuery"),
+    "c2_n10": dict(B=64, N=10, width=20, G=128, K=3, P=4, concat=True, mode="KeyQuery"),
+    "c1_n10": dict(B=1, N=10, width=20, G=128, K=2, P=1, concat=False, mode="KeyQuery"),
+    "c5_n1000": dict(B=128, N=1000, width=200, G=128, K=3, P=4, concat=True, mode="KeyQuery"),
+}
+DEFAULT_WORKLOAD = "c4_n1000"
+COMM_RADIUS = 7.0          # main.py:86
+SEED = 1337                # configs/dcpGAT_OE_Random.json:39
+
+
+def workload_name(w):
+    return (f"MAGAT GAT layer {w['mode']} B={w['B']}/GPU N={w['N']} ({w['width']}x{w['width']} map, commR=7) "
+            f"G=F={w['G']} K={w['K']} P={w['P']} {'concat' if w['concat'] else 'mean'}")
+
+
+def synth_gso(B, N, width, device, gen, chunk=64):
+    """Random-geometric GSO batch as the simulator builds it (utils/new_simulator.py:816-846): N distinct
+    integer cells on a width x width map, edge iff distance < 7, zero diagonal, scaled to (0,1].  The
+    reference divides by lambda_max; the layer only tests |S| > 1e-9, so the scale is 1/max-degree here."""
+    S = torch.empty((B, 1, N, N), dtype=torch.float32, device=device)
+    eye = torch.eye(N, dtype=torch.bool, device=device)
+    for b0 in range(0, B, chunk):
+        nb = min(chunk, B - b0)
+        cells = torch.rand((nb, width * width), device=device, generator=gen).argsort(dim=1)[:, :N]
+        pos = torch.stack((cells // width, cells % width), dim=2).to(torch.float32)
+        d = torch.cdist(pos, pos)
+        A = ((d < COMM_RADIUS) & ~eye).to(torch.float32)
+        deg = A.sum(dim=2).amax(dim=1).clamp_min(1.0)
+        S[b0:b0 + nb, 0] = A / deg[:, None, None]
+    return S
+
+
+def make_problem(w, device, seed):
+    from magat_pathplanning_b200 import GraphFilterBatchAttentional
+    gen = torch.Generator(device=device).manual_seed(seed)
+    B, N, G = w["B"], w["N"], w["G"]
+    S = synth_gso(B, N, w["width"], device, gen)
+    x_mem = torch.relu(torch.randn((B, N, G), device=device, generator=gen))      # [B,N,G] memory
+    C = w["P"] * G if w["concat"] else G
+    dy_mem = torch.randn((B, N, C), device=device, generator=gen)
+    torch.manual_seed(seed)
+    layer = GraphFilterBatchAttentional(G, G, w["K"], w["P"], 1, True, concatenate=w["concat"],
+                                        attentionMode=w["mode"]).to(device)
+    return layer, S, x_mem, dy_mem
+
+
+def alg_bytes(w, what):
+    """Compulsory traffic at the module boundary per batch."""
+    B, N, G = w["B"], w["N"], w["G"]
+    C = w["P"] * G if w["concat"] else G
+    fwd = B * (4 * N * N + 4 * G * N + 4 * C * N)
+    bwd = B * (4 * C * N + 8 * G * N)
+    return fwd if what == "fwd" else fwd + bwd
+
+
+class ClockSampler:
+    """SM clock + throttle reasons sampled while the timed region runs (NVML; nvidia-smi as fallback)."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, device_index, period=0.02):
+        self.period, self.samples, self.reasons, self.max_mhz = period, [], set(), None
+        self._stop = threading.Event()
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+                if not uuid.startswith("GPU-"):
+                    uuid = "GPU-" + uuid
+                self._h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except Exception:
+                self._h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self._nv = pynvml
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._h = None
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                if self._h is not None:
+                    self.samples.append(self._nv.nvmlDeviceGetClockInfo(self._h, self._nv.NVML_CLOCK_SM))
+                    try:
+                        r = self._nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                    except Exception:
+                        r = self._nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                    for bit, name in self.REASONS.items():
+                        if r & bit:
+                            self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def timed(fn, steps, warmup, dist_on, sampler=None):
+    for _ in range(warmup):
+        fn()
+    if dist_on:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if sampler is not None:
+        sampler.__enter__()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if sampler is not None:
+        sampler.__exit__()
+    if dist_on:
+        torch.distributed.barrier()
+    ms = e0.elapsed_time(e1) / steps
+    if dist_on:
+        t = torch.tensor([ms], device="cuda")
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def cpu_oracle_run(w, sample_B, steps, warmup, what="fwdbwd"):
+    """The CPU oracle (dense torch restatement of the reference, oracle/gat_oracle.py) on sample_B instances."""
+    from oracle import gat_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    gen = torch.Generator().manual_seed(SEED)
+    N, G, P, K = w["N"], w["G"], w["P"], w["K"]
+    S = synth_gso(sample_B, N, w["width"], torch.device("cpu"), gen, chunk=8)
+    x = torch.relu(torch.randn(sample_B, N, G, generator=gen)).permute(0, 2, 1)
+    C = P * G if w["concat"] else G
+    dy = torch.randn(sample_B, C, N, generator=gen)
+    params = orc.init_params(G, G, K, P, mode=w["mode"], generator=gen)
+
+    def run():
+        if what == "fwd":
+            with torch.no_grad():
+                orc.gat_layer_forward(x, S, params, mode=w["mode"], concatenate=w["concat"])
+        else:
+            orc.gat_layer_fwd_bwd(x, S, params, dy, mode=w["mode"], concatenate=w["concat"])
+    for _ in range(warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run()
+    dt = (time.perf_counter() - t0) / steps
+    return sample_B * N / dt, dt * 1e3, cores
+
+
+def run_reference(args, w, rank):
+    """`--impl reference`: the reference's CPU algorithm (oracle port; the Python reference itself cannot
+    travel to the GPU box) with every host thread, each step a bounded sample of the workload."""
+    if rank != 0:
+        return
+    sample_B = 8 if w["N"] >= 500 else min(w["B"], 64)
+    steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
+    v, ms, cores = cpu_oracle_run(w, sample_B, steps, warmup)
+    sample = f"{sample_B} of {w['B']} instances per step (dense [B,P,N,N] temporaries bound the batch), fwd+bwd"
+    print(json.dumps({
+        "impl": "reference", "metric": "agent-steps/sec GAT fwd+bwd", "value": v, "unit": "agent-steps/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(w), "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override instances per GPU")
+    ap.add_argument("--path", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    w = dict(WORKLOADS[args.workload])
+    if args.batch:
+        w["B"] = args.batch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, w, rank)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist_on = world > 1
+    if dist_on:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    from magat_pathplanning_b200 import _cabi
+    _cabi.check(_cabi.lib().magat_device_check())
+    L = _cabi.lib()
+
+    layer, S, x_mem, dy_mem = make_problem(w, dev, SEED + rank)
+    layer.path = args.path
+    x = x_mem.permute(0, 2, 1)                      # [B,G,N] view, as the planners pass it
+    dy = dy_mem.permute(0, 2, 1) if w["concat"] else dy_mem.permute(0, 2, 1).contiguous()
+    params = [p for p in layer.parameters()]
+    B, N = w["B"], w["N"]
+    units = B * N * world
+
+    def step_fwd():
+        with torch.no_grad():
+            layer.addGSO(S)
+            return layer(x)
+
+    def step_train():
+        for p in params:
+            p.grad = None
+        xg = x.detach().requires_grad_(True)
+        layer.addGSO(S)
+        y = layer(xg)
+        y.backward(dy)
+        if dist_on:
+            flat = torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None])
+            torch.distributed.all_reduce(flat)
+            flat.div_(world)
+        return y
+
+    # ---- device-resident timing -------------------------------------------------------------
+    c0 = L.magat_launch_count()
+    step_train()
+    launches_per_step = L.magat_launch_count() - c0
+    sampler = ClockSampler(local_rank)
+    ms_train = timed(step_train, args.steps, args.warmup, dist_on, sampler)
+    clocks = sampler.summary()
+    ms_fwd = timed(step_fwd, args.steps, args.warmup, dist_on)
+
+    # ---- per-kernel CUDA-event times of the forward path (rank 0) --------------------------------
+    kernels, fwd_kernel_ms = [], None
+    if rank == 0:
+        torch.cuda.synchronize()
+        L.magat_profile_enable(1)
+        reps = 3
+        for _ in range(reps):
+            step_fwd()
+        torch.cuda.synchronize()
+        rec = _cabi.profile_collect()
+        L.magat_profile_enable(0)
+        kernels = [{"kernel": n, "launches_per_step": c // reps, "ms_per_step": t / reps} for n, c, t in rec]
+        fwd_kernel_ms = sum(k["ms_per_step"] for k in kernels)
+
+    # ---- end to end from pinned host buffers --------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        S_h = torch.empty(S.shape, dtype=S.dtype, pin_memory=True)
+        S_h.copy_(S)
+        x_h = torch.empty(x_mem.shape, dtype=x_mem.dtype, pin_memory=True)
+        x_h.copy_(x_mem)
+        S_d, x_d = torch.empty_like(S), torch.empty_like(x_mem)
+
+        def step_e2e():
+            S_d.copy_(S_h, non_blocking=True)
+            x_d.copy_(x_h, non_blocking=True)
+            for p in params:
+                p.grad = None
+            xg = x_d.permute(0, 2, 1).requires_grad_(True)
+            layer.addGSO(S_d)
+            y = layer(xg)
+            loss = (y * dy).sum()
+            loss.backward()
+            return float(loss.item())           # D2H read of the step's result
+        e2e_steps = max(2, min(args.steps, 5))
+        ms_e2e = timed(step_e2e, e2e_steps, 1, dist_on)
+        e2e = {"value": units / (ms_e2e * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": S_h.numel() * S_h.element_size() + x_h.numel() * 4,
+               "d2h_bytes_per_step": 4, "steps": e2e_steps,
+               "note": "dense fp32 GSO (4N^2 B per instance) crosses PCIe every step, as the reference API passes it"}
+        del S_h, x_h, S_d, x_d
+
+    if rank != 0:
+        if dist_on:
+            torch.distributed.destroy_process_group()
+        return
+
+    peaks, peak_src = None, "fallback (B200_PROFILING.md)"
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        pass
+    hbm_peak = float(peaks["hbm_gbs"]) if peaks else 6650.0
+    bytes_fwd = alg_bytes(w, "fwd")
+    achieved = bytes_fwd / (fwd_kernel_ms * 1e-3) / 1e9 if fwd_kernel_ms else None
+    top = max(kernels, key=lambda k: k["ms_per_step"]) if kernels else None
+    roofline = {
+        "bound": "hbm", "kernel": f"forward path ({sum(k['launches_per_step'] for k in kernels)} launches: "
+                                  "GSO scan + neighbour lists + attention + taps + projection)",
+        "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": (achieved / hbm_peak if achieved else None),
+        "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_step": bytes_fwd,
+        "fwd_kernel_ms_per_step": fwd_kernel_ms, "dominant_kernel": top, "kernels": kernels,
+    }
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        sample_B = 8 if N >= 500 else min(B, 64)
+        reps = 3 if N >= 500 else 5
+        v, ms, cores = cpu_oracle_run(w, sample_B, reps, 1)
+        cpu_baseline = {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port",
+                        "sample": f"{sample_B} of {B} instances x {reps} steps, fwd+bwd, torch CPU fp32, "
+                                  f"{ms:.0f} ms/step (oracle/gat_oracle.py)"}
+
+    out = {
+        "metric": "agent-steps/sec GAT fwd+bwd", "value": units / (ms_train * 1e-3), "unit": "agent-steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_train,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(w), "instances_per_gpu": B, "agents": N, "path": args.path,
+                   "l2": "inputs larger than L2 (GSO batch %.2f GB)" % (S.numel() * 4 / 1e9)
+                         if S.numel() * 4 > 126e6 else "inputs smaller than L2; no flush",
+                   "parallelism": f"batch-sharded x{world}, grad all-reduce (NCCL)" if dist_on else "1 GPU"},
+        "fwd": {"value": units / (ms_fwd * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms_fwd},
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+        "gpu_launches": int(launches_per_step) * args.steps, "gpu_launches_per_step": int(launches_per_step),
+        "clocks": clocks,
+    }
+    print(json.dumps(out))
+    if dist_on:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -50,7 +50,7 @@ def _require_cuda(t: torch.Tensor, what: str):
 class Adjacency:
     """Neighbour lists of one GSO batch (device tensors; layouts in include/magat_gat.h)."""
 
-    __slots__ = ("B", "N", "D", "nbr_out", "nbr_in", "slot_in", "symmetric_hint")
+    __slots__ = ("B", "N", "D", "nbr_out", "nbr_in", "slot_in")
 
     def __init__(self, B, N, D, nbr_out, nbr_in, slot_in):
         self.B, self.N, self.D = B, N, D
@@ -108,6 +108,14 @@ def _node_major(x: torch.Tensor):
     return xt
 
 
+def _sn(xt):      # size-1 dims carry arbitrary strides
+    return xt.stride(1) if xt.shape[1] > 1 else xt.shape[2]
+
+
+def _sb(xt):
+    return xt.stride(0) if xt.shape[0] > 1 else xt.shape[1] * _sn(xt)
+
+
 class _Meta:
     __slots__ = ("mode", "concat", "relu", "path", "G", "F", "K", "P", "has_bias")
 
@@ -142,7 +150,7 @@ class _GATFunction(torch.autograd.Function):
                                 device=dev)
             a = _cabi.FwdArgs(B=B, N=N, G=G, F=F, K=K, P=P, D=D, mode=meta.mode, concat=int(meta.concat),
                               relu=int(meta.relu), path=meta.path, reserved=0,
-                              x=xt.data_ptr(), x_sb=xt.stride(0), x_sn=xt.stride(1),
+                              x=xt.data_ptr(), x_sb=_sb(xt), x_sn=_sn(xt),
                               nbr_out=adj.nbr_out.data_ptr(), nbr_in=adj.nbr_in.data_ptr(),
                               slot_in=adj.slot_in.data_ptr(),
                               weight=weight_c.data_ptr(), mixer=_p(mixer_c), weight_bias=_p(wb_c),
@@ -165,8 +173,9 @@ class _GATFunction(torch.autograd.Function):
         F, K, P, D = meta.F, meta.K, meta.P, adj.D
         gm = meta.mode == _cabi.MODE_GAT_MODIFIED
         need = ctx.needs_input_grad
-        need_dx, need_dw = need[0], need[1]
-        need_dmix = gm and (need[2] or need[3])
+        # K == 1: the attention never reaches y, so the reference leaves weight/mixer/weight_bias grads None
+        need_dx, need_dw = need[0], (need[1] and K > 1)
+        need_dmix = gm and K > 1 and (need[2] or need[3])
         need_df, need_db = need[4], (need[5] and meta.has_bias)
         if dy.dtype != torch.float32:
             dy = dy.float()
@@ -187,7 +196,7 @@ class _GATFunction(torch.autograd.Function):
                               relu=int(meta.relu), path=meta.path,
                               need_dx=int(need_dx), need_dweight=int(need_dw), need_dfilter=int(need_df),
                               need_dbias=int(need_db), need_dmixer=int(need_dmix),
-                              x=xt.data_ptr(), x_sb=xt.stride(0), x_sn=xt.stride(1),
+                              x=xt.data_ptr(), x_sb=_sb(xt), x_sn=_sn(xt),
                               nbr_out=adj.nbr_out.data_ptr(), nbr_in=adj.nbr_in.data_ptr(),
                               slot_in=adj.slot_in.data_ptr(),
                               weight=weight_c.data_ptr(), mixer=_p(mixer_c), weight_bias=_p(wb_c),
