@@ -10,6 +10,8 @@
 // Nothing N x N is ever materialised: the GSO arrives here already as padded neighbour lists
 // (gso_scan.cu).  This file is the path for every shape; the tcgen05 path (gat_tc.cu) replaces
 // the two dense projections for the shapes it covers.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "simt_gemm.cuh"
 
@@ -204,20 +206,45 @@ static int validate_common(int B, int N, int G, int F, int K, int P, int D, int 
   return MAGAT_OK;
 }
 
-int forward_tc(const magat_gat_fwd_args* a, cudaStream_t st);   // gat_tc.cu
+// gat_tc.cu
 bool tc_supported(const magat_gat_fwd_args* a);
+size_t tc_wprep_floats(int G, int F, int K, int P, int mode);
+int tc_score_projection(const magat_gat_fwd_args* a, const __nv_bfloat16* wt_hi, const __nv_bfloat16* wt_lo,
+                        cudaStream_t st);
+int tc_tap_projection(const magat_gat_fwd_args* a, const __nv_bfloat16* h_hi, const __nv_bfloat16* h_lo,
+                      cudaStream_t st);
+int tc_split_weights(const float* src, long n, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st);
+int tc_split_weights_t(const float* W, int G, int P, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st);
 
-int forward_simt(const magat_gat_fwd_args* a, cudaStream_t st) {
+static size_t simt_wprep_floats(int G, int P, int mode) {
+  const size_t n = mode == MAGAT_MODE_GAT_MODIFIED ? (size_t)P * 2 * G + (size_t)P * 2 : 0;
+  return (n + 3) & ~(size_t)3;     // keeps the bf16 region behind it 16 B aligned
+}
+
+static int forward_impl(const magat_gat_fwd_args* a, cudaStream_t st, bool use_tc) {
   const int B = a->B, N = a->N, G = a->G, F = a->F, K = a->K, P = a->P, D = a->D;
   const long rows = (long)B * N;
   const int row_blocks = cdiv(rows, 8);
   const XLoad xl{a->x, a->x_sb, a->x_sn, N};
   int rc;
+  // bf16 hi/lo copies of the weights for the tcgen05 projections
+  __nv_bfloat16* tcw = reinterpret_cast<__nv_bfloat16*>(a->wprep + simt_wprep_floats(G, P, a->mode));
+  const size_t nW = (size_t)P * G * G, nH = (size_t)P * F * K * G;
+  __nv_bfloat16 *wt_hi = nullptr, *wt_lo = nullptr, *h_hi = tcw, *h_lo = tcw + nH;
+  if (a->mode == MAGAT_MODE_KEYQUERY) { wt_hi = tcw; wt_lo = tcw + nW; h_hi = tcw + 2 * nW; h_lo = h_hi + nH; }
+  if (use_tc) {
+    if (a->mode == MAGAT_MODE_KEYQUERY && (rc = tc_split_weights_t(a->weight, G, P, wt_hi, wt_lo, st))) return rc;
+    if ((rc = tc_split_weights(a->filterWeight, (long)nH, h_hi, h_lo, st))) return rc;
+  }
   // 1. score projection
   if (a->mode == MAGAT_MODE_KEYQUERY) {
-    dim3 grid(cdiv(rows, 64), cdiv((long)P * G, 64), 1);
-    k_node_gemm<<<grid, 256, 0, st>>>(rows, P * G, G, xl, KqWLoad{a->weight, G}, StoreEpi{a->sproj, P * G});
-    if ((rc = check_launch("k_node_gemm(score projection)", st))) return rc;
+    if (use_tc) {
+      if ((rc = tc_score_projection(a, wt_hi, wt_lo, st))) return rc;
+    } else {
+      dim3 grid(cdiv(rows, 64), cdiv((long)P * G, 64), 1);
+      k_node_gemm<<<grid, 256, 0, st>>>(rows, P * G, G, xl, KqWLoad{a->weight, G}, StoreEpi{a->sproj, P * G});
+      if ((rc = check_launch("k_node_gemm(score projection)", st))) return rc;
+    }
     k_attention<MAGAT_MODE_KEYQUERY><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj, a->nbr_out,
                                                                   rows, N, G, P, D, a->att);
   } else {
@@ -239,6 +266,7 @@ int forward_simt(const magat_gat_fwd_args* a, cudaStream_t st) {
     if ((rc = check_launch("k_tap_gather", st))) return rc;
   }
   // 3. per-(head, tap) projection + bias + activation + concat / head mean
+  if (use_tc) return tc_tap_projection(a, h_hi, h_lo, st);
   const int per_head = a->concat ? 1 : 0;
   const ZLoad zl{a->x, a->x_sb, a->x_sn, a->taps, N, G, K, P, per_head};
   const HLoad hl{a->filterWeight, G, K, F, per_head};
@@ -253,9 +281,7 @@ int forward_simt(const magat_gat_fwd_args* a, cudaStream_t st) {
 using namespace magat;
 
 extern "C" size_t magat_gat_wprep_floats(int G, int F, int K, int P, int mode) {
-  (void)F; (void)K;
-  if (mode == MAGAT_MODE_GAT_MODIFIED) return (size_t)P * 2 * G + (size_t)P * 2;
-  return 4;
+  return simt_wprep_floats(G, P, mode) + tc_wprep_floats(G, F, K, P, mode);
 }
 
 extern "C" int magat_gat_forward(const magat_gat_fwd_args* a, void* stream) {
@@ -273,8 +299,7 @@ extern "C" int magat_gat_forward(const magat_gat_fwd_args* a, void* stream) {
   prof_begin(st);
   if (a->path == MAGAT_PATH_TCGEN05) {
     MAGAT_REQUIRE(tc_supported(a), MAGAT_E_UNSUPPORTED, "magat_gat_forward: shape not covered by the tcgen05 path");
-    return forward_tc(a, st);
+    return forward_impl(a, st, true);
   }
-  if (a->path == MAGAT_PATH_AUTO && tc_supported(a)) return forward_tc(a, st);
-  return forward_simt(a, st);
+  return forward_impl(a, st, a->path == MAGAT_PATH_AUTO && tc_supported(a));
 }

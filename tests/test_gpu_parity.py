@@ -203,3 +203,60 @@ def test_oracle_parity_larger(mode, concat, G, F, K, P, B, N, gso):
     for k in PARAMS:
         if g_ref[k] is not None:
             assert rel_err(getattr(layer, k).grad, g_ref[k]) < TOL, k
+
+
+# ---- tcgen05 (bf16 hi/lo split) projections ---------------------------------------------------
+# Same 1e-4 bar; the three-pass split is expected near 1e-5.
+
+@pytest.mark.parametrize("name", ["kq_mean_c1", "kq_concat_c2", "kq_n130_g128"])
+def test_tc_path_golden(golden, name):
+    d, meta = golden.case(name)
+    dev = torch.device("cuda:0")
+    layer = make_layer(meta, d, dev, path="tcgen05")
+    x = d["x"].to(dev).requires_grad_(True)
+    layer.addGSO(d["S"].to(dev))
+    y = layer(x)
+    assert rel_err(y, d["y"]) < TOL
+    assert np.abs(layer.aij - d["aij"].numpy()).max() < TOL
+    y.backward(d["dy"].to(dev))
+    assert rel_err(x.grad, d["grad.x"]) < TOL
+    for k in PARAMS:
+        if ("grad." + k) in d:
+            assert rel_err(getattr(layer, k).grad, d["grad." + k]) < TOL, k
+
+
+@pytest.mark.parametrize("mode,concat,G,F,K,P,B,N", [
+    ("KeyQuery", True, 128, 128, 3, 4, 8, 200),
+    ("KeyQuery", False, 128, 128, 2, 2, 3, 150),
+    ("GAT_modified", True, 128, 128, 3, 4, 4, 100),
+    ("GAT_modified", False, 64, 128, 2, 3, 5, 77),
+    ("KeyQuery", True, 256, 256, 2, 1, 2, 50),
+])
+def test_tc_path_oracle(mode, concat, G, F, K, P, B, N):
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(4242 + N + G)
+    params = orc.init_params(G, F, K, P, mode=mode, generator=gen, weight_bias_std=0.1)
+    S = orc.random_geometric_gso(B, N, generator=gen)
+    x = torch.relu(torch.randn(B, N, G, generator=gen)).permute(0, 2, 1)
+    y_ref, aij_ref = orc.gat_layer_forward(x, S, params, mode=mode, concatenate=concat)
+    meta = dict(G=G, F=F, K=K, P=P, concat=concat, mode=mode)
+    layer = make_layer(meta, {"param." + k: v for k, v in params.items() if v is not None}, dev, path="tcgen05")
+    layer.addGSO(S.to(dev))
+    with torch.no_grad():
+        y = layer(x.to(dev))
+        layer.path = "simt"
+        y_simt = layer(x.to(dev))
+    e_tc, e_simt = rel_err(y, y_ref), rel_err(y_simt, y_ref)
+    print(f"tcgen05 err {e_tc:.2e}  simt err {e_simt:.2e}")
+    assert e_tc < TOL
+    assert (torch.from_numpy(layer.aij) - aij_ref).abs().max() < TOL
+
+
+def test_tc_path_rejects_uncovered_shape(golden):
+    from magat_pathplanning_b200._cabi import MagatError
+    d, meta = golden.case("kq_concat_n10")          # G = 16
+    dev = torch.device("cuda:0")
+    layer = make_layer(meta, d, dev, path="tcgen05")
+    layer.addGSO(d["S"].to(dev))
+    with pytest.raises(MagatError, match="not covered"):
+        layer(d["x"].to(dev))
