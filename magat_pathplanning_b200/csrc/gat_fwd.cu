@@ -134,6 +134,138 @@ __global__ void __launch_bounds__(256) k_tap_gather(const float* __restrict__ x,
   }
 }
 
+// ---- vectorised variants for the common shapes (P in {1,2,4}, 16 B aligned rows) -----------------
+__device__ __forceinline__ void fma4(float4& acc, float a, const float4& v) {
+  acc.x = fmaf(a, v.x, acc.x); acc.y = fmaf(a, v.y, acc.y); acc.z = fmaf(a, v.z, acc.z); acc.w = fmaf(a, v.w, acc.w);
+}
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// u_k[j] for all heads at once: one warp per receiver, each lane owns 4 consecutive features of
+// every 128-feature slab, neighbour indices are read coalesced and broadcast by shuffle.
+template <int PT>
+__global__ void __launch_bounds__(256) k_tap_gather_v(const float* __restrict__ x, long x_sb, long x_sn,
+                                                      const float* __restrict__ att,
+                                                      const int32_t* __restrict__ nbr_in,
+                                                      const int32_t* __restrict__ slot_in, long rows, int N,
+                                                      int G, int K, int D, int k, float* __restrict__ taps) {
+  const int lane = threadIdx.x & 31;
+  const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  const long b = row / N;
+  const int32_t* nb = nbr_in + row * D;
+  const int32_t* sl = slot_in + row * D;
+  const int Km1 = K - 1;
+  for (int gb = 0; gb < G; gb += 128) {       // warp-uniform trip count: the shuffles below need every lane
+    const int g0 = gb + lane * 4;
+    const bool act = g0 < G;
+    float4 acc[PT];
+#pragma unroll
+    for (int p = 0; p < PT; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s0 = 0; s0 < D; s0 += 32) {
+      const int my_i = (s0 + lane < D) ? nb[s0 + lane] : -1;
+      const int my_sl = (s0 + lane < D) ? sl[s0 + lane] : 0;
+      const int cnt = __popc(__ballot_sync(0xffffffffu, my_i >= 0));
+      for (int s = 0; s < cnt; ++s) {
+        const int i = __shfl_sync(0xffffffffu, my_i, s);
+        const int slot = __shfl_sync(0xffffffffu, my_sl, s);
+        const long ri = b * N + i;
+        const float* ap = att + ((size_t)ri * D + slot) * PT;
+        float a[PT];
+        if (PT == 4) {
+          const float4 a4 = __ldg(reinterpret_cast<const float4*>(ap));
+          a[0] = a4.x; a[1 % PT] = a4.y; a[2 % PT] = a4.z; a[3 % PT] = a4.w;
+        } else {
+#pragma unroll
+          for (int p = 0; p < PT; ++p) a[p] = __ldg(ap + p);
+        }
+        if (!act) continue;
+        if (k == 1) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(x + b * x_sb + (long)i * x_sn + g0));
+#pragma unroll
+          for (int p = 0; p < PT; ++p) fma4(acc[p], a[p], v);
+        } else {
+#pragma unroll
+          for (int p = 0; p < PT; ++p) {
+            const float4 v = *reinterpret_cast<const float4*>(taps + (((size_t)ri * PT + p) * Km1 + (k - 2)) * G + g0);
+            fma4(acc[p], a[p], v);
+          }
+        }
+      }
+      if (cnt < 32) break;
+    }
+    if (act) {
+#pragma unroll
+      for (int p = 0; p < PT; ++p)
+        *reinterpret_cast<float4*>(taps + (((size_t)row * PT + p) * Km1 + (k - 1)) * G + g0) = acc[p];
+    }
+  }
+}
+
+// KeyQuery scores + row softmax, D <= 32: lane s owns slot s; G = 128 * GV.
+template <int PT, int GV>
+__global__ void __launch_bounds__(256) k_attention_kq_v(const float* __restrict__ x, long x_sb, long x_sn,
+                                                        const float* __restrict__ sproj,
+                                                        const int32_t* __restrict__ nbr_out, long rows, int N,
+                                                        int D, float* __restrict__ att) {
+  constexpr int G = 128 * GV;
+  const int lane = threadIdx.x & 31;
+  const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  const long b = row / N;
+  const int my_j = lane < D ? nbr_out[row * D + lane] : -1;
+  const int deg = __popc(__ballot_sync(0xffffffffu, my_j >= 0));
+  float e[PT];
+#pragma unroll
+  for (int p = 0; p < PT; ++p) e[p] = -INFINITY;
+  if (deg > 0) {
+    float4 r[PT][GV];
+#pragma unroll
+    for (int p = 0; p < PT; ++p)
+#pragma unroll
+      for (int v = 0; v < GV; ++v)
+        r[p][v] = __ldg(reinterpret_cast<const float4*>(sproj + ((size_t)row * PT + p) * G + v * 128 + lane * 4));
+    for (int s = 0; s < deg; ++s) {
+      const int j = __shfl_sync(0xffffffffu, my_j, s);
+      const float* xj = x + b * x_sb + (long)j * x_sn + lane * 4;
+      float4 xv[GV];
+#pragma unroll
+      for (int v = 0; v < GV; ++v) xv[v] = __ldg(reinterpret_cast<const float4*>(xj + v * 128));
+#pragma unroll
+      for (int p = 0; p < PT; ++p) {
+        float d = 0.f;
+#pragma unroll
+        for (int v = 0; v < GV; ++v) d += dot4(r[p][v], xv[v]);
+        d = warp_sum(d);
+        if (lane == s) e[p] = d;
+      }
+    }
+  }
+  float a[PT];
+#pragma unroll
+  for (int p = 0; p < PT; ++p) {
+    const float mx = warp_max(e[p]);
+    const float ex = lane < deg ? expf(e[p] - mx) : 0.f;
+    const float sum = warp_sum(ex);
+    a[p] = lane < deg ? ex / sum : 0.f;
+  }
+  if (lane < D) {
+    float* dst = att + ((size_t)row * D + lane) * PT;
+    if (PT == 4) {
+      *reinterpret_cast<float4*>(dst) = make_float4(a[0], a[1 % PT], a[2 % PT], a[3 % PT]);
+    } else {
+#pragma unroll
+      for (int p = 0; p < PT; ++p) dst[p] = a[p];
+    }
+  }
+}
+
 // ---- functors for the tile GEMMs ----------------------------------------------------------
 struct XLoad {   // A(m, g): node features
   const float* x; long x_sb, x_sn; int N;
@@ -226,6 +358,9 @@ static int forward_impl(const magat_gat_fwd_args* a, cudaStream_t st, bool use_t
   const long rows = (long)B * N;
   const int row_blocks = cdiv(rows, 8);
   const XLoad xl{a->x, a->x_sb, a->x_sn, N};
+  const bool vec_ok = (G % 4 == 0) && (a->x_sn % 4 == 0) && (a->x_sb % 4 == 0) && (((uintptr_t)a->x) % 16 == 0) &&
+                      (((uintptr_t)a->att) % 16 == 0) && (((uintptr_t)a->taps) % 16 == 0) &&
+                      (((uintptr_t)a->sproj) % 16 == 0);
   int rc;
   // bf16 hi/lo copies of the weights for the tcgen05 projections
   __nv_bfloat16* tcw = reinterpret_cast<__nv_bfloat16*>(a->wprep + simt_wprep_floats(G, P, a->mode));
@@ -245,8 +380,19 @@ static int forward_impl(const magat_gat_fwd_args* a, cudaStream_t st, bool use_t
       k_node_gemm<<<grid, 256, 0, st>>>(rows, P * G, G, xl, KqWLoad{a->weight, G}, StoreEpi{a->sproj, P * G});
       if ((rc = check_launch("k_node_gemm(score projection)", st))) return rc;
     }
-    k_attention<MAGAT_MODE_KEYQUERY><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj, a->nbr_out,
-                                                                  rows, N, G, P, D, a->att);
+    bool fast = vec_ok && D <= 32 && (G == 128 || G == 256);
+#define MAGAT_ATT(PT, GV) \
+  k_attention_kq_v<PT, GV><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj, a->nbr_out, rows, N, D, a->att)
+    if (fast && P == 4 && G == 128) MAGAT_ATT(4, 1);
+    else if (fast && P == 4 && G == 256) MAGAT_ATT(4, 2);
+    else if (fast && P == 2 && G == 128) MAGAT_ATT(2, 1);
+    else if (fast && P == 2 && G == 256) MAGAT_ATT(2, 2);
+    else if (fast && P == 1 && G == 128) MAGAT_ATT(1, 1);
+    else if (fast && P == 1 && G == 256) MAGAT_ATT(1, 2);
+    else
+      k_attention<MAGAT_MODE_KEYQUERY><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj, a->nbr_out,
+                                                                    rows, N, G, P, D, a->att);
+#undef MAGAT_ATT
   } else {
     float* cvec = a->wprep;
     float* dvec = a->wprep + (size_t)P * 2 * G;
@@ -261,8 +407,16 @@ static int forward_impl(const magat_gat_fwd_args* a, cudaStream_t st, bool use_t
   if ((rc = check_launch("k_attention", st))) return rc;
   // 2. taps
   for (int k = 1; k < K; ++k) {
-    k_tap_gather<<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->att, a->nbr_in, a->slot_in, rows, N, G,
-                                             P, K, D, k, a->taps);
+#define MAGAT_GATHER(PT) \
+  k_tap_gather_v<PT><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->att, a->nbr_in, a->slot_in, rows, N, G, K, \
+                                                 D, k, a->taps)
+    if (vec_ok && P == 4) MAGAT_GATHER(4);
+    else if (vec_ok && P == 2) MAGAT_GATHER(2);
+    else if (vec_ok && P == 1) MAGAT_GATHER(1);
+    else
+      k_tap_gather<<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->att, a->nbr_in, a->slot_in, rows, N, G,
+                                               P, K, D, k, a->taps);
+#undef MAGAT_GATHER
     if ((rc = check_launch("k_tap_gather", st))) return rc;
   }
   // 3. per-(head, tap) projection + bias + activation + concat / head mean
