@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define MAGAT_ABI_VERSION 2
+#define MAGAT_ABI_VERSION 4
 
 enum {
   MAGAT_OK = 0,
@@ -100,6 +100,8 @@ typedef struct magat_gat_fwd_args {
   /* outputs */
   float* y; int64_t y_sb, y_sn, y_sc;
   float* att;                 /* [B][N][D][P] */
+  float* ain;                 /* [B][N][P][D] receiver-major copy of att (scratch of the fused tcgen05 kernel; may be
+                                 NULL, which disables that kernel); needs D % 4 == 0 */
   float* taps;                /* [B][N][P][K-1][G] (unused when K == 1) */
   /* scratch (caller allocated) */
   float* wprep;               /* magat_gat_wprep_floats(...) floats */
@@ -108,18 +110,25 @@ typedef struct magat_gat_fwd_args {
 
 size_t magat_gat_wprep_floats(int G, int F, int K, int P, int mode);
 int magat_gat_forward(const magat_gat_fwd_args* a, void* stream);
+/* How many tap planes (k = 1..) of a->taps the forward call leaves valid for these arguments: K-1, or 1
+ * when the fused tcgen05 kernel gathers the second tap on the fly.  Pass it on as bwd.taps_valid. */
+int magat_gat_forward_taps_valid(const magat_gat_fwd_args* a);
 
 /* ---- backward (what autograd does over graphML.py:1180-1286,713-823,1724-1827) ---- */
 typedef struct magat_gat_bwd_args {
   int32_t B, N, G, F, K, P, D;
   int32_t mode, concat, relu, path;
   int32_t need_dx, need_dweight, need_dfilter, need_dbias, need_dmixer;   /* requires_grad gating */
+  int32_t taps_valid;   /* tap planes k = 1..taps_valid of `taps` hold data (magat_gat_forward_taps_valid) */
+  int32_t reserved;
   /* saved from forward */
   const float* x; int64_t x_sb, x_sn;
   const int32_t* nbr_out; const int32_t* nbr_in; const int32_t* slot_in;
   const float* weight; const float* mixer; const float* weight_bias; const float* filterWeight;
   const float* y; int64_t y_sb, y_sn, y_sc;   /* forward output (post activation) */
-  const float* att; const float* taps; const float* wprep; const float* sproj;
+  const float* att;
+  float* taps;                /* planes above taps_valid are (re)computed here */
+  const float* wprep; const float* sproj;
   /* incoming gradient, same logical shape as y, own strides */
   const float* dy; int64_t dy_sb, dy_sn, dy_sc;
   /* outputs: written (not accumulated); any may be NULL when the matching need_* is 0 */

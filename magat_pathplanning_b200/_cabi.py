@@ -12,7 +12,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmagat_gat.so")
-ABI_VERSION = 2
+ABI_VERSION = 4
 
 MODE_KEYQUERY, MODE_GAT_MODIFIED = 0, 1
 DT_F32, DT_F64 = 0, 1
@@ -20,7 +20,7 @@ PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
 
 EXPORTS = (
     "magat_abi_version", "magat_last_error", "magat_device_check", "magat_gso_scan",
-    "magat_gso_build_ell", "magat_gat_wprep_floats", "magat_gat_forward",
+    "magat_gso_build_ell", "magat_gat_wprep_floats", "magat_gat_forward", "magat_gat_forward_taps_valid",
     "magat_gat_bwd_partial_floats", "magat_gat_backward", "magat_gat_attention_dense",
     "magat_launch_count", "magat_profile_enable", "magat_profile_collect",
 )
@@ -35,14 +35,14 @@ class FwdArgs(C.Structure):
         ("nbr_out", _ptr), ("nbr_in", _ptr), ("slot_in", _ptr),
         ("weight", _ptr), ("mixer", _ptr), ("weight_bias", _ptr), ("filterWeight", _ptr), ("bias", _ptr),
         ("y", _ptr), ("y_sb", _i64), ("y_sn", _i64), ("y_sc", _i64),
-        ("att", _ptr), ("taps", _ptr), ("wprep", _ptr), ("sproj", _ptr),
+        ("att", _ptr), ("ain", _ptr), ("taps", _ptr), ("wprep", _ptr), ("sproj", _ptr),
     ]
 
 
 class BwdArgs(C.Structure):
     _fields_ = [(n, _i32) for n in ("B", "N", "G", "F", "K", "P", "D", "mode", "concat", "relu", "path",
                                     "need_dx", "need_dweight", "need_dfilter", "need_dbias",
-                                    "need_dmixer")] + [
+                                    "need_dmixer", "taps_valid", "reserved")] + [
         ("x", _ptr), ("x_sb", _i64), ("x_sn", _i64),
         ("nbr_out", _ptr), ("nbr_in", _ptr), ("slot_in", _ptr),
         ("weight", _ptr), ("mixer", _ptr), ("weight_bias", _ptr), ("filterWeight", _ptr),
@@ -87,6 +87,8 @@ def lib():
         L.magat_gat_wprep_floats.argtypes = [C.c_int] * 5
         L.magat_gat_wprep_floats.restype = C.c_size_t
         L.magat_gat_forward.argtypes = [C.POINTER(FwdArgs), _ptr]
+        L.magat_gat_forward_taps_valid.argtypes = [C.POINTER(FwdArgs)]
+        L.magat_gat_forward_taps_valid.restype = C.c_int
         L.magat_gat_bwd_partial_floats.argtypes = [C.c_int] * 7
         L.magat_gat_bwd_partial_floats.restype = C.c_size_t
         L.magat_gat_backward.argtypes = [C.POINTER(BwdArgs), _ptr]

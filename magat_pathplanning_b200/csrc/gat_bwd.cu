@@ -261,6 +261,10 @@ __global__ void __launch_bounds__(128) k_gm_param_bwd(const float* __restrict__ 
   }
 }
 
+int run_tap_gather(const float* x, long x_sb, long x_sn, const float* att, const int32_t* nbr_in,
+                   const int32_t* slot_in, int B, int N, int G, int K, int P, int D, int k, float* taps,
+                   float* ain, cudaStream_t st);   // gat_fwd.cu
+
 static int pick_splits(long R, int tiles) {
   long s = (148l * 4 + tiles - 1) / tiles;
   const long cap = (R + 255) / 256;
@@ -336,6 +340,11 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
                 N, F, a->concat, a->relu, a->concat ? 1.f : 1.f / (float)P};
   const ZNode zn{a->x, a->x_sb, a->x_sn, a->taps, N, G, K, P};
   const bool need_scores = a->need_dx || a->need_dweight || (gm && a->need_dmixer);
+  // the fused forward keeps only u_1 in memory: rebuild the later taps before anything reads them
+  for (int k = (a->taps_valid < 1 ? 1 : a->taps_valid + 1); k < K; ++k)
+    if ((rc = run_tap_gather(a->x, a->x_sb, a->x_sn, a->att, a->nbr_in, a->slot_in, B, N, G, K, P, D, k,
+                             a->taps, nullptr, st)))
+      return rc;
 
   if (a->need_dbias) {
     if ((rc = rowred(rows, 1, F, 1, OneLoad{}, DPreSumP{dp, P}, a->partial, a->dbias, st, "k_rowred_gemm(dbias)")))

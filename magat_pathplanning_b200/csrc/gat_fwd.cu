@@ -148,13 +148,16 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // u_k[j] for all heads at once: one warp per receiver, each lane owns 4 consecutive features of
-// every 128-feature slab, neighbour indices are read coalesced and broadcast by shuffle.
+// every 128-feature slab; lane s fetches the attention values of in-edge s (all heads) and they are
+// broadcast by shuffle.  When `ain` is given the in-edge values are also stored receiver-major,
+// ain[j][p][s] = A_p[nbr_in[j][s], j] (0 beyond the degree), which is what the fused tcgen05 kernel reads.
 template <int PT>
 __global__ void __launch_bounds__(256) k_tap_gather_v(const float* __restrict__ x, long x_sb, long x_sn,
                                                       const float* __restrict__ att,
                                                       const int32_t* __restrict__ nbr_in,
                                                       const int32_t* __restrict__ slot_in, long rows, int N,
-                                                      int G, int K, int D, int k, float* __restrict__ taps) {
+                                                      int G, int K, int D, int k, float* __restrict__ taps,
+                                                      float* __restrict__ ain) {
   const int lane = threadIdx.x & 31;
   const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= rows) return;
@@ -170,22 +173,31 @@ __global__ void __launch_bounds__(256) k_tap_gather_v(const float* __restrict__ 
     for (int p = 0; p < PT; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int s0 = 0; s0 < D; s0 += 32) {
       const int my_i = (s0 + lane < D) ? nb[s0 + lane] : -1;
-      const int my_sl = (s0 + lane < D) ? sl[s0 + lane] : 0;
+      float am[PT];
+#pragma unroll
+      for (int p = 0; p < PT; ++p) am[p] = 0.f;
+      if (my_i >= 0) {
+        const float* ap = att + ((size_t)(b * N + my_i) * D + sl[s0 + lane]) * PT;
+        if (PT == 4) {
+          const float4 a4 = __ldg(reinterpret_cast<const float4*>(ap));
+          am[0] = a4.x; am[1 % PT] = a4.y; am[2 % PT] = a4.z; am[3 % PT] = a4.w;
+        } else {
+#pragma unroll
+          for (int p = 0; p < PT; ++p) am[p] = __ldg(ap + p);
+        }
+      }
+      if (ain != nullptr && gb == 0 && s0 + lane < D) {
+#pragma unroll
+        for (int p = 0; p < PT; ++p) ain[((size_t)row * PT + p) * D + s0 + lane] = am[p];
+      }
       const int cnt = __popc(__ballot_sync(0xffffffffu, my_i >= 0));
       for (int s = 0; s < cnt; ++s) {
         const int i = __shfl_sync(0xffffffffu, my_i, s);
-        const int slot = __shfl_sync(0xffffffffu, my_sl, s);
-        const long ri = b * N + i;
-        const float* ap = att + ((size_t)ri * D + slot) * PT;
         float a[PT];
-        if (PT == 4) {
-          const float4 a4 = __ldg(reinterpret_cast<const float4*>(ap));
-          a[0] = a4.x; a[1 % PT] = a4.y; a[2 % PT] = a4.z; a[3 % PT] = a4.w;
-        } else {
 #pragma unroll
-          for (int p = 0; p < PT; ++p) a[p] = __ldg(ap + p);
-        }
+        for (int p = 0; p < PT; ++p) a[p] = __shfl_sync(0xffffffffu, am[p], s);
         if (!act) continue;
+        const long ri = b * N + i;
         if (k == 1) {
           const float4 v = __ldg(reinterpret_cast<const float4*>(x + b * x_sb + (long)i * x_sn + g0));
 #pragma unroll
@@ -198,7 +210,14 @@ __global__ void __launch_bounds__(256) k_tap_gather_v(const float* __restrict__ 
           }
         }
       }
-      if (cnt < 32) break;
+      if (cnt < 32) {
+        // zero the rest of ain beyond this block
+        if (ain != nullptr && gb == 0)
+          for (int s = s0 + 32 + lane; s < D; s += 32)
+#pragma unroll
+            for (int p = 0; p < PT; ++p) ain[((size_t)row * PT + p) * D + s] = 0.f;
+        break;
+      }
     }
     if (act) {
 #pragma unroll
@@ -348,6 +367,28 @@ int tc_tap_projection(const magat_gat_fwd_args* a, const __nv_bfloat16* h_hi, co
 int tc_split_weights(const float* src, long n, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st);
 int tc_split_weights_t(const float* W, int G, int P, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st);
 
+bool tap_tc_supported(const magat_gat_fwd_args* a);              // gat_tap_tc.cu
+int tap_tc_forward(const magat_gat_fwd_args* a, cudaStream_t st);
+
+// one level of the tap recursion, u_k from u_{k-1} (k >= 1), for every head
+int run_tap_gather(const float* x, long x_sb, long x_sn, const float* att, const int32_t* nbr_in,
+                   const int32_t* slot_in, int B, int N, int G, int K, int P, int D, int k, float* taps,
+                   float* ain, cudaStream_t st) {
+  const long rows = (long)B * N;
+  const int row_blocks = cdiv(rows, 8);
+  const bool vec_ok = (G % 4 == 0) && (x_sn % 4 == 0) && (x_sb % 4 == 0) && (((uintptr_t)x) % 16 == 0) &&
+                      (((uintptr_t)att) % 16 == 0) && (((uintptr_t)taps) % 16 == 0);
+#define MAGAT_GATHER(PT) \
+  k_tap_gather_v<PT><<<row_blocks, 256, 0, st>>>(x, x_sb, x_sn, att, nbr_in, slot_in, rows, N, G, K, D, k, taps, ain)
+  if (vec_ok && P == 4) MAGAT_GATHER(4);
+  else if (vec_ok && P == 2) MAGAT_GATHER(2);
+  else if (vec_ok && P == 1) MAGAT_GATHER(1);
+  else
+    k_tap_gather<<<row_blocks, 256, 0, st>>>(x, x_sb, x_sn, att, nbr_in, slot_in, rows, N, G, P, K, D, k, taps);
+#undef MAGAT_GATHER
+  return check_launch("k_tap_gather", st);
+}
+
 static size_t simt_wprep_floats(int G, int P, int mode) {
   const size_t n = mode == MAGAT_MODE_GAT_MODIFIED ? (size_t)P * 2 * G + (size_t)P * 2 : 0;
   return (n + 3) & ~(size_t)3;     // keeps the bf16 region behind it 16 B aligned
@@ -405,21 +446,15 @@ static int forward_impl(const magat_gat_fwd_args* a, cudaStream_t st, bool use_t
                                                                       a->nbr_out, rows, N, G, P, D, a->att);
   }
   if ((rc = check_launch("k_attention", st))) return rc;
-  // 2. taps
-  for (int k = 1; k < K; ++k) {
-#define MAGAT_GATHER(PT) \
-  k_tap_gather_v<PT><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->att, a->nbr_in, a->slot_in, rows, N, G, K, \
-                                                 D, k, a->taps)
-    if (vec_ok && P == 4) MAGAT_GATHER(4);
-    else if (vec_ok && P == 2) MAGAT_GATHER(2);
-    else if (vec_ok && P == 1) MAGAT_GATHER(1);
-    else
-      k_tap_gather<<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->att, a->nbr_in, a->slot_in, rows, N, G,
-                                               P, K, D, k, a->taps);
-#undef MAGAT_GATHER
-    if ((rc = check_launch("k_tap_gather", st))) return rc;
-  }
+  // 2. taps (the fused tcgen05 kernel gathers the second tap itself and only needs u_1 in memory)
+  const bool fused = use_tc && tap_tc_supported(a);
+  const int k_last = fused ? (K - 1 < 1 ? K - 1 : 1) : K - 1;
+  for (int k = 1; k <= k_last; ++k)
+    if ((rc = run_tap_gather(a->x, a->x_sb, a->x_sn, a->att, a->nbr_in, a->slot_in, B, N, G, K, P, D, k, a->taps,
+                             (fused && k == 1) ? a->ain : nullptr, st)))
+      return rc;
   // 3. per-(head, tap) projection + bias + activation + concat / head mean
+  if (fused) return tap_tc_forward(a, st);
   if (use_tc) return tc_tap_projection(a, h_hi, h_lo, st);
   const int per_head = a->concat ? 1 : 0;
   const ZLoad zl{a->x, a->x_sb, a->x_sn, a->taps, N, G, K, P, per_head};
@@ -436,6 +471,14 @@ using namespace magat;
 
 extern "C" size_t magat_gat_wprep_floats(int G, int F, int K, int P, int mode) {
   return simt_wprep_floats(G, P, mode) + tc_wprep_floats(G, F, K, P, mode);
+}
+
+// number of tap planes (k = 1 .. K-1) magat_gat_forward leaves valid in a->taps for these arguments
+extern "C" int magat_gat_forward_taps_valid(const magat_gat_fwd_args* a) {
+  if (a == nullptr || a->K <= 1) return 0;
+  const bool use_tc = a->path == MAGAT_PATH_TCGEN05 || (a->path == MAGAT_PATH_AUTO && tc_supported(a));
+  if (use_tc && tc_supported(a) && tap_tc_supported(a)) return 1;
+  return a->K - 1;
 }
 
 extern "C" int magat_gat_forward(const magat_gat_fwd_args* a, void* stream) {

