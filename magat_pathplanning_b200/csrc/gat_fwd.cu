@@ -191,22 +191,43 @@ __global__ void __launch_bounds__(256) k_tap_gather_v(const float* __restrict__ 
         for (int p = 0; p < PT; ++p) ain[((size_t)row * PT + p) * D + s0 + lane] = am[p];
       }
       const int cnt = __popc(__ballot_sync(0xffffffffu, my_i >= 0));
-      for (int s = 0; s < cnt; ++s) {
-        const int i = __shfl_sync(0xffffffffu, my_i, s);
-        float a[PT];
+      for (int s = 0; s < cnt; s += 4) {     // four neighbours per round: their row loads overlap
+        int iu[4];
+        float au[4][PT];
 #pragma unroll
-        for (int p = 0; p < PT; ++p) a[p] = __shfl_sync(0xffffffffu, am[p], s);
+        for (int u = 0; u < 4; ++u) {
+          iu[u] = __shfl_sync(0xffffffffu, my_i, (s + u) & 31);
+#pragma unroll
+          for (int p = 0; p < PT; ++p) au[u][p] = __shfl_sync(0xffffffffu, am[p], (s + u) & 31);
+          if (s + u >= cnt) iu[u] = -1;
+        }
         if (!act) continue;
-        const long ri = b * N + i;
         if (k == 1) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(x + b * x_sb + (long)i * x_sn + g0));
+          float4 v[4];
 #pragma unroll
-          for (int p = 0; p < PT; ++p) fma4(acc[p], a[p], v);
+          for (int u = 0; u < 4; ++u)
+            v[u] = iu[u] >= 0 ? __ldg(reinterpret_cast<const float4*>(x + b * x_sb + (long)iu[u] * x_sn + g0))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int p = 0; p < PT; ++p) fma4(acc[p], au[u][p], v[u]);
         } else {
 #pragma unroll
-          for (int p = 0; p < PT; ++p) {
-            const float4 v = *reinterpret_cast<const float4*>(taps + (((size_t)ri * PT + p) * Km1 + (k - 2)) * G + g0);
-            fma4(acc[p], a[p], v);
+          for (int u = 0; u < 4; u += 2) {
+            float4 v[2][PT];
+#pragma unroll
+            for (int w = 0; w < 2; ++w)
+#pragma unroll
+              for (int p = 0; p < PT; ++p)
+                v[w][p] = iu[u + w] >= 0
+                              ? *reinterpret_cast<const float4*>(
+                                    taps + (((size_t)(b * N + iu[u + w]) * PT + p) * Km1 + (k - 2)) * G + g0)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int w = 0; w < 2; ++w)
+#pragma unroll
+              for (int p = 0; p < PT; ++p) fma4(acc[p], au[u + w][p], v[w][p]);
           }
         }
       }
@@ -368,6 +389,8 @@ int tc_split_weights(const float* src, long n, __nv_bfloat16* hi, __nv_bfloat16*
 int tc_split_weights_t(const float* W, int G, int P, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st);
 
 bool tap_tc_supported(const magat_gat_fwd_args* a);              // gat_tap_tc.cu
+bool score_tc_supported(const magat_gat_fwd_args* a);
+int score_tc_forward(const magat_gat_fwd_args* a, float* wt, cudaStream_t st);
 int tap_tc_forward(const magat_gat_fwd_args* a, cudaStream_t st);
 
 // one level of the tap recursion, u_k from u_{k-1} (k >= 1), for every head
@@ -403,18 +426,25 @@ static int forward_impl(const magat_gat_fwd_args* a, cudaStream_t st, bool use_t
                       (((uintptr_t)a->att) % 16 == 0) && (((uintptr_t)a->taps) % 16 == 0) &&
                       (((uintptr_t)a->sproj) % 16 == 0);
   int rc;
-  // bf16 hi/lo copies of the weights for the tcgen05 projections
-  __nv_bfloat16* tcw = reinterpret_cast<__nv_bfloat16*>(a->wprep + simt_wprep_floats(G, P, a->mode));
+  // scratch for the tcgen05 projections: transposed fp32 W (KeyQuery), then bf16 hi/lo copies of the weights
   const size_t nW = (size_t)P * G * G, nH = (size_t)P * F * K * G;
+  float* wt_f32 = a->wprep + simt_wprep_floats(G, P, a->mode);
+  __nv_bfloat16* tcw = reinterpret_cast<__nv_bfloat16*>(wt_f32 + (a->mode == MAGAT_MODE_KEYQUERY ? nW : 0));
+  const bool fused = use_tc && tap_tc_supported(a);
+  const bool score_fused = use_tc && score_tc_supported(a);
   __nv_bfloat16 *wt_hi = nullptr, *wt_lo = nullptr, *h_hi = tcw, *h_lo = tcw + nH;
   if (a->mode == MAGAT_MODE_KEYQUERY) { wt_hi = tcw; wt_lo = tcw + nW; h_hi = tcw + 2 * nW; h_lo = h_hi + nH; }
   if (use_tc) {
-    if (a->mode == MAGAT_MODE_KEYQUERY && (rc = tc_split_weights_t(a->weight, G, P, wt_hi, wt_lo, st))) return rc;
-    if ((rc = tc_split_weights(a->filterWeight, (long)nH, h_hi, h_lo, st))) return rc;
+    if (a->mode == MAGAT_MODE_KEYQUERY && !score_fused &&
+        (rc = tc_split_weights_t(a->weight, G, P, wt_hi, wt_lo, st)))
+      return rc;
+    if (!fused && (rc = tc_split_weights(a->filterWeight, (long)nH, h_hi, h_lo, st))) return rc;
   }
   // 1. score projection
   if (a->mode == MAGAT_MODE_KEYQUERY) {
-    if (use_tc) {
+    if (score_fused) {
+      if ((rc = score_tc_forward(a, wt_f32, st))) return rc;
+    } else if (use_tc) {
       if ((rc = tc_score_projection(a, wt_hi, wt_lo, st))) return rc;
     } else {
       dim3 grid(cdiv(rows, 64), cdiv((long)P * G, 64), 1);
@@ -447,7 +477,6 @@ static int forward_impl(const magat_gat_fwd_args* a, cudaStream_t st, bool use_t
   }
   if ((rc = check_launch("k_attention", st))) return rc;
   // 2. taps (the fused tcgen05 kernel gathers the second tap itself and only needs u_1 in memory)
-  const bool fused = use_tc && tap_tc_supported(a);
   const int k_last = fused ? (K - 1 < 1 ? K - 1 : 1) : K - 1;
   for (int k = 1; k <= k_last; ++k)
     if ((rc = run_tap_gather(a->x, a->x_sb, a->x_sn, a->att, a->nbr_in, a->slot_in, B, N, G, K, P, D, k, a->taps,

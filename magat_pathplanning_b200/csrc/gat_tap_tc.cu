@@ -11,11 +11,12 @@
 // [F=128 lanes x 64 nodes] is double buffered in the remaining 128 TMEM columns; the epilogue warps
 // add bias, apply ReLU, transpose through shared memory and store full 512 B rows of y.
 //
-//   warps 0-7   producers, two groups of four that alternate K chunks ([64 nodes x 64 k] -> hi/lo tiles,
-//               SWIZZLE_128B K-major, 8-stage ring)
-//   warps 8-11  epilogue (TMEM lanes q*32.. for warp q)
-//   warp  12    MMA issuer (one thread)
+//   warps 0-15  producers, four groups of four; group g builds every fourth 128-wide K slice
+//               ([64 nodes x 128 k] -> hi/lo tiles, SWIZZLE_128B K-major) into its own smem stage
+//   warps 16-19 epilogue (TMEM lanes q*32.. for warp 16+q)
+//   warp  20    MMA issuer (one thread): 24 MMAs per stage, then tcgen05.commit frees the stage
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -25,15 +26,15 @@ namespace magat {
 namespace {
 
 constexpr int TN = 64;                       // nodes per tile = UMMA N
-constexpr int BK = 64;                       // K elements per chunk
-constexpr int STAGES = 8;
-constexpr int CH_BYTES = TN * BK * 2;        // 8 KB: one bf16 [64 x 64] tile
-constexpr int STAGE_BYTES = 2 * CH_BYTES;    // hi + lo
+constexpr int SK = 128;                      // K elements per stage = two 64-wide swizzle atoms
+constexpr int STAGES = 4;                    // one per producer group
+constexpr int ATOM_BYTES = TN * 64 * 2;      // 8 KB: bf16 [64 rows x 64 k], SWIZZLE_128B
+constexpr int STAGE_BYTES = 4 * ATOM_BYTES;  // hi atom 0/1, lo atom 0/1
 constexpr int FT = 128;                      // out-features = UMMA M = TMEM lanes
 constexpr int EPI_BYTES = TN * FT * 4;       // 32 KB transposition buffer
-constexpr int PROD_WARPS = 8, PROD_GROUP = 128;
-constexpr int EPI_WARP0 = 8, MMA_WARP = 12;
-constexpr int THREADS = 13 * 32;
+constexpr int PROD_WARPS = 16, PROD_GROUP = 128;
+constexpr int EPI_WARP0 = 16, MMA_WARP = 20;
+constexpr int THREADS = 21 * 32;
 constexpr int ACC_COL0 = 384;                // accumulators: columns 384 + 64 a
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
 
@@ -46,12 +47,20 @@ struct TapParams {
   const float* H;        // filterWeight [P][F][K*G]
   const float* bias; int relu;
   float* y; long y_sb, y_sn;     // channel stride 1
+  int dbg;                       // MAGAT_DBG experiments (0 in production)
 };
 
-__device__ __forceinline__ void ld8(const float* p, float* v) {
-  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
-  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+__device__ __forceinline__ void split_store(uint8_t* hi_dst, uint8_t* lo_dst, const float4& a, const float4& b) {
+  uint4 hi, lo;
+  tc::split2(a.x, a.y, hi.x, lo.x);
+  tc::split2(a.z, a.w, hi.y, lo.y);
+  tc::split2(b.x, b.y, hi.z, lo.z);
+  tc::split2(b.z, b.w, hi.w, lo.w);
+  *reinterpret_cast<uint4*>(hi_dst) = hi;
+  *reinterpret_cast<uint4*>(lo_dst) = lo;
+}
+__device__ __forceinline__ void fma44(float4& acc, float a, const float4& v) {
+  acc.x = fmaf(a, v.x, acc.x); acc.y = fmaf(a, v.y, acc.y); acc.z = fmaf(a, v.z, acc.z); acc.w = fmaf(a, v.w, acc.w);
 }
 
 __global__ void __launch_bounds__(THREADS, 1) k_tap_tc(const __grid_constant__ TapParams p) {
@@ -69,8 +78,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_tap_tc(const __grid_constant__ T
   const int head = blockIdx.x % p.P;
   const int slot = blockIdx.x / p.P, nslots = gridDim.x / p.P;
   const int KG = p.K * p.G;
-  const int nchunks = KG / BK;
-  const int cps = p.G / BK;                  // chunks per K segment
+  const int nst = KG / SK;                   // stages (128-wide K slices) per tile
+  const int sps = p.G / SK;                  // stages per K segment
   const long tiles = (p.rows + TN - 1) / TN;
 
   if (threadIdx.x == 0) {
@@ -94,17 +103,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_tap_tc(const __grid_constant__ T
   if (warp < 4) {
     const int f = warp * 32 + lane;          // TMEM lane = output feature
     const float* hrow = p.H + ((size_t)head * FT + f) * KG;
-    for (int k0 = 0; k0 < KG; k0 += 64) {
-      uint32_t hi[32], lo[32];
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int k0 = 0; k0 < KG; k0 += 32) {
+      uint32_t hi[16], lo[16];
 #pragma unroll
-      for (int j = 0; j < 32; j += 2) {
+      for (int j = 0; j < 16; j += 2) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(hrow + k0 + 2 * j));
         tc::split2(v.x, v.y, hi[j], lo[j]);
         tc::split2(v.z, v.w, hi[j + 1], lo[j + 1]);
       }
-      const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-      tc::tmem_st32(lane_addr + (uint32_t)(k0 / 2), hi);
-      tc::tmem_st32(lane_addr + (uint32_t)(KG / 2 + k0 / 2), lo);
+      tc::tmem_st16(lane_addr + (uint32_t)(k0 / 2), hi);
+      tc::tmem_st16(lane_addr + (uint32_t)(KG / 2 + k0 / 2), lo);
     }
     tc::tmem_st_wait();
   }
@@ -114,111 +123,110 @@ __global__ void __launch_bounds__(THREADS, 1) k_tap_tc(const __grid_constant__ T
 
   if (warp < PROD_WARPS) {
     // ===== producers ======================================================================
-    const int grp = warp >> 2;
+    // Four groups of 128 threads; group g builds every stage-chunk q with q % 4 == g, always into smem stage g.
+    // A thread owns the 16 B column group c16 (+8 for the second atom) of rows r0 + 16 i.  32-bit index math
+    // (the host guarantees rows * P * D < 2^31).
+    const unsigned grp = warp >> 2;
     const int tg = threadIdx.x & (PROD_GROUP - 1);
     const int c16 = tg & 7;
-    const int r0 = tg >> 3;                   // rows r0 + 16 i, i < 4
-    const long u1_row = (long)p.P * (p.K - 1) * p.G;
-    long q = 0;                               // running chunk counter of the CTA
+    const int r0 = tg >> 3;
+    const unsigned N = (unsigned)p.N, D = (unsigned)p.D;
+    const int rows = (int)p.rows;
+    const unsigned u1_row4 = (unsigned)(p.P * (p.K - 1) * p.G) >> 2;      // float4 per node in the taps buffer
+    const float4* u1h4 = reinterpret_cast<const float4*>(p.u1 + (long)head * (p.K - 1) * p.G);
+    const float4* x4 = reinterpret_cast<const float4*>(p.x);
+    uint8_t* st = smem + (size_t)grp * STAGE_BYTES;
+    uint32_t sw_off[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sw_off[i] = tc::sw128_offset(r0 + 16 * i, c16);
+    unsigned q = 0;                           // running stage-chunk counter of the CTA
     for (long tile = slot; tile < tiles; tile += nslots) {
-      const long m0 = tile * TN;
-      for (int c = 0; c < nchunks; ++c, ++q) {
-        if ((q & 1) != grp) continue;
-        const int stage = (int)(q % STAGES);
-        const uint32_t phase = (uint32_t)((q / STAGES) & 1);
-        const int seg = c / cps;
-        const int k0 = (c - seg * cps) * BK + c16 * 8;
-        float v[4][8];
+      const int m0 = (int)(tile * TN);
+      for (int s = 0; s < nst; ++s, ++q) {
+        if ((q & 3u) != grp) continue;
+        const uint32_t phase = (q >> 2) & 1u;
+        const int seg = s / sps;
+        const unsigned k4 = (unsigned)(((s - seg * sps) * SK + c16 * 8) >> 2);    // float4 offset inside the row
         if (seg < 2) {
+          // x or u_1: straight copy.  All 16 loads of the thread are in flight before the stage is awaited.
+          float4 va[2][4], vb[2][4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const long m = m0 + r0 + 16 * i;
-            if (m < p.rows) {
-              const float* src;
+            const int m = m0 + r0 + 16 * i;
+            const float4* src = nullptr;
+            if (m < rows && !(p.dbg & 1)) {
               if (seg == 0) {
-                const long b = m / p.N;
-                src = p.x + b * p.x_sb + (m - b * p.N) * p.x_sn + k0;
+                const unsigned b = (unsigned)m / N;
+                src = x4 + (((long)b * p.x_sb + (long)((unsigned)m - b * N) * p.x_sn) >> 2) + k4;
               } else {
-                src = p.u1 + (m * p.P + head) * (long)(p.K - 1) * p.G + k0;
+                src = u1h4 + (size_t)(unsigned)m * u1_row4 + k4;
               }
-              ld8(src, v[i]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[i][e] = 0.f;
             }
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              if (src != nullptr) {
+                va[hh][i] = __ldg(src + hh * 16);
+                vb[hh][i] = __ldg(src + hh * 16 + 1);
+              } else {
+                va[hh][i] = vb[hh][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+            }
+          }
+          tc::mbar_wait(&empty[grp], phase ^ 1);
+          if (!(p.dbg & 2)) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                split_store(st + hh * ATOM_BYTES + sw_off[i], st + (2 + hh) * ATOM_BYTES + sw_off[i], va[hh][i],
+                            vb[hh][i]);
           }
         } else {
-          // second tap gathered on the fly: u_2[j] = sum_i A_p[i,j] u_1^p[i].  Index and weight lists of
-          // a row are contiguous (nbr_in, ain), read four entries at a time; the row loads of two rows x
-          // four entries are issued together so a thread keeps 256 B in flight.
-#pragma unroll
+          // second tap gathered on the fly: u_2[j] = sum_i A_p[i,j] u_1^p[i].  One (row, atom) at a time, four
+          // neighbour rows (128 B) in flight per thread; index / weight lists are contiguous per receiver.
+          tc::mbar_wait(&empty[grp], phase ^ 1);
+#pragma unroll 1
           for (int i = 0; i < 4; ++i) {
+            const int m = m0 + r0 + 16 * i;
+            const bool live = m < rows && !(p.dbg & 1);
+            const unsigned bN = live ? ((unsigned)m / N) * N : 0u;
+            const int32_t* nb = p.nbr_in + (unsigned)(live ? m : 0) * D;
+            const float* aw_p = p.ain + ((unsigned)(live ? m : 0) * (unsigned)p.P + head) * D;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[i][e] = 0.f;
-          }
-          const float* u1h = p.u1 + (long)head * (p.K - 1) * p.G + k0;
+            for (int hh = 0; hh < 2; ++hh) {
+              float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+              if (live) {
+                for (unsigned s0 = 0; s0 < D; s0 += 4) {
+                  const int4 id = __ldg(reinterpret_cast<const int4*>(nb + s0));
+                  if (id.x < 0) break;                       // lists are packed
+                  const float4 aw = __ldg(reinterpret_cast<const float4*>(aw_p + s0));
+                  const int ids[4] = {id.x, id.y, id.z, id.w};
+                  const float aws[4] = {aw.x, aw.y, aw.z, aw.w};
+                  float4 ta[4], tb[4];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            long mm[2], bN[2];
-            bool valid[2];
+                  for (int e = 0; e < 4; ++e) {
+                    if (ids[e] >= 0) {
+                      const float4* src = u1h4 + (size_t)(bN + (unsigned)ids[e]) * u1_row4 + k4 + hh * 16;
+                      ta[e] = __ldg(src);
+                      tb[e] = __ldg(src + 1);
+                    } else {
+                      ta[e] = tb[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                  }
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              mm[j] = m0 + r0 + 16 * (2 * h + j);
-              valid[j] = mm[j] < p.rows;
-              bN[j] = valid[j] ? (mm[j] / p.N) * p.N : 0;
-            }
-            for (int s0 = 0; s0 < p.D; s0 += 4) {
-              int id[2][4];
-              float aw[2][4];
-#pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                if (valid[j]) {
-                  const int4 i4 = __ldg(reinterpret_cast<const int4*>(p.nbr_in + mm[j] * p.D + s0));
-                  const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.ain + (mm[j] * p.P + head) * p.D + s0));
-                  id[j][0] = i4.x; id[j][1] = i4.y; id[j][2] = i4.z; id[j][3] = i4.w;
-                  aw[j][0] = a4.x; aw[j][1] = a4.y; aw[j][2] = a4.z; aw[j][3] = a4.w;
-                } else {
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) { id[j][e] = -1; aw[j][e] = 0.f; }
-                }
-              }
-              if (id[0][0] < 0 && id[1][0] < 0) break;      // lists are packed: nothing further in either row
-              float t[2][4][8];
-#pragma unroll
-              for (int j = 0; j < 2; ++j)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  if (id[j][e] >= 0) {
-                    ld8(u1h + (bN[j] + id[j][e]) * u1_row, t[j][e]);
-                  } else {
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) t[j][e][c] = 0.f;
+                  for (int e = 0; e < 4; ++e) {
+                    fma44(a, aws[e], ta[e]);
+                    fma44(b, aws[e], tb[e]);
                   }
                 }
-#pragma unroll
-              for (int j = 0; j < 2; ++j)
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-#pragma unroll
-                  for (int c = 0; c < 8; ++c) v[2 * h + j][c] = fmaf(aw[j][e], t[j][e][c], v[2 * h + j][c]);
+              }
+              if (!(p.dbg & 2))
+                split_store(st + hh * ATOM_BYTES + sw_off[i], st + (2 + hh) * ATOM_BYTES + sw_off[i], a, b);
             }
           }
         }
-        tc::mbar_wait(&empty[stage], phase ^ 1);
-        uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 hi, lo;
-          tc::split2(v[i][0], v[i][1], hi.x, lo.x);
-          tc::split2(v[i][2], v[i][3], hi.y, lo.y);
-          tc::split2(v[i][4], v[i][5], hi.z, lo.z);
-          tc::split2(v[i][6], v[i][7], hi.w, lo.w);
-          const uint32_t off = tc::sw128_offset(r0 + 16 * i, c16);
-          *reinterpret_cast<uint4*>(st + off) = hi;
-          *reinterpret_cast<uint4*>(st + CH_BYTES + off) = lo;
-        }
         tc::fence_proxy_async();
-        tc::mbar_arrive(&full[stage]);
+        tc::mbar_arrive(&full[grp]);
       }
     }
   } else if (warp < MMA_WARP) {
@@ -233,28 +241,38 @@ __global__ void __launch_bounds__(THREADS, 1) k_tap_tc(const __grid_constant__ T
       tc::mbar_wait(&acc_full[acc], acc_phase);
       tc::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(ACC_COL0 + acc * TN);
-      float v[64];
-      tc::tmem_ld32(taddr, v);
-      tc::tmem_ld32(taddr + 32, v + 32);
-      tc::tmem_ld_wait();
-      tc::tc_fence_before();
-      tc::mbar_arrive(&acc_empty[acc]);        // accumulator drained into registers
 #pragma unroll
-      for (int n = 0; n < TN; ++n) {
-        float o = v[n] + bias;
-        if (p.relu) o = fmaxf(o, 0.f);
-        epi[n * FT + f] = o;
+      for (int half = 0; half < 2; ++half) {
+        float v[32];
+        tc::tmem_ld32(taddr + 32 * half, v);
+        tc::tmem_ld_wait();
+        if (half == 1) {
+          tc::tc_fence_before();
+          tc::mbar_arrive(&acc_empty[acc]);    // accumulator drained into registers
+        }
+        if (!(p.dbg & 16)) {
+#pragma unroll
+          for (int n = 0; n < 32; ++n) {
+            float o = v[n] + bias;
+            if (p.relu) o = fmaxf(o, 0.f);
+            epi[(32 * half + n) * FT + f] = o;
+          }
+        }
       }
       tc::named_bar_sync(1, 128);
       // 64 rows x 512 B, each warp 16 rows, one float4 per lane
+      if (!(p.dbg & 4)) {
 #pragma unroll 4
-      for (int i = 0; i < 16; ++i) {
-        const int n = qd * 16 + i;
-        const long m = m0 + n;
-        if (m < p.rows) {
-          const long b = m / p.N;
-          const float4 o = *reinterpret_cast<const float4*>(epi + n * FT + lane * 4);
-          __stcs(reinterpret_cast<float4*>(p.y + b * p.y_sb + (m - b * p.N) * p.y_sn + (long)head * FT + lane * 4), o);
+        for (int i = 0; i < 16; ++i) {
+          const int n = qd * 16 + i;
+          const long m = m0 + n;
+          if (m < p.rows) {
+            const unsigned b = (unsigned)m / (unsigned)p.N;
+            const float4 o = *reinterpret_cast<const float4*>(epi + n * FT + lane * 4);
+            __stcs(reinterpret_cast<float4*>(p.y + (long)b * p.y_sb + (long)((unsigned)m - b * (unsigned)p.N) * p.y_sn +
+                                             (long)head * FT + lane * 4),
+                   o);
+          }
         }
       }
       tc::named_bar_sync(1, 128);
@@ -265,30 +283,37 @@ __global__ void __launch_bounds__(THREADS, 1) k_tap_tc(const __grid_constant__ T
     constexpr uint32_t idesc = tc::make_idesc_bf16(FT, TN);
     int acc = 0;
     uint32_t acc_phase = 0;
-    long q = 0;
+    unsigned q = 0;
     for (long tile = slot; tile < tiles; tile += nslots) {
       tc::mbar_wait(&acc_empty[acc], acc_phase ^ 1);
       tc::tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(ACC_COL0 + acc * TN);
-      for (int c = 0; c < nchunks; ++c, ++q) {
-        const int stage = (int)(q % STAGES);
-        const uint32_t phase = (uint32_t)((q / STAGES) & 1);
+      for (int s = 0; s < nst; ++s, ++q) {
+        const int stage = (int)(q & 3u);
+        const uint32_t phase = (q >> 2) & 1u;
         tc::mbar_wait(&full[stage], phase);
         tc::tc_fence_after();
         if (lane == 0) {
           const uint32_t sb = tc::smem_u32(smem + (size_t)stage * STAGE_BYTES);
-          const uint64_t z_hi = tc::make_sw128_desc(sb), z_lo = tc::make_sw128_desc(sb + CH_BYTES);
-          const uint32_t h_hi = tmem_base + (uint32_t)(c * (BK / 2));
+          const uint32_t h_hi = tmem_base + (uint32_t)(s * (SK / 2));
           const uint32_t h_lo = h_hi + (uint32_t)(KG / 2);
+          if (!(p.dbg & 32)) {
 #pragma unroll
-          for (int kk = 0; kk < BK / 16; ++kk) {
-            const uint64_t adv = (uint64_t)((kk * 32) >> 4);
-            tc::umma_bf16_ts(tmem_d, h_hi + kk * 8, z_hi + adv, idesc, (c | kk) != 0);
-            tc::umma_bf16_ts(tmem_d, h_lo + kk * 8, z_hi + adv, idesc, 1);
-            tc::umma_bf16_ts(tmem_d, h_hi + kk * 8, z_lo + adv, idesc, 1);
+            for (int at = 0; at < 2; ++at) {
+              const uint64_t z_hi = tc::make_sw128_desc(sb + at * ATOM_BYTES);
+              const uint64_t z_lo = tc::make_sw128_desc(sb + (2 + at) * ATOM_BYTES);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t adv = (uint64_t)((kk * 32) >> 4);
+                const uint32_t col = (uint32_t)(at * 32 + kk * 8);
+                tc::umma_bf16_ts(tmem_d, h_hi + col, z_hi + adv, idesc, (s | at | kk) != 0);
+                tc::umma_bf16_ts(tmem_d, h_lo + col, z_hi + adv, idesc, 1);
+                tc::umma_bf16_ts(tmem_d, h_hi + col, z_lo + adv, idesc, 1);
+              }
+            }
           }
           tc::umma_commit(&empty[stage]);
-          if (c == nchunks - 1) tc::umma_commit(&acc_full[acc]);
+          if (s == nst - 1) tc::umma_commit(&acc_full[acc]);
         }
         __syncwarp();
       }
@@ -303,23 +328,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_tap_tc(const __grid_constant__ T
   }
 }
 
-}  // namespace
-
-bool tap_tc_supported(const magat_gat_fwd_args* a) {
-  if (!a->concat || a->K > 3 || a->F != FT) return false;
-  if (a->G % BK != 0 || a->K * a->G > ACC_COL0) return false;
-  if (a->y_sc != 1 || (a->y_sn % 4) != 0 || (a->y_sb % 4) != 0 || ((uintptr_t)a->y % 16) != 0) return false;
-  if ((a->x_sn % 4) != 0 || (a->x_sb % 4) != 0 || ((uintptr_t)a->x % 16) != 0) return false;
-  if (a->K > 1 && ((uintptr_t)a->taps % 16) != 0) return false;
-  if (a->P > 64) return false;
-  if (a->K > 2 && (a->ain == nullptr || a->D % 4 != 0 || ((uintptr_t)a->ain % 16) != 0 ||
-                   ((uintptr_t)a->nbr_in % 16) != 0))
-    return false;
-  return true;
+// Wt[p][g'][g] = W[p][g][g']: the KeyQuery score projection R = X W_p as the same "weights in TMEM" GEMM
+__global__ void __launch_bounds__(256) k_transpose_w(const float* __restrict__ W, int G, long n,
+                                                     float* __restrict__ Wt) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;   // i = (p*G + g') * G + g
+  if (i >= n) return;
+  const int g = (int)(i % G);
+  const long pg = i / G;
+  const int gp = (int)(pg % G);
+  const long p = pg / G;
+  Wt[i] = W[(p * G + g) * G + gp];
 }
 
-// needs tap k = 1 (u_1) in a->taps when K >= 2; never reads or writes tap k = 2
-int tap_tc_forward(const magat_gat_fwd_args* a, cudaStream_t st) {
+int launch_tap_tc(const TapParams& tp, int P, cudaStream_t st, const char* what) {
   static int sm_count = 0;
   static bool attr_set = false;
   if (!attr_set) {
@@ -333,6 +354,61 @@ int tap_tc_forward(const magat_gat_fwd_args* a, cudaStream_t st) {
     }
     attr_set = true;
   }
+  TapParams tq = tp;
+  const char* dbg = getenv("MAGAT_DBG");
+  tq.dbg = dbg ? atoi(dbg) : 0;
+  const long tiles = (tp.rows + TN - 1) / TN;
+  long slots = sm_count / P;
+  if (slots < 1) slots = 1;
+  if (slots > tiles) slots = tiles;
+  k_tap_tc<<<(int)(slots * P), THREADS, SMEM_BYTES, st>>>(tq);
+  return check_launch(what, st);
+}
+
+}  // namespace
+
+// KeyQuery score projection sproj[m][p*G + g'] = sum_g x[m][g] W[p][g][g'] on the fused kernel (K = 1, no
+// bias / activation).  wt is P*G*G floats of scratch.
+bool score_tc_supported(const magat_gat_fwd_args* a) {
+  if (a->mode != MAGAT_MODE_KEYQUERY || a->G != FT || a->P > 64) return false;
+  if ((a->x_sn % 4) != 0 || (a->x_sb % 4) != 0 || ((uintptr_t)a->x % 16) != 0 || ((uintptr_t)a->sproj % 16) != 0)
+    return false;
+  if ((long)a->B * a->N * a->D * a->P >= (1l << 31)) return false;
+  return true;
+}
+
+int score_tc_forward(const magat_gat_fwd_args* a, float* wt, cudaStream_t st) {
+  const long n = (long)a->P * a->G * a->G;
+  k_transpose_w<<<cdiv(n, 256), 256, 0, st>>>(a->weight, a->G, n, wt);
+  int rc = check_launch("k_transpose_w", st);
+  if (rc) return rc;
+  TapParams tp{};
+  tp.rows = (long)a->B * a->N;
+  tp.N = a->N; tp.G = a->G; tp.K = 1; tp.P = a->P; tp.D = a->D;
+  tp.x = a->x; tp.x_sb = a->x_sb; tp.x_sn = a->x_sn;
+  tp.u1 = nullptr; tp.ain = nullptr; tp.nbr_in = nullptr;
+  tp.H = wt;
+  tp.bias = nullptr; tp.relu = 0;
+  tp.y = a->sproj; tp.y_sb = (long)a->N * a->P * a->G; tp.y_sn = (long)a->P * a->G;
+  return launch_tap_tc(tp, a->P, st, "k_tap_tc(score projection)");
+}
+
+bool tap_tc_supported(const magat_gat_fwd_args* a) {
+  if (!a->concat || a->K > 3 || a->F != FT) return false;
+  if (a->G % SK != 0 || a->K * a->G > ACC_COL0) return false;
+  if (a->y_sc != 1 || (a->y_sn % 4) != 0 || (a->y_sb % 4) != 0 || ((uintptr_t)a->y % 16) != 0) return false;
+  if ((a->x_sn % 4) != 0 || (a->x_sb % 4) != 0 || ((uintptr_t)a->x % 16) != 0) return false;
+  if (a->K > 1 && ((uintptr_t)a->taps % 16) != 0) return false;
+  if (a->P > 64) return false;
+  if ((long)a->B * a->N * a->D * a->P >= (1l << 31)) return false;     // 32-bit index math in the kernel
+  if (a->K > 2 && (a->ain == nullptr || a->D % 4 != 0 || ((uintptr_t)a->ain % 16) != 0 ||
+                   ((uintptr_t)a->nbr_in % 16) != 0))
+    return false;
+  return true;
+}
+
+// needs tap k = 1 (u_1) in a->taps when K >= 2; never reads or writes tap k = 2
+int tap_tc_forward(const magat_gat_fwd_args* a, cudaStream_t st) {
   TapParams tp{};
   tp.rows = (long)a->B * a->N;
   tp.N = a->N; tp.G = a->G; tp.K = a->K; tp.P = a->P; tp.D = a->D;
@@ -342,12 +418,7 @@ int tap_tc_forward(const magat_gat_fwd_args* a, cudaStream_t st) {
   tp.H = a->filterWeight;
   tp.bias = a->bias; tp.relu = a->relu;
   tp.y = a->y; tp.y_sb = a->y_sb; tp.y_sn = a->y_sn;
-  const long tiles = (tp.rows + TN - 1) / TN;
-  long slots = sm_count / a->P;
-  if (slots < 1) slots = 1;
-  if (slots > tiles) slots = tiles;
-  k_tap_tc<<<(int)(slots * a->P), THREADS, SMEM_BYTES, st>>>(tp);
-  return check_launch("k_tap_tc(fused taps + projection)", st);
+  return launch_tap_tc(tp, a->P, st, "k_tap_tc(fused taps + projection)");
 }
 
 }  // namespace magat

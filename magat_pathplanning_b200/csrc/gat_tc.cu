@@ -298,7 +298,7 @@ int launch_gemm(const GemmParams& gp, cudaStream_t st, const char* what) {
 size_t tc_wprep_floats(int G, int F, int K, int P, int mode) {
   size_t bf = 2 * (size_t)P * F * K * G;
   if (mode == MAGAT_MODE_KEYQUERY) bf += 2 * (size_t)P * G * G;
-  return bf / 2 + 8;
+  return bf / 2 + 8 + (mode == MAGAT_MODE_KEYQUERY ? (size_t)P * G * G : 0);
 }
 
 bool tc_shape_ok(int G, int F, int K, int P, int concat) {
