@@ -291,7 +291,7 @@ def main():
     ms_fwd = timed(step_fwd, args.steps, args.warmup, dist_on)
 
     # ---- per-kernel CUDA-event times of the forward path (rank 0) --------------------------------
-    kernels, fwd_kernel_ms = [], None
+    kernels, fwd_kernel_ms, train_kernels = [], None, []
     if rank == 0:
         torch.cuda.synchronize()
         L.magat_profile_enable(1)
@@ -303,6 +303,13 @@ def main():
         L.magat_profile_enable(0)
         kernels = [{"kernel": n, "launches_per_step": c // reps, "ms_per_step": t / reps} for n, c, t in rec]
         fwd_kernel_ms = sum(k["ms_per_step"] for k in kernels)
+        L.magat_profile_enable(1)
+        for _ in range(reps):
+            step_train()
+        torch.cuda.synchronize()
+        rec = _cabi.profile_collect()
+        L.magat_profile_enable(0)
+        train_kernels = [{"kernel": n, "launches_per_step": c // reps, "ms_per_step": t / reps} for n, c, t in rec]
 
     # ---- end to end from pinned host buffers --------------------------------------------------
     e2e = None
@@ -373,7 +380,7 @@ def main():
                          if S.numel() * 4 > 126e6 else "inputs smaller than L2; no flush",
                    "parallelism": f"batch-sharded x{world}, grad all-reduce (NCCL)" if dist_on else "1 GPU"},
         "fwd": {"value": units / (ms_fwd * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms_fwd},
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+        "roofline": roofline, "train_kernels": train_kernels, "cpu_baseline": cpu_baseline, "e2e": e2e,
         "gpu_launches": int(launches_per_step) * args.steps, "gpu_launches_per_step": int(launches_per_step),
         "clocks": clocks,
     }

@@ -9,6 +9,8 @@
 //                 dcvec_t = sum_n {c,r}_n x_n ; ddvec_t = sum_n {c,r}_n ; then the chain through
 //                 cvec_t = W^T a_t, dvec_t = a_t . wb  (gat_fwd.cu k_gm_prep)
 // mixer / weight_bias receive no gradient in KeyQuery mode (the reference leaves grad = None).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "simt_gemm.cuh"
 
@@ -265,6 +267,20 @@ int run_tap_gather(const float* x, long x_sb, long x_sn, const float* att, const
                    const int32_t* slot_in, int B, int N, int G, int K, int P, int D, int k, float* taps,
                    float* ain, cudaStream_t st);   // gat_fwd.cu
 
+// gat_wgrad_tc.cu
+size_t wgrad_tc_partial_floats(int G, int F, int K, int P);
+bool wgrad_tc_supported(const magat_gat_bwd_args* a);
+int wgrad_tc_dfilter(const magat_gat_bwd_args* a, cudaStream_t st);
+int wgrad_tc_dweight(const magat_gat_bwd_args* a, cudaStream_t st);
+
+// gat_tap_tc.cu / gat_tc.cu
+bool gz_tc_supported(const magat_gat_bwd_args* a);
+int gz_tc_backward(const magat_gat_bwd_args* a, float* ht, cudaStream_t st);
+bool dx_tc_supported(const magat_gat_bwd_args* a);
+int tc_dx_accumulate(const magat_gat_bwd_args* a, const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo,
+                     cudaStream_t st);
+int tc_split_weights(const float* src, long n, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st);
+
 static int pick_splits(long R, int tiles) {
   long s = (148l * 4 + tiles - 1) / tiles;
   const long cap = (R + 255) / 256;
@@ -306,6 +322,7 @@ extern "C" size_t magat_gat_bwd_partial_floats(int B, int N, int G, int F, int K
   m = max(m, need(1, F, 1));
   if (mode == MAGAT_MODE_KEYQUERY) m = max(m, need(G, G, P));
   else m = max(m, need(2l * P, G + 1, 1) + (size_t)2 * P * (G + 1));
+  m = max(m, wgrad_tc_partial_floats(G, F, K, P));
   return m;
 }
 
@@ -350,14 +367,20 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
     if ((rc = rowred(rows, 1, F, 1, OneLoad{}, DPreSumP{dp, P}, a->partial, a->dbias, st, "k_rowred_gemm(dbias)")))
       return rc;
   }
+  const bool tc_wgrad = a->path != MAGAT_PATH_SIMT && wgrad_tc_supported(a);
   if (a->need_dfilter) {
-    if ((rc = rowred(rows, F, KG, P, DPreR{dp}, ZRed{zn, G}, a->partial, a->dfilterWeight, st,
-                     "k_rowred_gemm(dfilterWeight)")))
+    if (tc_wgrad) {
+      if ((rc = wgrad_tc_dfilter(a, st))) return rc;
+    } else if ((rc = rowred(rows, F, KG, P, DPreR{dp}, ZRed{zn, G}, a->partial, a->dfilterWeight, st,
+                            "k_rowred_gemm(dfilterWeight)")))
       return rc;
   }
   if (!need_scores) return MAGAT_OK;
 
-  {  // gz = dP H
+  if (a->path != MAGAT_PATH_SIMT && gz_tc_supported(a)) {
+    // scratch: transposed taps in `partial` (free between the weight-gradient launches)
+    if ((rc = gz_tc_backward(a, a->partial, st))) return rc;
+  } else {  // gz = dP H
     dim3 grid(cdiv(rows, 64), cdiv(KG, 64), P);
     HtLoad hl{a->filterWeight, KG, F};
     k_node_gemm<<<grid, 256, 0, st>>>(rows, KG, F, DPreA{dp}, hl, GzEpi{a->gz, P, KG});
@@ -378,15 +401,22 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
                                                                 a->slot_in, rows, N, G, P, K, D, a->rc,
                                                                 a->need_dx ? a->dx : nullptr);
     if ((rc = check_launch("k_col_bwd", st))) return rc;
-    if (a->need_dx) {
+    if (a->need_dx && a->path != MAGAT_PATH_SIMT && dx_tc_supported(a)) {
+      __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(a->partial);
+      __nv_bfloat16* w_lo = w_hi + (size_t)P * G * G;
+      if ((rc = tc_split_weights(a->weight, (long)P * G * G, w_hi, w_lo, st))) return rc;
+      if ((rc = tc_dx_accumulate(a, w_hi, w_lo, st))) return rc;
+    } else if (a->need_dx) {
       dim3 grid(cdiv(rows, 64), cdiv(G, 64), 1);
       k_node_gemm<<<grid, 256, 0, st>>>(rows, G, P * G, RcLoad{a->rc, P * G}, WtLoad{a->weight, G},
                                         AccEpi{a->dx, G});
       if ((rc = check_launch("k_node_gemm(dx += W dR)", st))) return rc;
     }
     if (a->need_dweight) {
-      if ((rc = rowred(rows, G, G, P, XRed{a->x, a->x_sb, a->x_sn, N}, RcRed{a->rc, P, G}, a->partial, a->dweight,
-                       st, "k_rowred_gemm(dweight)")))
+      if (tc_wgrad) {
+        if ((rc = wgrad_tc_dweight(a, st))) return rc;
+      } else if ((rc = rowred(rows, G, G, P, XRed{a->x, a->x_sb, a->x_sn, N}, RcRed{a->rc, P, G}, a->partial,
+                              a->dweight, st, "k_rowred_gemm(dweight)")))
         return rc;
     }
   } else {

@@ -42,6 +42,8 @@ struct TapParams {
   long rows;             // B * N
   int N, G, K, P, D;
   const float* x; long x_sb, x_sn;
+  int x_hdiv; long x_hmul;               // head h reads x + (h / x_hdiv) * x_hmul (0 in the forward)
+  const float* mask; long m_sb, m_sn;    // optional: x is zeroed where mask <= 0 (same head offset rule)
   const float* u1;       // taps buffer, tap k = 1 of head p of node m at u1 + (m*P + p)*(K-1)*G
   const float* ain; const int32_t* nbr_in;   // ain[m][p][s] = A_p[nbr_in[m][s], m]
   const float* H;        // filterWeight [P][F][K*G]
@@ -134,7 +136,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_tap_tc(const __grid_constant__ T
     const int rows = (int)p.rows;
     const unsigned u1_row4 = (unsigned)(p.P * (p.K - 1) * p.G) >> 2;      // float4 per node in the taps buffer
     const float4* u1h4 = reinterpret_cast<const float4*>(p.u1 + (long)head * (p.K - 1) * p.G);
-    const float4* x4 = reinterpret_cast<const float4*>(p.x);
+    const long x_hoff = p.x_hmul ? (long)(head / p.x_hdiv) * p.x_hmul : 0;
+    const float4* x4 = reinterpret_cast<const float4*>(p.x + x_hoff);
+    const float4* mk4 = p.mask ? reinterpret_cast<const float4*>(p.mask + x_hoff) : nullptr;
     uint8_t* st = smem + (size_t)grp * STAGE_BYTES;
     uint32_t sw_off[4];
 #pragma unroll
@@ -154,10 +158,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_tap_tc(const __grid_constant__ T
           for (int i = 0; i < 4; ++i) {
             const int m = m0 + r0 + 16 * i;
             const float4* src = nullptr;
+            const float4* msk = nullptr;
             if (m < rows && !(p.dbg & 1)) {
               if (seg == 0) {
                 const unsigned b = (unsigned)m / N;
                 src = x4 + (((long)b * p.x_sb + (long)((unsigned)m - b * N) * p.x_sn) >> 2) + k4;
+                if (mk4) msk = mk4 + (((long)b * p.m_sb + (long)((unsigned)m - b * N) * p.m_sn) >> 2) + k4;
               } else {
                 src = u1h4 + (size_t)(unsigned)m * u1_row4 + k4;
               }
@@ -169,6 +175,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_tap_tc(const __grid_constant__ T
                 vb[hh][i] = __ldg(src + hh * 16 + 1);
               } else {
                 va[hh][i] = vb[hh][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+              if (msk != nullptr) {
+                const float4 ma = __ldg(msk + hh * 16), mb = __ldg(msk + hh * 16 + 1);
+                float4& A = va[hh][i];
+                float4& Bv = vb[hh][i];
+                A.x = ma.x > 0.f ? A.x : 0.f; A.y = ma.y > 0.f ? A.y : 0.f;
+                A.z = ma.z > 0.f ? A.z : 0.f; A.w = ma.w > 0.f ? A.w : 0.f;
+                Bv.x = mb.x > 0.f ? Bv.x : 0.f; Bv.y = mb.y > 0.f ? Bv.y : 0.f;
+                Bv.z = mb.z > 0.f ? Bv.z : 0.f; Bv.w = mb.w > 0.f ? Bv.w : 0.f;
               }
             }
           }
@@ -386,11 +401,53 @@ int score_tc_forward(const magat_gat_fwd_args* a, float* wt, cudaStream_t st) {
   tp.rows = (long)a->B * a->N;
   tp.N = a->N; tp.G = a->G; tp.K = 1; tp.P = a->P; tp.D = a->D;
   tp.x = a->x; tp.x_sb = a->x_sb; tp.x_sn = a->x_sn;
+  tp.x_hdiv = 1; tp.x_hmul = 0; tp.mask = nullptr;
   tp.u1 = nullptr; tp.ain = nullptr; tp.nbr_in = nullptr;
   tp.H = wt;
   tp.bias = nullptr; tp.relu = 0;
   tp.y = a->sproj; tp.y_sb = (long)a->N * a->P * a->G; tp.y_sn = (long)a->P * a->G;
   return launch_tap_tc(tp, a->P, st, "k_tap_tc(score projection)");
+}
+
+// Ht[(p*K + k)][g][f] = H[p][f][k][g]: the backward projection gz = dP H as the same kernel
+__global__ void __launch_bounds__(256) k_transpose_h(const float* __restrict__ H, int F, int K, int G, long n,
+                                                     float* __restrict__ Ht) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;   // i = ((p*K + k)*G + g)*F + f
+  if (i >= n) return;
+  const int f = (int)(i % F);
+  long r = i / F;
+  const int g = (int)(r % G);
+  r /= G;
+  const int k = (int)(r % K);
+  const long p = r / K;
+  Ht[i] = H[((p * F + f) * K + k) * G + g];
+}
+
+bool gz_tc_supported(const magat_gat_bwd_args* a) {
+  if (!a->concat || a->G != FT || a->F % SK != 0 || a->F > ACC_COL0 || a->P * a->K > 64) return false;
+  if (a->dy_sc != 1 || (a->dy_sn % 4) || (a->dy_sb % 4) || ((uintptr_t)a->dy % 16)) return false;
+  if (a->relu && (a->y_sc != 1 || (a->y_sn % 4) || (a->y_sb % 4) || ((uintptr_t)a->y % 16))) return false;
+  if (((uintptr_t)a->gz % 16) != 0) return false;
+  if ((long)a->B * a->N * a->D * a->P >= (1l << 31)) return false;
+  return true;
+}
+
+// gz[m][p][k][g] = sum_f dP[m][p*F + f] H[p][f][k][g], dP = dY * relu'(y).  ht: P*K*G*F floats of scratch.
+int gz_tc_backward(const magat_gat_bwd_args* a, float* ht, cudaStream_t st) {
+  const long n = (long)a->P * a->K * a->G * a->F;
+  k_transpose_h<<<cdiv(n, 256), 256, 0, st>>>(a->filterWeight, a->F, a->K, a->G, n, ht);
+  int rc = check_launch("k_transpose_h", st);
+  if (rc) return rc;
+  TapParams tp{};
+  tp.rows = (long)a->B * a->N;
+  tp.N = a->N; tp.G = a->F; tp.K = 1; tp.P = a->P * a->K; tp.D = a->D;
+  tp.x = a->dy; tp.x_sb = a->dy_sb; tp.x_sn = a->dy_sn;
+  tp.x_hdiv = a->K; tp.x_hmul = a->F;
+  tp.mask = a->relu ? a->y : nullptr; tp.m_sb = a->y_sb; tp.m_sn = a->y_sn;
+  tp.H = ht;
+  tp.bias = nullptr; tp.relu = 0;
+  tp.y = a->gz; tp.y_sn = (long)a->P * a->K * a->G; tp.y_sb = (long)a->N * tp.y_sn;
+  return launch_tap_tc(tp, tp.P, st, "k_tap_tc(gz = dP H)");
 }
 
 bool tap_tc_supported(const magat_gat_fwd_args* a) {
@@ -413,6 +470,7 @@ int tap_tc_forward(const magat_gat_fwd_args* a, cudaStream_t st) {
   tp.rows = (long)a->B * a->N;
   tp.N = a->N; tp.G = a->G; tp.K = a->K; tp.P = a->P; tp.D = a->D;
   tp.x = a->x; tp.x_sb = a->x_sb; tp.x_sn = a->x_sn;
+  tp.x_hdiv = 1; tp.x_hmul = 0; tp.mask = nullptr;
   tp.u1 = a->taps;
   tp.ain = a->ain; tp.nbr_in = a->nbr_in;
   tp.H = a->filterWeight;

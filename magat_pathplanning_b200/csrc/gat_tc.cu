@@ -51,7 +51,7 @@ struct GemmParams {
   int segs_per_tile;       // K-segments reduced into one output tile
   int Z;                   // independent z slices (heads); z picks segs [z*segs_per_tile, ...)
   int n_tiles;             // BN-wide column tiles per z
-  int epi;                 // 0: plain store to c[m * ldc + z * z_cols + n]; 1: y epilogue
+  int epi;                 // 0: store to c[m * ldc + z * z_cols + n]; 2: accumulate into it; 1: y epilogue
   float* c; long ldc; int z_cols;
   // y epilogue: v * scale + bias[n]; relu; y[b*y_sb + node*y_sn + (z*z_cols + n)*y_sc]
   float* y; long y_sb, y_sn, y_sc; const float* bias; int relu; float scale;
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_tc_gemm(const __grid_constan
       float* crow = nullptr;
       long ybase = 0;
       if (m < p.M) {
-        if (p.epi == 0) {
+        if (p.epi != 1) {
           crow = p.c + m * p.ldc + (long)z * p.z_cols + n0;
         } else {
           const long b = m / p.n_per_b;
@@ -185,6 +185,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_tc_gemm(const __grid_constan
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               *reinterpret_cast<float4*>(crow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else if (p.epi == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o = *reinterpret_cast<float4*>(crow + c0 + j);
+              o.x += v[j]; o.y += v[j + 1]; o.z += v[j + 2]; o.w += v[j + 3];
+              *reinterpret_cast<float4*>(crow + c0 + j) = o;
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -366,6 +373,33 @@ int tc_tap_projection(const magat_gat_fwd_args* a, const __nv_bfloat16* h_hi, co
       gp.seg[p * K + k] = s;
     }
   return launch_gemm(gp, st, "k_tc_gemm(tap projection)");
+}
+
+bool dx_tc_supported(const magat_gat_bwd_args* a) {
+  if (a->mode != MAGAT_MODE_KEYQUERY || a->G % BK != 0 || a->G % BN != 0 || a->P > MAX_SEGS) return false;
+  if (((uintptr_t)a->rc % 16) != 0 || ((uintptr_t)a->dx % 16) != 0) return false;
+  return true;
+}
+
+// KeyQuery: dx[m][g] += sum_{p,g'} dR[m][p][g'] W[p][g][g'];  w_hi / w_lo: bf16 split of `weight` as stored
+int tc_dx_accumulate(const magat_gat_bwd_args* a, const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo,
+                     cudaStream_t st) {
+  const int G = a->G, P = a->P;
+  GemmParams gp{};
+  gp.M = (long)a->B * a->N;
+  gp.n_per_b = a->N;
+  gp.chunks_per_seg = G / BK;
+  gp.segs_per_tile = P;
+  gp.Z = 1;
+  gp.n_tiles = G / BN;
+  gp.epi = 2;
+  gp.c = a->dx;
+  gp.ldc = G;
+  gp.z_cols = 0;
+  for (int p = 0; p < P; ++p)
+    gp.seg[p] = Seg{a->rc + (long)p * G, (long)a->N * P * G, (long)P * G, w_hi + (long)p * G * G,
+                    w_lo + (long)p * G * G, (long)G};
+  return launch_gemm(gp, st, "k_tc_gemm(dx += dR W^T)");
 }
 
 int tc_split_weights(const float* src, long n, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st) {

@@ -1,0 +1,342 @@
+// Weight gradients on tcgen05: reductions over the NODE axis,
+//     dC[z][i][j] = sum_m  A[m][z*az + i] * B_z[m][j],        i < 128, j < NB <= 384
+// which is dfilterWeight (A = dP = dY * relu'(y), B = the stacked taps [x | u_1 | u_2] of head z) and, for
+// KeyQuery, dweight (A = x, B = dR_z).  Both operands live in memory node-major (features contiguous),
+// so the reduction index is the SLOW index: the tiles are stored exactly as they are read -- 128 B rows of
+// 64 bf16 features per node -- and handed to the tensor core as MN-major operands (SWIZZLE_128B, LBO =
+// stride between 64-feature atoms, SBO = stride between 8-node groups); no transposition anywhere.
+// fp32 accuracy comes from the same three-pass bf16 hi/lo split as the forward kernels.
+//
+// Persistent CTA per (z, slot): accumulates its share of the nodes into TMEM (128 lanes x NB columns, fp32)
+// over the whole kernel, then writes ONE partial tile; a tiny kernel sums the partials (deterministic).
+//   warps 0-7  producers: 32-node stages {A hi/lo [32 x 128], B hi/lo [32 x NB]}, 3-stage ring
+//   warp  8    MMA issuer: per 16-node step 3 x (N=256 [+ N=128]) tcgen05.mma, both operands from smem
+//   warps 0-3  double as the epilogue at the end (TMEM -> partial tile)
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace magat {
+
+namespace {
+
+constexpr int SN = 32;                         // nodes per stage (MMA K = 16 -> 2 steps)
+constexpr int MI = 128;                        // rows of dC = UMMA M
+constexpr int MAX_NB = 384;
+constexpr int A_BYTES = SN * MI * 2;           // 8 KB per hi or lo
+constexpr int B_BYTES = SN * MAX_NB * 2;       // 24 KB per hi or lo
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 64 KB
+constexpr int STAGES = 3;
+constexpr int ATOM_STRIDE = SN * 128;          // bytes between 64-feature atoms (LBO)
+constexpr int PROD_THREADS = 256;
+constexpr int MMA_WARP = 8;
+constexpr int THREADS = 9 * 32;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+
+struct Src {                 // node-major fp32 rows: row m at p + (m / N) * sb + (m % N) * sn  (+ z * zoff)
+  const float* p; long sb, sn, zoff;
+};
+
+struct WgradParams {
+  long rows; int N;
+  int Z, NB;                 // slices (heads), columns of dC per slice (multiple of 128, <= 384)
+  Src a;                     // 128 features per node
+  Src b[3];                  // NB / 128 segments of 128 features
+  const float* mask_y; long my_sb, my_sn, my_zoff;   // optional: A = a * (mask_y > 0)  (dP from dY and y)
+  float a_scale;
+  float* partial;            // [Z][nslots][128][NB]
+};
+
+// MN-major SWIZZLE_128B operand: LBO = bytes between 64-element atoms along M/N, SBO = bytes between
+// 8-row groups along K (1024), version 1, layout type 2.
+__device__ __forceinline__ uint64_t make_mn_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(ATOM_STRIDE >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16, D = F32, A = B = BF16, both MN-major (bits 15, 16 = 1)
+__host__ __device__ constexpr uint32_t make_idesc_mn(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* done = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int z = blockIdx.x % p.Z;
+  const int slot = blockIdx.x / p.Z, nslots = gridDim.x / p.Z;
+  const long nstages = (p.rows + SN - 1) / SN;
+  const int nseg = p.NB / 128;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      tc::mbar_init(&full[s], PROD_THREADS);
+      tc::mbar_init(&empty[s], 1);
+    }
+    tc::mbar_init(done, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == MMA_WARP) tc::tmem_alloc<512>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < MMA_WARP) {
+    // ===== producers ======================================================================
+    const int t = threadIdx.x;                 // 0..255
+    const int c = t & 15;                      // 16 B chunk (8 features) of the 128-feature row
+    const int r0 = t >> 4;                     // rows r0, r0 + 16
+    const unsigned N = (unsigned)p.N;
+    const int rows = (int)p.rows;
+    // byte offset inside an operand region: atom (c / 8), row r, chunk (c % 8) swizzled by the row
+    uint32_t off[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int r = r0 + 16 * i;
+      off[i] = (uint32_t)((c >> 3) * ATOM_STRIDE + r * 128 + (((c & 7) ^ (r & 7)) << 4));
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long sidx = slot; sidx < nstages; sidx += nslots) {
+      const int m0 = (int)(sidx * SN);
+      float4 va[4][2][2];                      // [source][row][half]
+      float4 vm[2][2];
+      bool has_mask = p.mask_y != nullptr;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int m = m0 + r0 + 16 * i;
+        const bool live = m < rows;
+        const unsigned mu = live ? (unsigned)m : 0u;
+        const unsigned b = mu / N, n = mu - b * N;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          const Src& sc = s == 0 ? p.a : p.b[s - 1];
+          if (live && (s == 0 || s - 1 < nseg)) {
+            const float4* src = reinterpret_cast<const float4*>(sc.p + (long)b * sc.sb + (long)n * sc.sn +
+                                                                (long)z * sc.zoff + c * 8);
+            va[s][i][0] = __ldg(src);
+            va[s][i][1] = __ldg(src + 1);
+          } else {
+            va[s][i][0] = va[s][i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        if (has_mask && live) {
+          const float4* src = reinterpret_cast<const float4*>(p.mask_y + (long)b * p.my_sb + (long)n * p.my_sn +
+                                                              (long)z * p.my_zoff + c * 8);
+          vm[i][0] = __ldg(src);
+          vm[i][1] = __ldg(src + 1);
+        } else {
+          vm[i][0] = vm[i][1] = make_float4(1.f, 1.f, 1.f, 1.f);
+        }
+      }
+      // A = a * scale * (y > 0)
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float4& v = va[0][i][h];
+          const float4 mk = vm[i][h];
+          v.x = mk.x > 0.f ? v.x * p.a_scale : 0.f;
+          v.y = mk.y > 0.f ? v.y * p.a_scale : 0.f;
+          v.z = mk.z > 0.f ? v.z * p.a_scale : 0.f;
+          v.w = mk.w > 0.f ? v.w * p.a_scale : 0.f;
+        }
+      tc::mbar_wait(&empty[stage], phase ^ 1);
+      uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        if (s > 0 && s - 1 >= nseg) continue;
+        uint8_t* hi_base = s == 0 ? st : st + 2 * A_BYTES + (s - 1) * 2 * ATOM_STRIDE;
+        uint8_t* lo_base = s == 0 ? st + A_BYTES : hi_base + B_BYTES;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          uint4 hi, lo;
+          tc::split2(va[s][i][0].x, va[s][i][0].y, hi.x, lo.x);
+          tc::split2(va[s][i][0].z, va[s][i][0].w, hi.y, lo.y);
+          tc::split2(va[s][i][1].x, va[s][i][1].y, hi.z, lo.z);
+          tc::split2(va[s][i][1].z, va[s][i][1].w, hi.w, lo.w);
+          *reinterpret_cast<uint4*>(hi_base + off[i]) = hi;
+          *reinterpret_cast<uint4*>(lo_base + off[i]) = lo;
+        }
+      }
+      tc::fence_proxy_async();
+      tc::mbar_arrive(&full[stage]);
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+    // ===== epilogue (warps 0-3): the accumulated tile -> this CTA's partial =====================
+    if (warp < 4) {
+      tc::mbar_wait(done, 0);
+      tc::tc_fence_after();
+      const int i_row = warp * 32 + lane;
+      float* dst = p.partial + (((size_t)z * nslots + slot) * MI + i_row) * p.NB;
+      const bool any = slot < nstages;           // a CTA without work never touched TMEM: write zeros
+      for (int c0 = 0; c0 < p.NB; c0 += 32) {
+        float v[32];
+        if (any) {
+          tc::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+          tc::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+  } else {
+    // ===== MMA issuer =====================================================================
+    const uint32_t idesc256 = make_idesc_mn(MI, 256), idesc128 = make_idesc_mn(MI, 128);
+    int stage = 0;
+    uint32_t phase = 0;
+    bool first = true;
+    for (long sidx = slot; sidx < nstages; sidx += nslots) {
+      tc::mbar_wait(&full[stage], phase);
+      tc::tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sb = tc::smem_u32(smem + (size_t)stage * STAGE_BYTES);
+        const uint32_t a_hi = sb, a_lo = sb + A_BYTES, b_hi = sb + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < SN / 16; ++kk) {
+          const uint32_t kofs = (uint32_t)(kk * 2 * 1024);          // 16 nodes = two 8-row groups
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t aa = (pass == 1 ? a_lo : a_hi) + kofs;
+            const uint32_t bb = (pass == 2 ? b_lo : b_hi) + kofs;
+            const uint32_t accum = (first && kk == 0 && pass == 0) ? 0u : 1u;
+            if (p.NB >= 256) {
+              tc::umma_bf16(tmem_base, make_mn_desc(aa), make_mn_desc(bb), idesc256, accum);
+              if (p.NB > 256)
+                tc::umma_bf16(tmem_base + 256, make_mn_desc(aa), make_mn_desc(bb + 4 * ATOM_STRIDE), idesc128, accum);
+            } else {
+              tc::umma_bf16(tmem_base, make_mn_desc(aa), make_mn_desc(bb), idesc128, accum);
+            }
+          }
+        }
+        tc::umma_commit(&empty[stage]);
+        first = false;
+      }
+      __syncwarp();
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+    if (lane == 0) tc::umma_commit(done);
+    __syncwarp();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// out[z][e] = sum_s partial[(z * nslots + s) * per + e]
+__global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ partial, int nslots, long per,
+                                                      long total, float* __restrict__ out) {
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const long zz = e / per, l = e - zz * per;
+  const float* q = partial + (size_t)zz * nslots * per + l;
+  float s = 0.f;
+  for (int k = 0; k < nslots; ++k) s += q[(size_t)k * per];
+  out[e] = s;
+}
+
+int wgrad_nslots(int Z) {
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  int s = sm_count / Z;
+  return s < 1 ? 1 : s;
+}
+
+int launch_wgrad(WgradParams& wp, float* out, cudaStream_t st, const char* what) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(k_wgrad_tc): %s", cudaGetErrorString(e));
+      return MAGAT_E_CUDA;
+    }
+    attr_set = true;
+  }
+  const int nslots = wgrad_nslots(wp.Z);
+  k_wgrad_tc<<<nslots * wp.Z, THREADS, SMEM_BYTES, st>>>(wp);
+  int rc = check_launch(what, st);
+  if (rc) return rc;
+  const long per = (long)MI * wp.NB, total = per * wp.Z;
+  k_wgrad_reduce<<<cdiv(total, 256), 256, 0, st>>>(wp.partial, nslots, per, total, out);
+  return check_launch("k_wgrad_reduce", st);
+}
+
+bool aligned16(const void* p) { return ((uintptr_t)p % 16) == 0; }
+
+}  // namespace
+
+// floats of `partial` scratch the tcgen05 weight-gradient kernels need
+size_t wgrad_tc_partial_floats(int G, int F, int K, int P) {
+  (void)G;
+  return (size_t)wgrad_nslots(P) * P * MI * (size_t)(K * G > 128 ? K * G : 128) + (size_t)F * 0;
+}
+
+bool wgrad_tc_supported(const magat_gat_bwd_args* a) {
+  if (a->F != MI || a->G != 128 || a->K > 3 || !a->concat) return false;
+  if ((a->x_sn % 4) || (a->x_sb % 4) || !aligned16(a->x) || !aligned16(a->dy) || !aligned16(a->y)) return false;
+  if (a->dy_sc != 1 || a->y_sc != 1 || (a->dy_sn % 4) || (a->dy_sb % 4) || (a->y_sn % 4) || (a->y_sb % 4)) return false;
+  if (a->K > 1 && !aligned16(a->taps)) return false;
+  if ((long)a->B * a->N >= (1l << 31)) return false;
+  return true;
+}
+
+// dfilterWeight[p][f][k*G + g] = sum_m dP[m][p*F + f] * u_k^p[m][g]
+int wgrad_tc_dfilter(const magat_gat_bwd_args* a, cudaStream_t st) {
+  WgradParams wp{};
+  wp.rows = (long)a->B * a->N;
+  wp.N = a->N;
+  wp.Z = a->P;
+  wp.NB = a->K * a->G;
+  wp.a = Src{a->dy, a->dy_sb, a->dy_sn, (long)a->F};
+  wp.mask_y = a->relu ? a->y : nullptr;
+  wp.my_sb = a->y_sb; wp.my_sn = a->y_sn; wp.my_zoff = a->F;
+  wp.a_scale = 1.f;
+  wp.b[0] = Src{a->x, a->x_sb, a->x_sn, 0};
+  const long tap_row = (long)a->P * (a->K - 1) * a->G;
+  for (int k = 1; k < a->K; ++k)
+    wp.b[k] = Src{a->taps + (long)(k - 1) * a->G, (long)a->N * tap_row, tap_row, (long)(a->K - 1) * a->G};
+  wp.partial = a->partial;
+  return launch_wgrad(wp, a->dfilterWeight, st, "k_wgrad_tc(dfilterWeight)");
+}
+
+// KeyQuery: dweight[p][g][g'] = sum_m x[m][g] * dR[m][p][g']
+int wgrad_tc_dweight(const magat_gat_bwd_args* a, cudaStream_t st) {
+  WgradParams wp{};
+  wp.rows = (long)a->B * a->N;
+  wp.N = a->N;
+  wp.Z = a->P;
+  wp.NB = 128;
+  wp.a = Src{a->x, a->x_sb, a->x_sn, 0};
+  wp.mask_y = nullptr;
+  wp.a_scale = 1.f;
+  const long rc_row = (long)a->P * a->G;
+  wp.b[0] = Src{a->rc, (long)a->N * rc_row, rc_row, (long)a->G};
+  wp.partial = a->partial;
+  return launch_wgrad(wp, a->dweight, st, "k_wgrad_tc(dweight)");
+}
+
+}  // namespace magat
