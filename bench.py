@@ -252,6 +252,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.distributed.init_process_group("nccl", device_id=dev)
     from magat_pathplanning_b200 import _cabi
+    from magat_pathplanning_b200.dist import allreduce_gradients
     _cabi.check(_cabi.lib().magat_device_check())
     L = _cabi.lib()
 
@@ -276,9 +277,7 @@ def main():
         y = layer(xg)
         y.backward(dy)
         if dist_on:
-            flat = torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None])
-            torch.distributed.all_reduce(flat)
-            flat.div_(world)
+            allreduce_gradients(params)          # one flat NCCL all-reduce (magat_pathplanning_b200/dist.py)
         return y
 
     # ---- device-resident timing -------------------------------------------------------------

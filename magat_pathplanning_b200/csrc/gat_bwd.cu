@@ -209,6 +209,250 @@ __global__ void __launch_bounds__(256) k_col_bwd(const float* __restrict__ gz, c
   }
 }
 
+// ---- vectorised variants (G == 128, D <= 32, P in {1,2,4}, 16 B aligned rows) --------------------------
+__device__ __forceinline__ void bfma4(float4& acc, float a, const float4& v) {
+  acc.x = fmaf(a, v.x, acc.x); acc.y = fmaf(a, v.y, acc.y); acc.z = fmaf(a, v.z, acc.z); acc.w = fmaf(a, v.w, acc.w);
+}
+__device__ __forceinline__ float bdot4(const float4& a, const float4& b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+template <int PT>
+__device__ __forceinline__ void ldp(const float* p, float* a) {
+  if (PT == 4) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    a[0] = v.x; a[1 % PT] = v.y; a[2 % PT] = v.z; a[3 % PT] = v.w;
+  } else {
+#pragma unroll
+    for (int q = 0; q < PT; ++q) a[q] = p[q];
+  }
+}
+template <int PT>
+__device__ __forceinline__ void stp(float* p, const float* a) {
+  if (PT == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(a[0], a[1 % PT], a[2 % PT], a[3 % PT]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < PT; ++q) p[q] = a[q];
+  }
+}
+
+// tap recursion backward, level k: one warp per sender row, lane l owns features 4l..4l+3 and out-slot l.
+template <int PT>
+__global__ void __launch_bounds__(256) k_tap_bwd_v(const float* __restrict__ x, long x_sb, long x_sn,
+                                                   const float* __restrict__ taps, const float* __restrict__ att,
+                                                   const int32_t* __restrict__ nbr_out, long rows, int N, int K, int D,
+                                                   int k, int first, float* __restrict__ gz, float* __restrict__ datt) {
+  constexpr int G = 128;
+  const int lane = threadIdx.x & 31;
+  const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  const long b = row / N;
+  const int g0 = lane * 4;
+  const int my_j = lane < D ? nbr_out[row * D + lane] : -1;
+  const int deg = __popc(__ballot_sync(0xffffffffu, my_j >= 0));
+  if (deg == 0) {
+    if (first && lane < D) {
+      float z[PT];
+#pragma unroll
+      for (int q = 0; q < PT; ++q) z[q] = 0.f;
+      stp<PT>(datt + ((size_t)row * D + lane) * PT, z);
+    }
+    return;
+  }
+  float am[PT], dsum[PT];
+#pragma unroll
+  for (int q = 0; q < PT; ++q) { am[q] = 0.f; dsum[q] = 0.f; }
+  if (my_j >= 0) ldp<PT>(att + ((size_t)row * D + lane) * PT, am);
+  float4 u[PT], acc[PT];
+#pragma unroll
+  for (int q = 0; q < PT; ++q) {
+    acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    u[q] = (k == 1) ? __ldg(reinterpret_cast<const float4*>(x + b * x_sb + (row - b * N) * x_sn + g0))
+                    : __ldg(reinterpret_cast<const float4*>(taps + (((size_t)row * PT + q) * (K - 1) + (k - 2)) * G + g0));
+  }
+  for (int s = 0; s < deg; s += 2) {
+    int jj[2];
+    float4 gv[2][PT];
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      jj[w] = __shfl_sync(0xffffffffu, my_j, (s + w) & 31);
+      if (s + w >= deg) jj[w] = -1;
+#pragma unroll
+      for (int q = 0; q < PT; ++q)
+        gv[w][q] = jj[w] >= 0 ? *reinterpret_cast<const float4*>(gz + ((((size_t)(b * N + jj[w])) * PT + q) * K + k) * G + g0)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+#pragma unroll
+      for (int q = 0; q < PT; ++q) {
+        const float a = __shfl_sync(0xffffffffu, am[q], (s + w) & 31);
+        float d = bdot4(u[q], gv[w][q]);
+        d = warp_sum(d);
+        if (lane == s + w) dsum[q] = d;
+        bfma4(acc[q], a, gv[w][q]);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < PT; ++q) {
+    float4* dst = reinterpret_cast<float4*>(gz + (((size_t)row * PT + q) * K + (k - 1)) * G + g0);
+    float4 o = *dst;
+    o.x += acc[q].x; o.y += acc[q].y; o.z += acc[q].z; o.w += acc[q].w;
+    *dst = o;
+  }
+  if (lane < D) {
+    float* da = datt + ((size_t)row * D + lane) * PT;
+    float o[PT];
+    if (first) {
+#pragma unroll
+      for (int q = 0; q < PT; ++q) o[q] = dsum[q];
+    } else {
+      ldp<PT>(da, o);
+#pragma unroll
+      for (int q = 0; q < PT; ++q) o[q] += dsum[q];
+    }
+    stp<PT>(da, o);
+  }
+}
+
+// KeyQuery softmax backward + dR_i = sum_j de[i,j] x_j.  datt <- de in place.
+template <int PT>
+__global__ void __launch_bounds__(256) k_softmax_bwd_kq_v(const float* __restrict__ x, long x_sb, long x_sn,
+                                                          const float* __restrict__ att,
+                                                          const int32_t* __restrict__ nbr_out, long rows, int N,
+                                                          int D, int has_datt, float* __restrict__ datt,
+                                                          float* __restrict__ rc) {
+  constexpr int G = 128;
+  const int lane = threadIdx.x & 31;
+  const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  const long b = row / N;
+  const int g0 = lane * 4;
+  const int my_j = lane < D ? nbr_out[row * D + lane] : -1;
+  const int deg = __popc(__ballot_sync(0xffffffffu, my_j >= 0));
+  float a[PT], da[PT], de[PT];
+#pragma unroll
+  for (int q = 0; q < PT; ++q) { a[q] = 0.f; da[q] = 0.f; }
+  if (my_j >= 0) {
+    ldp<PT>(att + ((size_t)row * D + lane) * PT, a);
+    if (has_datt) ldp<PT>(datt + ((size_t)row * D + lane) * PT, da);
+  }
+#pragma unroll
+  for (int q = 0; q < PT; ++q) {
+    const float dot = warp_sum(a[q] * da[q]);
+    de[q] = a[q] * (da[q] - dot);
+  }
+  if (lane < D) stp<PT>(datt + ((size_t)row * D + lane) * PT, de);
+  float4 acc[PT];
+#pragma unroll
+  for (int q = 0; q < PT; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < deg; s += 4) {
+    float4 xv[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int j = __shfl_sync(0xffffffffu, my_j, (s + w) & 31);
+      xv[w] = (s + w < deg) ? __ldg(reinterpret_cast<const float4*>(x + b * x_sb + (long)j * x_sn + g0))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int w = 0; w < 4; ++w)
+#pragma unroll
+      for (int q = 0; q < PT; ++q) {
+        const float d = __shfl_sync(0xffffffffu, de[q], (s + w) & 31);
+        bfma4(acc[q], s + w < deg ? d : 0.f, xv[w]);
+      }
+  }
+#pragma unroll
+  for (int q = 0; q < PT; ++q) *reinterpret_cast<float4*>(rc + ((size_t)row * PT + q) * G + g0) = acc[q];
+}
+
+// KeyQuery column side: dx_j = sum_p gU_0[j] + sum_{i in in(j)} sum_p de_p[i,j] R_i^p
+template <int PT>
+__global__ void __launch_bounds__(256) k_col_bwd_kq_v(const float* __restrict__ gz, const float* __restrict__ datt,
+                                                      const float* __restrict__ sproj,
+                                                      const int32_t* __restrict__ nbr_in,
+                                                      const int32_t* __restrict__ slot_in, long rows, int N, int K,
+                                                      int D, float* __restrict__ dx) {
+  constexpr int G = 128;
+  const int lane = threadIdx.x & 31;
+  const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  const long b = row / N;
+  const int g0 = lane * 4;
+  const int my_i = lane < D ? nbr_in[row * D + lane] : -1;
+  const int deg = __popc(__ballot_sync(0xffffffffu, my_i >= 0));
+  float de[PT];
+#pragma unroll
+  for (int q = 0; q < PT; ++q) de[q] = 0.f;
+  if (my_i >= 0) ldp<PT>(datt + ((size_t)(b * N + my_i) * D + slot_in[row * D + lane]) * PT, de);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int q = 0; q < PT; ++q) {
+    const float4 v = *reinterpret_cast<const float4*>(gz + (((size_t)row * PT + q) * K + 0) * G + g0);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  for (int s = 0; s < deg; s += 2) {
+    float4 rv[2][PT];
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      const int i = __shfl_sync(0xffffffffu, my_i, (s + w) & 31);
+#pragma unroll
+      for (int q = 0; q < PT; ++q)
+        rv[w][q] = (s + w < deg) ? __ldg(reinterpret_cast<const float4*>(sproj + ((size_t)(b * N + i) * PT + q) * G + g0))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int w = 0; w < 2; ++w)
+#pragma unroll
+      for (int q = 0; q < PT; ++q) {
+        const float d = __shfl_sync(0xffffffffu, de[q], (s + w) & 31);
+        bfma4(acc, s + w < deg ? d : 0.f, rv[w][q]);
+      }
+  }
+  *reinterpret_cast<float4*>(dx + (size_t)row * G + g0) = acc;
+}
+
+// dbias partials: each block sums `chunk` rows of dP for every channel (coalesced, 8 rows in flight per
+// thread), one partial row per block
+__global__ void __launch_bounds__(256) k_dbias_partial(DPre dp, long rows, int C, int P, int F, int chunk,
+                                                       float* __restrict__ partial) {
+  const long r_begin = (long)blockIdx.x * chunk;
+  const long r_end = min(rows, r_begin + chunk);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int p = dp.concat ? c / F : 0, f = dp.concat ? c - p * F : c;
+    float s[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s[u] = 0.f;
+    long r = r_begin;
+    for (; r + 8 <= r_end; r += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s[u] += dp(r + u, p, f);
+    }
+    for (; r < r_end; ++r) s[0] += dp(r, p, f);
+    partial[(size_t)blockIdx.x * C + c] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+  }
+}
+// dbias[f] = (concat ? sum_p : P *) sum_blocks partial[block][p*F + f]; one block per f, fixed-order tree
+__global__ void __launch_bounds__(256) k_dbias_final(const float* __restrict__ partial, int nblocks, int C, int P,
+                                                     int F, int concat, float* __restrict__ dbias) {
+  __shared__ float red[256];
+  const int f = blockIdx.x;
+  const int np = concat ? P : 1;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < nblocks * np; i += blockDim.x) {
+    const int k = i / np, p = i - k * np;
+    s += partial[(size_t)k * C + p * F + f];
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) dbias[f] = concat ? red[0] : red[0] * (float)P;   // mean: every head sees dP = dY / P
+}
+
 // KeyQuery: dx[m][g] += sum_{p,g'} W[p][g][g'] dR[m][p][g']
 struct RcLoad { const float* rc; int PG; __device__ __forceinline__ float operator()(long m, int k, int) const { return __ldg(rc + (size_t)m * PG + k); } };
 struct WtLoad {   // B(k = p*G+g', n = g) = W[p][g][g']
@@ -364,8 +608,13 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
       return rc;
 
   if (a->need_dbias) {
-    if ((rc = rowred(rows, 1, F, 1, OneLoad{}, DPreSumP{dp, P}, a->partial, a->dbias, st, "k_rowred_gemm(dbias)")))
-      return rc;
+    const int C = a->concat ? P * F : F;
+    const int nblocks = 148 * 8;
+    const int chunk = cdiv(rows, nblocks);
+    k_dbias_partial<<<nblocks, 256, 0, st>>>(dp, rows, C, P, F, chunk, a->partial);
+    if ((rc = check_launch("k_dbias_partial", st))) return rc;
+    k_dbias_final<<<F, 256, 0, st>>>(a->partial, nblocks, C, P, F, a->concat, a->dbias);
+    if ((rc = check_launch("k_dbias_final", st))) return rc;
   }
   const bool tc_wgrad = a->path != MAGAT_PATH_SIMT && wgrad_tc_supported(a);
   if (a->need_dfilter) {
@@ -386,20 +635,47 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
     k_node_gemm<<<grid, 256, 0, st>>>(rows, KG, F, DPreA{dp}, hl, GzEpi{a->gz, P, KG});
     if ((rc = check_launch("k_node_gemm(gz)", st))) return rc;
   }
+  const bool vec = G == 128 && D <= 32 && (a->x_sn % 4) == 0 && (a->x_sb % 4) == 0 && ((uintptr_t)a->x % 16) == 0 &&
+                   ((uintptr_t)a->gz % 16) == 0 && ((uintptr_t)a->att % 16) == 0 && ((uintptr_t)a->datt % 16) == 0 &&
+                   ((uintptr_t)a->rc % 16) == 0 && ((uintptr_t)a->sproj % 16) == 0 &&
+                   (K == 1 || ((uintptr_t)a->taps % 16) == 0) && (P == 1 || P == 2 || P == 4);
   for (int k = K - 1; k >= 1; --k) {
-    k_tap_bwd<<<row_blocks, 256, 0, st>>>(zn, a->att, a->nbr_out, rows, N, G, P, K, D, k, k == K - 1 ? 1 : 0,
-                                          a->gz, a->datt);
+    const int first = k == K - 1 ? 1 : 0;
+#define MAGAT_TB(PT) \
+  k_tap_bwd_v<PT><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->taps, a->att, a->nbr_out, rows, N, K, D, k, \
+                                              first, a->gz, a->datt)
+    if (vec && P == 4) MAGAT_TB(4);
+    else if (vec && P == 2) MAGAT_TB(2);
+    else if (vec && P == 1) MAGAT_TB(1);
+    else
+      k_tap_bwd<<<row_blocks, 256, 0, st>>>(zn, a->att, a->nbr_out, rows, N, G, P, K, D, k, first, a->gz, a->datt);
+#undef MAGAT_TB
     if ((rc = check_launch("k_tap_bwd", st))) return rc;
   }
   const int has_datt = K > 1 ? 1 : 0;
   if (!gm) {
-    k_softmax_bwd<MAGAT_MODE_KEYQUERY><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj, a->att,
-                                                                    a->nbr_out, rows, N, G, P, D, has_datt,
-                                                                    a->datt, a->rc);
+#define MAGAT_SB(PT) \
+  k_softmax_bwd_kq_v<PT><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->att, a->nbr_out, rows, N, D, has_datt, \
+                                                     a->datt, a->rc)
+    if (vec && P == 4) MAGAT_SB(4);
+    else if (vec && P == 2) MAGAT_SB(2);
+    else if (vec && P == 1) MAGAT_SB(1);
+    else
+      k_softmax_bwd<MAGAT_MODE_KEYQUERY><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj, a->att,
+                                                                      a->nbr_out, rows, N, G, P, D, has_datt,
+                                                                      a->datt, a->rc);
+#undef MAGAT_SB
     if ((rc = check_launch("k_softmax_bwd", st))) return rc;
-    k_col_bwd<MAGAT_MODE_KEYQUERY><<<row_blocks, 256, 0, st>>>(a->gz, a->datt, a->sproj, nullptr, a->nbr_in,
-                                                                a->slot_in, rows, N, G, P, K, D, a->rc,
-                                                                a->need_dx ? a->dx : nullptr);
+#define MAGAT_CB(PT) \
+  k_col_bwd_kq_v<PT><<<row_blocks, 256, 0, st>>>(a->gz, a->datt, a->sproj, a->nbr_in, a->slot_in, rows, N, K, D, a->dx)
+    if (vec && a->need_dx && P == 4) MAGAT_CB(4);
+    else if (vec && a->need_dx && P == 2) MAGAT_CB(2);
+    else if (vec && a->need_dx && P == 1) MAGAT_CB(1);
+    else
+      k_col_bwd<MAGAT_MODE_KEYQUERY><<<row_blocks, 256, 0, st>>>(a->gz, a->datt, a->sproj, nullptr, a->nbr_in,
+                                                                  a->slot_in, rows, N, G, P, K, D, a->rc,
+                                                                  a->need_dx ? a->dx : nullptr);
+#undef MAGAT_CB
     if ((rc = check_launch("k_col_bwd", st))) return rc;
     if (a->need_dx && a->path != MAGAT_PATH_SIMT && dx_tc_supported(a)) {
       __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(a->partial);

@@ -47,3 +47,48 @@ def load_reference_graphml(ref: str = DEFAULT_REF):
     sys.modules[name] = mod
     sys.modules["utils.graphUtils"].graphML = mod
     return mod
+
+
+def load_reference_planner(name: str = "decentralplanner_GAT", ref: str = DEFAULT_REF):
+    """Load one of the reference's planner model files (graphs/models/<name>.py) by path with the
+    packages it imports stubbed (recipe: SURVEY.md section 8c).  Build-container only."""
+    gml = load_reference_graphml(ref)
+    for pkg in ("graphs", "graphs.models"):
+        if pkg not in sys.modules:
+            m = types.ModuleType(pkg)
+            m.__path__ = []
+            sys.modules[pkg] = m
+    if "torchsummaryX" not in sys.modules:
+        ts = types.ModuleType("torchsummaryX")
+        ts.summary = lambda *a, **k: None          # imported at decentralplanner_GAT.py:11, never called
+        sys.modules["torchsummaryX"] = ts
+
+    def by_path(modname, relpath):
+        if modname in sys.modules and getattr(sys.modules[modname], "__magat_ref__", False):
+            return sys.modules[modname]
+        spec = importlib.util.spec_from_file_location(modname, os.path.join(ref, relpath))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[modname] = mod
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            spec.loader.exec_module(mod)
+        mod.__magat_ref__ = True
+        return mod
+
+    by_path("graphs.weights_initializer", "graphs/weights_initializer.py")
+    by_path("graphs.models.resnet_pytorch", "graphs/models/resnet_pytorch.py")
+    return by_path("graphs.models." + name, f"graphs/models/{name}.py"), gml
+
+
+class PlannerConfig(dict):
+    """Attribute dict with the fields the planners read (graphs/models/decentralplanner_GAT.py)."""
+    __getattr__ = dict.__getitem__
+
+    @classmethod
+    def default(cls, **kw):
+        c = cls(num_agents=10, map_w=20, map_h=20, FOV=9, numInputFeatures=128, nGraphFilterTaps=3,
+                nAttentionHeads=4, use_dropout=False, CNN_mode="Default", attentionMode="KeyQuery",
+                AttentionConcat=True, GSO_mode="dist_GSO", device="cpu", bottleneckFeature=32,
+                bottleneckMode=None, batch_numAgent=False, return_attentionGSO=False)
+        c.update(kw)
+        return c
