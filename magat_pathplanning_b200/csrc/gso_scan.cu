@@ -1,7 +1,10 @@
 // GSO -> adjacency.  The dense graph-shift operator is only ever used as an edge mask
 // (|S| > 1e-9, graphML.py:1274-1276 and :808-809); this file reads it exactly once and
 // turns it into bit masks and padded neighbour lists.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace magat {
 
@@ -109,6 +112,146 @@ __global__ void __launch_bounds__(256) k_gso_scan_v4(const T* __restrict__ S, in
   }
 }
 
+// ---- TMA-staged scan ----------------------------------------------------------------------------
+// Persistent CTAs; one elected thread streams whole GSO rows into a shared-memory ring with bulk async copies
+// (cp.async.bulk, completion counted on an mbarrier), so ~190 KB per SM are in flight no matter how few
+// registers or warps are resident; eight consumer warps turn each staged chunk into row words (three
+// xor-shuffles per row) and accumulate the transposed column words in registers over the 32 rows of a band.
+template <typename T> struct Edge4;
+template <> struct Edge4<float> {
+  static __device__ __forceinline__ uint32_t nib(const float* p) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    return (uint32_t)(fabsf(v.x) > 1e-9f) | ((uint32_t)(fabsf(v.y) > 1e-9f) << 1) |
+           ((uint32_t)(fabsf(v.z) > 1e-9f) << 2) | ((uint32_t)(fabsf(v.w) > 1e-9f) << 3);
+  }
+};
+template <> struct Edge4<double> {
+  static __device__ __forceinline__ uint32_t nib(const double* p) {
+    const double2 a = *reinterpret_cast<const double2*>(p);
+    const double2 b = *(reinterpret_cast<const double2*>(p) + 1);
+    return (uint32_t)(fabs(a.x) > 1e-9) | ((uint32_t)(fabs(a.y) > 1e-9) << 1) | ((uint32_t)(fabs(b.x) > 1e-9) << 2) |
+           ((uint32_t)(fabs(b.y) > 1e-9) << 3);
+  }
+};
+
+constexpr int kScanWarps = 8;                 // consumer warps; warp 8 is the copy issuer
+constexpr int kScanRing = 192 * 1024;
+
+template <typename T, int R>
+__global__ void __launch_bounds__((kScanWarps + 1) * 32, 1) k_gso_scan_tma(const T* __restrict__ S, int N, int W,
+                                                                           long bands, int nstages,
+                                                                           uint32_t* __restrict__ rowbits,
+                                                                           uint32_t* __restrict__ colbits) {
+  extern __shared__ uint8_t scan_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)scan_smem_raw + 127) & ~(uintptr_t)127);
+  const size_t row_bytes = (size_t)N * sizeof(T);
+  const size_t chunk_bytes = (size_t)R * row_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)nstages * chunk_bytes);
+  uint64_t* empty = full + nstages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nstages; ++s) {
+      tc::mbar_init(&full[s], 1);
+      tc::mbar_init(&empty[s], kScanWarps);
+    }
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+  const int chunks_per_band = 32 / R;
+  const int segs = (N + 127) / 128;
+
+  if (warp == kScanWarps) {
+    // ===== copy issuer ======================================================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long band = blockIdx.x; band < bands; band += gridDim.x) {
+        const long b = band / W;
+        const int i0 = (int)(band - b * W) * 32;
+        for (int c = 0; c < chunks_per_band; ++c) {
+          const int r_first = i0 + c * R;
+          int nrows = N - r_first;
+          if (nrows > R) nrows = R;
+          if (nrows <= 0) break;
+          tc::mbar_wait(&empty[stage], phase ^ 1);
+          tc::mbar_arrive_expect_tx(&full[stage], (uint32_t)(nrows * row_bytes));
+          const T* src = S + ((size_t)b * N + r_first) * N;
+          // rows of one instance are contiguous: one bulk copy for the whole chunk
+          tc::bulk_g2s(smem + (size_t)stage * chunk_bytes, src, (uint32_t)(nrows * row_bytes), &full[stage]);
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===== consumers ========================================================================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long band = blockIdx.x; band < bands; band += gridDim.x) {
+      const long b = band / W;
+      const int rb = (int)(band - b * W);
+      const int i0 = rb * 32;
+      // column accumulators for up to 2 segments per warp (N <= 2048 in this kernel)
+      uint32_t col[2][4];
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) col[q][e] = 0u;
+      for (int c = 0; c < chunks_per_band; ++c) {
+        const int r_first = i0 + c * R;
+        int nrows = N - r_first;
+        if (nrows > R) nrows = R;
+        if (nrows <= 0) break;
+        tc::mbar_wait(&full[stage], phase);
+        const T* tile = reinterpret_cast<const T*>(smem + (size_t)stage * chunk_bytes);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int seg = warp + q * kScanWarps;
+          if (seg >= segs) break;
+          const int j0 = seg * 128 + lane * 4;
+          const bool jin = j0 < N;
+          uint32_t nb[R], v[R];
+#pragma unroll
+          for (int r = 0; r < R; ++r) nb[r] = (jin && r < nrows) ? Edge4<T>::nib(tile + (size_t)r * N + j0) : 0u;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const int rr = c * R + r;                       // row inside the band
+            col[q][0] |= (nb[r] & 1u) << rr;
+            col[q][1] |= ((nb[r] >> 1) & 1u) << rr;
+            col[q][2] |= ((nb[r] >> 2) & 1u) << rr;
+            col[q][3] |= ((nb[r] >> 3) & 1u) << rr;
+            v[r] = nb[r] << (4 * (lane & 7));
+          }
+#pragma unroll
+          for (int o = 1; o <= 4; o <<= 1)
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[r] |= __shfl_xor_sync(0xffffffffu, v[r], o);
+          const int w = seg * 4 + (lane >> 3);
+          if ((lane & 7) == 0 && w < W) {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+              if (r < nrows) rowbits[((size_t)b * N + r_first + r) * W + w] = v[r];
+          }
+        }
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&empty[stage]);
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int seg = warp + q * kScanWarps;
+        const int j0 = seg * 128 + lane * 4;
+        if (seg < segs && j0 < N) {
+          uint32_t* cb = colbits + ((size_t)b * N + j0) * W + rb;
+          cb[0] = col[q][0];
+          cb[W] = col[q][1];
+          cb[2 * (size_t)W] = col[q][2];
+          cb[3 * (size_t)W] = col[q][3];
+        }
+      }
+    }
+  }
+}
+
 // stats[0] max out-degree, [1] max in-degree, [2] number of edges, [3] symmetric flag.
 __global__ void __launch_bounds__(256) k_gso_stats(const uint32_t* __restrict__ rowbits,
                                                    const uint32_t* __restrict__ colbits, long rows,
@@ -141,13 +284,9 @@ __global__ void __launch_bounds__(256) k_gso_stats(const uint32_t* __restrict__ 
   }
 }
 
-// Enumerate the set bits of a W-word bit row into out[0..D) (ascending), -1 padded.
-// rank_of != nullptr additionally stores, for every listed index i, the position of `self`
-// inside row i of `rank_bits` (number of set bits below `self`).
-__device__ __forceinline__ void list_bits(const uint32_t* __restrict__ bits, int W, int D, int lane,
-                                          int32_t* __restrict__ out,
-                                          const uint32_t* __restrict__ rank_bits_b, int self,
-                                          int32_t* __restrict__ rank_out) {
+// Enumerate the set bits of a W-word bit row into out[0..D) (ascending), -1 padded; returns the count.
+__device__ __forceinline__ int list_bits(const uint32_t* __restrict__ bits, int W, int D, int lane,
+                                         int32_t* __restrict__ out) {
   int base = 0;
   for (int w0 = 0; w0 < W; w0 += 32) {
     const int w = w0 + lane;
@@ -158,27 +297,17 @@ __device__ __forceinline__ void list_bits(const uint32_t* __restrict__ bits, int
     while (word) {
       const int bit = __ffs(word) - 1;
       word &= word - 1;
-      const int idx = w * 32 + bit;
-      if (pos < D) {
-        out[pos] = idx;
-        if (rank_out) {
-          const uint32_t* r = rank_bits_b + (size_t)idx * W;
-          int rank = 0;
-          const int sw = self >> 5;
-          for (int q = 0; q < sw; ++q) rank += __popc(r[q]);
-          rank += __popc(r[sw] & ((1u << (self & 31)) - 1u));
-          rank_out[pos] = rank;
-        }
-      }
+      if (pos < D) out[pos] = w * 32 + bit;
       ++pos;
     }
   }
-  for (int s = base + lane; s < D; s += 32) {
-    out[s] = -1;
-    if (rank_out) rank_out[s] = 0;
-  }
+  for (int s = base + lane; s < D; s += 32) out[s] = -1;
+  return base;
 }
 
+// One warp per node: out-list from its row bits, in-list from its column bits, and for every in-edge
+// (i -> n) the slot of n inside row i's out-list = number of set bits of row i below n (one coalesced
+// read of row i's words + a warp reduction per edge).
 __global__ void __launch_bounds__(256) k_build_ell(const uint32_t* __restrict__ rowbits,
                                                    const uint32_t* __restrict__ colbits, long rows,
                                                    int N, int W, int D, int32_t* __restrict__ nbr_out,
@@ -189,9 +318,28 @@ __global__ void __launch_bounds__(256) k_build_ell(const uint32_t* __restrict__ 
   if (row >= rows) return;
   const long b = row / N;
   const int n = (int)(row - b * N);
-  list_bits(rowbits + row * W, W, D, lane, nbr_out + row * D, nullptr, 0, nullptr);
-  list_bits(colbits + row * W, W, D, lane, nbr_in + row * D, rowbits + (size_t)b * N * W, n,
-            slot_in + row * D);
+  list_bits(rowbits + row * W, W, D, lane, nbr_out + row * D);
+  int32_t* nin = nbr_in + row * D;
+  int deg_in = list_bits(colbits + row * W, W, D, lane, nin);
+  if (deg_in > D) deg_in = D;
+  __syncwarp();
+  const int sw = n >> 5;
+  const uint32_t below = (1u << (n & 31)) - 1u;
+  const int grp = lane >> 3, gl = lane & 7;           // four in-edges at a time, eight lanes each
+  for (int s0 = 0; s0 < deg_in; s0 += 4) {
+    const int s = s0 + grp;
+    int rank = 0;
+    if (s < deg_in) {
+      const int i = nin[s];
+      const uint32_t* r = rowbits + ((size_t)b * N + i) * W;
+      for (int w = gl; w <= sw; w += 8) rank += __popc(w < sw ? r[w] : (r[w] & below));
+    }
+    rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+    rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+    rank += __shfl_xor_sync(0xffffffffu, rank, 4);
+    if (gl == 0 && s < deg_in) slot_in[row * D + s] = rank;
+  }
+  for (int s = deg_in + lane; s < D; s += 32) slot_in[row * D + s] = 0;
 }
 
 // att[B][N][D][P] -> dense aij[B][P][N][N] (mean_heads == 0) or head-mean [B][N][N].
@@ -231,7 +379,45 @@ extern "C" int magat_gso_scan(const void* S, int s_dtype, int B, int N, uint32_t
   cudaStream_t st = (cudaStream_t)stream;
   prof_begin(st);
   const int W = (N + 31) / 32;
-  if (N % 4 == 0 && ((uintptr_t)S % 16) == 0) {
+  const size_t esz = s_dtype == MAGAT_DT_F32 ? 4 : 8;
+  int R = 32;
+  while (R > 1 && (size_t)R * N * esz > 32 * 1024) R >>= 1;
+  const bool tma_ok = N % 4 == 0 && ((uintptr_t)S % 16) == 0 && N <= 2048 && (size_t)R * N * esz <= 48 * 1024 &&
+                      getenv("MAGAT_SCAN_NO_TMA") == nullptr;
+  if (tma_ok) {
+    static int sm_count = 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+      attr_set = true;
+    }
+    const size_t chunk_bytes = (size_t)R * N * esz;
+    int nstages = (int)(kScanRing / chunk_bytes);
+    if (nstages > 16) nstages = 16;
+    const long bands = (long)B * W;
+    const int grid = (int)(bands < sm_count ? bands : sm_count);
+    const size_t smem = (size_t)nstages * chunk_bytes + 2 * nstages * 8 + 256;
+#define MAGAT_SCAN(TT, RR)                                                                                      \
+  do {                                                                                                         \
+    cudaFuncSetAttribute(k_gso_scan_tma<TT, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanRing + 1024); \
+    k_gso_scan_tma<TT, RR><<<grid, (kScanWarps + 1) * 32, smem, st>>>((const TT*)S, N, W, bands, nstages, rowbits, \
+                                                                      colbits);                                \
+  } while (0)
+#define MAGAT_SCAN_R(TT)                          \
+  switch (R) {                                    \
+    case 32: MAGAT_SCAN(TT, 32); break;           \
+    case 16: MAGAT_SCAN(TT, 16); break;           \
+    case 8: MAGAT_SCAN(TT, 8); break;             \
+    case 4: MAGAT_SCAN(TT, 4); break;             \
+    case 2: MAGAT_SCAN(TT, 2); break;             \
+    default: MAGAT_SCAN(TT, 1); break;            \
+  }
+    if (s_dtype == MAGAT_DT_F32) MAGAT_SCAN_R(float) else MAGAT_SCAN_R(double)
+#undef MAGAT_SCAN_R
+#undef MAGAT_SCAN
+  } else if (N % 4 == 0 && ((uintptr_t)S % 16) == 0) {
     const int segs = cdiv(N, 128);
     const long units = (long)B * W * segs;
     const int blocks = cdiv(units, 8);

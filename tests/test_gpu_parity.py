@@ -260,3 +260,38 @@ def test_tc_path_rejects_uncovered_shape(golden):
     layer.addGSO(d["S"].to(dev))
     with pytest.raises(MagatError, match="not covered"):
         layer(d["x"].to(dev))
+
+
+@pytest.mark.parametrize("N", [1, 5, 12, 36, 100, 130, 1000, 1004])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_gso_scan_and_neighbour_lists(N, dtype):
+    """GSO -> bit masks -> padded lists against the dense mask |S| > 1e-9 (graphML.py:1274-1276), incl. NaN,
+    negative and sub-tolerance entries, asymmetric masks, every scan kernel variant (scalar, vector, TMA ring)."""
+    from magat_pathplanning_b200 import build_adjacency
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(99 + N)
+    B = 3
+    S = (torch.rand(B, 1, N, N, generator=gen) < min(0.5, 6.0 / max(N, 1))).to(dtype)
+    S = S * torch.randn(B, 1, N, N, generator=gen).to(dtype)
+    if N > 4:
+        S[:, :, 2, 3] = float("nan")
+        S[:, :, 3, 4] = 5e-10
+        S[:, :, 4, 1] = -3e-9
+        S[:, :, 0, :] = 0
+    mask = (S.abs() > 1e-9)[:, 0]                               # [B,N,N]
+    adj = build_adjacency(S.to(dev))
+    out, inn, slot = adj.nbr_out.cpu(), adj.nbr_in.cpu(), adj.slot_in.cpu()
+    D = adj.D
+    assert D % 4 == 0 and D >= max(int(mask.sum(2).max()), int(mask.sum(1).max()), 1)
+    for b in range(B):
+        for i in range(N):
+            want = torch.nonzero(mask[b, i]).flatten().tolist()
+            got = [v for v in out[b, i].tolist() if v >= 0]
+            assert got == want and out[b, i, len(want):].eq(-1).all()
+            want_in = torch.nonzero(mask[b, :, i]).flatten().tolist()
+            got_in = [v for v in inn[b, i].tolist() if v >= 0]
+            assert got_in == want_in
+            for s, src in enumerate(want_in):
+                assert out[b, src, slot[b, i, s]] == i
+        if N >= 1000:
+            break                                               # one instance is enough at this size
