@@ -32,6 +32,7 @@
  *   nbr_out  [B][N][D]   int32, receivers j of sender-row i, ascending, -1 padded
  *   nbr_in   [B][N][D]   int32, senders i of column j, ascending, -1 padded
  *   slot_in  [B][N][D]   int32, position of j inside nbr_out[b][i][:] for the same entry of nbr_in
+ *   slot_out [B][N][D]   int32, position of i inside nbr_in[b][j][:] for the same entry of nbr_out
  *   att      [B][N][D][P] attention value A_p[i, nbr_out[i][s]] (row-softmax, graphML.py:1284)
  *   taps     [B][N][P][K-1][G]  u_k = u_{k-1} A for k = 1..K-1 (graphML.py:1756-1759)
  *   sproj    KeyQuery: [B][N][P][G], R_i^p = W_p^T x_i so that e_p[i,j] = R_i^p . x_j (:1257-1262);
@@ -47,7 +48,7 @@
 extern "C" {
 #endif
 
-#define MAGAT_ABI_VERSION 4
+#define MAGAT_ABI_VERSION 5
 
 enum {
   MAGAT_OK = 0,
@@ -78,7 +79,8 @@ int magat_gso_scan(const void* S, int s_dtype, int B, int N,
 
 /* Bit masks -> padded neighbour lists of width D (D >= max(stats[0], stats[1]), D >= 1). */
 int magat_gso_build_ell(const uint32_t* rowbits, const uint32_t* colbits, int B, int N, int D,
-                        int32_t* nbr_out, int32_t* nbr_in, int32_t* slot_in, void* stream);
+                        int32_t* nbr_out, int32_t* nbr_in, int32_t* slot_in, int32_t* slot_out /* may be NULL */,
+                        void* stream);
 
 /* ---- forward (replaces GraphFilterBatchAttentional.forward, graphML.py:4636-4667) ---- */
 typedef struct magat_gat_fwd_args {
@@ -91,6 +93,7 @@ typedef struct magat_gat_fwd_args {
   /* inputs */
   const float* x; int64_t x_sb, x_sn;
   const int32_t* nbr_out; const int32_t* nbr_in; const int32_t* slot_in;
+  const int32_t* slot_out;    /* may be NULL (then ain is filled by the gather kernel instead of the attention kernel) */
   /* parameters, in the reference's shapes (graphML.py:4579-4597) */
   const float* weight;        /* KeyQuery [P][1][G][G]; GAT_modified [P][1][F][G] */
   const float* mixer;         /* [P][1][2F] (GAT_modified only; may be NULL for KeyQuery) */

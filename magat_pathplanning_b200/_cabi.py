@@ -12,7 +12,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmagat_gat.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 MODE_KEYQUERY, MODE_GAT_MODIFIED = 0, 1
 DT_F32, DT_F64 = 0, 1
@@ -32,7 +32,7 @@ class FwdArgs(C.Structure):
     _fields_ = [(n, _i32) for n in ("B", "N", "G", "F", "K", "P", "D", "mode", "concat", "relu", "path",
                                     "reserved")] + [
         ("x", _ptr), ("x_sb", _i64), ("x_sn", _i64),
-        ("nbr_out", _ptr), ("nbr_in", _ptr), ("slot_in", _ptr),
+        ("nbr_out", _ptr), ("nbr_in", _ptr), ("slot_in", _ptr), ("slot_out", _ptr),
         ("weight", _ptr), ("mixer", _ptr), ("weight_bias", _ptr), ("filterWeight", _ptr), ("bias", _ptr),
         ("y", _ptr), ("y_sb", _i64), ("y_sn", _i64), ("y_sc", _i64),
         ("att", _ptr), ("ain", _ptr), ("taps", _ptr), ("wprep", _ptr), ("sproj", _ptr),
@@ -83,7 +83,7 @@ def lib():
         L.magat_last_error.restype = C.c_char_p
         L.magat_device_check.restype = C.c_int
         L.magat_gso_scan.argtypes = [_ptr, C.c_int, C.c_int, C.c_int, _ptr, _ptr, _ptr, _ptr]
-        L.magat_gso_build_ell.argtypes = [_ptr, _ptr, C.c_int, C.c_int, C.c_int, _ptr, _ptr, _ptr, _ptr]
+        L.magat_gso_build_ell.argtypes = [_ptr, _ptr, C.c_int, C.c_int, C.c_int, _ptr, _ptr, _ptr, _ptr, _ptr]
         L.magat_gat_wprep_floats.argtypes = [C.c_int] * 5
         L.magat_gat_wprep_floats.restype = C.c_size_t
         L.magat_gat_forward.argtypes = [C.POINTER(FwdArgs), _ptr]

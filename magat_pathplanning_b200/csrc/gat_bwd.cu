@@ -238,7 +238,7 @@ __device__ __forceinline__ void stp(float* p, const float* a) {
 
 // tap recursion backward, level k: one warp per sender row, lane l owns features 4l..4l+3 and out-slot l.
 template <int PT>
-__global__ void __launch_bounds__(256) k_tap_bwd_v(const float* __restrict__ x, long x_sb, long x_sn,
+__global__ void __launch_bounds__(256, 3) k_tap_bwd_v(const float* __restrict__ x, long x_sb, long x_sn,
                                                    const float* __restrict__ taps, const float* __restrict__ att,
                                                    const int32_t* __restrict__ nbr_out, long rows, int N, int K, int D,
                                                    int k, int first, float* __restrict__ gz, float* __restrict__ datt) {
@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(128) k_gm_param_bwd(const float* __restrict__ 
 
 int run_tap_gather(const float* x, long x_sb, long x_sn, const float* att, const int32_t* nbr_in,
                    const int32_t* slot_in, int B, int N, int G, int K, int P, int D, int k, float* taps,
-                   float* ain, cudaStream_t st);   // gat_fwd.cu
+                   float* ain, int ain_ready, cudaStream_t st);   // gat_fwd.cu
 
 // gat_wgrad_tc.cu
 size_t wgrad_tc_partial_floats(int G, int F, int K, int P);
@@ -604,7 +604,7 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
   // the fused forward keeps only u_1 in memory: rebuild the later taps before anything reads them
   for (int k = (a->taps_valid < 1 ? 1 : a->taps_valid + 1); k < K; ++k)
     if ((rc = run_tap_gather(a->x, a->x_sb, a->x_sn, a->att, a->nbr_in, a->slot_in, B, N, G, K, P, D, k,
-                             a->taps, nullptr, st)))
+                             a->taps, nullptr, 0, st)))
       return rc;
 
   if (a->need_dbias) {

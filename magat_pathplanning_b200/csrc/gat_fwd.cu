@@ -48,7 +48,8 @@ template <int MODE>
 __global__ void __launch_bounds__(256) k_attention(const float* __restrict__ x, long x_sb, long x_sn,
                                                    const float* __restrict__ sproj,
                                                    const int32_t* __restrict__ nbr_out, long rows, int N,
-                                                   int G, int P, int D, float* __restrict__ att) {
+                                                   int G, int P, int D, float* __restrict__ att,
+                                                   const int32_t* __restrict__ slot_out, float* __restrict__ ain) {
   const int lane = threadIdx.x & 31;
   const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= rows) return;
@@ -97,7 +98,11 @@ __global__ void __launch_bounds__(256) k_attention(const float* __restrict__ x, 
     }
     sum = warp_sum(sum);
     const float inv = 1.f / sum;
-    for (int s = lane; s < deg; s += 32) arow[(size_t)s * P + p] *= inv;
+    for (int s = lane; s < deg; s += 32) {
+      const float v = arow[(size_t)s * P + p] * inv;
+      arow[(size_t)s * P + p] = v;
+      if (ain != nullptr) ain[((size_t)(b * N + nb[s]) * P + p) * D + slot_out[row * D + s]] = v;
+    }
   }
 }
 
@@ -152,12 +157,12 @@ __device__ __forceinline__ float warp_max(float v) {
 // broadcast by shuffle.  When `ain` is given the in-edge values are also stored receiver-major,
 // ain[j][p][s] = A_p[nbr_in[j][s], j] (0 beyond the degree), which is what the fused tcgen05 kernel reads.
 template <int PT>
-__global__ void __launch_bounds__(256) k_tap_gather_v(const float* __restrict__ x, long x_sb, long x_sn,
+__global__ void __launch_bounds__(256, 4) k_tap_gather_v(const float* __restrict__ x, long x_sb, long x_sn,
                                                       const float* __restrict__ att,
                                                       const int32_t* __restrict__ nbr_in,
                                                       const int32_t* __restrict__ slot_in, long rows, int N,
                                                       int G, int K, int D, int k, float* __restrict__ taps,
-                                                      float* __restrict__ ain) {
+                                                      float* __restrict__ ain, int ain_ready) {
   const int lane = threadIdx.x & 31;
   const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= rows) return;
@@ -176,7 +181,10 @@ __global__ void __launch_bounds__(256) k_tap_gather_v(const float* __restrict__ 
       float am[PT];
 #pragma unroll
       for (int p = 0; p < PT; ++p) am[p] = 0.f;
-      if (my_i >= 0) {
+      if (my_i >= 0 && ain_ready) {
+#pragma unroll
+        for (int p = 0; p < PT; ++p) am[p] = __ldg(ain + ((size_t)row * PT + p) * D + s0 + lane);
+      } else if (my_i >= 0) {
         const float* ap = att + ((size_t)(b * N + my_i) * D + sl[s0 + lane]) * PT;
         if (PT == 4) {
           const float4 a4 = __ldg(reinterpret_cast<const float4*>(ap));
@@ -186,7 +194,7 @@ __global__ void __launch_bounds__(256) k_tap_gather_v(const float* __restrict__ 
           for (int p = 0; p < PT; ++p) am[p] = __ldg(ap + p);
         }
       }
-      if (ain != nullptr && gb == 0 && s0 + lane < D) {
+      if (ain != nullptr && !ain_ready && gb == 0 && s0 + lane < D) {
 #pragma unroll
         for (int p = 0; p < PT; ++p) ain[((size_t)row * PT + p) * D + s0 + lane] = am[p];
       }
@@ -233,7 +241,7 @@ __global__ void __launch_bounds__(256) k_tap_gather_v(const float* __restrict__ 
       }
       if (cnt < 32) {
         // zero the rest of ain beyond this block
-        if (ain != nullptr && gb == 0)
+        if (ain != nullptr && !ain_ready && gb == 0)
           for (int s = s0 + 32 + lane; s < D; s += 32)
 #pragma unroll
             for (int p = 0; p < PT; ++p) ain[((size_t)row * PT + p) * D + s] = 0.f;
@@ -253,7 +261,9 @@ template <int PT, int GV>
 __global__ void __launch_bounds__(256) k_attention_kq_v(const float* __restrict__ x, long x_sb, long x_sn,
                                                         const float* __restrict__ sproj,
                                                         const int32_t* __restrict__ nbr_out, long rows, int N,
-                                                        int D, float* __restrict__ att) {
+                                                        int D, float* __restrict__ att,
+                                                        const int32_t* __restrict__ slot_out,
+                                                        float* __restrict__ ain) {
   constexpr int G = 128 * GV;
   const int lane = threadIdx.x & 31;
   const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -302,6 +312,12 @@ __global__ void __launch_bounds__(256) k_attention_kq_v(const float* __restrict_
     } else {
 #pragma unroll
       for (int p = 0; p < PT; ++p) dst[p] = a[p];
+    }
+    // receiver-major copy: A_p[i, j] lands at slot (position of i in j's in-list) of ain[j][p][:]
+    if (ain != nullptr && lane < deg) {
+      float* r = ain + ((size_t)(b * N + my_j) * PT) * D + slot_out[row * D + lane];
+#pragma unroll
+      for (int p = 0; p < PT; ++p) r[(size_t)p * D] = a[p];
     }
   }
 }
@@ -396,13 +412,14 @@ int tap_tc_forward(const magat_gat_fwd_args* a, cudaStream_t st);
 // one level of the tap recursion, u_k from u_{k-1} (k >= 1), for every head
 int run_tap_gather(const float* x, long x_sb, long x_sn, const float* att, const int32_t* nbr_in,
                    const int32_t* slot_in, int B, int N, int G, int K, int P, int D, int k, float* taps,
-                   float* ain, cudaStream_t st) {
+                   float* ain, int ain_ready, cudaStream_t st) {
   const long rows = (long)B * N;
   const int row_blocks = cdiv(rows, 8);
   const bool vec_ok = (G % 4 == 0) && (x_sn % 4 == 0) && (x_sb % 4 == 0) && (((uintptr_t)x) % 16 == 0) &&
                       (((uintptr_t)att) % 16 == 0) && (((uintptr_t)taps) % 16 == 0);
 #define MAGAT_GATHER(PT) \
-  k_tap_gather_v<PT><<<row_blocks, 256, 0, st>>>(x, x_sb, x_sn, att, nbr_in, slot_in, rows, N, G, K, D, k, taps, ain)
+  k_tap_gather_v<PT><<<row_blocks, 256, 0, st>>>(x, x_sb, x_sn, att, nbr_in, slot_in, rows, N, G, K, D, k, taps, ain, \
+                                                 ain_ready)
   if (vec_ok && P == 4) MAGAT_GATHER(4);
   else if (vec_ok && P == 2) MAGAT_GATHER(2);
   else if (vec_ok && P == 1) MAGAT_GATHER(1);
@@ -440,6 +457,9 @@ static int forward_impl(const magat_gat_fwd_args* a, cudaStream_t st, bool use_t
       return rc;
     if (!fused && (rc = tc_split_weights(a->filterWeight, (long)nH, h_hi, h_lo, st))) return rc;
   }
+  // the attention kernel also scatters the receiver-major copy `ain` when the caller provides it
+  const int32_t* so = (a->ain && a->slot_out) ? a->slot_out : nullptr;
+  float* ain_w = so ? a->ain : nullptr;
   // 1. score projection
   if (a->mode == MAGAT_MODE_KEYQUERY) {
     if (score_fused) {
@@ -453,7 +473,8 @@ static int forward_impl(const magat_gat_fwd_args* a, cudaStream_t st, bool use_t
     }
     bool fast = vec_ok && D <= 32 && (G == 128 || G == 256);
 #define MAGAT_ATT(PT, GV) \
-  k_attention_kq_v<PT, GV><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj, a->nbr_out, rows, N, D, a->att)
+  k_attention_kq_v<PT, GV><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj, a->nbr_out, rows, N, D, a->att, \
+                                                       so, ain_w)
     if (fast && P == 4 && G == 128) MAGAT_ATT(4, 1);
     else if (fast && P == 4 && G == 256) MAGAT_ATT(4, 2);
     else if (fast && P == 2 && G == 128) MAGAT_ATT(2, 1);
@@ -462,7 +483,7 @@ static int forward_impl(const magat_gat_fwd_args* a, cudaStream_t st, bool use_t
     else if (fast && P == 1 && G == 256) MAGAT_ATT(1, 2);
     else
       k_attention<MAGAT_MODE_KEYQUERY><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj, a->nbr_out,
-                                                                    rows, N, G, P, D, a->att);
+                                                                    rows, N, G, P, D, a->att, so, ain_w);
 #undef MAGAT_ATT
   } else {
     float* cvec = a->wprep;
@@ -473,14 +494,14 @@ static int forward_impl(const magat_gat_fwd_args* a, cudaStream_t st, bool use_t
     k_node_gemm<<<grid, 256, 0, st>>>(rows, 2 * P, G, xl, GmCLoad{cvec, G}, GmEpi{a->sproj, dvec, 2 * P});
     if ((rc = check_launch("k_node_gemm(mixer projection)", st))) return rc;
     k_attention<MAGAT_MODE_GAT_MODIFIED><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj,
-                                                                      a->nbr_out, rows, N, G, P, D, a->att);
+                                                                      a->nbr_out, rows, N, G, P, D, a->att, so, ain_w);
   }
   if ((rc = check_launch("k_attention", st))) return rc;
   // 2. taps (the fused tcgen05 kernel gathers the second tap itself and only needs u_1 in memory)
   const int k_last = fused ? (K - 1 < 1 ? K - 1 : 1) : K - 1;
   for (int k = 1; k <= k_last; ++k)
     if ((rc = run_tap_gather(a->x, a->x_sb, a->x_sn, a->att, a->nbr_in, a->slot_in, B, N, G, K, P, D, k, a->taps,
-                             (fused && k == 1) ? a->ain : nullptr, st)))
+                             (ain_w || (fused && k == 1)) ? a->ain : nullptr, ain_w ? 1 : 0, st)))
       return rc;
   // 3. per-(head, tap) projection + bias + activation + concat / head mean
   if (fused) return tap_tc_forward(a, st);

@@ -216,7 +216,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_tap_tc(const __grid_constant__ T
                   if (id.x < 0) break;                       // lists are packed
                   const float4 aw = __ldg(reinterpret_cast<const float4*>(aw_p + s0));
                   const int ids[4] = {id.x, id.y, id.z, id.w};
-                  const float aws[4] = {aw.x, aw.y, aw.z, aw.w};
+                  // weights of absent entries may be uninitialised memory: force 0 so 0 * garbage never makes a NaN
+                  const float aws[4] = {id.x >= 0 ? aw.x : 0.f, id.y >= 0 ? aw.y : 0.f, id.z >= 0 ? aw.z : 0.f,
+                                        id.w >= 0 ? aw.w : 0.f};
                   float4 ta[4], tb[4];
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {

@@ -312,13 +312,15 @@ __global__ void __launch_bounds__(256) k_build_ell(const uint32_t* __restrict__ 
                                                    const uint32_t* __restrict__ colbits, long rows,
                                                    int N, int W, int D, int32_t* __restrict__ nbr_out,
                                                    int32_t* __restrict__ nbr_in,
-                                                   int32_t* __restrict__ slot_in) {
+                                                   int32_t* __restrict__ slot_in,
+                                                   int32_t* __restrict__ slot_out) {
   const int lane = threadIdx.x & 31;
   const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= rows) return;
   const long b = row / N;
   const int n = (int)(row - b * N);
-  list_bits(rowbits + row * W, W, D, lane, nbr_out + row * D);
+  int deg_out = list_bits(rowbits + row * W, W, D, lane, nbr_out + row * D);
+  if (deg_out > D) deg_out = D;
   int32_t* nin = nbr_in + row * D;
   int deg_in = list_bits(colbits + row * W, W, D, lane, nin);
   if (deg_in > D) deg_in = D;
@@ -340,6 +342,23 @@ __global__ void __launch_bounds__(256) k_build_ell(const uint32_t* __restrict__ 
     if (gl == 0 && s < deg_in) slot_in[row * D + s] = rank;
   }
   for (int s = deg_in + lane; s < D; s += 32) slot_in[row * D + s] = 0;
+  if (slot_out == nullptr) return;
+  // out-edge (n -> j): position of n inside column j's in-list = set bits of column j below n
+  const int32_t* nout = nbr_out + row * D;
+  for (int s0 = 0; s0 < deg_out; s0 += 4) {
+    const int s = s0 + grp;
+    int rank = 0;
+    if (s < deg_out) {
+      const int j = nout[s];
+      const uint32_t* c = colbits + ((size_t)b * N + j) * W;
+      for (int w = gl; w <= sw; w += 8) rank += __popc(w < sw ? c[w] : (c[w] & below));
+    }
+    rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+    rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+    rank += __shfl_xor_sync(0xffffffffu, rank, 4);
+    if (gl == 0 && s < deg_out) slot_out[row * D + s] = rank;
+  }
+  for (int s = deg_out + lane; s < D; s += 32) slot_out[row * D + s] = 0;
 }
 
 // att[B][N][D][P] -> dense aij[B][P][N][N] (mean_heads == 0) or head-mean [B][N][N].
@@ -442,7 +461,7 @@ extern "C" int magat_gso_scan(const void* S, int s_dtype, int B, int N, uint32_t
 
 extern "C" int magat_gso_build_ell(const uint32_t* rowbits, const uint32_t* colbits, int B, int N,
                                    int D, int32_t* nbr_out, int32_t* nbr_in, int32_t* slot_in,
-                                   void* stream) {
+                                   int32_t* slot_out, void* stream) {
   MAGAT_REQUIRE(rowbits && colbits && nbr_out && nbr_in && slot_in, MAGAT_E_BAD_ARG,
                 "magat_gso_build_ell: null pointer");
   MAGAT_REQUIRE(B >= 1 && N >= 1 && D >= 1, MAGAT_E_BAD_ARG, "magat_gso_build_ell: B=%d N=%d D=%d", B, N, D);
@@ -450,7 +469,7 @@ extern "C" int magat_gso_build_ell(const uint32_t* rowbits, const uint32_t* colb
   const int W = (N + 31) / 32;
   prof_begin((cudaStream_t)stream);
   k_build_ell<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(rowbits, colbits, rows, N, W, D,
-                                                               nbr_out, nbr_in, slot_in);
+                                                               nbr_out, nbr_in, slot_in, slot_out);
   return check_launch("k_build_ell", (cudaStream_t)stream);
 }
 

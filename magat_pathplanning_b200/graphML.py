@@ -50,11 +50,11 @@ def _require_cuda(t: torch.Tensor, what: str):
 class Adjacency:
     """Neighbour lists of one GSO batch (device tensors; layouts in include/magat_gat.h)."""
 
-    __slots__ = ("B", "N", "D", "nbr_out", "nbr_in", "slot_in")
+    __slots__ = ("B", "N", "D", "nbr_out", "nbr_in", "slot_in", "slot_out")
 
-    def __init__(self, B, N, D, nbr_out, nbr_in, slot_in):
+    def __init__(self, B, N, D, nbr_out, nbr_in, slot_in, slot_out):
         self.B, self.N, self.D = B, N, D
-        self.nbr_out, self.nbr_in, self.slot_in = nbr_out, nbr_in, slot_in
+        self.nbr_out, self.nbr_in, self.slot_in, self.slot_out = nbr_out, nbr_in, slot_in, slot_out
 
 
 def build_adjacency(S: torch.Tensor) -> Adjacency:
@@ -92,9 +92,10 @@ def build_adjacency(S: torch.Tensor) -> Adjacency:
         nbr_out = torch.empty((B, N, D), dtype=torch.int32, device=dev)
         nbr_in = torch.empty((B, N, D), dtype=torch.int32, device=dev)
         slot_in = torch.empty((B, N, D), dtype=torch.int32, device=dev)
+        slot_out = torch.empty((B, N, D), dtype=torch.int32, device=dev)
         _cabi.check(L.magat_gso_build_ell(rowbits.data_ptr(), colbits.data_ptr(), B, N, D, nbr_out.data_ptr(),
-                                          nbr_in.data_ptr(), slot_in.data_ptr(), st))
-    return Adjacency(B, N, D, nbr_out, nbr_in, slot_in)
+                                          nbr_in.data_ptr(), slot_in.data_ptr(), slot_out.data_ptr(), st))
+    return Adjacency(B, N, D, nbr_out, nbr_in, slot_in, slot_out)
 
 
 def _node_major(x: torch.Tensor):
@@ -145,7 +146,7 @@ class _GATFunction(torch.autograd.Function):
                 y_mem = torch.empty((B, C_out, N), dtype=torch.float32, device=dev)
                 y = y_mem
             att = torch.empty((B, N, D, P), dtype=torch.float32, device=dev)
-            ain = torch.empty((B, N, P, D), dtype=torch.float32, device=dev) if K > 2 else None
+            ain = torch.empty((B, N, P, D), dtype=torch.float32, device=dev) if K > 1 else None
             taps = torch.empty((B, N, P, max(K - 1, 1), G), dtype=torch.float32, device=dev) if K > 1 else None
             wprep = torch.empty(L.magat_gat_wprep_floats(G, F, K, P, meta.mode), dtype=torch.float32, device=dev)
             sproj = torch.empty((B, N, P, G if meta.mode == _cabi.MODE_KEYQUERY else 2), dtype=torch.float32,
@@ -154,7 +155,7 @@ class _GATFunction(torch.autograd.Function):
                               relu=int(meta.relu), path=meta.path, reserved=0,
                               x=xt.data_ptr(), x_sb=_sb(xt), x_sn=_sn(xt),
                               nbr_out=adj.nbr_out.data_ptr(), nbr_in=adj.nbr_in.data_ptr(),
-                              slot_in=adj.slot_in.data_ptr(),
+                              slot_in=adj.slot_in.data_ptr(), slot_out=adj.slot_out.data_ptr(),
                               weight=weight_c.data_ptr(), mixer=_p(mixer_c), weight_bias=_p(wb_c),
                               filterWeight=filt_c.data_ptr(), bias=_p(bias_c),
                               y=y_mem.data_ptr(), y_sb=y.stride(0), y_sn=y.stride(2), y_sc=y.stride(1),

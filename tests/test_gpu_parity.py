@@ -280,7 +280,7 @@ def test_gso_scan_and_neighbour_lists(N, dtype):
         S[:, :, 0, :] = 0
     mask = (S.abs() > 1e-9)[:, 0]                               # [B,N,N]
     adj = build_adjacency(S.to(dev))
-    out, inn, slot = adj.nbr_out.cpu(), adj.nbr_in.cpu(), adj.slot_in.cpu()
+    out, inn, slot, sout = adj.nbr_out.cpu(), adj.nbr_in.cpu(), adj.slot_in.cpu(), adj.slot_out.cpu()
     D = adj.D
     assert D % 4 == 0 and D >= max(int(mask.sum(2).max()), int(mask.sum(1).max()), 1)
     for b in range(B):
@@ -293,5 +293,7 @@ def test_gso_scan_and_neighbour_lists(N, dtype):
             assert got_in == want_in
             for s, src in enumerate(want_in):
                 assert out[b, src, slot[b, i, s]] == i
+            for s, dst in enumerate(want):
+                assert inn[b, dst, sout[b, i, s]] == i
         if N >= 1000:
             break                                               # one instance is enough at this size
