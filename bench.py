@@ -250,7 +250,10 @@ def main():
     dist_on = world > 1
     if dist_on:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.distributed.init_process_group("nccl", device_id=dev)
+        import datetime
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"            # keep stdout to the one JSON line
+        torch.distributed.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     from magat_pathplanning_b200 import _cabi
     from magat_pathplanning_b200.dist import allreduce_gradients
     _cabi.check(_cabi.lib().magat_device_check())
@@ -290,8 +293,9 @@ def main():
     ms_fwd = timed(step_fwd, args.steps, args.warmup, dist_on)
 
     # ---- per-kernel CUDA-event times of the forward path (rank 0) --------------------------------
+    # (every rank runs these steps -- step_train holds a collective -- but only rank 0 reports them)
     kernels, fwd_kernel_ms, train_kernels = [], None, []
-    if rank == 0:
+    if True:
         torch.cuda.synchronize()
         L.magat_profile_enable(1)
         reps = 3

@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tap_tc(const __grid_constant__ T
 #pragma unroll 1
           for (int i = 0; i < 4; ++i) {
             const int m = m0 + r0 + 16 * i;
-            const bool live = m < rows && !(p.dbg & 1);
+            const bool live = m < rows && !(p.dbg & 1) && !(p.dbg & 128);
             const unsigned bN = live ? ((unsigned)m / N) * N : 0u;
             const int32_t* nb = p.nbr_in + (unsigned)(live ? m : 0) * D;
             const float* aw_p = p.ain + ((unsigned)(live ? m : 0) * (unsigned)p.P + head) * D;
