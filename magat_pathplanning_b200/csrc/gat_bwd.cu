@@ -514,7 +514,7 @@ int run_tap_gather(const float* x, long x_sb, long x_sn, const float* att, const
 // gat_wgrad_tc.cu
 size_t wgrad_tc_partial_floats(int G, int F, int K, int P);
 bool wgrad_tc_supported(const magat_gat_bwd_args* a);
-int wgrad_tc_dfilter(const magat_gat_bwd_args* a, cudaStream_t st);
+int wgrad_tc_dfilter(const magat_gat_bwd_args* a, bool with_dbias, cudaStream_t st);
 int wgrad_tc_dweight(const magat_gat_bwd_args* a, cudaStream_t st);
 
 // gat_tap_tc.cu / gat_tc.cu
@@ -607,7 +607,9 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
                              a->taps, nullptr, 0, st)))
       return rc;
 
-  if (a->need_dbias) {
+  const bool tc_wgrad = a->path != MAGAT_PATH_SIMT && wgrad_tc_supported(a);
+  const bool dbias_in_wgrad = a->need_dbias && a->need_dfilter && tc_wgrad;
+  if (a->need_dbias && !dbias_in_wgrad) {
     const int C = a->concat ? P * F : F;
     const int nblocks = 148 * 8;
     const int chunk = cdiv(rows, nblocks);
@@ -616,10 +618,9 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
     k_dbias_final<<<F, 256, 0, st>>>(a->partial, nblocks, C, P, F, a->concat, a->dbias);
     if ((rc = check_launch("k_dbias_final", st))) return rc;
   }
-  const bool tc_wgrad = a->path != MAGAT_PATH_SIMT && wgrad_tc_supported(a);
   if (a->need_dfilter) {
     if (tc_wgrad) {
-      if ((rc = wgrad_tc_dfilter(a, st))) return rc;
+      if ((rc = wgrad_tc_dfilter(a, dbias_in_wgrad, st))) return rc;
     } else if ((rc = rowred(rows, F, KG, P, DPreR{dp}, ZRed{zn, G}, a->partial, a->dfilterWeight, st,
                             "k_rowred_gemm(dfilterWeight)")))
       return rc;

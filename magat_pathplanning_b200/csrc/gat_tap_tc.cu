@@ -49,6 +49,7 @@ struct TapParams {
   const float* H;        // filterWeight [P][F][K*G]
   const float* bias; int relu;
   float* y; long y_sb, y_sn;     // channel stride 1
+  int gather_u2;                 // 1: tap k = 2 is gathered on the fly from u_1; 0: read from the taps buffer
   int dbg;                       // MAGAT_DBG experiments (0 in production)
 };
 
@@ -151,8 +152,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_tap_tc(const __grid_constant__ T
         const uint32_t phase = (q >> 2) & 1u;
         const int seg = s / sps;
         const unsigned k4 = (unsigned)(((s - seg * sps) * SK + c16 * 8) >> 2);    // float4 offset inside the row
-        if (seg < 2) {
-          // x or u_1: straight copy.  All 16 loads of the thread are in flight before the stage is awaited.
+        if (seg < 2 || !p.gather_u2) {
+          // x or a materialised tap: straight copy.  All 16 loads of the thread are in flight before the stage is awaited.
           float4 va[2][4], vb[2][4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tap_tc(const __grid_constant__ T
                 src = x4 + (((long)b * p.x_sb + (long)((unsigned)m - b * N) * p.x_sn) >> 2) + k4;
                 if (mk4) msk = mk4 + (((long)b * p.m_sb + (long)((unsigned)m - b * N) * p.m_sn) >> 2) + k4;
               } else {
-                src = u1h4 + (size_t)(unsigned)m * u1_row4 + k4;
+                src = u1h4 + (size_t)(unsigned)m * u1_row4 + (unsigned)((seg - 1) * (p.G >> 2)) + k4;
               }
             }
 #pragma unroll
@@ -452,6 +453,17 @@ int gz_tc_backward(const magat_gat_bwd_args* a, float* ht, cudaStream_t st) {
   return launch_tap_tc(tp, tp.P, st, "k_tap_tc(gz = dP H)");
 }
 
+// MAGAT_FUSE_U2=1 keeps the second tap out of HBM (gathered by the producer warps); measured slower than
+// materialising it with k_tap_gather_v (0.87 ms of exposed gather against 0.47 + 0.15 ms), so it is opt-in.
+bool tap_tc_gathers_u2() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MAGAT_FUSE_U2");
+    v = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  return v == 1;
+}
+
 bool tap_tc_supported(const magat_gat_fwd_args* a) {
   if (!a->concat || a->K > 3 || a->F != FT) return false;
   if (a->G % SK != 0 || a->K * a->G > ACC_COL0) return false;
@@ -460,7 +472,7 @@ bool tap_tc_supported(const magat_gat_fwd_args* a) {
   if (a->K > 1 && ((uintptr_t)a->taps % 16) != 0) return false;
   if (a->P > 64) return false;
   if ((long)a->B * a->N * a->D * a->P >= (1l << 31)) return false;     // 32-bit index math in the kernel
-  if (a->K > 2 && (a->ain == nullptr || a->D % 4 != 0 || ((uintptr_t)a->ain % 16) != 0 ||
+  if (a->K > 2 && tap_tc_gathers_u2() && (a->ain == nullptr || a->D % 4 != 0 || ((uintptr_t)a->ain % 16) != 0 ||
                    ((uintptr_t)a->nbr_in % 16) != 0))
     return false;
   return true;
@@ -474,6 +486,7 @@ int tap_tc_forward(const magat_gat_fwd_args* a, cudaStream_t st) {
   tp.x = a->x; tp.x_sb = a->x_sb; tp.x_sn = a->x_sn;
   tp.x_hdiv = 1; tp.x_hmul = 0; tp.mask = nullptr;
   tp.u1 = a->taps;
+  tp.gather_u2 = tap_tc_gathers_u2() ? 1 : 0;
   tp.ain = a->ain; tp.nbr_in = a->nbr_in;
   tp.H = a->filterWeight;
   tp.bias = a->bias; tp.relu = a->relu;

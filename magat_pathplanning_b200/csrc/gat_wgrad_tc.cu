@@ -32,7 +32,8 @@ constexpr int ATOM_STRIDE = SN * 128;          // bytes between 64-feature atoms
 constexpr int PROD_THREADS = 256;
 constexpr int MMA_WARP = 8;
 constexpr int THREADS = 9 * 32;
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+constexpr int RED_BYTES = 16 * MI * 4;          // column-sum staging (dbias)
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + RED_BYTES + 1024 + 256;
 
 struct Src {                 // node-major fp32 rows: row m at p + (m / N) * sb + (m % N) * sn  (+ z * zoff)
   const float* p; long sb, sn, zoff;
@@ -46,6 +47,7 @@ struct WgradParams {
   const float* mask_y; long my_sb, my_sn, my_zoff;   // optional: A = a * (mask_y > 0)  (dP from dY and y)
   float a_scale;
   float* partial;            // [Z][nslots][128][NB]
+  float* colsum_partial;     // optional [Z][nslots][128]: per-CTA column sums of the (masked, scaled) A rows
 };
 
 // MN-major SWIZZLE_128B operand: LBO = bytes between 64-element atoms along M/N, SBO = bytes between
@@ -68,7 +70,8 @@ __host__ __device__ constexpr uint32_t make_idesc_mn(int M, int N) {
 __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
+  float* red = reinterpret_cast<float*>(smem + (size_t)STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES + RED_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* done = bars + 2 * STAGES;
@@ -110,6 +113,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const __grid_constant__
     }
     int stage = 0;
     uint32_t phase = 0;
+    float4 cs0 = make_float4(0.f, 0.f, 0.f, 0.f), cs1 = cs0;      // column sums of A (features c*8 .. c*8+7)
     for (long sidx = slot; sidx < nstages; sidx += nslots) {
       const int m0 = (int)(sidx * SN);
       float4 va[4][2][2];                      // [source][row][half]
@@ -153,6 +157,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const __grid_constant__
           v.y = mk.y > 0.f ? v.y * p.a_scale : 0.f;
           v.z = mk.z > 0.f ? v.z * p.a_scale : 0.f;
           v.w = mk.w > 0.f ? v.w * p.a_scale : 0.f;
+          float4& cs = h == 0 ? cs0 : cs1;
+          cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
         }
       tc::mbar_wait(&empty[stage], phase ^ 1);
       uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
@@ -175,6 +181,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const __grid_constant__
       tc::fence_proxy_async();
       tc::mbar_arrive(&full[stage]);
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
+    }
+    // column sums (dbias): 16 row-threads per feature chunk -> smem -> fixed-order sum
+    if (p.colsum_partial != nullptr) {
+      *reinterpret_cast<float4*>(red + r0 * MI + c * 8) = cs0;
+      *reinterpret_cast<float4*>(red + r0 * MI + c * 8 + 4) = cs1;
+      tc::named_bar_sync(2, PROD_THREADS);
+      if (t < MI) {
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) s += red[r * MI + t];
+        p.colsum_partial[((size_t)z * nslots + slot) * MI + t] = s;
+      }
     }
     // ===== epilogue (warps 0-3): the accumulated tile -> this CTA's partial =====================
     if (warp < 4) {
@@ -255,6 +273,14 @@ __global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ 
   out[e] = s;
 }
 
+// dbias[f] = sum over heads z and CTA slots of the column-sum partials
+__global__ void __launch_bounds__(128) k_dbias_from_colsums(const float* __restrict__ cp, int n, float* __restrict__ dbias) {
+  const int f = threadIdx.x;
+  float s = 0.f;
+  for (int i = 0; i < n; ++i) s += cp[(size_t)i * MI + f];
+  dbias[f] = s;
+}
+
 int wgrad_nslots(int Z) {
   static int sm_count = 0;
   if (!sm_count) {
@@ -292,7 +318,8 @@ bool aligned16(const void* p) { return ((uintptr_t)p % 16) == 0; }
 // floats of `partial` scratch the tcgen05 weight-gradient kernels need
 size_t wgrad_tc_partial_floats(int G, int F, int K, int P) {
   (void)G;
-  return (size_t)wgrad_nslots(P) * P * MI * (size_t)(K * G > 128 ? K * G : 128) + (size_t)F * 0;
+  return (size_t)wgrad_nslots(P) * P * MI * (size_t)(K * G > 128 ? K * G : 128) + (size_t)wgrad_nslots(P) * P * MI +
+         (size_t)F * 0;
 }
 
 bool wgrad_tc_supported(const magat_gat_bwd_args* a) {
@@ -305,7 +332,7 @@ bool wgrad_tc_supported(const magat_gat_bwd_args* a) {
 }
 
 // dfilterWeight[p][f][k*G + g] = sum_m dP[m][p*F + f] * u_k^p[m][g]
-int wgrad_tc_dfilter(const magat_gat_bwd_args* a, cudaStream_t st) {
+int wgrad_tc_dfilter(const magat_gat_bwd_args* a, bool with_dbias, cudaStream_t st) {
   WgradParams wp{};
   wp.rows = (long)a->B * a->N;
   wp.N = a->N;
@@ -320,7 +347,13 @@ int wgrad_tc_dfilter(const magat_gat_bwd_args* a, cudaStream_t st) {
   for (int k = 1; k < a->K; ++k)
     wp.b[k] = Src{a->taps + (long)(k - 1) * a->G, (long)a->N * tap_row, tap_row, (long)(a->K - 1) * a->G};
   wp.partial = a->partial;
-  return launch_wgrad(wp, a->dfilterWeight, st, "k_wgrad_tc(dfilterWeight)");
+  const int nslots = wgrad_nslots(a->P);
+  // concat mode: dbias[f] = sum_{m,p} dP[m][p*F+f] falls out of the A tiles this kernel already streams
+  wp.colsum_partial = with_dbias ? a->partial + (size_t)nslots * a->P * MI * wp.NB : nullptr;
+  int rc = launch_wgrad(wp, a->dfilterWeight, st, "k_wgrad_tc(dfilterWeight)");
+  if (rc || !with_dbias) return rc;
+  k_dbias_from_colsums<<<1, 128, 0, st>>>(wp.colsum_partial, nslots * a->P, a->dbias);
+  return check_launch("k_dbias_from_colsums", st);
 }
 
 // KeyQuery: dweight[p][g][g'] = sum_m x[m][g] * dR[m][p][g']
@@ -336,6 +369,7 @@ int wgrad_tc_dweight(const magat_gat_bwd_args* a, cudaStream_t st) {
   const long rc_row = (long)a->P * a->G;
   wp.b[0] = Src{a->rc, (long)a->N * rc_row, rc_row, (long)a->G};
   wp.partial = a->partial;
+  wp.colsum_partial = nullptr;
   return launch_wgrad(wp, a->dweight, st, "k_wgrad_tc(dweight)");
 }
 
