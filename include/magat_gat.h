@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define MAGAT_ABI_VERSION 5
+#define MAGAT_ABI_VERSION 6
 
 enum {
   MAGAT_OK = 0,
@@ -152,6 +152,17 @@ int magat_gat_backward(const magat_gat_bwd_args* a, void* stream);
  * that returnAttentionGSO returns.  `out` must be zero filled by the caller. */
 int magat_gat_attention_dense(const float* att, const int32_t* nbr_out, int B, int N, int D, int P,
                               int mean_heads, float* out, void* stream);
+
+/* ---- small-graph forward (inference): the whole layer for one instance in one CTA, ONE launch ----
+ * For the simulator loop of the reference (B = 1, N <= 64 agents per step under torch.no_grad(),
+ * agents/decentralplannerlocal_OnlineExpert_GAT.py:1039-1044).  Takes the dense GSO directly; writes y and, when
+ * aij_or_null is given, the dense attention [B][P][N][N] (graphML.py:4650).  Nothing is kept for backward. */
+int magat_gat_small_supported(int N, int G, int F, int K, int P, int concat);
+int magat_gat_forward_small(const void* S, int s_dtype, const float* x, int64_t x_sb, int64_t x_sn,
+                            const float* weight, const float* mixer, const float* weight_bias,
+                            const float* filterWeight, const float* bias, float* y, int64_t y_sb, int64_t y_sn,
+                            int64_t y_sc, float* aij_or_null, int B, int N, int G, int F, int K, int P, int mode,
+                            int concat, int relu, void* stream);
 
 /* ---- launch accounting / measurement hooks (bench.py, tests) ----
  * magat_launch_count: kernels launched by this library in this process so far.

@@ -12,7 +12,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmagat_gat.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 MODE_KEYQUERY, MODE_GAT_MODIFIED = 0, 1
 DT_F32, DT_F64 = 0, 1
@@ -23,6 +23,7 @@ EXPORTS = (
     "magat_gso_build_ell", "magat_gat_wprep_floats", "magat_gat_forward", "magat_gat_forward_taps_valid",
     "magat_gat_bwd_partial_floats", "magat_gat_backward", "magat_gat_attention_dense",
     "magat_launch_count", "magat_profile_enable", "magat_profile_collect",
+    "magat_gat_small_supported", "magat_gat_forward_small",
 )
 
 _i32, _i64, _ptr = C.c_int32, C.c_int64, C.c_void_p
@@ -97,6 +98,11 @@ def lib():
         for name in ("magat_gso_scan", "magat_gso_build_ell", "magat_gat_forward", "magat_gat_backward",
                      "magat_gat_attention_dense"):
             getattr(L, name).restype = C.c_int
+        L.magat_gat_small_supported.argtypes = [C.c_int] * 6
+        L.magat_gat_small_supported.restype = C.c_int
+        L.magat_gat_forward_small.argtypes = ([_ptr, C.c_int, _ptr, _i64, _i64] + [_ptr] * 5 + [_ptr, _i64, _i64, _i64, _ptr]
+                                              + [C.c_int] * 9 + [_ptr])
+        L.magat_gat_forward_small.restype = C.c_int
         L.magat_launch_count.restype = C.c_long
         L.magat_profile_enable.argtypes = [C.c_int]
         L.magat_profile_enable.restype = None

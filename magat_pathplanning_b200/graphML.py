@@ -28,7 +28,7 @@ zeroTolerance = 1e-9     # graphML.py:45
 infiniteNumber = 1e12    # graphML.py:46
 
 #: no host sync for the ELL width below this node count (width = N)
-_SMALL_N = 48
+_NOSYNC_N = 48
 
 _PATH = {"auto": _cabi.PATH_AUTO, "simt": _cabi.PATH_SIMT, "tcgen05": _cabi.PATH_TCGEN05}
 
@@ -83,7 +83,7 @@ def build_adjacency(S: torch.Tensor) -> Adjacency:
         stats[3] = 1
         _cabi.check(L.magat_gso_scan(S.data_ptr(), _cabi.DT_F32 if S.dtype == torch.float32 else _cabi.DT_F64,
                                      B, N, rowbits.data_ptr(), colbits.data_ptr(), stats.data_ptr(), st))
-        if N <= _SMALL_N:
+        if N <= _NOSYNC_N:
             D = N
         else:
             h = stats.cpu()
@@ -228,10 +228,73 @@ def _mode_of(attentionMode: str) -> int:
     raise ValueError(f"unsupported attentionMode {attentionMode!r}")
 
 
+#: single-CTA-per-instance inference kernel: only for the simulator's shape, a handful of instances of <= 64
+#: agents (measured: 0.08 ms at B=1 against 0.19 ms for the 9-launch path, but 2-7x slower than it from B=64 up,
+#: where every CTA re-reads the same weight lines from L2)
+_SMALL_N_MAX, _SMALL_B = 64, 4
+
+
+class SparseAttention:
+    """Attention of the last forward as the kernels keep it (sender-major lists); densified on demand."""
+
+    def __init__(self, att, adj):
+        self.att, self.adj = att, adj
+
+    def dense(self):
+        return attention_dense(self.att, self.adj)
+
+    def dense_mean(self):
+        return attention_dense(self.att, self.adj, mean_heads=True)
+
+
+class DenseAttention:
+    """Attention written densely by the small-graph kernel, [B,P,N,N]."""
+
+    def __init__(self, aij):
+        self.aij = aij
+
+    def dense(self):
+        return self.aij.unsqueeze(2)
+
+    def dense_mean(self):
+        return self.aij.mean(dim=1, keepdim=True)
+
+
+def _small_forward(x, S, filterWeight, mixer, weight, weight_bias, bias, mode, concatenate, relu):
+    """Inference-only single-launch path (magat_gat_forward_small)."""
+    L = _cabi.lib()
+    dev = x.device
+    B, G, N = x.shape
+    P, F, _, K, _ = filterWeight.shape
+    S = S.detach()
+    if S.dtype not in (torch.float32, torch.float64):
+        S = S.to(torch.float32)
+    if not S.is_contiguous():
+        S = S.contiguous()
+    xt = _node_major(x.detach())
+    w, h = weight.detach().contiguous(), filterWeight.detach().contiguous()
+    mx = None if mixer is None else mixer.detach().contiguous()
+    wb = None if weight_bias is None else weight_bias.detach().contiguous()
+    bs = None if bias is None else bias.detach().contiguous()
+    with torch.cuda.device(dev):
+        if concatenate:
+            y_mem = torch.empty((B, N, P * F), dtype=torch.float32, device=dev)
+            y = y_mem.permute(0, 2, 1)
+        else:
+            y_mem = torch.empty((B, F, N), dtype=torch.float32, device=dev)
+            y = y_mem
+        aij = torch.empty((B, P, N, N), dtype=torch.float32, device=dev)
+        _cabi.check(L.magat_gat_forward_small(
+            S.data_ptr(), _cabi.DT_F32 if S.dtype == torch.float32 else _cabi.DT_F64, xt.data_ptr(), _sb(xt), _sn(xt),
+            w.data_ptr(), _p(mx), _p(wb), h.data_ptr(), _p(bs), y_mem.data_ptr(), y.stride(0), y.stride(2), y.stride(1),
+            aij.data_ptr(), B, N, G, F, K, P, mode, int(concatenate), int(relu), _stream(dev)))
+    return y, DenseAttention(aij)
+
+
 def gat_layer(x, S, filterWeight, mixer, weight, weight_bias, bias, *, mode: int, concatenate: bool,
               relu: bool = True, path: str = "auto", adjacency: Optional[Adjacency] = None):
-    """One call of the fused layer.  Returns ``(y, att, adjacency)``; ``att`` is the sparse attention
-    ([B,N,D,P], see include/magat_gat.h) that ``attention_dense`` expands on demand."""
+    """One call of the fused layer.  Returns ``(y, attention)``; ``attention.dense()`` / ``.dense_mean()`` give
+    ``aij`` [B,P,1,N,N] / its head mean on demand."""
     _require_cuda(x, "x")
     assert len(x.shape) == 3
     P, F, E, K, G = filterWeight.shape
@@ -239,6 +302,17 @@ def gat_layer(x, S, filterWeight, mixer, weight, weight_bias, bias, *, mode: int
     assert x.shape[1] == G                       # graphML.py:1735
     if x.dtype != torch.float32:
         x = x.float()
+    B_, N_ = x.shape[0], x.shape[2]
+    needs_grad = torch.is_grad_enabled() and any(
+        t is not None and t.requires_grad for t in (x, filterWeight, mixer, weight, weight_bias, bias))
+    if (adjacency is None and path == "auto" and not needs_grad and S is not None and S.shape[2] == N_
+            and N_ <= _SMALL_N_MAX and B_ <= _SMALL_B
+            and (mode != _cabi.MODE_KEYQUERY or F == G)
+            and _cabi.lib().magat_gat_small_supported(N_, G, F, K, P, int(concatenate))):
+        _require_cuda(S, "the GSO")
+        assert len(S.shape) == 4 and S.shape[1] == 1 and S.shape[3] == N_ and S.shape[0] == B_
+        return _small_forward(x, S, filterWeight, mixer if mode != _cabi.MODE_KEYQUERY else None, weight,
+                              weight_bias if mode != _cabi.MODE_KEYQUERY else None, bias, mode, concatenate, relu)
     adj = adjacency if adjacency is not None else build_adjacency(S)
     assert adj.B == x.shape[0] and adj.N == x.shape[2]
     if mode == _cabi.MODE_KEYQUERY:
@@ -257,7 +331,7 @@ def gat_layer(x, S, filterWeight, mixer, weight, weight_bias, bias, *, mode: int
     else:
         mixer_in, wb_in = mixer, weight_bias
     y, att = _GATFunction.apply(x, weight, mixer_in, wb_in, filterWeight, bias, adj, meta)
-    return y, att, adj
+    return y, SparseAttention(att.detach(), adj)
 
 
 def attention_dense(att: torch.Tensor, adj: Adjacency, mean_heads: bool = False) -> torch.Tensor:
@@ -277,9 +351,9 @@ def attention_dense(att: torch.Tensor, adj: Adjacency, mean_heads: bool = False)
 def _functional(h, x, a, W, W_b, S, b, mode):
     P, F = h.shape[0], h.shape[1]
     B, N = x.shape[0], x.shape[2]
-    y, att, adj = gat_layer(x, S, h, a, W, W_b, b, mode=mode, concatenate=True, relu=False)
+    y, att = gat_layer(x, S, h, a, W, W_b, b, mode=mode, concatenate=True, relu=False)
     y = y.permute(0, 2, 1).reshape(B, N, P, F).permute(0, 2, 3, 1)      # B x P x F x N
-    return y, attention_dense(att, adj)
+    return y, att.dense()
 
 
 def graphAttentionLSIGFBatch_KeyQuery(h, x, a, W, W_b, S, b=None):
@@ -297,8 +371,8 @@ def _attention_only(x, a, W, W_b, S, mode):
     F = G if mode == _cabi.MODE_KEYQUERY else W.shape[2]
     h = torch.zeros((P, F, E, 1, G), dtype=torch.float32, device=x.device)
     with torch.no_grad():
-        _, att, adj = gat_layer(x, S, h, a, W, W_b, None, mode=mode, concatenate=True, relu=False)
-    return attention_dense(att, adj)
+        _, att = gat_layer(x, S, h, a, W, W_b, None, mode=mode, concatenate=True, relu=False)
+    return att.dense()
 
 
 def learnAttentionGSOBatch_KeyQuery(x, a, W, S, negative_slope=0.2):
@@ -375,8 +449,7 @@ class GraphFilterBatchAttentional(nn.Module):
     @property
     def aij(self):
         if self._aij is None and self._last is not None:
-            att, adj = self._last
-            self._aij = attention_dense(att, adj).cpu().numpy()
+            self._aij = self._last.dense().cpu().numpy()
         return self._aij
 
     @aij.setter
@@ -386,8 +459,7 @@ class GraphFilterBatchAttentional(nn.Module):
 
     def returnAttentionGSO(self):
         if self._aij is None and self._last is not None:
-            att, adj = self._last
-            return attention_dense(att, adj, mean_heads=True).cpu().numpy()
+            return self._last.dense_mean().cpu().numpy()
         aij = self.aij
         assert len(aij.shape) == 5
         assert aij.shape[2] == self.E
@@ -401,10 +473,10 @@ class GraphFilterBatchAttentional(nn.Module):
         if Nin < self.N:                 # graphML.py:4642-4646
             x = torch.cat((x, torch.zeros(B, F, self.N - Nin).type(x.dtype).to(x.device)), dim=2)
         fused_relu = self.nonlinearity in (nn.functional.relu, torch.relu)
-        y, att, adj = gat_layer(x, self.S, self.filterWeight, self.mixer, self.weight, self.weight_bias,
-                                self.bias, mode=_mode_of(self.attentionMode), concatenate=self.concatenate,
-                                relu=fused_relu, path=self.path)
-        self._last, self._aij = (att.detach(), adj), None
+        y, att = gat_layer(x, self.S, self.filterWeight, self.mixer, self.weight, self.weight_bias,
+                           self.bias, mode=_mode_of(self.attentionMode), concatenate=self.concatenate,
+                           relu=fused_relu, path=self.path)
+        self._last, self._aij = att, None
         if not fused_relu:
             y = self.nonlinearity(y)
         if Nin < self.N:

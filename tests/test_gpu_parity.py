@@ -297,3 +297,43 @@ def test_gso_scan_and_neighbour_lists(N, dtype):
                 assert inn[b, dst, sout[b, i, s]] == i
         if N >= 1000:
             break                                               # one instance is enough at this size
+
+
+# ---- single-launch small-graph inference kernel (the simulator's B = 1, N <= 64 use) --------------------
+
+SMALL_CASES = [n for n in golden_case_names() if n not in ("kq_b32p4_n100", "kq_n130_g128", "gm_n70_g64")]
+
+
+@pytest.mark.parametrize("name", SMALL_CASES)
+def test_small_graph_kernel_golden(golden, name):
+    from magat_pathplanning_b200 import _cabi
+    d, meta = golden.case(name)
+    dev = torch.device("cuda:0")
+    layer = make_layer(meta, d, dev, path="auto")
+    layer.addGSO(d["S"].to(dev))
+    L = _cabi.lib()
+    with torch.no_grad():
+        c0 = L.magat_launch_count()
+        y = layer(d["x"].to(dev))
+        launches = L.magat_launch_count() - c0
+    assert launches == 1, "inference on a small graph must be ONE kernel launch"
+    assert y.shape == d["y"].shape and rel_err(y, d["y"]) < TOL
+    if meta["concat"] and "Nin" not in meta:
+        B, C, N = y.shape
+        assert y.stride() == (N * C, 1, C) or N == 1
+    assert np.abs(layer.aij - d["aij"].numpy()).max() < TOL
+    assert np.abs(layer.returnAttentionGSO() - d["aij"].numpy().mean(axis=1)).max() < TOL
+
+
+def test_small_graph_kernel_not_used_when_training(golden):
+    from magat_pathplanning_b200 import _cabi
+    d, meta = golden.case("kq_concat_n10")
+    dev = torch.device("cuda:0")
+    layer = make_layer(meta, d, dev, path="auto")
+    layer.addGSO(d["S"].to(dev))
+    L = _cabi.lib()
+    c0 = L.magat_launch_count()
+    y = layer(d["x"].to(dev))                       # parameters require grad -> autograd path
+    assert L.magat_launch_count() - c0 > 1
+    y.backward(d["dy"].to(dev))
+    assert rel_err(layer.filterWeight.grad, d["grad.filterWeight"]) < TOL
