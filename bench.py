@@ -357,11 +357,19 @@ def main():
     bytes_fwd = alg_bytes(w, "fwd")
     achieved = bytes_fwd / (fwd_kernel_ms * 1e-3) / 1e9 if fwd_kernel_ms else None
     top = max(kernels, key=lambda k: k["ms_per_step"]) if kernels else None
+    traffic, traffic_src = None, None
+    try:
+        tdb = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if args.workload in tdb and not args.batch:
+            traffic = tdb[args.workload]["dram_bytes"]
+            traffic_src = "ncu dram__bytes_read+write.sum over the forward launches: profiles/" + tdb[args.workload]["source"]
+    except Exception:
+        pass
     roofline = {
         "bound": "hbm", "kernel": f"forward path ({sum(k['launches_per_step'] for k in kernels)} launches: "
                                   "GSO scan + neighbour lists + attention + taps + projection)",
         "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": (achieved / hbm_peak if achieved else None),
-        "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_step": bytes_fwd,
+        "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_step": bytes_fwd,
         "fwd_kernel_ms_per_step": fwd_kernel_ms, "dominant_kernel": top, "kernels": kernels,
     }
 
