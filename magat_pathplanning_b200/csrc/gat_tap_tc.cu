@@ -13,8 +13,8 @@
 //
 //   warps 0-15  producers, four groups of four; group g builds every fourth 128-wide K slice
 //               ([64 nodes x 128 k] -> hi/lo tiles, SWIZZLE_128B K-major) into its own smem stage
-//   warps 16-19 epilogue (TMEM lanes q*32.. for warp 16+q)
-//   warp  20    MMA issuer (one thread): 24 MMAs per stage, then tcgen05.commit frees the stage
+//   warps 16-23 epilogue (warp 16+e: TMEM lane quarter e%4, node half e/4)
+//   warp  24    MMA issuer (one thread): 24 MMAs per stage, then tcgen05.commit frees the stage
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -33,8 +33,7 @@ constexpr int STAGE_BYTES = 4 * ATOM_BYTES;  // hi atom 0/1, lo atom 0/1
 constexpr int FT = 128;                      // out-features = UMMA M = TMEM lanes
 constexpr int EPI_BYTES = TN * FT * 4;       // 32 KB transposition buffer
 constexpr int PROD_WARPS = 16, PROD_GROUP = 128;
-constexpr int EPI_WARP0 = 16, MMA_WARP = 20;
-constexpr int THREADS = 21 * 32;
+constexpr int EPI_WARP0 = 16;                 // epilogue warps 16 .. 16+EW-1, then the MMA warp
 constexpr int ACC_COL0 = 384;                // accumulators: columns 384 + 64 a
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
 
@@ -66,7 +65,11 @@ __device__ __forceinline__ void fma44(float4& acc, float a, const float4& v) {
   acc.x = fmaf(a, v.x, acc.x); acc.y = fmaf(a, v.y, acc.y); acc.z = fmaf(a, v.z, acc.z); acc.w = fmaf(a, v.w, acc.w);
 }
 
-__global__ void __launch_bounds__(THREADS, 1) k_tap_tc(const __grid_constant__ TapParams p) {
+// EW = epilogue warps: 8 for the K = 1 uses (score projection, backward gU), which are paced by the epilogue,
+// 4 for the K-tap projection, which is paced by the producers and wants their 96-register budget.
+template <int EW>
+__global__ void __launch_bounds__((17 + EW) * 32, 1) k_tap_tc(const __grid_constant__ TapParams p) {
+  constexpr int EPI_WARPS = EW, MMA_WARP = EPI_WARP0 + EW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   float* epi = reinterpret_cast<float*>(smem + (size_t)STAGES * STAGE_BYTES);
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tap_tc(const __grid_constant__ T
     }
     for (int a = 0; a < 2; ++a) {
       tc::mbar_init(&acc_full[a], 1);
-      tc::mbar_init(&acc_empty[a], 128);
+      tc::mbar_init(&acc_empty[a], EPI_WARPS * 32);
     }
     tc::fence_barrier_init();
   }
@@ -249,51 +252,66 @@ __global__ void __launch_bounds__(THREADS, 1) k_tap_tc(const __grid_constant__ T
     }
   } else if (warp < MMA_WARP) {
     // ===== epilogue =======================================================================
-    const int qd = warp - EPI_WARP0;          // == warp % 4: TMEM lane quarter
+    // Eight warps: warp e reads TMEM lane quarter (e & 3) (the quarter a warp may touch is warp % 4) and the
+    // 32-node half (e >> 2) of the accumulator, then stores 8 of the 64 output rows.  The first profile showed
+    // this role, not the MMAs or the producers, pacing the K = 1 uses of the kernel (4 warps busy 100 % of the
+    // time, a third of their instructions the emulated integer division m / N per stored row), hence the
+    // incremental (batch, node) bookkeeping below.
+    const int e = warp - EPI_WARP0;
+    const int qd = e & 3, half = e >> 2;
+    constexpr int HALVES = 8 / EW;             // 32-node halves of the accumulator this warp drains
+    constexpr int ROWS = TN / EW;              // output rows this warp stores
     const int f = qd * 32 + lane;
     const float bias = p.bias ? __ldg(p.bias + f) : 0.f;
+    const unsigned N = (unsigned)p.N;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (long tile = slot; tile < tiles; tile += nslots) {
       const long m0 = tile * TN;
       tc::mbar_wait(&acc_full[acc], acc_phase);
       tc::tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(ACC_COL0 + acc * TN);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      for (int hh = 0; hh < HALVES; ++hh) {
+        const int hsel = HALVES == 1 ? half : hh;
+        const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(ACC_COL0 + acc * TN + 32 * hsel);
         float v[32];
-        tc::tmem_ld32(taddr + 32 * half, v);
+        tc::tmem_ld32(taddr, v);
         tc::tmem_ld_wait();
-        if (half == 1) {
+        if (hh == HALVES - 1) {
           tc::tc_fence_before();
-          tc::mbar_arrive(&acc_empty[acc]);    // accumulator drained into registers
+          tc::mbar_arrive(&acc_empty[acc]);    // this warp's slice of the accumulator is in registers
         }
         if (!(p.dbg & 16)) {
+          float* col = epi + (32 * hsel) * FT + f;
+          if (p.relu) {
 #pragma unroll
-          for (int n = 0; n < 32; ++n) {
-            float o = v[n] + bias;
-            if (p.relu) o = fmaxf(o, 0.f);
-            epi[(32 * half + n) * FT + f] = o;
+            for (int n = 0; n < 32; ++n) col[n * FT] = fmaxf(v[n] + bias, 0.f);
+          } else {
+#pragma unroll
+            for (int n = 0; n < 32; ++n) col[n * FT] = v[n] + bias;
           }
         }
       }
-      tc::named_bar_sync(1, 128);
-      // 64 rows x 512 B, each warp 16 rows, one float4 per lane
+      tc::named_bar_sync(1, EPI_WARPS * 32);
+      // 64 rows x 512 B: each warp ROWS rows, one float4 per lane
       if (!(p.dbg & 4)) {
-#pragma unroll 4
-        for (int i = 0; i < 16; ++i) {
-          const int n = qd * 16 + i;
-          const long m = m0 + n;
-          if (m < p.rows) {
-            const unsigned b = (unsigned)m / (unsigned)p.N;
-            const float4 o = *reinterpret_cast<const float4*>(epi + n * FT + lane * 4);
-            __stcs(reinterpret_cast<float4*>(p.y + (long)b * p.y_sb + (long)((unsigned)m - b * (unsigned)p.N) * p.y_sn +
-                                             (long)head * FT + lane * 4),
-                   o);
+        const long mfirst = m0 + e * ROWS;
+        unsigned bq = (unsigned)mfirst / N;
+        unsigned r = (unsigned)mfirst - bq * N;
+        float* dst = p.y + (long)bq * p.y_sb + (long)r * p.y_sn + (long)head * FT + lane * 4;
+        const float* src = epi + (e * ROWS) * FT + lane * 4;
+        const long left = p.rows - mfirst;
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) {
+          if (i < left) __stcs(reinterpret_cast<float4*>(dst), *reinterpret_cast<const float4*>(src + i * FT));
+          dst += p.y_sn;
+          if (++r == N) {                       // next batch element
+            r = 0;
+            dst += p.y_sb - (long)N * p.y_sn;
           }
         }
       }
-      tc::named_bar_sync(1, 128);
+      tc::named_bar_sync(1, EPI_WARPS * 32);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
@@ -365,7 +383,9 @@ int launch_tap_tc(const TapParams& tp, int P, cudaStream_t st, const char* what)
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(k_tap_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(k_tap_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(k_tap_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(k_tap_tc): %s", cudaGetErrorString(e));
       return MAGAT_E_CUDA;
@@ -379,7 +399,8 @@ int launch_tap_tc(const TapParams& tp, int P, cudaStream_t st, const char* what)
   long slots = sm_count / P;
   if (slots < 1) slots = 1;
   if (slots > tiles) slots = tiles;
-  k_tap_tc<<<(int)(slots * P), THREADS, SMEM_BYTES, st>>>(tq);
+  if (tq.K == 1) k_tap_tc<8><<<(int)(slots * P), (17 + 8) * 32, SMEM_BYTES, st>>>(tq);
+  else k_tap_tc<4><<<(int)(slots * P), (17 + 4) * 32, SMEM_BYTES, st>>>(tq);
   return check_launch(what, st);
 }
 
