@@ -114,8 +114,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_tc_gemm(const __grid_constan
         for (int i = 0; i < 8; ++i) {
           const long m = m0 + r0 + 16 * i;
           if (m < p.M) {
-            const long b = m / p.n_per_b;
-            const float4* src = reinterpret_cast<const float4*>(sg.a + b * sg.a_sb + (m - b * p.n_per_b) * sg.a_sn +
+            const unsigned b = (unsigned)m / (unsigned)p.n_per_b;          // 32-bit: M < 2^31 (checked on the host)
+            const float4* src = reinterpret_cast<const float4*>(sg.a + (long)b * sg.a_sb +
+                                                                (long)((unsigned)m - b * (unsigned)p.n_per_b) * sg.a_sn +
                                                                 k0 + c16 * 8);
             va[i][0] = __ldg(src);
             va[i][1] = __ldg(src + 1);
@@ -171,8 +172,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_tc_gemm(const __grid_constan
         if (p.epi != 1) {
           crow = p.c + m * p.ldc + (long)z * p.z_cols + n0;
         } else {
-          const long b = m / p.n_per_b;
-          ybase = b * p.y_sb + (m - b * p.n_per_b) * p.y_sn + ((long)z * p.z_cols + n0) * p.y_sc;
+          const unsigned b = (unsigned)m / (unsigned)p.n_per_b;
+          ybase = (long)b * p.y_sb + (long)((unsigned)m - b * (unsigned)p.n_per_b) * p.y_sn +
+                  ((long)z * p.z_cols + n0) * p.y_sc;
         }
       }
 #pragma unroll 1
@@ -317,6 +319,7 @@ bool tc_shape_ok(int G, int F, int K, int P, int concat) {
 }
 
 bool tc_supported(const magat_gat_fwd_args* a) {
+  if ((long)a->B * a->N >= (1l << 31)) return false;
   if (!tc_shape_ok(a->G, a->F, a->K, a->P, a->concat)) return false;
   if ((a->x_sn % 4) != 0 || (a->x_sb % 4) != 0 || ((uintptr_t)a->x % 16) != 0) return false;
   if (a->mode == MAGAT_MODE_KEYQUERY && ((long)a->P * a->G) % BN != 0) return false;
@@ -376,6 +379,7 @@ int tc_tap_projection(const magat_gat_fwd_args* a, const __nv_bfloat16* h_hi, co
 }
 
 bool dx_tc_supported(const magat_gat_bwd_args* a) {
+  if ((long)a->B * a->N >= (1l << 31)) return false;
   if (a->mode != MAGAT_MODE_KEYQUERY || a->G % BK != 0 || a->G % BN != 0 || a->P > MAX_SEGS) return false;
   if (((uintptr_t)a->rc % 16) != 0 || ((uintptr_t)a->dx % 16) != 0) return false;
   return true;
