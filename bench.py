@@ -316,10 +316,20 @@ def main():
 
     # ---- end to end from pinned host buffers --------------------------------------------------
     e2e = None
-    if not args.no_e2e:
-        S_h = torch.empty(S.shape, dtype=S.dtype, pin_memory=True)
+    e2e_ok = 0 if args.no_e2e else 1
+    S_h = x_h = None
+    if e2e_ok:
+        try:
+            S_h = torch.empty(S.shape, dtype=S.dtype, pin_memory=True)
+            x_h = torch.empty(x_mem.shape, dtype=x_mem.dtype, pin_memory=True)
+        except Exception as exc:      # pinned allocation can fail on a crowded host: report, do not die
+            e2e_ok, e2e = 0, {"value": None, "error": f"pinned host allocation failed: {exc}"}
+    if dist_on:                       # every rank takes the same branch (the timed region holds barriers)
+        flag = torch.tensor([e2e_ok], device=dev)
+        torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+        e2e_ok = int(flag.item())
+    if e2e_ok:
         S_h.copy_(S)
-        x_h = torch.empty(x_mem.shape, dtype=x_mem.dtype, pin_memory=True)
         x_h.copy_(x_mem)
         S_d, x_d = torch.empty_like(S), torch.empty_like(x_mem)
 
@@ -337,8 +347,8 @@ def main():
         e2e_steps = max(2, min(args.steps, 5))
         ms_e2e = timed(step_e2e, e2e_steps, 1, dist_on)
         e2e = {"value": units / (ms_e2e * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": S_h.numel() * S_h.element_size() + x_h.numel() * 4,
-               "d2h_bytes_per_step": 4, "steps": e2e_steps,
+               "h2d_bytes_per_step": (S_h.numel() * S_h.element_size() + x_h.numel() * 4) * world,
+               "d2h_bytes_per_step": 4 * world, "steps": e2e_steps,
                "note": "dense fp32 GSO (4N^2 B per instance) crosses PCIe every step, as the reference API passes it"}
         del S_h, x_h, S_d, x_d
 
