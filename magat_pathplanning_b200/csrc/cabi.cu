@@ -45,6 +45,42 @@ void prof_begin(cudaStream_t st) {
   if (g_prof_on.load(std::memory_order_relaxed)) prof_record(nullptr, st);
 }
 
+// ---- per-device caches (one process may drive several devices) -----------------------------------
+static std::atomic<int> g_sm_count[64];
+static std::atomic<unsigned long long> g_attr_done[32];     // [kernel id] -> bit per device
+
+static int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  return dev;
+}
+
+int device_sm_count() {
+  const int dev = current_device();
+  int n = g_sm_count[dev].load(std::memory_order_relaxed);
+  if (n > 0) return n;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return 0;
+  }
+  g_sm_count[dev].store(n, std::memory_order_relaxed);
+  return n;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: do it once per (kernel, device)
+int ensure_dyn_smem(int kernel_id, const void* func, size_t bytes, const char* name) {
+  const int dev = current_device();
+  const unsigned long long bit = 1ull << dev;
+  if (g_attr_done[kernel_id].load(std::memory_order_acquire) & bit) return MAGAT_OK;
+  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(%s, %zu B): %s", name, bytes, cudaGetErrorString(e));
+    return MAGAT_E_CUDA;
+  }
+  g_attr_done[kernel_id].fetch_or(bit, std::memory_order_release);
+  return MAGAT_OK;
+}
+
 int check_launch(const char* what, cudaStream_t st) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

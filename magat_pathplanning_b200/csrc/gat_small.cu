@@ -267,14 +267,9 @@ extern "C" int magat_gat_forward_small(const void* S, int s_dtype, const float* 
   cudaStream_t st = (cudaStream_t)stream;
   prof_begin(st);
   const size_t smem = small_smem_bytes(N, G, F, K, concat);
-  static size_t attr_bytes = 0;
-  if (smem > 48 * 1024 && smem > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(k_gat_small_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(k_gat_small_fwd): %s", cudaGetErrorString(e));
-      return MAGAT_E_CUDA;
-    }
-    attr_bytes = 200 * 1024;
+  if (smem > 48 * 1024) {
+    int rc0 = ensure_dyn_smem(KID_SMALL, (const void*)k_gat_small_fwd, 200 * 1024, "k_gat_small_fwd");
+    if (rc0) return rc0;
   }
   SmallParams sp{N, G, F, K, P, mode, concat, relu, s_dtype, S, x, x_sb, x_sn, weight, mixer, weight_bias,
                  filterWeight, bias, y, y_sb, y_sn, y_sc, aij_or_null};

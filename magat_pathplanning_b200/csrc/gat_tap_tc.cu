@@ -25,6 +25,14 @@ namespace magat {
 
 namespace {
 
+// MAGAT_DBG=<bits> switches parts of the kernel off for bottleneck experiments (1 loads, 2 smem stores,
+// 4 global stores, 16 epilogue math, 32 MMAs, 128 gather).  Compiled out unless -DMAGAT_DBG_KNOBS.
+#ifdef MAGAT_DBG_KNOBS
+#define DBGBIT(p, b) ((p).dbg & (b))
+#else
+#define DBGBIT(p, b) 0
+#endif
+
 constexpr int TN = 64;                       // nodes per tile = UMMA N
 constexpr int SK = 128;                      // K elements per stage = two 64-wide swizzle atoms
 constexpr int STAGES = 4;                    // one per producer group
@@ -49,7 +57,7 @@ struct TapParams {
   const float* bias; int relu;
   float* y; long y_sb, y_sn;     // channel stride 1
   int gather_u2;                 // 1: tap k = 2 is gathered on the fly from u_1; 0: read from the taps buffer
-  int dbg;                       // MAGAT_DBG experiments (0 in production)
+  int dbg;                       // experiment knobs; only read when built with -DMAGAT_DBG_KNOBS
 };
 
 __device__ __forceinline__ void split_store(uint8_t* hi_dst, uint8_t* lo_dst, const float4& a, const float4& b) {
@@ -163,7 +171,7 @@ __global__ void __launch_bounds__((17 + EW) * 32, 1) k_tap_tc(const __grid_const
             const int m = m0 + r0 + 16 * i;
             const float4* src = nullptr;
             const float4* msk = nullptr;
-            if (m < rows && !(p.dbg & 1)) {
+            if (m < rows && !DBGBIT(p, 1)) {
               if (seg == 0) {
                 const unsigned b = (unsigned)m / N;
                 src = x4 + (((long)b * p.x_sb + (long)((unsigned)m - b * N) * p.x_sn) >> 2) + k4;
@@ -192,7 +200,7 @@ __global__ void __launch_bounds__((17 + EW) * 32, 1) k_tap_tc(const __grid_const
             }
           }
           tc::mbar_wait(&empty[grp], phase ^ 1);
-          if (!(p.dbg & 2)) {
+          if (!DBGBIT(p, 2)) {
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
@@ -207,7 +215,7 @@ __global__ void __launch_bounds__((17 + EW) * 32, 1) k_tap_tc(const __grid_const
 #pragma unroll 1
           for (int i = 0; i < 4; ++i) {
             const int m = m0 + r0 + 16 * i;
-            const bool live = m < rows && !(p.dbg & 1) && !(p.dbg & 128);
+            const bool live = m < rows && !DBGBIT(p, 1) && !DBGBIT(p, 128);
             const unsigned bN = live ? ((unsigned)m / N) * N : 0u;
             const int32_t* nb = p.nbr_in + (unsigned)(live ? m : 0) * D;
             const float* aw_p = p.ain + ((unsigned)(live ? m : 0) * (unsigned)p.P + head) * D;
@@ -241,7 +249,7 @@ __global__ void __launch_bounds__((17 + EW) * 32, 1) k_tap_tc(const __grid_const
                   }
                 }
               }
-              if (!(p.dbg & 2))
+              if (!DBGBIT(p, 2))
                 split_store(st + hh * ATOM_BYTES + sw_off[i], st + (2 + hh) * ATOM_BYTES + sw_off[i], a, b);
             }
           }
@@ -281,7 +289,7 @@ __global__ void __launch_bounds__((17 + EW) * 32, 1) k_tap_tc(const __grid_const
           tc::tc_fence_before();
           tc::mbar_arrive(&acc_empty[acc]);    // this warp's slice of the accumulator is in registers
         }
-        if (!(p.dbg & 16)) {
+        if (!DBGBIT(p, 16)) {
           float* col = epi + (32 * hsel) * FT + f;
           if (p.relu) {
 #pragma unroll
@@ -294,7 +302,7 @@ __global__ void __launch_bounds__((17 + EW) * 32, 1) k_tap_tc(const __grid_const
       }
       tc::named_bar_sync(1, EPI_WARPS * 32);
       // 64 rows x 512 B: each warp ROWS rows, one float4 per lane
-      if (!(p.dbg & 4)) {
+      if (!DBGBIT(p, 4)) {
         const long mfirst = m0 + e * ROWS;
         unsigned bq = (unsigned)mfirst / N;
         unsigned r = (unsigned)mfirst - bq * N;
@@ -333,7 +341,7 @@ __global__ void __launch_bounds__((17 + EW) * 32, 1) k_tap_tc(const __grid_const
           const uint32_t sb = tc::smem_u32(smem + (size_t)stage * STAGE_BYTES);
           const uint32_t h_hi = tmem_base + (uint32_t)(s * (SK / 2));
           const uint32_t h_lo = h_hi + (uint32_t)(KG / 2);
-          if (!(p.dbg & 32)) {
+          if (!DBGBIT(p, 32)) {
 #pragma unroll
             for (int at = 0; at < 2; ++at) {
               const uint64_t z_hi = tc::make_sw128_desc(sb + at * ATOM_BYTES);
@@ -377,21 +385,10 @@ __global__ void __launch_bounds__(256) k_transpose_w(const float* __restrict__ W
 }
 
 int launch_tap_tc(const TapParams& tp, int P, cudaStream_t st, const char* what) {
-  static int sm_count = 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(k_tap_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(k_tap_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(k_tap_tc): %s", cudaGetErrorString(e));
-      return MAGAT_E_CUDA;
-    }
-    attr_set = true;
-  }
+  const int sm_count = device_sm_count();
+  int rc0 = ensure_dyn_smem(KID_TAP_TC4, (const void*)k_tap_tc<4>, SMEM_BYTES, "k_tap_tc<4>");
+  if (!rc0) rc0 = ensure_dyn_smem(KID_TAP_TC8, (const void*)k_tap_tc<8>, SMEM_BYTES, "k_tap_tc<8>");
+  if (rc0) return rc0;
   TapParams tq = tp;
   const char* dbg = getenv("MAGAT_DBG");
   tq.dbg = dbg ? atoi(dbg) : 0;

@@ -281,19 +281,9 @@ __global__ void __launch_bounds__(256) k_split_weights_t(const float* __restrict
 }
 
 int launch_gemm(const GemmParams& gp, cudaStream_t st, const char* what) {
-  static int sm_count = 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(k_tc_gemm): %s", cudaGetErrorString(e));
-      return MAGAT_E_CUDA;
-    }
-    attr_set = true;
-  }
+  const int sm_count = device_sm_count();
+  int rc0 = ensure_dyn_smem(KID_TC_GEMM, (const void*)k_tc_gemm, SMEM_BYTES, "k_tc_gemm");
+  if (rc0) return rc0;
   const long tiles = ((gp.M + BM - 1) / BM) * gp.Z * gp.n_tiles;
   const int grid = (int)(tiles < sm_count ? tiles : sm_count);
   k_tc_gemm<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(gp);

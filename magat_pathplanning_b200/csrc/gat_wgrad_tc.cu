@@ -282,26 +282,13 @@ __global__ void __launch_bounds__(128) k_dbias_from_colsums(const float* __restr
 }
 
 int wgrad_nslots(int Z) {
-  static int sm_count = 0;
-  if (!sm_count) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-  }
-  int s = sm_count / Z;
+  const int s = device_sm_count() / Z;
   return s < 1 ? 1 : s;
 }
 
 int launch_wgrad(WgradParams& wp, float* out, cudaStream_t st, const char* what) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(k_wgrad_tc): %s", cudaGetErrorString(e));
-      return MAGAT_E_CUDA;
-    }
-    attr_set = true;
-  }
+  int rc0 = ensure_dyn_smem(KID_WGRAD, (const void*)k_wgrad_tc, SMEM_BYTES, "k_wgrad_tc");
+  if (rc0) return rc0;
   const int nslots = wgrad_nslots(wp.Z);
   k_wgrad_tc<<<nslots * wp.Z, THREADS, SMEM_BYTES, st>>>(wp);
   int rc = check_launch(what, st);

@@ -404,14 +404,7 @@ extern "C" int magat_gso_scan(const void* S, int s_dtype, int B, int N, uint32_t
   const bool tma_ok = N % 4 == 0 && ((uintptr_t)S % 16) == 0 && N <= 2048 && (size_t)R * N * esz <= 48 * 1024 &&
                       getenv("MAGAT_SCAN_NO_TMA") == nullptr;
   if (tma_ok) {
-    static int sm_count = 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-      attr_set = true;
-    }
+    const int sm_count = device_sm_count();
     const size_t chunk_bytes = (size_t)R * N * esz;
     int nstages = (int)(kScanRing / chunk_bytes);
     if (nstages > 16) nstages = 16;
@@ -420,7 +413,8 @@ extern "C" int magat_gso_scan(const void* S, int s_dtype, int B, int N, uint32_t
     const size_t smem = (size_t)nstages * chunk_bytes + 2 * nstages * 8 + 256;
 #define MAGAT_SCAN(TT, RR)                                                                                      \
   do {                                                                                                         \
-    cudaFuncSetAttribute(k_gso_scan_tma<TT, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanRing + 1024); \
+    const int kid = KID_SCAN_BASE + (sizeof(TT) == 8 ? 6 : 0) + (RR >= 32 ? 5 : RR >= 16 ? 4 : RR >= 8 ? 3 : RR >= 4 ? 2 : RR >= 2 ? 1 : 0); \
+    if (ensure_dyn_smem(kid, (const void*)k_gso_scan_tma<TT, RR>, kScanRing + 1024, "k_gso_scan_tma")) return MAGAT_E_CUDA; \
     k_gso_scan_tma<TT, RR><<<grid, (kScanWarps + 1) * 32, smem, st>>>((const TT*)S, N, W, bands, nstages, rowbits, \
                                                                       colbits);                                \
   } while (0)
