@@ -11,6 +11,8 @@
 // mixer / weight_bias receive no gradient in KeyQuery mode (the reference leaves grad = None).
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "simt_gemm.cuh"
 
@@ -241,7 +243,8 @@ template <int PT>
 __global__ void __launch_bounds__(256, 3) k_tap_bwd_v(const float* __restrict__ x, long x_sb, long x_sn,
                                                    const float* __restrict__ taps, const float* __restrict__ att,
                                                    const int32_t* __restrict__ nbr_out, long rows, int N, int K, int D,
-                                                   int k, int first, float* __restrict__ gz, float* __restrict__ datt) {
+                                                   int k, int first, float* __restrict__ gz, float* __restrict__ datt,
+                                                   float* __restrict__ g0sum) {
   constexpr int G = 128;
   const int lane = threadIdx.x & 31;
   const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -256,6 +259,15 @@ __global__ void __launch_bounds__(256, 3) k_tap_bwd_v(const float* __restrict__ 
 #pragma unroll
       for (int q = 0; q < PT; ++q) z[q] = 0.f;
       stp<PT>(datt + ((size_t)row * D + lane) * PT, z);
+    }
+    if (g0sum != nullptr) {                 // last level: the head sum of gU_0 is all that is left of this row
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < PT; ++q) {
+        const float4 o = *reinterpret_cast<const float4*>(gz + (((size_t)row * PT + q) * K + (k - 1)) * G + g0);
+        t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
+      }
+      *reinterpret_cast<float4*>(g0sum + (size_t)row * G + g0) = t;
     }
     return;
   }
@@ -294,12 +306,24 @@ __global__ void __launch_bounds__(256, 3) k_tap_bwd_v(const float* __restrict__ 
       }
     }
   }
+  if (g0sum != nullptr) {
+    // k == 1 and only dx consumes g_0 = gU_0 + A g_1: sum it over the heads here, in the order the column
+    // kernel used (heads ascending), instead of writing P rows back and reading them again
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-  for (int q = 0; q < PT; ++q) {
-    float4* dst = reinterpret_cast<float4*>(gz + (((size_t)row * PT + q) * K + (k - 1)) * G + g0);
-    float4 o = *dst;
-    o.x += acc[q].x; o.y += acc[q].y; o.z += acc[q].z; o.w += acc[q].w;
-    *dst = o;
+    for (int q = 0; q < PT; ++q) {
+      const float4 o = *reinterpret_cast<const float4*>(gz + (((size_t)row * PT + q) * K + (k - 1)) * G + g0);
+      t.x += o.x + acc[q].x; t.y += o.y + acc[q].y; t.z += o.z + acc[q].z; t.w += o.w + acc[q].w;
+    }
+    *reinterpret_cast<float4*>(g0sum + (size_t)row * G + g0) = t;
+  } else {
+#pragma unroll
+    for (int q = 0; q < PT; ++q) {
+      float4* dst = reinterpret_cast<float4*>(gz + (((size_t)row * PT + q) * K + (k - 1)) * G + g0);
+      float4 o = *dst;
+      o.x += acc[q].x; o.y += acc[q].y; o.z += acc[q].z; o.w += acc[q].w;
+      *dst = o;
+    }
   }
   if (lane < D) {
     float* da = datt + ((size_t)row * D + lane) * PT;
@@ -373,7 +397,7 @@ __global__ void __launch_bounds__(256) k_col_bwd_kq_v(const float* __restrict__ 
                                                       const float* __restrict__ sproj,
                                                       const int32_t* __restrict__ nbr_in,
                                                       const int32_t* __restrict__ slot_in, long rows, int N, int K,
-                                                      int D, float* __restrict__ dx) {
+                                                      int D, int g0_in_dx, float* __restrict__ dx) {
   constexpr int G = 128;
   const int lane = threadIdx.x & 31;
   const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -387,10 +411,14 @@ __global__ void __launch_bounds__(256) k_col_bwd_kq_v(const float* __restrict__ 
   for (int q = 0; q < PT; ++q) de[q] = 0.f;
   if (my_i >= 0) ldp<PT>(datt + ((size_t)(b * N + my_i) * D + slot_in[row * D + lane]) * PT, de);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (g0_in_dx) {                          // k_tap_bwd_v already left sum_p g_0^p in dx
+    acc = *reinterpret_cast<const float4*>(dx + (size_t)row * G + g0);
+  } else {
 #pragma unroll
-  for (int q = 0; q < PT; ++q) {
-    const float4 v = *reinterpret_cast<const float4*>(gz + (((size_t)row * PT + q) * K + 0) * G + g0);
-    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    for (int q = 0; q < PT; ++q) {
+      const float4 v = *reinterpret_cast<const float4*>(gz + (((size_t)row * PT + q) * K + 0) * G + g0);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
   }
   for (int s = 0; s < deg; s += 2) {
     float4 rv[2][PT];
@@ -640,11 +668,15 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
                    ((uintptr_t)a->gz % 16) == 0 && ((uintptr_t)a->att % 16) == 0 && ((uintptr_t)a->datt % 16) == 0 &&
                    ((uintptr_t)a->rc % 16) == 0 && ((uintptr_t)a->sproj % 16) == 0 &&
                    (K == 1 || ((uintptr_t)a->taps % 16) == 0) && (P == 1 || P == 2 || P == 4);
+  // KeyQuery, vector kernels: g_0 is only ever read as its head sum (for dx), so the last level of the recursion
+  // writes that sum straight into dx and the column kernel picks it up there
+  const bool g0_in_dx = vec && !gm && K > 1 && a->need_dx && getenv("MAGAT_BWD_NO_G0SUM") == nullptr;
   for (int k = K - 1; k >= 1; --k) {
     const int first = k == K - 1 ? 1 : 0;
+    float* g0sum = (k == 1 && g0_in_dx) ? a->dx : nullptr;
 #define MAGAT_TB(PT) \
   k_tap_bwd_v<PT><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->taps, a->att, a->nbr_out, rows, N, K, D, k, \
-                                              first, a->gz, a->datt)
+                                              first, a->gz, a->datt, g0sum)
     if (vec && P == 4) MAGAT_TB(4);
     else if (vec && P == 2) MAGAT_TB(2);
     else if (vec && P == 1) MAGAT_TB(1);
@@ -668,7 +700,8 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
 #undef MAGAT_SB
     if ((rc = check_launch("k_softmax_bwd", st))) return rc;
 #define MAGAT_CB(PT) \
-  k_col_bwd_kq_v<PT><<<row_blocks, 256, 0, st>>>(a->gz, a->datt, a->sproj, a->nbr_in, a->slot_in, rows, N, K, D, a->dx)
+  k_col_bwd_kq_v<PT><<<row_blocks, 256, 0, st>>>(a->gz, a->datt, a->sproj, a->nbr_in, a->slot_in, rows, N, K, D, \
+                                                 g0_in_dx ? 1 : 0, a->dx)
     if (vec && a->need_dx && P == 4) MAGAT_CB(4);
     else if (vec && a->need_dx && P == 2) MAGAT_CB(2);
     else if (vec && a->need_dx && P == 1) MAGAT_CB(1);

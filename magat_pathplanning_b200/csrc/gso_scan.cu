@@ -119,6 +119,13 @@ __global__ void __launch_bounds__(256) k_gso_scan_v4(const T* __restrict__ S, in
 // xor-shuffles per row) and accumulate the transposed column words in registers over the 32 rows of a band.
 template <typename T> struct Edge4;
 template <> struct Edge4<float> {
+  // Conservative "could these four entries hold an edge?": the OR of the four magnitudes (as integers) is at
+  // least their maximum, so a value <= bits(1e-9f) proves that none of them is an edge; NaNs compare high and
+  // fall through to the exact test.  The GSO is ~0.35 % dense, so most 16 B pieces stop here.
+  static __device__ __forceinline__ bool maybe(const float* p) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    return ((v.x | v.y | v.z | v.w) & 0x7fffffffu) > 0x3089705fu;
+  }
   static __device__ __forceinline__ uint32_t nib(const float* p) {
     const float4 v = *reinterpret_cast<const float4*>(p);
     return (uint32_t)(fabsf(v.x) > 1e-9f) | ((uint32_t)(fabsf(v.y) > 1e-9f) << 1) |
@@ -126,6 +133,12 @@ template <> struct Edge4<float> {
   }
 };
 template <> struct Edge4<double> {
+  static __device__ __forceinline__ bool maybe(const double* p) {
+    const uint4 a = *reinterpret_cast<const uint4*>(p);
+    const uint4 b = *(reinterpret_cast<const uint4*>(p) + 1);
+    // high words carry sign / exponent: |v| > 1e-9 needs (hi & 0x7fffffff) >= 0x3e112e0b (hi word of 1e-9)
+    return ((a.y | a.w | b.y | b.w) & 0x7fffffffu) >= 0x3e112e0bu;
+  }
   static __device__ __forceinline__ uint32_t nib(const double* p) {
     const double2 a = *reinterpret_cast<const double2*>(p);
     const double2 b = *(reinterpret_cast<const double2*>(p) + 1);
@@ -209,27 +222,31 @@ __global__ void __launch_bounds__((kScanWarps + 1) * 32, 1) k_gso_scan_tma(const
           if (seg >= segs) break;
           const int j0 = seg * 128 + lane * 4;
           const bool jin = j0 < N;
-          uint32_t nb[R], v[R];
-#pragma unroll
-          for (int r = 0; r < R; ++r) nb[r] = (jin && r < nrows) ? Edge4<T>::nib(tile + (size_t)r * N + j0) : 0u;
+          // rows of this 128-column piece that may hold an edge at all (warp-uniform mask)
+          uint32_t live = 0u;
 #pragma unroll
           for (int r = 0; r < R; ++r) {
-            const int rr = c * R + r;                       // row inside the band
-            col[q][0] |= (nb[r] & 1u) << rr;
-            col[q][1] |= ((nb[r] >> 1) & 1u) << rr;
-            col[q][2] |= ((nb[r] >> 2) & 1u) << rr;
-            col[q][3] |= ((nb[r] >> 3) & 1u) << rr;
-            v[r] = nb[r] << (4 * (lane & 7));
+            const bool m = jin && r < nrows && Edge4<T>::maybe(tile + (size_t)r * N + j0);
+            live |= (__any_sync(0xffffffffu, m) ? 1u : 0u) << r;
           }
-#pragma unroll
-          for (int o = 1; o <= 4; o <<= 1)
-#pragma unroll
-            for (int r = 0; r < R; ++r) v[r] |= __shfl_xor_sync(0xffffffffu, v[r], o);
           const int w = seg * 4 + (lane >> 3);
-          if ((lane & 7) == 0 && w < W) {
+          const bool wr = (lane & 7) == 0 && w < W;
 #pragma unroll
-            for (int r = 0; r < R; ++r)
-              if (r < nrows) rowbits[((size_t)b * N + r_first + r) * W + w] = v[r];
+          for (int r = 0; r < R; ++r) {
+            uint32_t v = 0u;
+            if ((live >> r) & 1u) {
+              const uint32_t nb = jin ? Edge4<T>::nib(tile + (size_t)r * N + j0) : 0u;
+              const int rr = c * R + r;                       // row inside the band
+              col[q][0] |= (nb & 1u) << rr;
+              col[q][1] |= ((nb >> 1) & 1u) << rr;
+              col[q][2] |= ((nb >> 2) & 1u) << rr;
+              col[q][3] |= ((nb >> 3) & 1u) << rr;
+              v = nb << (4 * (lane & 7));
+              v |= __shfl_xor_sync(0xffffffffu, v, 1);
+              v |= __shfl_xor_sync(0xffffffffu, v, 2);
+              v |= __shfl_xor_sync(0xffffffffu, v, 4);
+            }
+            if (wr && r < nrows) rowbits[((size_t)b * N + r_first + r) * W + w] = v;
           }
         }
         __syncwarp();
@@ -275,6 +292,47 @@ __global__ void __launch_bounds__(256) k_gso_stats(const uint32_t* __restrict__ 
     mi = max(mi, id);
     tot += od;
   }
+  sym = __all_sync(0xffffffffu, sym);
+  if (lane == 0) {
+    atomicMax(&stats[0], mo);
+    atomicMax(&stats[1], mi);
+    if (tot) atomicAdd(&stats[2], tot);
+    if (!sym) atomicExch(&stats[3], 0);
+  }
+}
+
+// Same statistics, W == 4 * LPR: LPR lanes share a row (one uint4 of each mask per lane), so a warp digests
+// 32 / LPR rows per load pair and the per-row sums cost log2(LPR) shuffles instead of five.
+template <int LPR>
+__global__ void __launch_bounds__(256) k_gso_stats_v(const uint4* __restrict__ rowbits4,
+                                                     const uint4* __restrict__ colbits4, long n4,
+                                                     int32_t* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const long stride = (long)gridDim.x * blockDim.x;
+  int mo = 0, mi = 0, tot = 0;
+  bool sym = true;
+  for (long base = (long)blockIdx.x * blockDim.x + (threadIdx.x - lane); base < n4; base += stride) {
+    const long t = base + lane;
+    uint4 r = make_uint4(0u, 0u, 0u, 0u), c = r;
+    if (t < n4) {
+      r = __ldcs(rowbits4 + t);
+      c = __ldcs(colbits4 + t);
+    }
+    int od = __popc(r.x) + __popc(r.y) + __popc(r.z) + __popc(r.w);
+    int id = __popc(c.x) + __popc(c.y) + __popc(c.z) + __popc(c.w);
+    sym = sym && r.x == c.x && r.y == c.y && r.z == c.z && r.w == c.w;
+    tot += od;
+#pragma unroll
+    for (int o = 1; o < LPR; o <<= 1) {
+      od += __shfl_xor_sync(0xffffffffu, od, o);
+      id += __shfl_xor_sync(0xffffffffu, id, o);
+    }
+    mo = max(mo, od);
+    mi = max(mi, id);
+  }
+  mo = warp_max_i(mo);
+  mi = warp_max_i(mi);
+  tot = warp_sum_i(tot);
   sym = __all_sync(0xffffffffu, sym);
   if (lane == 0) {
     atomicMax(&stats[0], mo);
@@ -359,6 +417,56 @@ __global__ void __launch_bounds__(256) k_build_ell(const uint32_t* __restrict__ 
     if (gl == 0 && s < deg_out) slot_out[row * D + s] = rank;
   }
   for (int s = deg_out + lane; s < D; s += 32) slot_out[row * D + s] = 0;
+}
+
+// ---- two-step list builder --------------------------------------------------------------------------
+// Step 1, one warp per node: out-list from the row bits, in-list from the column bits.
+__global__ void __launch_bounds__(256) k_build_lists(const uint32_t* __restrict__ rowbits,
+                                                     const uint32_t* __restrict__ colbits, long rows, int W, int D,
+                                                     int32_t* __restrict__ nbr_out, int32_t* __restrict__ nbr_in) {
+  const int lane = threadIdx.x & 31;
+  const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  list_bits(rowbits + row * W, W, D, lane, nbr_out + row * D);
+  list_bits(colbits + row * W, W, D, lane, nbr_in + row * D);
+}
+
+// position of `key` in the ascending, -1 padded list l[0..D) (the key is known to be present)
+__device__ __forceinline__ int find_slot(const int32_t* __restrict__ l, int D, int key) {
+  if ((D & 3) == 0 && D <= 32 && ((uintptr_t)l & 15) == 0) {
+    int pos = 0;
+    for (int s0 = 0; s0 < D; s0 += 4) {
+      const int4 v = __ldg(reinterpret_cast<const int4*>(l + s0));
+      // entries below the key (padding is -1: mask it out with the unsigned compare)
+      pos += ((unsigned)v.x < (unsigned)key) + ((unsigned)v.y < (unsigned)key) + ((unsigned)v.z < (unsigned)key) +
+             ((unsigned)v.w < (unsigned)key);
+    }
+    return pos;
+  }
+  int lo = 0, hi = D;                       // lower bound on the unsigned order (-1 sorts last)
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if ((unsigned)__ldg(l + mid) < (unsigned)key) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+// Step 2, one thread per list entry: where the same edge sits in the list of its other end point.
+__global__ void __launch_bounds__(256) k_build_slots(const int32_t* __restrict__ nbr_out,
+                                                     const int32_t* __restrict__ nbr_in, long rows, int N, int D,
+                                                     int32_t* __restrict__ slot_in, int32_t* __restrict__ slot_out) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rows * D) return;
+  const long row = t / D;
+  const long b = row / N;
+  const int n = (int)(row - b * N);
+  const int i = nbr_in[t];
+  slot_in[t] = i >= 0 ? find_slot(nbr_out + (b * N + i) * D, D, n) : 0;
+  if (slot_out != nullptr) {
+    const int j = nbr_out[t];
+    slot_out[t] = j >= 0 ? find_slot(nbr_in + (b * N + j) * D, D, n) : 0;
+  }
 }
 
 // att[B][N][D][P] -> dense aij[B][P][N][N] (mean_heads == 0) or head-mean [B][N][N].
@@ -448,8 +556,25 @@ extern "C" int magat_gso_scan(const void* S, int s_dtype, int B, int N, uint32_t
   int rc = check_launch("k_gso_scan", (cudaStream_t)stream);
   if (rc) return rc;
   const long rows = (long)B * N;
-  int blocks = (int)min((long)148 * 8, (rows + 7) / 8);
-  k_gso_stats<<<blocks, 256, 0, st>>>(rowbits, colbits, rows, W, stats);
+  const int lpr = W / 4;
+  if (W % 4 == 0 && lpr <= 32 && (lpr & (lpr - 1)) == 0 && ((uintptr_t)rowbits % 16) == 0 &&
+      ((uintptr_t)colbits % 16) == 0) {
+    const long n4 = rows * lpr;
+    const int blocks = (int)min((long)148 * 8, (n4 + 255) / 256);
+    const uint4* r4 = reinterpret_cast<const uint4*>(rowbits);
+    const uint4* c4 = reinterpret_cast<const uint4*>(colbits);
+    switch (lpr) {
+      case 1: k_gso_stats_v<1><<<blocks, 256, 0, st>>>(r4, c4, n4, stats); break;
+      case 2: k_gso_stats_v<2><<<blocks, 256, 0, st>>>(r4, c4, n4, stats); break;
+      case 4: k_gso_stats_v<4><<<blocks, 256, 0, st>>>(r4, c4, n4, stats); break;
+      case 8: k_gso_stats_v<8><<<blocks, 256, 0, st>>>(r4, c4, n4, stats); break;
+      case 16: k_gso_stats_v<16><<<blocks, 256, 0, st>>>(r4, c4, n4, stats); break;
+      default: k_gso_stats_v<32><<<blocks, 256, 0, st>>>(r4, c4, n4, stats); break;
+    }
+  } else {
+    int blocks = (int)min((long)148 * 8, (rows + 7) / 8);
+    k_gso_stats<<<blocks, 256, 0, st>>>(rowbits, colbits, rows, W, stats);
+  }
   return check_launch("k_gso_stats", (cudaStream_t)stream);
 }
 
@@ -461,10 +586,18 @@ extern "C" int magat_gso_build_ell(const uint32_t* rowbits, const uint32_t* colb
   MAGAT_REQUIRE(B >= 1 && N >= 1 && D >= 1, MAGAT_E_BAD_ARG, "magat_gso_build_ell: B=%d N=%d D=%d", B, N, D);
   const long rows = (long)B * N;
   const int W = (N + 31) / 32;
-  prof_begin((cudaStream_t)stream);
-  k_build_ell<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(rowbits, colbits, rows, N, W, D,
-                                                               nbr_out, nbr_in, slot_in, slot_out);
-  return check_launch("k_build_ell", (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin(st);
+  if (getenv("MAGAT_BUILD_ELL_V1") != nullptr) {       // the one-kernel builder (ranks by popcount), kept for A/B timing
+    k_build_ell<<<cdiv(rows, 8), 256, 0, st>>>(rowbits, colbits, rows, N, W, D, nbr_out, nbr_in, slot_in, slot_out);
+    return check_launch("k_build_ell", st);
+  }
+  MAGAT_REQUIRE(rows * D < (1l << 40), MAGAT_E_UNSUPPORTED, "magat_gso_build_ell: B*N*D too large");
+  k_build_lists<<<cdiv(rows, 8), 256, 0, st>>>(rowbits, colbits, rows, W, D, nbr_out, nbr_in);
+  int rc = check_launch("k_build_lists", st);
+  if (rc) return rc;
+  k_build_slots<<<cdiv(rows * D, 256), 256, 0, st>>>(nbr_out, nbr_in, rows, N, D, slot_in, slot_out);
+  return check_launch("k_build_slots", st);
 }
 
 extern "C" int magat_gat_attention_dense(const float* att, const int32_t* nbr_out, int B, int N,

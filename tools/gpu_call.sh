@@ -1,0 +1,27 @@
+#!/bin/bash
+# One gpurun call: GPU parity tests, the bench line, and (optionally) ncu captures.  Outputs under gpurun_out/.
+#   tools/gpu_call.sh <tag> [tests] [bench] [ncu_train] [ncu_fwd] [launches]
+set -u
+tag=$1; shift
+out=gpurun_out/$tag
+mkdir -p "$out"
+for what in "$@"; do
+  case $what in
+    tests)
+      timeout 600 python -m pytest tests -m gpu -x -q > "$out/tests.log" 2>&1; echo "tests rc=$?" | tee -a "$out/rc.txt"; tail -5 "$out/tests.log";;
+    bench)
+      timeout 600 python bench.py > "$out/bench.json" 2> "$out/bench.err"; echo "bench rc=$?" | tee -a "$out/rc.txt"; python tools/bench_summary.py "$out/bench.json" 2>/dev/null | head -60;;
+    ncu_train)
+      timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -f -k "regex:k_tap_tc|k_tap_bwd|k_wgrad_tc|k_attention|k_tap_gather|k_gso_scan|k_tc_gemm|k_col_bwd|k_softmax_bwd" -o "$out/prof_train" \
+        python tools/profile_step.py --what train > "$out/ncu_train.log" 2>&1; echo "ncu_train rc=$?" | tee -a "$out/rc.txt";;
+    ncu_fwd)
+      timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -f -o "$out/prof_fwd" \
+        python tools/profile_step.py --what fwd > "$out/ncu_fwd.log" 2>&1; echo "ncu_fwd rc=$?" | tee -a "$out/rc.txt";;
+    launches)
+      timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
+        --profile-from-start off --csv --log-file "$out/launches_train.csv" python tools/profile_step.py --what train \
+        > "$out/launches.log" 2>&1; echo "launches rc=$?" | tee -a "$out/rc.txt";;
+    *) echo "unknown step $what";;
+  esac
+done
+ls -la "$out"
