@@ -52,6 +52,10 @@ __device__ __forceinline__ int warp_excl_scan_i(int v, int lane) {
   return s - v;
 }
 
+// batch index of a flat node row when the host has checked B * N < 2^31: a 32-bit division (about a fifth of
+// the instructions of the emulated 64-bit one, which used to be ~15 % of the warp-per-node kernels)
+__device__ __forceinline__ long batch_of32(long row, int N) { return (long)((unsigned)row / (unsigned)N); }
+
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace magat

@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(256, 3) k_tap_bwd_v(const float* __restrict__ 
   const int lane = threadIdx.x & 31;
   const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= rows) return;
-  const long b = row / N;
+  const long b = batch_of32(row, N);
   const int g0 = lane * 4;
   const int my_j = lane < D ? nbr_out[row * D + lane] : -1;
   const int deg = __popc(__ballot_sync(0xffffffffu, my_j >= 0));
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(256) k_softmax_bwd_kq_v(const float* __restric
   const int lane = threadIdx.x & 31;
   const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= rows) return;
-  const long b = row / N;
+  const long b = batch_of32(row, N);
   const int g0 = lane * 4;
   const int my_j = lane < D ? nbr_out[row * D + lane] : -1;
   const int deg = __popc(__ballot_sync(0xffffffffu, my_j >= 0));
@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(256) k_col_bwd_kq_v(const float* __restrict__ 
   const int lane = threadIdx.x & 31;
   const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= rows) return;
-  const long b = row / N;
+  const long b = batch_of32(row, N);
   const int g0 = lane * 4;
   const int my_i = lane < D ? nbr_in[row * D + lane] : -1;
   const int deg = __popc(__ballot_sync(0xffffffffu, my_i >= 0));
@@ -667,7 +667,7 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
   const bool vec = G == 128 && D <= 32 && (a->x_sn % 4) == 0 && (a->x_sb % 4) == 0 && ((uintptr_t)a->x % 16) == 0 &&
                    ((uintptr_t)a->gz % 16) == 0 && ((uintptr_t)a->att % 16) == 0 && ((uintptr_t)a->datt % 16) == 0 &&
                    ((uintptr_t)a->rc % 16) == 0 && ((uintptr_t)a->sproj % 16) == 0 &&
-                   (K == 1 || ((uintptr_t)a->taps % 16) == 0) && (P == 1 || P == 2 || P == 4);
+                   (K == 1 || ((uintptr_t)a->taps % 16) == 0) && (P == 1 || P == 2 || P == 4) && rows < (1l << 31);
   // KeyQuery, vector kernels: g_0 is only ever read as its head sum (for dx), so the last level of the recursion
   // writes that sum straight into dx and the column kernel picks it up there
   const bool g0_in_dx = vec && !gm && K > 1 && a->need_dx && getenv("MAGAT_BWD_NO_G0SUM") == nullptr;

@@ -56,18 +56,25 @@ struct TapParams {
   const float* H;        // filterWeight [P][F][K*G]
   const float* bias; int relu;
   float* y; long y_sb, y_sn;     // channel stride 1
+  int epi_direct;                // 1: y rows are flat (y_sb == N * y_sn): the epilogue stores straight from registers
   int gather_u2;                 // 1: tap k = 2 is gathered on the fly from u_1; 0: read from the taps buffer
   int dbg;                       // experiment knobs; only read when built with -DMAGAT_DBG_KNOBS
 };
 
-__device__ __forceinline__ void split_store(uint8_t* hi_dst, uint8_t* lo_dst, const float4& a, const float4& b) {
+// hi_dst / lo_dst are shared-window addresses (tc::smem_u32): st.shared, not the generic ST the compiler emits for
+// pointers it cannot prove to be shared (the first source-level profile showed ST.E / LD.E on every smem access
+// of this kernel)
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void split_store(uint32_t hi_dst, uint32_t lo_dst, const float4& a, const float4& b) {
   uint4 hi, lo;
   tc::split2(a.x, a.y, hi.x, lo.x);
   tc::split2(a.z, a.w, hi.y, lo.y);
   tc::split2(b.x, b.y, hi.z, lo.z);
   tc::split2(b.z, b.w, hi.w, lo.w);
-  *reinterpret_cast<uint4*>(hi_dst) = hi;
-  *reinterpret_cast<uint4*>(lo_dst) = lo;
+  st_shared_v4(hi_dst, hi);
+  st_shared_v4(lo_dst, lo);
 }
 __device__ __forceinline__ void fma44(float4& acc, float a, const float4& v) {
   acc.x = fmaf(a, v.x, acc.x); acc.y = fmaf(a, v.y, acc.y); acc.z = fmaf(a, v.z, acc.z); acc.w = fmaf(a, v.w, acc.w);
@@ -151,7 +158,7 @@ __global__ void __launch_bounds__((17 + EW) * 32, 1) k_tap_tc(const __grid_const
     const long x_hoff = p.x_hmul ? (long)(head / p.x_hdiv) * p.x_hmul : 0;
     const float4* x4 = reinterpret_cast<const float4*>(p.x + x_hoff);
     const float4* mk4 = p.mask ? reinterpret_cast<const float4*>(p.mask + x_hoff) : nullptr;
-    uint8_t* st = smem + (size_t)grp * STAGE_BYTES;
+    const uint32_t st = tc::smem_u32(smem + (size_t)grp * STAGE_BYTES);
     uint32_t sw_off[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) sw_off[i] = tc::sw128_offset(r0 + 16 * i, c16);
@@ -274,6 +281,48 @@ __global__ void __launch_bounds__((17 + EW) * 32, 1) k_tap_tc(const __grid_const
     const unsigned N = (unsigned)p.N;
     int acc = 0;
     uint32_t acc_phase = 0;
+    if (p.epi_direct) {
+      // Flat output rows: lane f of the warp holds feature f of 32 consecutive nodes, so one scalar store per node
+      // is a full 128 B line of that node's row -- no transposition, no shared memory, no barrier between the
+      // epilogue warps.  (The staged variant below paced every use of this kernel: the MMA issuer spent its
+      // time waiting for acc_empty, profiles/r01b_ncu_tap_tc_roles.md.)
+      for (long tile = slot; tile < tiles; tile += nslots) {
+        const long m0 = tile * TN;
+        tc::mbar_wait(&acc_full[acc], acc_phase);
+        tc::tc_fence_after();
+#pragma unroll
+        for (int hh = 0; hh < HALVES; ++hh) {
+          const int hsel = HALVES == 1 ? half : hh;
+          const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(ACC_COL0 + acc * TN + 32 * hsel);
+          float v[32];
+          tc::tmem_ld32(taddr, v);
+          tc::tmem_ld_wait();
+          if (hh == HALVES - 1) {
+            tc::tc_fence_before();
+            tc::mbar_arrive(&acc_empty[acc]);    // this warp's slice of the accumulator is in registers
+          }
+          const long mrow = m0 + 32 * hsel;
+          float* dst = p.y + mrow * p.y_sn + (long)head * FT + f;
+          const long left = p.rows - mrow;
+          if (left >= 32) {
+#pragma unroll
+            for (int n = 0; n < 32; ++n) {
+              float o = v[n] + bias;
+              if (p.relu) o = fmaxf(o, 0.f);
+              __stcs(dst + (long)n * p.y_sn, o);
+            }
+          } else {
+#pragma unroll
+            for (int n = 0; n < 32; ++n) {
+              float o = v[n] + bias;
+              if (p.relu) o = fmaxf(o, 0.f);
+              if (n < left) __stcs(dst + (long)n * p.y_sn, o);
+            }
+          }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    } else
     for (long tile = slot; tile < tiles; tile += nslots) {
       const long m0 = tile * TN;
       tc::mbar_wait(&acc_full[acc], acc_phase);
@@ -392,6 +441,7 @@ int launch_tap_tc(const TapParams& tp, int P, cudaStream_t st, const char* what)
   TapParams tq = tp;
   const char* dbg = getenv("MAGAT_DBG");
   tq.dbg = dbg ? atoi(dbg) : 0;
+  tq.epi_direct = (tp.y_sb == (long)tp.N * tp.y_sn && getenv("MAGAT_EPI_STAGED") == nullptr) ? 1 : 0;
   const long tiles = (tp.rows + TN - 1) / TN;
   long slots = sm_count / P;
   if (slots < 1) slots = 1;

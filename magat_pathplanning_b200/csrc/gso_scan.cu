@@ -119,13 +119,6 @@ __global__ void __launch_bounds__(256) k_gso_scan_v4(const T* __restrict__ S, in
 // xor-shuffles per row) and accumulate the transposed column words in registers over the 32 rows of a band.
 template <typename T> struct Edge4;
 template <> struct Edge4<float> {
-  // Conservative "could these four entries hold an edge?": the OR of the four magnitudes (as integers) is at
-  // least their maximum, so a value <= bits(1e-9f) proves that none of them is an edge; NaNs compare high and
-  // fall through to the exact test.  The GSO is ~0.35 % dense, so most 16 B pieces stop here.
-  static __device__ __forceinline__ bool maybe(const float* p) {
-    const uint4 v = *reinterpret_cast<const uint4*>(p);
-    return ((v.x | v.y | v.z | v.w) & 0x7fffffffu) > 0x3089705fu;
-  }
   static __device__ __forceinline__ uint32_t nib(const float* p) {
     const float4 v = *reinterpret_cast<const float4*>(p);
     return (uint32_t)(fabsf(v.x) > 1e-9f) | ((uint32_t)(fabsf(v.y) > 1e-9f) << 1) |
@@ -133,12 +126,6 @@ template <> struct Edge4<float> {
   }
 };
 template <> struct Edge4<double> {
-  static __device__ __forceinline__ bool maybe(const double* p) {
-    const uint4 a = *reinterpret_cast<const uint4*>(p);
-    const uint4 b = *(reinterpret_cast<const uint4*>(p) + 1);
-    // high words carry sign / exponent: |v| > 1e-9 needs (hi & 0x7fffffff) >= 0x3e112e0b (hi word of 1e-9)
-    return ((a.y | a.w | b.y | b.w) & 0x7fffffffu) >= 0x3e112e0bu;
-  }
   static __device__ __forceinline__ uint32_t nib(const double* p) {
     const double2 a = *reinterpret_cast<const double2*>(p);
     const double2 b = *(reinterpret_cast<const double2*>(p) + 1);
@@ -222,31 +209,27 @@ __global__ void __launch_bounds__((kScanWarps + 1) * 32, 1) k_gso_scan_tma(const
           if (seg >= segs) break;
           const int j0 = seg * 128 + lane * 4;
           const bool jin = j0 < N;
-          // rows of this 128-column piece that may hold an edge at all (warp-uniform mask)
-          uint32_t live = 0u;
+          uint32_t nb[R], v[R];
+#pragma unroll
+          for (int r = 0; r < R; ++r) nb[r] = (jin && r < nrows) ? Edge4<T>::nib(tile + (size_t)r * N + j0) : 0u;
 #pragma unroll
           for (int r = 0; r < R; ++r) {
-            const bool m = jin && r < nrows && Edge4<T>::maybe(tile + (size_t)r * N + j0);
-            live |= (__any_sync(0xffffffffu, m) ? 1u : 0u) << r;
+            const int rr = c * R + r;                       // row inside the band
+            col[q][0] |= (nb[r] & 1u) << rr;
+            col[q][1] |= ((nb[r] >> 1) & 1u) << rr;
+            col[q][2] |= ((nb[r] >> 2) & 1u) << rr;
+            col[q][3] |= ((nb[r] >> 3) & 1u) << rr;
+            v[r] = nb[r] << (4 * (lane & 7));
           }
-          const int w = seg * 4 + (lane >> 3);
-          const bool wr = (lane & 7) == 0 && w < W;
 #pragma unroll
-          for (int r = 0; r < R; ++r) {
-            uint32_t v = 0u;
-            if ((live >> r) & 1u) {
-              const uint32_t nb = jin ? Edge4<T>::nib(tile + (size_t)r * N + j0) : 0u;
-              const int rr = c * R + r;                       // row inside the band
-              col[q][0] |= (nb & 1u) << rr;
-              col[q][1] |= ((nb >> 1) & 1u) << rr;
-              col[q][2] |= ((nb >> 2) & 1u) << rr;
-              col[q][3] |= ((nb >> 3) & 1u) << rr;
-              v = nb << (4 * (lane & 7));
-              v |= __shfl_xor_sync(0xffffffffu, v, 1);
-              v |= __shfl_xor_sync(0xffffffffu, v, 2);
-              v |= __shfl_xor_sync(0xffffffffu, v, 4);
-            }
-            if (wr && r < nrows) rowbits[((size_t)b * N + r_first + r) * W + w] = v;
+          for (int o = 1; o <= 4; o <<= 1)
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[r] |= __shfl_xor_sync(0xffffffffu, v[r], o);
+          const int w = seg * 4 + (lane >> 3);
+          if ((lane & 7) == 0 && w < W) {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+              if (r < nrows) rowbits[((size_t)b * N + r_first + r) * W + w] = v[r];
           }
         }
         __syncwarp();
@@ -458,14 +441,78 @@ __global__ void __launch_bounds__(256) k_build_slots(const int32_t* __restrict__
                                                      int32_t* __restrict__ slot_in, int32_t* __restrict__ slot_out) {
   const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= rows * D) return;
-  const long row = t / D;
-  const long b = row / N;
+  long row, b;
+  if (rows * D < (1l << 32)) {              // 32-bit divisions (the 64-bit ones are emulated)
+    row = (long)((unsigned)t / (unsigned)D);
+    b = (long)((unsigned)row / (unsigned)N);
+  } else {
+    row = t / D;
+    b = row / N;
+  }
   const int n = (int)(row - b * N);
   const int i = nbr_in[t];
   slot_in[t] = i >= 0 ? find_slot(nbr_out + (b * N + i) * D, D, n) : 0;
   if (slot_out != nullptr) {
     const int j = nbr_out[t];
     slot_out[t] = j >= 0 ? find_slot(nbr_in + (b * N + j) * D, D, n) : 0;
+  }
+}
+
+// ---- thread-per-row variants (W % 4 == 0, D % 4 == 0, D <= 32, 16 B aligned buffers) ---------------------
+// The warp-per-row kernels above spend ~100 instructions per row on shuffles for ~3.5 edges; here a lane owns
+// a whole row: WV independent 16 B loads, then the few set bits are written behind a -1 fill of the row.
+// blockIdx.y selects the list: 0 = out (row bits), 1 = in (column bits).
+__global__ void __launch_bounds__(128) k_build_lists_t(const uint4* __restrict__ rowbits4,
+                                                       const uint4* __restrict__ colbits4, long rows, int WV, int D,
+                                                       int32_t* __restrict__ nbr_out, int32_t* __restrict__ nbr_in) {
+  const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  const uint4* src = (blockIdx.y ? colbits4 : rowbits4) + row * WV;
+  int32_t* out = (blockIdx.y ? nbr_in : nbr_out) + row * D;
+  for (int s = 0; s < D; s += 4) *reinterpret_cast<int4*>(out + s) = make_int4(-1, -1, -1, -1);
+  int pos = 0;
+  for (int v0 = 0; v0 < WV; v0 += 8) {
+    uint4 w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = (v0 + i < WV) ? __ldcs(src + v0 + i) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t ws[4] = {w[i].x, w[i].y, w[i].z, w[i].w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t word = ws[c];
+        const int base = ((v0 + i) * 4 + c) * 32;
+        while (word) {
+          const int bit = __ffs(word) - 1;
+          word &= word - 1;
+          if (pos < D) out[pos] = base + bit;      // same thread, program order: lands on top of the fill
+          ++pos;
+        }
+      }
+    }
+  }
+}
+
+// slots of one list row per thread; blockIdx.y: 0 = slot_in (search the senders' out-lists), 1 = slot_out
+__global__ void __launch_bounds__(128) k_build_slots_t(const int32_t* __restrict__ nbr_out,
+                                                       const int32_t* __restrict__ nbr_in, long rows, int N, int D,
+                                                       int32_t* __restrict__ slot_in, int32_t* __restrict__ slot_out) {
+  const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  const bool second = blockIdx.y != 0;
+  const int32_t* mine = (second ? nbr_out : nbr_in) + row * D;
+  const int32_t* other = second ? nbr_in : nbr_out;
+  int32_t* slot = (second ? slot_out : slot_in) + row * D;
+  const long b = batch_of32(row, N);
+  const int n = (int)(row - b * N);
+  const int32_t* ob = other + b * N * D;
+  for (int s0 = 0; s0 < D; s0 += 4) {
+    const int4 id = __ldg(reinterpret_cast<const int4*>(mine + s0));
+    const int ids[4] = {id.x, id.y, id.z, id.w};
+    int r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) r[u] = ids[u] >= 0 ? find_slot(ob + (long)ids[u] * D, D, n) : 0;
+    *reinterpret_cast<int4*>(slot + s0) = make_int4(r[0], r[1], r[2], r[3]);
   }
 }
 
@@ -593,9 +640,22 @@ extern "C" int magat_gso_build_ell(const uint32_t* rowbits, const uint32_t* colb
     return check_launch("k_build_ell", st);
   }
   MAGAT_REQUIRE(rows * D < (1l << 40), MAGAT_E_UNSUPPORTED, "magat_gso_build_ell: B*N*D too large");
+  auto al16 = [](const void* q) { return ((uintptr_t)q % 16) == 0; };
+  const bool per_thread = W % 4 == 0 && D % 4 == 0 && D <= 32 && rows < (1l << 31) && al16(rowbits) && al16(colbits) &&
+                          al16(nbr_out) && al16(nbr_in) && al16(slot_in) && (slot_out == nullptr || al16(slot_out)) &&
+                          getenv("MAGAT_BUILD_WARP") == nullptr;
+  int rc;
+  if (per_thread) {
+    k_build_lists_t<<<dim3(cdiv(rows, 128), 2), 128, 0, st>>>(reinterpret_cast<const uint4*>(rowbits),
+                                                              reinterpret_cast<const uint4*>(colbits), rows, W / 4, D,
+                                                              nbr_out, nbr_in);
+    if ((rc = check_launch("k_build_lists", st))) return rc;
+    k_build_slots_t<<<dim3(cdiv(rows, 128), slot_out ? 2 : 1), 128, 0, st>>>(nbr_out, nbr_in, rows, N, D, slot_in,
+                                                                            slot_out);
+    return check_launch("k_build_slots", st);
+  }
   k_build_lists<<<cdiv(rows, 8), 256, 0, st>>>(rowbits, colbits, rows, W, D, nbr_out, nbr_in);
-  int rc = check_launch("k_build_lists", st);
-  if (rc) return rc;
+  if ((rc = check_launch("k_build_lists", st))) return rc;
   k_build_slots<<<cdiv(rows * D, 256), 256, 0, st>>>(nbr_out, nbr_in, rows, N, D, slot_in, slot_out);
   return check_launch("k_build_slots", st);
 }

@@ -21,6 +21,11 @@ for what in "$@"; do
       timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
         --profile-from-start off --csv --log-file "$out/launches_train.csv" python tools/profile_step.py --what train \
         > "$out/launches.log" 2>&1; echo "launches rc=$?" | tee -a "$out/rc.txt";;
+    ab:*)
+      # A/B of one environment knob: tools/gpu_call.sh tag ab:MAGAT_X=1
+      kv=${what#ab:}
+      env "$kv" timeout 300 python bench.py --no-cpu-baseline --no-e2e --steps 10 > "$out/bench_$kv.json" 2> "$out/bench_$kv.err"
+      echo "== $kv rc=$?"; python tools/bench_summary.py "$out/bench_$kv.json" 2>/dev/null | head -60;;
     *) echo "unknown step $what";;
   esac
 done
