@@ -257,79 +257,6 @@ __global__ void __launch_bounds__(256, 4) k_tap_gather_v(const float* __restrict
   }
 }
 
-// The same gather once the receiver-major weights exist (ain written by the attention kernel) and D % 4 == 0:
-// neighbour ids and weights are read with warp-uniform 16 B loads (one broadcast transaction each) instead of
-// being handed round by shuffles, which halves the instruction count of the kernel.
-template <int PT>
-__global__ void __launch_bounds__(256, 4) k_tap_gather_v2(const float* __restrict__ x, long x_sb, long x_sn,
-                                                       const int32_t* __restrict__ nbr_in,
-                                                       const float* __restrict__ ain, long rows, int N, int G,
-                                                       int K, int D, int k, float* __restrict__ taps) {
-  const int lane = threadIdx.x & 31;
-  const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (row >= rows) return;
-  const long b = batch_of32(row, N);
-  const int4* nb4 = reinterpret_cast<const int4*>(nbr_in + row * D);
-  const float* aw = ain + (size_t)row * PT * D;
-  const int Km1 = K - 1;
-  const float* xb = x + b * x_sb;
-  const float* tb = taps + ((size_t)(b * N) * PT * Km1 + (k >= 2 ? k - 2 : 0)) * G;   // tap k-1 of node 0 of the batch
-  const size_t t_node = (size_t)PT * Km1 * G, t_head = (size_t)Km1 * G;
-  for (int gb = 0; gb < G; gb += 128) {
-    const int g0 = gb + lane * 4;
-    const bool act = g0 < G;
-    float4 acc[PT];
-#pragma unroll
-    for (int p = 0; p < PT; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s0 = 0; s0 < D; s0 += 4) {
-      const int4 id = __ldg(nb4 + (s0 >> 2));
-      if (id.x < 0) break;                               // lists are packed; warp-uniform
-      const int ids[4] = {id.x, id.y, id.z, id.w};
-      float wgt[PT][4];
-#pragma unroll
-      for (int p = 0; p < PT; ++p) {
-        const float4 w4 = __ldg(reinterpret_cast<const float4*>(aw + p * D + s0));
-        // entries past the in-degree were never written: force 0 so 0 * garbage never makes a NaN
-        wgt[p][0] = w4.x; wgt[p][1] = ids[1] >= 0 ? w4.y : 0.f;
-        wgt[p][2] = ids[2] >= 0 ? w4.z : 0.f; wgt[p][3] = ids[3] >= 0 ? w4.w : 0.f;
-      }
-      if (!act) continue;
-      if (k == 1) {
-        float4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          v[u] = ids[u] >= 0 ? __ldg(reinterpret_cast<const float4*>(xb + (long)ids[u] * x_sn + g0))
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-          for (int p = 0; p < PT; ++p) fma4(acc[p], wgt[p][u], v[u]);
-      } else {
-#pragma unroll
-        for (int u = 0; u < 4; u += 2) {
-          float4 v[2][PT];
-#pragma unroll
-          for (int w = 0; w < 2; ++w)
-#pragma unroll
-            for (int p = 0; p < PT; ++p)
-              v[w][p] = ids[u + w] >= 0
-                            ? *reinterpret_cast<const float4*>(tb + (size_t)ids[u + w] * t_node + p * t_head + g0)
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int w = 0; w < 2; ++w)
-#pragma unroll
-            for (int p = 0; p < PT; ++p) fma4(acc[p], wgt[p][u + w], v[w][p]);
-        }
-      }
-    }
-    if (act) {
-#pragma unroll
-      for (int p = 0; p < PT; ++p)
-        *reinterpret_cast<float4*>(taps + (((size_t)row * PT + p) * Km1 + (k - 1)) * G + g0) = acc[p];
-    }
-  }
-}
-
 // KeyQuery scores + row softmax, D <= 32: lane s owns slot s; G = 128 * GV.
 template <int PT, int GV>
 __global__ void __launch_bounds__(256) k_attention_kq_v(const float* __restrict__ x, long x_sb, long x_sn,
@@ -392,117 +319,6 @@ __global__ void __launch_bounds__(256) k_attention_kq_v(const float* __restrict_
       float* r = ain + ((size_t)(b * N + my_j) * PT) * D + slot_out[row * D + lane];
 #pragma unroll
       for (int p = 0; p < PT; ++p) r[(size_t)p * D] = a[p];
-    }
-  }
-}
-
-// Sum NV per-lane values over the warp at once: every step halves the number of live values while it doubles
-// the lanes each of them has absorbed, so NV sums cost NV - 1 + (5 - log2 NV) shuffles instead of 5 NV.
-// The lane's result is the sum with index (lane >> (5 - log2 NV)) (lanes of one group all hold it).
-template <int NV>
-__device__ __forceinline__ float warp_multi_sum(float (&v)[NV], int lane) {
-  int off = 16;
-#pragma unroll
-  for (int n = NV; n > 1; n >>= 1, off >>= 1) {
-    const bool hi = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < n / 2; ++i) {
-      const float keep = hi ? v[i + n / 2] : v[i];
-      const float send = hi ? v[i] : v[i + n / 2];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-#pragma unroll
-  for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
-  return v[0];
-}
-template <int NV> struct Log2 { static constexpr int v = 1 + Log2<NV / 2>::v; };
-template <> struct Log2<1> { static constexpr int v = 0; };
-
-// KeyQuery scores + row softmax, G = 128, D <= 32: lane s owns slot s.  Four neighbour rows are in flight per
-// round and their 4 * PT dot products are reduced together (warp_multi_sum); with D <= 16 the softmax
-// reductions stay inside the lower half-warp.
-template <int PT>
-__global__ void __launch_bounds__(256) k_attention_kq_v2(const float* __restrict__ x, long x_sb, long x_sn,
-                                                         const float* __restrict__ sproj,
-                                                         const int32_t* __restrict__ nbr_out, long rows, int N,
-                                                         int D, float* __restrict__ att,
-                                                         const int32_t* __restrict__ slot_out,
-                                                         float* __restrict__ ain) {
-  constexpr int G = 128, NV = 4 * PT, SH = 5 - Log2<NV>::v;
-  const int lane = threadIdx.x & 31;
-  const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (row >= rows) return;
-  const long b = batch_of32(row, N);
-  const int my_j = lane < D ? __ldg(nbr_out + row * D + lane) : -1;
-  const int deg = __popc(__ballot_sync(0xffffffffu, my_j >= 0));
-  float e[PT];
-#pragma unroll
-  for (int p = 0; p < PT; ++p) e[p] = -INFINITY;
-  if (deg > 0) {
-    float4 r[PT];
-#pragma unroll
-    for (int p = 0; p < PT; ++p)
-      r[p] = __ldg(reinterpret_cast<const float4*>(sproj + ((size_t)row * PT + p) * G + lane * 4));
-    const float* xb = x + b * x_sb + lane * 4;
-    for (int s0 = 0; s0 < deg; s0 += 4) {
-      float4 xv[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int j = __shfl_sync(0xffffffffu, my_j, (s0 + u) & 31);
-        xv[u] = (s0 + u < deg) ? __ldg(reinterpret_cast<const float4*>(xb + (long)j * x_sn))
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      float d[NV];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int p = 0; p < PT; ++p) d[u * PT + p] = dot4(r[p], xv[u]);
-      const float tot = warp_multi_sum<NV>(d, lane);      // sum (u, p) sits in the lanes (u * PT + p) << SH ...
-      const bool mine = (lane >> 2) == (s0 >> 2);
-#pragma unroll
-      for (int p = 0; p < PT; ++p) {
-        const float v = __shfl_sync(0xffffffffu, tot, (((lane & 3) * PT + p) << SH) & 31);
-        if (mine) e[p] = v;
-      }
-    }
-  }
-  float a[PT];
-  if (D <= 16) {
-#pragma unroll
-    for (int p = 0; p < PT; ++p) {
-      const float ev = lane < deg ? e[p] : -INFINITY;
-      float mx = ev;
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      const float ex = lane < deg ? expf(ev - mx) : 0.f;
-      float sum = ex;
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      a[p] = lane < deg ? ex / sum : 0.f;
-    }
-  } else {
-#pragma unroll
-    for (int p = 0; p < PT; ++p) {
-      const float ev = lane < deg ? e[p] : -INFINITY;
-      const float mx = warp_max(ev);
-      const float ex = lane < deg ? expf(ev - mx) : 0.f;
-      const float sum = warp_sum(ex);
-      a[p] = lane < deg ? ex / sum : 0.f;
-    }
-  }
-  if (lane < D) {
-    float* dst = att + ((size_t)row * D + lane) * PT;
-    if (PT == 4) {
-      *reinterpret_cast<float4*>(dst) = make_float4(a[0], a[1 % PT], a[2 % PT], a[3 % PT]);
-    } else {
-#pragma unroll
-      for (int p = 0; p < PT; ++p) dst[p] = a[p];
-    }
-    if (ain != nullptr && lane < deg) {
-      float* rr = ain + ((size_t)(b * N + my_j) * PT) * D + slot_out[row * D + lane];
-#pragma unroll
-      for (int p = 0; p < PT; ++p) rr[(size_t)p * D] = a[p];
     }
   }
 }
@@ -606,20 +422,12 @@ int run_tap_gather(const float* x, long x_sb, long x_sn, const float* att, const
 #define MAGAT_GATHER(PT) \
   k_tap_gather_v<PT><<<row_blocks, 256, 0, st>>>(x, x_sb, x_sn, att, nbr_in, slot_in, rows, N, G, K, D, k, taps, ain, \
                                                  ain_ready)
-#define MAGAT_GATHER2(PT) \
-  k_tap_gather_v2<PT><<<row_blocks, 256, 0, st>>>(x, x_sb, x_sn, nbr_in, ain, rows, N, G, K, D, k, taps)
-  const bool v2 = vec_ok && ain != nullptr && ain_ready && D % 4 == 0 && (((uintptr_t)ain) % 16 == 0) &&
-                  (((uintptr_t)nbr_in) % 16 == 0) && getenv("MAGAT_GATHER_V1") == nullptr;
-  if (v2 && P == 4) MAGAT_GATHER2(4);
-  else if (v2 && P == 2) MAGAT_GATHER2(2);
-  else if (v2 && P == 1) MAGAT_GATHER2(1);
-  else if (vec_ok && P == 4) MAGAT_GATHER(4);
+  if (vec_ok && P == 4) MAGAT_GATHER(4);
   else if (vec_ok && P == 2) MAGAT_GATHER(2);
   else if (vec_ok && P == 1) MAGAT_GATHER(1);
   else
     k_tap_gather<<<row_blocks, 256, 0, st>>>(x, x_sb, x_sn, att, nbr_in, slot_in, rows, N, G, P, K, D, k, taps);
 #undef MAGAT_GATHER
-#undef MAGAT_GATHER2
   return check_launch("k_tap_gather", st);
 }
 
@@ -669,14 +477,7 @@ static int forward_impl(const magat_gat_fwd_args* a, cudaStream_t st, bool use_t
 #define MAGAT_ATT(PT, GV) \
   k_attention_kq_v<PT, GV><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj, a->nbr_out, rows, N, D, a->att, \
                                                        so, ain_w)
-#define MAGAT_ATT2(PT) \
-  k_attention_kq_v2<PT><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj, a->nbr_out, rows, N, D, a->att, \
-                                                    so, ain_w)
-    const bool v2 = fast && G == 128 && getenv("MAGAT_ATT_V1") == nullptr;
-    if (v2 && P == 4) MAGAT_ATT2(4);
-    else if (v2 && P == 2) MAGAT_ATT2(2);
-    else if (v2 && P == 1) MAGAT_ATT2(1);
-    else if (fast && P == 4 && G == 128) MAGAT_ATT(4, 1);
+    if (fast && P == 4 && G == 128) MAGAT_ATT(4, 1);
     else if (fast && P == 4 && G == 256) MAGAT_ATT(4, 2);
     else if (fast && P == 2 && G == 128) MAGAT_ATT(2, 1);
     else if (fast && P == 2 && G == 256) MAGAT_ATT(2, 2);
@@ -686,7 +487,6 @@ static int forward_impl(const magat_gat_fwd_args* a, cudaStream_t st, bool use_t
       k_attention<MAGAT_MODE_KEYQUERY><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj, a->nbr_out,
                                                                     rows, N, G, P, D, a->att, so, ain_w);
 #undef MAGAT_ATT
-#undef MAGAT_ATT2
   } else {
     float* cvec = a->wprep;
     float* dvec = a->wprep + (size_t)P * 2 * G;

@@ -56,6 +56,7 @@ struct TapParams {
   const float* H;        // filterWeight [P][F][K*G]
   const float* bias; int relu;
   float* y; long y_sb, y_sn;     // channel stride 1
+  int nout;                      // v2 kernel: P counts weight blocks; nout consecutive blocks share one operand tile
   int epi_direct;                // 1: y rows are flat (y_sb == N * y_sn): the epilogue stores straight from registers
   int gather_u2;                 // 1: tap k = 2 is gathered on the fly from u_1; 0: read from the taps buffer
   int dbg;                       // experiment knobs; only read when built with -DMAGAT_DBG_KNOBS
@@ -421,6 +422,304 @@ __global__ void __launch_bounds__((17 + EW) * 32, 1) k_tap_tc(const __grid_const
   }
 }
 
+// ================================================================================================================
+// v2: the same GEMM with a TMA-fed operand pipeline.
+//
+// The source-level profile of the kernel above (profiles/r01b_tap_tc_lsu.md) showed the LSU data pipe 71 % busy and
+// every role queueing behind it: producer threads holding 16 global loads each (spilling), generic-space shared
+// stores, the staged epilogue.  Here nothing but the unavoidable fp32 -> bf16 hi/lo conversion goes through the
+// LSU:
+//   warp 21      copy issuer: raw fp32 node rows -> shared-memory ring with cp.async.bulk (one 32 KB copy when the
+//                64 rows are contiguous, else one 512 B copy per row), completion on an mbarrier; 128 KB in flight
+//   warps 0-15   converters, two groups of eight: LDS.128 of a raw row piece (conflict free), optional ReLU mask,
+//                hi/lo split, two 8 B shared stores into the SWIZZLE_128B operand stage of the group
+//   warp 20      MMA issuer; with nout > 1 the SAME operand stage is multiplied by nout weight blocks held in TMEM
+//                (backward: the K taps of a head share dP; score projection: two heads share x), so the input is
+//                read and converted once instead of nout times
+//   warps 16-19  epilogue: tcgen05.ld, bias / ReLU, one coalesced 128 B store per node and warp
+constexpr int V2_NOP = 2;                               // operand stages (one per converter group)
+constexpr int V2_RAW_BYTES = 128 * 1024;                // raw ring: 4 slots of 32 KB, or 2 of 64 KB with a mask
+constexpr int V2_CONV_WARPS = 16, V2_GROUP = 256;
+constexpr int V2_EPI_WARP0 = 16, V2_EPI_WARPS = 4, V2_MMA_WARP = 20, V2_TMA_WARP = 21, V2_THREADS = 22 * 32;
+constexpr size_t V2_SMEM_BYTES = (size_t)V2_NOP * STAGE_BYTES + V2_RAW_BYTES + 1024 + 256;
+
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+
+template <bool MASKED>
+__global__ void __launch_bounds__(V2_THREADS, 1) k_tap_tc2(const __grid_constant__ TapParams p) {
+  constexpr int NRAW = MASKED ? 2 : 4;
+  constexpr int SLOT_BYTES = V2_RAW_BYTES / NRAW;
+  constexpr int TILE_BYTES = TN * SK * 4;               // 32 KB of fp32
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* raw = smem + (size_t)V2_NOP * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(raw + V2_RAW_BYTES);
+  uint64_t* op_full = bars;                  // [2]  256 converter arrivals
+  uint64_t* op_empty = bars + 2;             // [2]  tcgen05.commit
+  uint64_t* raw_full = bars + 4;             // [4]  expect_tx + bulk copies
+  uint64_t* raw_empty = bars + 8;            // [4]  8 warp arrivals
+  uint64_t* acc_full = bars + 12;            // [2]
+  uint64_t* acc_empty = bars + 14;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nout = p.nout;
+  const int ngroups = p.P / nout;                        // head groups: a CTA serves heads hg*nout .. hg*nout+nout-1
+  const int hg = blockIdx.x % ngroups;
+  const int slot = blockIdx.x / ngroups, nslots = gridDim.x / ngroups;
+  const int nst = (p.K * p.G) / SK;                      // 128-wide K slices per output tile
+  const int sps = p.G / SK;
+  const int KS = nst * SK;                               // reduction length of one output
+  const int KGtot = nout * KS;                           // <= 384: weight columns hi [0, KGtot/2), lo [KGtot/2, KGtot)
+  const long tiles = (p.rows + TN - 1) / TN;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < V2_NOP; ++s) {
+      tc::mbar_init(&op_full[s], V2_GROUP);
+      tc::mbar_init(&op_empty[s], 1);
+    }
+    for (int s = 0; s < NRAW; ++s) {
+      tc::mbar_init(&raw_full[s], 1);
+      tc::mbar_init(&raw_empty[s], V2_GROUP / 32);
+    }
+    for (int a = 0; a < 2; ++a) {
+      tc::mbar_init(&acc_full[a], 1);
+      tc::mbar_init(&acc_empty[a], V2_EPI_WARPS * 32);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == V2_MMA_WARP) tc::tmem_alloc<512>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // ---- weight blocks of this head group -> TMEM --------------------------------------------------------
+  if (warp < 4) {
+    const int f = warp * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int o = 0; o < nout; ++o) {
+      const float* hrow = p.H + ((size_t)(hg * nout + o) * FT + f) * KS;
+      for (int k0 = 0; k0 < KS; k0 += 32) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(hrow + k0 + 2 * j));
+          tc::split2(v.x, v.y, hi[j], lo[j]);
+          tc::split2(v.z, v.w, hi[j + 1], lo[j + 1]);
+        }
+        const uint32_t col = (uint32_t)((o * KS + k0) / 2);
+        tc::tmem_st16(lane_addr + col, hi);
+        tc::tmem_st16(lane_addr + (uint32_t)(KGtot / 2) + col, lo);
+      }
+    }
+    tc::tmem_st_wait();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+
+  if (warp == V2_TMA_WARP) {
+    // ===== copy issuer ====================================================================================
+    const unsigned N = (unsigned)p.N;
+    const long x_hoff = p.x_hmul ? (long)((hg * nout) / p.x_hdiv) * p.x_hmul : 0;
+    const bool x_flat = p.x_sb == (long)p.N * p.x_sn;
+    const bool x_block = x_flat && p.x_sn == SK && p.G == SK;          // 64 rows = one contiguous 32 KB block
+    const size_t u_row = (size_t)p.P * (p.K - 1) * p.G;                  // floats per node in the taps buffer
+    unsigned q = 0;
+    for (long tile = slot; tile < tiles; tile += nslots) {
+      const long m0 = tile * TN;
+      const int nvalid = (int)((p.rows - m0) < TN ? (p.rows - m0) : TN);
+      for (int s = 0; s < nst; ++s, ++q) {
+        const int r = (int)(q % NRAW);
+        const uint32_t ph = (q / NRAW) & 1u;
+        tc::mbar_wait(&raw_empty[r], ph ^ 1);
+        uint8_t* dst = raw + (size_t)r * SLOT_BYTES;
+        const int seg = s / sps;
+        const int koff = (s - seg * sps) * SK;
+        if (lane == 0) tc::mbar_arrive_expect_tx(&raw_full[r], (uint32_t)(nvalid * SK * 4) * (MASKED ? 2u : 1u));
+        __syncwarp();
+        if (seg == 0 && x_block && !MASKED) {
+          if (lane == 0) tc::bulk_g2s(dst, p.x + x_hoff + m0 * SK, (uint32_t)(nvalid * SK * 4), &raw_full[r]);
+        } else {
+          for (int i = lane; i < nvalid; i += 32) {
+            const long m = m0 + i;
+            const float* src;
+            const float* msk = nullptr;
+            if (seg == 0) {
+              long off;
+              if (x_flat) {
+                off = m * p.x_sn;
+              } else {
+                const unsigned b = (unsigned)m / N;
+                off = (long)b * p.x_sb + (long)((unsigned)m - b * N) * p.x_sn;
+              }
+              src = p.x + x_hoff + off + koff;
+              if (MASKED) {
+                const unsigned b = (unsigned)m / N;
+                msk = p.mask + x_hoff + (long)b * p.m_sb + (long)((unsigned)m - b * N) * p.m_sn + koff;
+              }
+            } else {
+              src = p.u1 + (size_t)m * u_row + (size_t)(hg * nout) * (p.K - 1) * p.G + (size_t)(seg - 1) * p.G + koff;
+            }
+            tc::bulk_g2s(dst + (size_t)i * (SK * 4), src, SK * 4, &raw_full[r]);
+            if (MASKED) tc::bulk_g2s(dst + TILE_BYTES + (size_t)i * (SK * 4), msk, SK * 4, &raw_full[r]);
+          }
+        }
+      }
+    }
+  } else if (warp < V2_CONV_WARPS) {
+    // ===== converters =====================================================================================
+    // Group g (8 warps) owns operand stage g and builds every stage-chunk q with q % 2 == g.  Warp w of the group
+    // converts rows w, w + 8, ...; lane l owns k = 4l .. 4l+3 of the 128-wide slice (one conflict-free LDS.128 per
+    // row), i.e. half h = l & 1 of 16 B chunk c = (l >> 1) & 7 of swizzle atom l >> 4.
+    const unsigned grp = warp >> 3;
+    const int wg = warp & 7;
+    const uint32_t op_s = tc::smem_u32(smem + (size_t)grp * STAGE_BYTES) + (uint32_t)((lane >> 4) * ATOM_BYTES) +
+                          (uint32_t)((lane & 1) * 8);
+    const int c = (lane >> 1) & 7;
+    const uint32_t raw_s = tc::smem_u32(raw) + (uint32_t)(lane * 16);
+    unsigned q = 0;
+    for (long tile = slot; tile < tiles; tile += nslots) {
+      for (int s = 0; s < nst; ++s, ++q) {
+        if ((q & 1u) != grp) continue;
+        const int r = (int)(q % NRAW);
+        tc::mbar_wait(&raw_full[r], (q / NRAW) & 1u);
+        tc::mbar_wait(&op_empty[grp], ((q >> 1) & 1u) ^ 1u);
+        const uint32_t src = raw_s + (uint32_t)(r * SLOT_BYTES);
+        constexpr int RB = MASKED ? 4 : 8;              // rows in flight per thread
+#pragma unroll
+        for (int r0 = 0; r0 < 8; r0 += RB) {
+          float4 v[RB];
+#pragma unroll
+          for (int i = 0; i < RB; ++i) v[i] = ld_shared_v4(src + (uint32_t)((wg + 8 * (r0 + i)) * (SK * 4)));
+          if (MASKED) {
+#pragma unroll
+            for (int i = 0; i < RB; ++i) {
+              const float4 mk = ld_shared_v4(src + (uint32_t)TILE_BYTES + (uint32_t)((wg + 8 * (r0 + i)) * (SK * 4)));
+              v[i].x = mk.x > 0.f ? v[i].x : 0.f; v[i].y = mk.y > 0.f ? v[i].y : 0.f;
+              v[i].z = mk.z > 0.f ? v[i].z : 0.f; v[i].w = mk.w > 0.f ? v[i].w : 0.f;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < RB; ++i) {
+            const int row = wg + 8 * (r0 + i);
+            uint32_t h0, l0, h1, l1;
+            tc::split2(v[i].x, v[i].y, h0, l0);
+            tc::split2(v[i].z, v[i].w, h1, l1);
+            const uint32_t off = tc::sw128_offset(row, c);
+            st_shared_v2(op_s + off, h0, h1);
+            st_shared_v2(op_s + 2 * ATOM_BYTES + off, l0, l1);
+          }
+        }
+        tc::fence_proxy_async();
+        tc::mbar_arrive(&op_full[grp]);
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&raw_empty[r]);
+      }
+    }
+  } else if (warp < V2_MMA_WARP) {
+    // ===== epilogue =======================================================================================
+    const int qd = warp - V2_EPI_WARP0;                  // TMEM lane quarter (= warp % 4)
+    const int f = qd * 32 + lane;
+    const float bias = p.bias ? __ldg(p.bias + f) : 0.f;
+    unsigned oc = 0;
+    for (long tile = slot; tile < tiles; tile += nslots) {
+      const long m0 = tile * TN;
+      for (int o = 0; o < nout; ++o, ++oc) {
+        const int acc = (int)(oc & 1u);
+        tc::mbar_wait(&acc_full[acc], (oc >> 1) & 1u);
+        tc::tc_fence_after();
+        float* ybase = p.y + (long)(hg * nout + o) * FT + f;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(ACC_COL0 + acc * TN + 32 * hh);
+          float v[32];
+          tc::tmem_ld32(taddr, v);
+          tc::tmem_ld_wait();
+          if (hh == 1) {
+            tc::tc_fence_before();
+            tc::mbar_arrive(&acc_empty[acc]);
+          }
+          const long mrow = m0 + 32 * hh;
+          float* dst = ybase + mrow * p.y_sn;
+          const long left = p.rows - mrow;
+          if (left >= 32) {
+#pragma unroll
+            for (int n = 0; n < 32; ++n) {
+              float ov = v[n] + bias;
+              if (p.relu) ov = fmaxf(ov, 0.f);
+              __stcs(dst + (long)n * p.y_sn, ov);
+            }
+          } else {
+#pragma unroll
+            for (int n = 0; n < 32; ++n) {
+              float ov = v[n] + bias;
+              if (p.relu) ov = fmaxf(ov, 0.f);
+              if (n < left) __stcs(dst + (long)n * p.y_sn, ov);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == V2_MMA_WARP) {
+    // ===== MMA issuer =====================================================================================
+    constexpr uint32_t idesc = tc::make_idesc_bf16(FT, TN);
+    unsigned q = 0, oc = 0;
+    for (long tile = slot; tile < tiles; tile += nslots) {
+      for (int o = 0; o < nout; ++o, ++oc) {
+        const int acc = (int)(oc & 1u);
+        tc::mbar_wait(&acc_empty[acc], ((oc >> 1) & 1u) ^ 1u);
+        tc::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(ACC_COL0 + acc * TN);
+        for (int s = 0; s < nst; ++s) {
+          const unsigned qq = q + (unsigned)s;
+          const int stage = (int)(qq & 1u);
+          if (o == 0) {
+            tc::mbar_wait(&op_full[stage], (qq >> 1) & 1u);
+            tc::tc_fence_after();
+          }
+          if (lane == 0) {
+            const uint32_t sb = tc::smem_u32(smem + (size_t)stage * STAGE_BYTES);
+            const uint32_t h_hi = tmem_base + (uint32_t)((o * nst + s) * (SK / 2));
+            const uint32_t h_lo = h_hi + (uint32_t)(KGtot / 2);
+#pragma unroll
+            for (int at = 0; at < 2; ++at) {
+              const uint64_t z_hi = tc::make_sw128_desc(sb + at * ATOM_BYTES);
+              const uint64_t z_lo = tc::make_sw128_desc(sb + (2 + at) * ATOM_BYTES);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t adv = (uint64_t)((kk * 32) >> 4);
+                const uint32_t col = (uint32_t)(at * 32 + kk * 8);
+                tc::umma_bf16_ts(tmem_d, h_hi + col, z_hi + adv, idesc, (s | at | kk) != 0);
+                tc::umma_bf16_ts(tmem_d, h_lo + col, z_hi + adv, idesc, 1);
+                tc::umma_bf16_ts(tmem_d, h_hi + col, z_lo + adv, idesc, 1);
+              }
+            }
+            if (o == nout - 1) tc::umma_commit(&op_empty[stage]);
+            if (s == nst - 1) tc::umma_commit(&acc_full[acc]);
+          }
+          __syncwarp();
+        }
+      }
+      q += (unsigned)nst;
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == V2_MMA_WARP) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // Wt[p][g'][g] = W[p][g][g']: the KeyQuery score projection R = X W_p as the same "weights in TMEM" GEMM
 __global__ void __launch_bounds__(256) k_transpose_w(const float* __restrict__ W, int G, long n,
                                                      float* __restrict__ Wt) {
@@ -433,16 +732,42 @@ __global__ void __launch_bounds__(256) k_transpose_w(const float* __restrict__ W
   Wt[i] = W[(p * G + g) * G + gp];
 }
 
+// v2 needs flat outputs, contiguous 512 B source rows, no on-the-fly second tap; nout > 1 only with one K slice
+bool tap_tc2_ok(const TapParams& tp) {
+  if (getenv("MAGAT_TAP_V1") != nullptr) return false;
+  if (tp.nout < 1 || tp.P % tp.nout != 0) return false;
+  const int nst = tp.K * tp.G / SK;
+  if (tp.G % SK != 0 || tp.nout * nst * SK > ACC_COL0 || (tp.nout > 1 && nst != 1)) return false;
+  if (tp.y_sb != (long)tp.N * tp.y_sn || tp.gather_u2) return false;
+  if (tp.mask && ((tp.m_sn % 4) != 0 || (tp.m_sb % 4) != 0 || ((uintptr_t)tp.mask % 16) != 0)) return false;
+  return true;
+}
+
 int launch_tap_tc(const TapParams& tp, int P, cudaStream_t st, const char* what) {
   const int sm_count = device_sm_count();
-  int rc0 = ensure_dyn_smem(KID_TAP_TC4, (const void*)k_tap_tc<4>, SMEM_BYTES, "k_tap_tc<4>");
-  if (!rc0) rc0 = ensure_dyn_smem(KID_TAP_TC8, (const void*)k_tap_tc<8>, SMEM_BYTES, "k_tap_tc<8>");
-  if (rc0) return rc0;
   TapParams tq = tp;
   const char* dbg = getenv("MAGAT_DBG");
   tq.dbg = dbg ? atoi(dbg) : 0;
-  tq.epi_direct = (tp.y_sb == (long)tp.N * tp.y_sn && getenv("MAGAT_EPI_STAGED") == nullptr) ? 1 : 0;
   const long tiles = (tp.rows + TN - 1) / TN;
+  if (tap_tc2_ok(tp)) {
+    int rc0 = ensure_dyn_smem(KID_TAP_TC2, (const void*)k_tap_tc2<false>, V2_SMEM_BYTES, "k_tap_tc2<false>");
+    if (!rc0) rc0 = ensure_dyn_smem(KID_TAP_TC2M, (const void*)k_tap_tc2<true>, V2_SMEM_BYTES, "k_tap_tc2<true>");
+    if (rc0) return rc0;
+    const int ngroups = tp.P / tp.nout;
+    long slots = sm_count / ngroups;
+    if (slots < 1) slots = 1;
+    if (slots > tiles) slots = tiles;
+    tq.epi_direct = 1;
+    if (tp.mask) k_tap_tc2<true><<<(int)(slots * ngroups), V2_THREADS, V2_SMEM_BYTES, st>>>(tq);
+    else k_tap_tc2<false><<<(int)(slots * ngroups), V2_THREADS, V2_SMEM_BYTES, st>>>(tq);
+    return check_launch(what, st);
+  }
+  // v1: one weight block per CTA
+  tq.nout = 1;
+  int rc0 = ensure_dyn_smem(KID_TAP_TC4, (const void*)k_tap_tc<4>, SMEM_BYTES, "k_tap_tc<4>");
+  if (!rc0) rc0 = ensure_dyn_smem(KID_TAP_TC8, (const void*)k_tap_tc<8>, SMEM_BYTES, "k_tap_tc<8>");
+  if (rc0) return rc0;
+  tq.epi_direct = (tp.y_sb == (long)tp.N * tp.y_sn && getenv("MAGAT_EPI_STAGED") == nullptr) ? 1 : 0;
   long slots = sm_count / P;
   if (slots < 1) slots = 1;
   if (slots > tiles) slots = tiles;
@@ -477,6 +802,8 @@ int score_tc_forward(const magat_gat_fwd_args* a, float* wt, cudaStream_t st) {
   tp.H = wt;
   tp.bias = nullptr; tp.relu = 0;
   tp.y = a->sproj; tp.y_sb = (long)a->N * a->P * a->G; tp.y_sn = (long)a->P * a->G;
+  // heads that share one converted x tile (their W_p^T blocks sit side by side in TMEM)
+  tp.nout = (a->P % 3 == 0) ? 3 : (a->P % 2 == 0) ? 2 : 1;
   return launch_tap_tc(tp, a->P, st, "k_tap_tc(score projection)");
 }
 
@@ -511,7 +838,9 @@ int gz_tc_backward(const magat_gat_bwd_args* a, float* ht, cudaStream_t st) {
   if (rc) return rc;
   TapParams tp{};
   tp.rows = (long)a->B * a->N;
+  // P*K weight blocks Ht[p*K + k]; the K blocks of a head share one converted dP_p tile (nout = K)
   tp.N = a->N; tp.G = a->F; tp.K = 1; tp.P = a->P * a->K; tp.D = a->D;
+  tp.nout = a->K;
   tp.x = a->dy; tp.x_sb = a->dy_sb; tp.x_sn = a->dy_sn;
   tp.x_hdiv = a->K; tp.x_hmul = a->F;
   tp.mask = a->relu ? a->y : nullptr; tp.m_sb = a->y_sb; tp.m_sn = a->y_sn;
@@ -559,6 +888,7 @@ int tap_tc_forward(const magat_gat_fwd_args* a, cudaStream_t st) {
   tp.H = a->filterWeight;
   tp.bias = a->bias; tp.relu = a->relu;
   tp.y = a->y; tp.y_sb = a->y_sb; tp.y_sn = a->y_sn;
+  tp.nout = 1;
   return launch_tap_tc(tp, a->P, st, "k_tap_tc(fused taps + projection)");
 }
 

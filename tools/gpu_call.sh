@@ -7,6 +7,11 @@ out=gpurun_out/$tag
 mkdir -p "$out"
 for what in "$@"; do
   case $what in
+    quick)
+      # the tcgen05 path alone under a short timeout: a pipeline deadlock must not eat the call
+      timeout 240 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "tc_path" > "$out/quick.log" 2>&1; rc=$?
+      echo "quick rc=$rc" | tee -a "$out/rc.txt"; tail -15 "$out/quick.log"
+      if [ $rc -ne 0 ]; then echo "quick failed: skipping the rest"; break; fi;;
     tests)
       timeout 600 python -m pytest tests -m gpu -x -q > "$out/tests.log" 2>&1; echo "tests rc=$?" | tee -a "$out/rc.txt"; tail -5 "$out/tests.log";;
     bench)
