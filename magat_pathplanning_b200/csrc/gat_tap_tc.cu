@@ -15,6 +15,7 @@
 //               ([64 nodes x 128 k] -> hi/lo tiles, SWIZZLE_128B K-major) into its own smem stage
 //   warps 16-23 epilogue (warp 16+e: TMEM lane quarter e%4, node half e/4)
 //   warp  24    MMA issuer (one thread): 24 MMAs per stage, then tcgen05.commit frees the stage
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -46,6 +47,10 @@ constexpr int ACC_COL0 = 384;                // accumulators: columns 384 + 64 a
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
 
 struct TapParams {
+  // v2 kernel: 2-D views [rows][row stride] of x, the optional mask and the taps buffer; one box = 64 rows x 128 floats
+  alignas(64) CUtensorMap tm_x;
+  alignas(64) CUtensorMap tm_m;
+  alignas(64) CUtensorMap tm_u;
   long rows;             // B * N
   int N, G, K, P, D;
   const float* x; long x_sb, x_sn;
@@ -429,8 +434,9 @@ __global__ void __launch_bounds__((17 + EW) * 32, 1) k_tap_tc(const __grid_const
 // every role queueing behind it: producer threads holding 16 global loads each (spilling), generic-space shared
 // stores, the staged epilogue.  Here nothing but the unavoidable fp32 -> bf16 hi/lo conversion goes through the
 // LSU:
-//   warp 21      copy issuer: raw fp32 node rows -> shared-memory ring with cp.async.bulk (one 32 KB copy when the
-//                64 rows are contiguous, else one 512 B copy per row), completion on an mbarrier; 128 KB in flight
+//   warp 21      copy issuer: raw fp32 node rows -> shared-memory ring, one cp.async.bulk.tensor.2d per 64 x 128 box
+//                (per-row 512 B bulk copies capped the K-tap use at ~70 cycles per row), mbarrier completion;
+//                128 KB in flight
 //   warps 0-15   converters, two groups of eight: LDS.128 of a raw row piece (conflict free), optional ReLU mask,
 //                hi/lo split, two 8 B shared stores into the SWIZZLE_128B operand stage of the group
 //   warp 20      MMA issuer; with nout > 1 the SAME operand stage is multiplied by nout weight blocks held in TMEM
@@ -528,49 +534,29 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_tap_tc2(const __grid_constant
 
   if (warp == V2_TMA_WARP) {
     // ===== copy issuer ====================================================================================
-    const unsigned N = (unsigned)p.N;
-    const long x_hoff = p.x_hmul ? (long)((hg * nout) / p.x_hdiv) * p.x_hmul : 0;
-    const bool x_flat = p.x_sb == (long)p.N * p.x_sn;
-    const bool x_block = x_flat && p.x_sn == SK && p.G == SK;          // 64 rows = one contiguous 32 KB block
-    const size_t u_row = (size_t)p.P * (p.K - 1) * p.G;                  // floats per node in the taps buffer
-    unsigned q = 0;
-    for (long tile = slot; tile < tiles; tile += nslots) {
-      const long m0 = tile * TN;
-      const int nvalid = (int)((p.rows - m0) < TN ? (p.rows - m0) : TN);
-      for (int s = 0; s < nst; ++s, ++q) {
-        const int r = (int)(q % NRAW);
-        const uint32_t ph = (q / NRAW) & 1u;
-        tc::mbar_wait(&raw_empty[r], ph ^ 1);
-        uint8_t* dst = raw + (size_t)r * SLOT_BYTES;
-        const int seg = s / sps;
-        const int koff = (s - seg * sps) * SK;
-        if (lane == 0) tc::mbar_arrive_expect_tx(&raw_full[r], (uint32_t)(nvalid * SK * 4) * (MASKED ? 2u : 1u));
-        __syncwarp();
-        if (seg == 0 && x_block && !MASKED) {
-          if (lane == 0) tc::bulk_g2s(dst, p.x + x_hoff + m0 * SK, (uint32_t)(nvalid * SK * 4), &raw_full[r]);
-        } else {
-          for (int i = lane; i < nvalid; i += 32) {
-            const long m = m0 + i;
-            const float* src;
-            const float* msk = nullptr;
-            if (seg == 0) {
-              long off;
-              if (x_flat) {
-                off = m * p.x_sn;
-              } else {
-                const unsigned b = (unsigned)m / N;
-                off = (long)b * p.x_sb + (long)((unsigned)m - b * N) * p.x_sn;
-              }
-              src = p.x + x_hoff + off + koff;
-              if (MASKED) {
-                const unsigned b = (unsigned)m / N;
-                msk = p.mask + x_hoff + (long)b * p.m_sb + (long)((unsigned)m - b * N) * p.m_sn + koff;
-              }
-            } else {
-              src = p.u1 + (size_t)m * u_row + (size_t)(hg * nout) * (p.K - 1) * p.G + (size_t)(seg - 1) * p.G + koff;
-            }
-            tc::bulk_g2s(dst + (size_t)i * (SK * 4), src, SK * 4, &raw_full[r]);
-            if (MASKED) tc::bulk_g2s(dst + TILE_BYTES + (size_t)i * (SK * 4), msk, SK * 4, &raw_full[r]);
+    // One tensor copy (cp.async.bulk.tensor.2d) per 64-row x 128-float box; rows past the end are zero filled by
+    // the TMA unit, so every stage carries the same byte count.
+    if (lane == 0) {
+      const int x_c0 = p.x_hmul ? (int)(((hg * nout) / p.x_hdiv) * p.x_hmul) : 0;
+      const int u_c0 = (hg * nout) * (p.K - 1) * p.G;
+      const uint64_t tmx = reinterpret_cast<uint64_t>(&p.tm_x);
+      const uint64_t tmm = reinterpret_cast<uint64_t>(&p.tm_m);
+      const uint64_t tmu = reinterpret_cast<uint64_t>(&p.tm_u);
+      unsigned q = 0;
+      for (long tile = slot; tile < tiles; tile += nslots) {
+        const int m0 = (int)(tile * TN);
+        for (int s = 0; s < nst; ++s, ++q) {
+          const int r = (int)(q % NRAW);
+          tc::mbar_wait(&raw_empty[r], ((q / NRAW) & 1u) ^ 1u);
+          const uint32_t dst = tc::smem_u32(raw + (size_t)r * SLOT_BYTES);
+          const int seg = s / sps;
+          const int koff = (s - seg * sps) * SK;
+          tc::mbar_arrive_expect_tx(&raw_full[r], (uint32_t)TILE_BYTES * (MASKED ? 2u : 1u));
+          if (seg == 0) {
+            tc::tensor_g2s_2d(dst, tmx, x_c0 + koff, m0, &raw_full[r]);
+            if (MASKED) tc::tensor_g2s_2d(dst + TILE_BYTES, tmm, x_c0 + koff, m0, &raw_full[r]);
+          } else {
+            tc::tensor_g2s_2d(dst, tmu, u_c0 + (seg - 1) * p.G + koff, m0, &raw_full[r]);
           }
         }
       }
@@ -732,14 +718,57 @@ __global__ void __launch_bounds__(256) k_transpose_w(const float* __restrict__ W
   Wt[i] = W[(p * G + g) * G + gp];
 }
 
-// v2 needs flat outputs, contiguous 512 B source rows, no on-the-fly second tap; nout > 1 only with one K slice
-bool tap_tc2_ok(const TapParams& tp) {
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+    else
+      cudaGetLastError();
+    tried = true;
+  }
+  return fn;
+}
+
+// fp32 matrix [rows][width] with a row stride of `stride` floats, box = TN rows x SK floats, zero fill out of bounds
+bool make_row_map(CUtensorMap* tm, const float* base, long rows, long width, long stride) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (enc == nullptr || base == nullptr) return false;
+  if (((uintptr_t)base % 16) != 0 || (stride % 4) != 0 || width < SK || rows < 1) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)stride * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)SK, (cuuint32_t)TN};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// v2 needs flat inputs and outputs (one row stride over the whole batch), no on-the-fly second tap; nout > 1 only
+// with one K slice.  Fills the tensor maps of tq.
+bool tap_tc2_prepare(TapParams& tq, int x_width) {
   if (getenv("MAGAT_TAP_V1") != nullptr) return false;
-  if (tp.nout < 1 || tp.P % tp.nout != 0) return false;
-  const int nst = tp.K * tp.G / SK;
-  if (tp.G % SK != 0 || tp.nout * nst * SK > ACC_COL0 || (tp.nout > 1 && nst != 1)) return false;
-  if (tp.y_sb != (long)tp.N * tp.y_sn || tp.gather_u2) return false;
-  if (tp.mask && ((tp.m_sn % 4) != 0 || (tp.m_sb % 4) != 0 || ((uintptr_t)tp.mask % 16) != 0)) return false;
+  if (tq.nout < 1 || tq.P % tq.nout != 0 || tq.rows >= (1l << 31)) return false;
+  const int nst = tq.K * tq.G / SK;
+  if (tq.G % SK != 0 || tq.nout * nst * SK > ACC_COL0 || (tq.nout > 1 && nst != 1)) return false;
+  if (tq.y_sb != (long)tq.N * tq.y_sn || tq.gather_u2) return false;
+  if (tq.x_sb != (long)tq.N * tq.x_sn) return false;
+  if (!make_row_map(&tq.tm_x, tq.x, tq.rows, x_width, tq.x_sn)) return false;
+  if (tq.mask) {
+    if (tq.m_sb != (long)tq.N * tq.m_sn || !make_row_map(&tq.tm_m, tq.mask, tq.rows, x_width, tq.m_sn)) return false;
+  }
+  if (tq.K > 1) {
+    const long uw = (long)tq.P * (tq.K - 1) * tq.G;
+    if (!make_row_map(&tq.tm_u, tq.u1, tq.rows, uw, uw)) return false;
+  }
   return true;
 }
 
@@ -749,7 +778,9 @@ int launch_tap_tc(const TapParams& tp, int P, cudaStream_t st, const char* what)
   const char* dbg = getenv("MAGAT_DBG");
   tq.dbg = dbg ? atoi(dbg) : 0;
   const long tiles = (tp.rows + TN - 1) / TN;
-  if (tap_tc2_ok(tp)) {
+  // logical width of an x row: every weight-block group reads its own 128-wide (G-wide) column window
+  const int x_width = tp.x_hmul ? (int)(((tp.P - 1) / tp.x_hdiv) * tp.x_hmul) + tp.G : tp.G;
+  if (tap_tc2_prepare(tq, x_width)) {
     int rc0 = ensure_dyn_smem(KID_TAP_TC2, (const void*)k_tap_tc2<false>, V2_SMEM_BYTES, "k_tap_tc2<false>");
     if (!rc0) rc0 = ensure_dyn_smem(KID_TAP_TC2M, (const void*)k_tap_tc2<true>, V2_SMEM_BYTES, "k_tap_tc2<true>");
     if (rc0) return rc0;
