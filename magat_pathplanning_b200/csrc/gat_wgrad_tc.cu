@@ -9,8 +9,11 @@
 //
 // Persistent CTA per (z, slot): accumulates its share of the nodes into TMEM (128 lanes x NB columns, fp32)
 // over the whole kernel, then writes ONE partial tile; a tiny kernel sums the partials (deterministic).
-//   warps 0-7  producers: 32-node stages {A hi/lo [32 x 128], B hi/lo [32 x NB]}, 3-stage ring
-//   warp  8    MMA issuer: per 16-node step 3 x (N=256 [+ N=128]) tcgen05.mma, both operands from smem
+//   warps 0-15 producers, two groups of eight that build alternate 32-node stages {A hi/lo [32 x 128], B hi/lo
+//              [32 x NB]} of a 3-stage ring.  A thread's loads sit in registers until its stage is free, so ONE group
+//              keeps only one stage of loads (80 KB per SM) in flight; the ncu profile showed the kernel waiting on
+//              exactly those loads at 3.7 TB/s, hence the second group
+//   warp  16   MMA issuer: per 16-node step 3 x (N=256 [+ N=128]) tcgen05.mma, both operands from smem
 //   warps 0-3  double as the epilogue at the end (TMEM -> partial tile)
 #include <cuda_bf16.h>
 
@@ -29,10 +32,11 @@ constexpr int B_BYTES = SN * MAX_NB * 2;       // 24 KB per hi or lo
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 64 KB
 constexpr int STAGES = 3;
 constexpr int ATOM_STRIDE = SN * 128;          // bytes between 64-feature atoms (LBO)
-constexpr int PROD_THREADS = 256;
-constexpr int MMA_WARP = 8;
-constexpr int THREADS = 9 * 32;
-constexpr int RED_BYTES = 16 * MI * 4;          // column-sum staging (dbias)
+constexpr int PROD_THREADS = 256;              // per group
+constexpr int PROD_GROUPS = 2;
+constexpr int MMA_WARP = 16;
+constexpr int THREADS = 17 * 32;
+constexpr int RED_BYTES = PROD_GROUPS * 16 * MI * 4;          // column-sum staging (dbias)
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + RED_BYTES + 1024 + 256;
 
 struct Src {                 // node-major fp32 rows: row m at p + (m / N) * sb + (m % N) * sn  (+ z * zoff)
@@ -99,7 +103,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const __grid_constant__
 
   if (warp < MMA_WARP) {
     // ===== producers ======================================================================
-    const int t = threadIdx.x;                 // 0..255
+    const int t = threadIdx.x & (PROD_THREADS - 1);     // 0..255 inside the group
+    const int grp = threadIdx.x / PROD_THREADS;
     const int c = t & 15;                      // 16 B chunk (8 features) of the 128-feature row
     const int r0 = t >> 4;                     // rows r0, r0 + 16
     const unsigned N = (unsigned)p.N;
@@ -114,7 +119,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const __grid_constant__
     int stage = 0;
     uint32_t phase = 0;
     float4 cs0 = make_float4(0.f, 0.f, 0.f, 0.f), cs1 = cs0;      // column sums of A (features c*8 .. c*8+7)
-    for (long sidx = slot; sidx < nstages; sidx += nslots) {
+    int it = 0;
+    for (long sidx = slot; sidx < nstages; sidx += nslots, ++it) {
+      if ((it & (PROD_GROUPS - 1)) != grp) {   // the other group's stage
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        continue;
+      }
       const int m0 = (int)(sidx * SN);
       float4 va[4][2][2];                      // [source][row][half]
       float4 vm[2][2];
@@ -184,14 +194,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const __grid_constant__
     }
     // column sums (dbias): 16 row-threads per feature chunk -> smem -> fixed-order sum
     if (p.colsum_partial != nullptr) {
-      *reinterpret_cast<float4*>(red + r0 * MI + c * 8) = cs0;
-      *reinterpret_cast<float4*>(red + r0 * MI + c * 8 + 4) = cs1;
-      tc::named_bar_sync(2, PROD_THREADS);
-      if (t < MI) {
+      *reinterpret_cast<float4*>(red + (grp * 16 + r0) * MI + c * 8) = cs0;
+      *reinterpret_cast<float4*>(red + (grp * 16 + r0) * MI + c * 8 + 4) = cs1;
+      tc::named_bar_sync(2, PROD_GROUPS * PROD_THREADS);
+      if (threadIdx.x < MI) {
         float s = 0.f;
 #pragma unroll
-        for (int r = 0; r < 16; ++r) s += red[r * MI + t];
-        p.colsum_partial[((size_t)z * nslots + slot) * MI + t] = s;
+        for (int r = 0; r < PROD_GROUPS * 16; ++r) s += red[r * MI + threadIdx.x];
+        p.colsum_partial[((size_t)z * nslots + slot) * MI + threadIdx.x] = s;
       }
     }
     // ===== epilogue (warps 0-3): the accumulated tile -> this CTA's partial =====================
