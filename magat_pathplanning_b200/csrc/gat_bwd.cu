@@ -549,6 +549,8 @@ int wgrad_tc_dweight(const magat_gat_bwd_args* a, cudaStream_t st);
 bool gz_tc_supported(const magat_gat_bwd_args* a);
 int gz_tc_backward(const magat_gat_bwd_args* a, float* ht, cudaStream_t st);
 bool dx_tc_supported(const magat_gat_bwd_args* a);
+bool dx_tap_supported(const magat_gat_bwd_args* a);                 // gat_tap_tc.cu
+int dx_tap_accumulate(const magat_gat_bwd_args* a, float* wcat, cudaStream_t st);
 int tc_dx_accumulate(const magat_gat_bwd_args* a, const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo,
                      cudaStream_t st);
 int tc_split_weights(const float* src, long n, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st);
@@ -711,7 +713,14 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
                                                                   a->need_dx ? a->dx : nullptr);
 #undef MAGAT_CB
     if ((rc = check_launch("k_col_bwd", st))) return rc;
-    if (a->need_dx && a->path != MAGAT_PATH_SIMT && dx_tc_supported(a)) {
+    int dx_done = 0;
+    if (a->need_dx && a->path != MAGAT_PATH_SIMT && dx_tap_supported(a)) {
+      rc = dx_tap_accumulate(a, a->partial, st);
+      if (rc > 0) return rc;
+      dx_done = rc == 0;
+    }
+    if (dx_done) {
+    } else if (a->need_dx && a->path != MAGAT_PATH_SIMT && dx_tc_supported(a)) {
       __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(a->partial);
       __nv_bfloat16* w_lo = w_hi + (size_t)P * G * G;
       if ((rc = tc_split_weights(a->weight, (long)P * G * G, w_hi, w_lo, st))) return rc;

@@ -21,6 +21,7 @@
 
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "tma_host.cuh"
 
 namespace magat {
 
@@ -62,6 +63,8 @@ struct TapParams {
   const float* bias; int relu;
   float* y; long y_sb, y_sn;     // channel stride 1
   int nout;                      // v2 kernel: P counts weight blocks; nout consecutive blocks share one operand tile
+  int accum;                     // v2 kernel: y += result (the caller guarantees one weight-block group, i.e. no two CTAs
+                                 // ever touch the same output row)
   int epi_direct;                // 1: y rows are flat (y_sb == N * y_sn): the epilogue stores straight from registers
   int gather_u2;                 // 1: tap k = 2 is gathered on the fly from u_1; 0: read from the taps buffer
   int dbg;                       // experiment knobs; only read when built with -DMAGAT_DBG_KNOBS
@@ -449,14 +452,6 @@ constexpr int V2_CONV_WARPS = 16, V2_GROUP = 256;
 constexpr int V2_EPI_WARP0 = 16, V2_EPI_WARPS = 4, V2_MMA_WARP = 20, V2_TMA_WARP = 21, V2_THREADS = 22 * 32;
 constexpr size_t V2_SMEM_BYTES = (size_t)V2_NOP * STAGE_BYTES + V2_RAW_BYTES + 1024 + 256;
 
-__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
-  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
-}
 
 template <bool MASKED>
 __global__ void __launch_bounds__(V2_THREADS, 1) k_tap_tc2(const __grid_constant__ TapParams p) {
@@ -585,11 +580,11 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_tap_tc2(const __grid_constant
         for (int r0 = 0; r0 < 8; r0 += RB) {
           float4 v[RB];
 #pragma unroll
-          for (int i = 0; i < RB; ++i) v[i] = ld_shared_v4(src + (uint32_t)((wg + 8 * (r0 + i)) * (SK * 4)));
+          for (int i = 0; i < RB; ++i) v[i] = tc::ld_shared_v4(src + (uint32_t)((wg + 8 * (r0 + i)) * (SK * 4)));
           if (MASKED) {
 #pragma unroll
             for (int i = 0; i < RB; ++i) {
-              const float4 mk = ld_shared_v4(src + (uint32_t)TILE_BYTES + (uint32_t)((wg + 8 * (r0 + i)) * (SK * 4)));
+              const float4 mk = tc::ld_shared_v4(src + (uint32_t)TILE_BYTES + (uint32_t)((wg + 8 * (r0 + i)) * (SK * 4)));
               v[i].x = mk.x > 0.f ? v[i].x : 0.f; v[i].y = mk.y > 0.f ? v[i].y : 0.f;
               v[i].z = mk.z > 0.f ? v[i].z : 0.f; v[i].w = mk.w > 0.f ? v[i].w : 0.f;
             }
@@ -601,8 +596,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_tap_tc2(const __grid_constant
             tc::split2(v[i].x, v[i].y, h0, l0);
             tc::split2(v[i].z, v[i].w, h1, l1);
             const uint32_t off = tc::sw128_offset(row, c);
-            st_shared_v2(op_s + off, h0, h1);
-            st_shared_v2(op_s + 2 * ATOM_BYTES + off, l0, l1);
+            tc::st_shared_v2(op_s + off, h0, h1);
+            tc::st_shared_v2(op_s + 2 * ATOM_BYTES + off, l0, l1);
           }
         }
         tc::fence_proxy_async();
@@ -637,6 +632,11 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_tap_tc2(const __grid_constant
           const long mrow = m0 + 32 * hh;
           float* dst = ybase + mrow * p.y_sn;
           const long left = p.rows - mrow;
+          if (p.accum) {
+#pragma unroll
+            for (int n = 0; n < 32; ++n)
+              if (n < left) v[n] += dst[(long)n * p.y_sn];
+          }
           if (left >= 32) {
 #pragma unroll
             for (int n = 0; n < 32; ++n) {
@@ -718,40 +718,6 @@ __global__ void __launch_bounds__(256) k_transpose_w(const float* __restrict__ W
   Wt[i] = W[(p * G + g) * G + gp];
 }
 
-// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (no link-time dependency on libcuda)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(f);
-    else
-      cudaGetLastError();
-    tried = true;
-  }
-  return fn;
-}
-
-// fp32 matrix [rows][width] with a row stride of `stride` floats, box = TN rows x SK floats, zero fill out of bounds
-bool make_row_map(CUtensorMap* tm, const float* base, long rows, long width, long stride) {
-  EncodeTiledFn enc = encode_tiled_fn();
-  if (enc == nullptr || base == nullptr) return false;
-  if (((uintptr_t)base % 16) != 0 || (stride % 4) != 0 || width < SK || rows < 1) return false;
-  const cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)stride * 4};
-  const cuuint32_t box[2] = {(cuuint32_t)SK, (cuuint32_t)TN};
-  const cuuint32_t estr[2] = {1, 1};
-  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 // v2 needs flat inputs and outputs (one row stride over the whole batch), no on-the-fly second tap; nout > 1 only
 // with one K slice.  Fills the tensor maps of tq.
 bool tap_tc2_prepare(TapParams& tq, int x_width) {
@@ -761,18 +727,18 @@ bool tap_tc2_prepare(TapParams& tq, int x_width) {
   if (tq.G % SK != 0 || tq.nout * nst * SK > ACC_COL0 || (tq.nout > 1 && nst != 1)) return false;
   if (tq.y_sb != (long)tq.N * tq.y_sn || tq.gather_u2) return false;
   if (tq.x_sb != (long)tq.N * tq.x_sn) return false;
-  if (!make_row_map(&tq.tm_x, tq.x, tq.rows, x_width, tq.x_sn)) return false;
+  if (!tma::make_row_map(&tq.tm_x, tq.x, tq.rows, x_width, tq.x_sn, TN, SK)) return false;
   if (tq.mask) {
-    if (tq.m_sb != (long)tq.N * tq.m_sn || !make_row_map(&tq.tm_m, tq.mask, tq.rows, x_width, tq.m_sn)) return false;
+    if (tq.m_sb != (long)tq.N * tq.m_sn || !tma::make_row_map(&tq.tm_m, tq.mask, tq.rows, x_width, tq.m_sn, TN, SK)) return false;
   }
   if (tq.K > 1) {
     const long uw = (long)tq.P * (tq.K - 1) * tq.G;
-    if (!make_row_map(&tq.tm_u, tq.u1, tq.rows, uw, uw)) return false;
+    if (!tma::make_row_map(&tq.tm_u, tq.u1, tq.rows, uw, uw, TN, SK)) return false;
   }
   return true;
 }
 
-int launch_tap_tc(const TapParams& tp, int P, cudaStream_t st, const char* what) {
+int launch_tap_tc(const TapParams& tp, int P, cudaStream_t st, const char* what, bool v2_only = false) {
   const int sm_count = device_sm_count();
   TapParams tq = tp;
   const char* dbg = getenv("MAGAT_DBG");
@@ -793,6 +759,7 @@ int launch_tap_tc(const TapParams& tp, int P, cudaStream_t st, const char* what)
     else k_tap_tc2<false><<<(int)(slots * ngroups), V2_THREADS, V2_SMEM_BYTES, st>>>(tq);
     return check_launch(what, st);
   }
+  if (v2_only) return -1;
   // v1: one weight block per CTA
   tq.nout = 1;
   int rc0 = ensure_dyn_smem(KID_TAP_TC4, (const void*)k_tap_tc<4>, SMEM_BYTES, "k_tap_tc<4>");
@@ -879,6 +846,56 @@ int gz_tc_backward(const magat_gat_bwd_args* a, float* ht, cudaStream_t st) {
   tp.bias = nullptr; tp.relu = 0;
   tp.y = a->gz; tp.y_sn = (long)a->P * a->K * a->G; tp.y_sb = (long)a->N * tp.y_sn;
   return launch_tap_tc(tp, tp.P, st, "k_tap_tc(gz = dP H)");
+}
+
+// Wcat[h][g][pl*G + g'] = W[2h + pl][g][g'] (block h starts at h * G * 2G; its rows are G * nsl long, nsl = heads in it)
+__global__ void __launch_bounds__(256) k_pack_wcat(const float* __restrict__ W, int G, int P, float* __restrict__ wcat) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;       // i = (p*G + g)*G + g'
+  if (i >= (long)P * G * G) return;
+  const int gp = (int)(i % G);
+  const long r = i / G;
+  const int g = (int)(r % G);
+  const int p = (int)(r / G);
+  const int h = p >> 1, pl = p & 1;
+  const int nsl = (P - 2 * h) >= 2 ? 2 : 1;
+  wcat[(size_t)h * G * 2 * G + (size_t)g * (G * nsl) + pl * G + gp] = W[i];
+}
+
+bool dx_tap_supported(const magat_gat_bwd_args* a) {
+  if (a->mode != MAGAT_MODE_KEYQUERY || a->G != FT || getenv("MAGAT_DX_V1") != nullptr) return false;
+  if (((uintptr_t)a->rc % 16) != 0 || ((uintptr_t)a->dx % 16) != 0 || ((uintptr_t)a->partial % 16) != 0) return false;
+  if ((long)a->B * a->N >= (1l << 31)) return false;
+  return true;
+}
+
+// KeyQuery: dx[m][g] += sum_{p,g'} dR[m][p][g'] W[p][g][g'] on the TMA-fed kernel, two heads (K slices) per launch --
+// four heads of weights do not fit TMEM next to the accumulators.  wcat: P*G*G floats of scratch.
+// Returns -1 when the v2 kernel cannot take the shapes (caller falls back to k_tc_gemm).
+int dx_tap_accumulate(const magat_gat_bwd_args* a, float* wcat, cudaStream_t st) {
+  const int G = a->G, P = a->P;
+  TapParams tp{};
+  tp.rows = (long)a->B * a->N;
+  tp.N = a->N; tp.K = 1; tp.P = 1; tp.D = a->D; tp.nout = 1;
+  tp.x_sn = (long)P * G; tp.x_sb = (long)a->N * tp.x_sn;
+  tp.x_hdiv = 1; tp.x_hmul = 0;
+  tp.y = a->dx; tp.y_sn = G; tp.y_sb = (long)a->N * G;
+  tp.accum = 1;
+  {  // probe with the first launch's shape before touching the scratch
+    TapParams t0 = tp;
+    t0.G = G * (P >= 2 ? 2 : 1); t0.x = a->rc; t0.H = wcat;
+    if (!tap_tc2_prepare(t0, t0.G)) return -1;
+  }
+  k_pack_wcat<<<cdiv((long)P * G * G, 256), 256, 0, st>>>(a->weight, G, P, wcat);
+  int rc = check_launch("k_pack_wcat", st);
+  if (rc) return rc;
+  for (int h = 0; 2 * h < P; ++h) {
+    const int nsl = (P - 2 * h) >= 2 ? 2 : 1;
+    tp.G = G * nsl;
+    tp.x = a->rc + (long)h * 2 * G;
+    tp.H = wcat + (size_t)h * G * 2 * G;
+    if ((rc = launch_tap_tc(tp, 1, st, "k_tap_tc(dx += dR W^T)", true))) return rc;
+  }
+  return MAGAT_OK;
 }
 
 // MAGAT_FUSE_U2=1 keeps the second tap out of HBM (gathered by the producer warps); measured slower than

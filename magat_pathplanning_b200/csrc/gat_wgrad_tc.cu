@@ -17,8 +17,11 @@
 //   warps 0-3  double as the epilogue at the end (TMEM -> partial tile)
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "tma_host.cuh"
 
 namespace magat {
 
@@ -271,6 +274,241 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const __grid_constant__
   }
 }
 
+// ================================================================================================================
+// v2: the same reduction with a TMA-fed operand pipeline (flat, 16 B aligned sources).  The register-staged
+// producers above stream at 3.7 TB/s however many of them are in flight (a second producer group changed
+// nothing); tensor copies into shared memory plus converter warps that only touch shared memory reached
+// 5-6 TB/s in the forward projection kernel (gat_tap_tc.cu, k_tap_tc2), so the same structure is used here:
+//   warp 17      copy issuer: per 16-node stage one box [16 x 128] fp32 per source (A, mask, <= 3 B segments)
+//   warps 0-15   converters, two groups of eight building alternate operand stages; warp w converts row pieces
+//                w and w + 8 of every source (lane = 4 features), A rows also masked, scaled and column-summed
+//   warp 16      MMA issuer (one 16-node K step per stage), warps 0-3 drain TMEM at the end
+constexpr int V2_SN = 16;
+constexpr int V2_A_BYTES = V2_SN * MI * 2;              // 4 KB per hi or lo
+constexpr int V2_B_BYTES = V2_SN * MAX_NB * 2;          // 12 KB per hi or lo
+constexpr int V2_OP_BYTES = 2 * V2_A_BYTES + 2 * V2_B_BYTES;     // 32 KB
+constexpr int V2_ATOM_STRIDE = V2_SN * 128;             // 2 KB between 64-feature atoms
+constexpr int V2_BOX_BYTES = V2_SN * 128 * 4;           // 8 KB: one raw source box
+constexpr int V2_RAW_SLOT = 5 * V2_BOX_BYTES;           // A, mask, B0, B1, B2
+constexpr int V2_NRAW = 3;
+constexpr int V2_NOP = 2;
+constexpr int V2_GROUP = 256;
+constexpr int V2_MMA_WARP = 16, V2_TMA_WARP = 17, V2_THREADS = 18 * 32;
+constexpr int V2_RED_BYTES = 16 * MI * 4;
+constexpr size_t V2_SMEM_BYTES = (size_t)V2_NOP * V2_OP_BYTES + (size_t)V2_NRAW * V2_RAW_SLOT + V2_RED_BYTES + 1024 + 256;
+
+struct Wgrad2Params {
+  alignas(64) CUtensorMap tm_a;       // A source rows (dY or x)
+  alignas(64) CUtensorMap tm_m;       // mask rows (y), same column window as A
+  alignas(64) CUtensorMap tm_b0;      // B segment 0 (x or dR)
+  alignas(64) CUtensorMap tm_u;       // B segments 1.. (taps buffer)
+  long rows;
+  int Z, NB;
+  int a_zoff, b0_zoff, u_zoff, u_seg;      // column offsets: z * zoff (+ (seg - 1) * u_seg for the taps)
+  int has_mask;
+  float a_scale;
+  float* partial;
+  float* colsum_partial;
+};
+
+__device__ __forceinline__ uint64_t make_mn_desc2(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(V2_ATOM_STRIDE >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(V2_THREADS, 1) k_wgrad_tc2(const __grid_constant__ Wgrad2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* raw = smem + (size_t)V2_NOP * V2_OP_BYTES;
+  float* red = reinterpret_cast<float*>(raw + (size_t)V2_NRAW * V2_RAW_SLOT);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(red) + V2_RED_BYTES);
+  uint64_t* op_full = bars;            // [2]
+  uint64_t* op_empty = bars + 2;       // [2]
+  uint64_t* raw_full = bars + 4;       // [3]
+  uint64_t* raw_empty = bars + 7;      // [3]
+  uint64_t* done = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int z = blockIdx.x % p.Z;
+  const int slot = blockIdx.x / p.Z, nslots = gridDim.x / p.Z;
+  const long nstages = (p.rows + V2_SN - 1) / V2_SN;
+  const int nseg = p.NB / 128;
+  const int nsrc = 1 + nseg;                         // converted sources per stage (the mask is not one)
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < V2_NOP; ++s) {
+      tc::mbar_init(&op_full[s], V2_GROUP);
+      tc::mbar_init(&op_empty[s], 1);
+    }
+    for (int s = 0; s < V2_NRAW; ++s) {
+      tc::mbar_init(&raw_full[s], 1);
+      tc::mbar_init(&raw_empty[s], V2_GROUP / 32);
+    }
+    tc::mbar_init(done, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == V2_MMA_WARP) tc::tmem_alloc<512>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == V2_TMA_WARP) {
+    // ===== copy issuer ====================================================================================
+    if (lane == 0) {
+      const uint64_t tma_ = reinterpret_cast<uint64_t>(&p.tm_a), tmm = reinterpret_cast<uint64_t>(&p.tm_m);
+      const uint64_t tmb = reinterpret_cast<uint64_t>(&p.tm_b0), tmu = reinterpret_cast<uint64_t>(&p.tm_u);
+      const uint32_t bytes = (uint32_t)V2_BOX_BYTES * (uint32_t)(nsrc + (p.has_mask ? 1 : 0));
+      unsigned q = 0;
+      for (long sidx = slot; sidx < nstages; sidx += nslots, ++q) {
+        const int r = (int)(q % V2_NRAW);
+        tc::mbar_wait(&raw_empty[r], ((q / V2_NRAW) & 1u) ^ 1u);
+        const uint32_t dst = tc::smem_u32(raw + (size_t)r * V2_RAW_SLOT);
+        const int m0 = (int)(sidx * V2_SN);
+        tc::mbar_arrive_expect_tx(&raw_full[r], bytes);
+        tc::tensor_g2s_2d(dst, tma_, z * p.a_zoff, m0, &raw_full[r]);
+        if (p.has_mask) tc::tensor_g2s_2d(dst + V2_BOX_BYTES, tmm, z * p.a_zoff, m0, &raw_full[r]);
+        tc::tensor_g2s_2d(dst + 2 * V2_BOX_BYTES, tmb, z * p.b0_zoff, m0, &raw_full[r]);
+        for (int s = 1; s < nseg; ++s)
+          tc::tensor_g2s_2d(dst + (2 + s) * V2_BOX_BYTES, tmu, z * p.u_zoff + (s - 1) * p.u_seg, m0, &raw_full[r]);
+      }
+    }
+  } else if (warp < V2_MMA_WARP) {
+    // ===== converters =====================================================================================
+    const unsigned grp = warp >> 3;
+    const int wg = warp & 7;
+    // lane l owns features 4l .. 4l+3 of a 128-feature row: half (l & 1) of chunk (l >> 1) & 7 of atom l >> 4
+    const uint32_t lane_off = (uint32_t)((lane >> 4) * V2_ATOM_STRIDE) + (uint32_t)((lane & 1) * 8);
+    const int c8 = (lane >> 1) & 7;
+    const uint32_t op_s = tc::smem_u32(smem + (size_t)grp * V2_OP_BYTES);
+    const uint32_t raw_s = tc::smem_u32(raw) + (uint32_t)(lane * 16);
+    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+    unsigned q = 0;
+    for (long sidx = slot; sidx < nstages; sidx += nslots, ++q) {
+      if ((q & 1u) != grp) continue;
+      const int r = (int)(q % V2_NRAW);
+      tc::mbar_wait(&raw_full[r], (q / V2_NRAW) & 1u);
+      tc::mbar_wait(&op_empty[grp], ((q >> 1) & 1u) ^ 1u);
+      const uint32_t src = raw_s + (uint32_t)(r * V2_RAW_SLOT);
+      // rows wg and wg + 8 of every source; all loads first
+      float4 v[4][2], mk[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const uint32_t ro = (uint32_t)((wg + 8 * i) * 512);
+        v[0][i] = tc::ld_shared_v4(src + ro);
+        mk[i] = p.has_mask ? tc::ld_shared_v4(src + V2_BOX_BYTES + ro) : make_float4(1.f, 1.f, 1.f, 1.f);
+#pragma unroll
+        for (int s = 0; s < 3; ++s)
+          v[1 + s][i] = s < nseg ? tc::ld_shared_v4(src + (uint32_t)((2 + s) * V2_BOX_BYTES) + ro)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        float4& a = v[0][i];
+        a.x = mk[i].x > 0.f ? a.x * p.a_scale : 0.f;
+        a.y = mk[i].y > 0.f ? a.y * p.a_scale : 0.f;
+        a.z = mk[i].z > 0.f ? a.z * p.a_scale : 0.f;
+        a.w = mk[i].w > 0.f ? a.w * p.a_scale : 0.f;
+        cs.x += a.x; cs.y += a.y; cs.z += a.z; cs.w += a.w;
+      }
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        if (s > 0 && s - 1 >= nseg) continue;
+        const uint32_t hi_base = op_s + (s == 0 ? 0u : (uint32_t)(2 * V2_A_BYTES + (s - 1) * 2 * V2_ATOM_STRIDE));
+        const uint32_t lo_base = s == 0 ? op_s + (uint32_t)V2_A_BYTES : hi_base + (uint32_t)V2_B_BYTES;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int row = wg + 8 * i;
+          uint32_t h0, l0, h1, l1;
+          tc::split2(v[s][i].x, v[s][i].y, h0, l0);
+          tc::split2(v[s][i].z, v[s][i].w, h1, l1);
+          const uint32_t off = lane_off + (uint32_t)(row * 128 + ((c8 ^ (row & 7)) << 4));
+          tc::st_shared_v2(hi_base + off, h0, h1);
+          tc::st_shared_v2(lo_base + off, l0, l1);
+        }
+      }
+      tc::fence_proxy_async();
+      tc::mbar_arrive(&op_full[grp]);
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&raw_empty[r]);
+    }
+    // column sums (dbias): 16 warps x 128 features -> smem -> fixed-order sum
+    if (p.colsum_partial != nullptr) {
+      *reinterpret_cast<float4*>(red + warp * MI + lane * 4) = cs;
+      tc::named_bar_sync(2, 2 * V2_GROUP);
+      if (threadIdx.x < MI) {
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) s += red[r * MI + threadIdx.x];
+        p.colsum_partial[((size_t)z * nslots + slot) * MI + threadIdx.x] = s;
+      }
+    }
+    // ===== epilogue (warps 0-3) ===========================================================================
+    if (warp < 4) {
+      tc::mbar_wait(done, 0);
+      tc::tc_fence_after();
+      const int i_row = warp * 32 + lane;
+      float* dst = p.partial + (((size_t)z * nslots + slot) * MI + i_row) * p.NB;
+      const bool any = slot < nstages;
+      for (int c0 = 0; c0 < p.NB; c0 += 32) {
+        float v[32];
+        if (any) {
+          tc::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+          tc::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+  } else {
+    // ===== MMA issuer =====================================================================================
+    const uint32_t idesc256 = make_idesc_mn(MI, 256), idesc128 = make_idesc_mn(MI, 128);
+    unsigned q = 0;
+    for (long sidx = slot; sidx < nstages; sidx += nslots, ++q) {
+      const int stage = (int)(q & 1u);
+      tc::mbar_wait(&op_full[stage], (q >> 1) & 1u);
+      tc::tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sb = tc::smem_u32(smem + (size_t)stage * V2_OP_BYTES);
+        const uint32_t a_hi = sb, a_lo = sb + V2_A_BYTES, b_hi = sb + 2 * V2_A_BYTES, b_lo = b_hi + V2_B_BYTES;
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t aa = pass == 1 ? a_lo : a_hi;
+          const uint32_t bb = pass == 2 ? b_lo : b_hi;
+          const uint32_t accum = (q == 0 && pass == 0) ? 0u : 1u;
+          if (p.NB >= 256) {
+            tc::umma_bf16(tmem_base, make_mn_desc2(aa), make_mn_desc2(bb), idesc256, accum);
+            if (p.NB > 256)
+              tc::umma_bf16(tmem_base + 256, make_mn_desc2(aa), make_mn_desc2(bb + 4 * V2_ATOM_STRIDE), idesc128, accum);
+          } else {
+            tc::umma_bf16(tmem_base, make_mn_desc2(aa), make_mn_desc2(bb), idesc128, accum);
+          }
+        }
+        tc::umma_commit(&op_empty[stage]);
+      }
+      __syncwarp();
+    }
+    if (lane == 0) tc::umma_commit(done);
+    __syncwarp();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == V2_MMA_WARP) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // out[z][e] = sum_s partial[(z * nslots + s) * per + e]
 __global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ partial, int nslots, long per,
                                                       long total, float* __restrict__ out) {
@@ -296,11 +534,54 @@ int wgrad_nslots(int Z) {
   return s < 1 ? 1 : s;
 }
 
+// v2 when every source is a flat [rows][stride] matrix; fills the tensor maps
+bool wgrad2_prepare(const WgradParams& wp, Wgrad2Params& q) {
+  if (getenv("MAGAT_WGRAD_V1") != nullptr) return false;
+  if (wp.rows >= (1l << 31) || wp.NB % 128 != 0 || wp.NB > MAX_NB) return false;
+  auto flat = [&](const Src& s) { return s.sb == (long)wp.N * s.sn; };
+  const int nseg = wp.NB / 128;
+  if (!flat(wp.a) || !flat(wp.b[0])) return false;
+  // widths: the last slice's 128-column window must lie inside the row
+  const long a_w = (long)(wp.Z - 1) * wp.a.zoff + MI;
+  const long b0_w = (long)(wp.Z - 1) * wp.b[0].zoff + 128;
+  if (a_w > wp.a.sn || b0_w > wp.b[0].sn) return false;
+  if (!tma::make_row_map(&q.tm_a, wp.a.p, wp.rows, a_w, wp.a.sn, V2_SN, 128)) return false;
+  if (!tma::make_row_map(&q.tm_b0, wp.b[0].p, wp.rows, b0_w, wp.b[0].sn, V2_SN, 128)) return false;
+  q.has_mask = wp.mask_y != nullptr;
+  if (q.has_mask) {
+    if (wp.my_sb != (long)wp.N * wp.my_sn || wp.my_zoff != wp.a.zoff || a_w > wp.my_sn) return false;
+    if (!tma::make_row_map(&q.tm_m, wp.mask_y, wp.rows, a_w, wp.my_sn, V2_SN, 128)) return false;
+  }
+  q.u_zoff = 0; q.u_seg = 0;
+  if (nseg > 1) {
+    // segments 1.. are consecutive 128-wide windows of one buffer (the taps rows)
+    const Src& u = wp.b[1];
+    if (!flat(u)) return false;
+    for (int s = 2; s < nseg; ++s)
+      if (wp.b[s].sn != u.sn || wp.b[s].sb != u.sb || wp.b[s].zoff != u.zoff || wp.b[s].p != u.p + (long)(s - 1) * 128)
+        return false;
+    const long u_w = (long)(wp.Z - 1) * u.zoff + (long)(nseg - 1) * 128;
+    if (u_w > u.sn || !tma::make_row_map(&q.tm_u, u.p, wp.rows, u_w, u.sn, V2_SN, 128)) return false;
+    q.u_zoff = (int)u.zoff; q.u_seg = 128;
+  }
+  q.rows = wp.rows; q.Z = wp.Z; q.NB = wp.NB;
+  q.a_zoff = (int)wp.a.zoff; q.b0_zoff = (int)wp.b[0].zoff;
+  q.a_scale = wp.a_scale; q.partial = wp.partial; q.colsum_partial = wp.colsum_partial;
+  return true;
+}
+
 int launch_wgrad(WgradParams& wp, float* out, cudaStream_t st, const char* what) {
-  int rc0 = ensure_dyn_smem(KID_WGRAD, (const void*)k_wgrad_tc, SMEM_BYTES, "k_wgrad_tc");
-  if (rc0) return rc0;
   const int nslots = wgrad_nslots(wp.Z);
-  k_wgrad_tc<<<nslots * wp.Z, THREADS, SMEM_BYTES, st>>>(wp);
+  Wgrad2Params q{};
+  if (wgrad2_prepare(wp, q)) {
+    int rc0 = ensure_dyn_smem(KID_WGRAD2, (const void*)k_wgrad_tc2, V2_SMEM_BYTES, "k_wgrad_tc2");
+    if (rc0) return rc0;
+    k_wgrad_tc2<<<nslots * wp.Z, V2_THREADS, V2_SMEM_BYTES, st>>>(q);
+  } else {
+    int rc0 = ensure_dyn_smem(KID_WGRAD, (const void*)k_wgrad_tc, SMEM_BYTES, "k_wgrad_tc");
+    if (rc0) return rc0;
+    k_wgrad_tc<<<nslots * wp.Z, THREADS, SMEM_BYTES, st>>>(wp);
+  }
   int rc = check_launch(what, st);
   if (rc) return rc;
   const long per = (long)MI * wp.NB, total = per * wp.Z;

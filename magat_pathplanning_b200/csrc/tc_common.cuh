@@ -180,6 +180,17 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// explicit shared-window accesses (32-bit addresses from smem_u32): the compiler emits generic LD/ST for pointers
+// whose address space it cannot prove
+__device__ __forceinline__ float4 ld_shared_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+
 // ---- fp32 -> bf16 hi / lo split ------------------------------------------------------------
 // v ~= hi + lo with hi = bf16_rn(v), lo = bf16_rn(v - hi): 16 mantissa bits; the products
 // hi*hi' + lo*hi' + hi*lo' carry a relative error of about 2^-16 ("BF16 x3").
