@@ -1,5 +1,6 @@
 // Error plumbing + version / device probes of the C ABI (include/magat_gat.h).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -82,7 +83,9 @@ int ensure_dyn_smem(int kernel_id, const void* func, size_t bytes, const char* n
 }
 
 int check_launch(const char* what, cudaStream_t st) {
+  static const bool sync_check = getenv("MAGAT_SYNC_CHECK") != nullptr;     // debugging: pin an asynchronous fault to its kernel
   cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && sync_check) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) {
     set_error("%s: %s", what, cudaGetErrorString(e));
     return MAGAT_E_CUDA;

@@ -290,12 +290,19 @@ constexpr int V2_OP_BYTES = 2 * V2_A_BYTES + 2 * V2_B_BYTES;     // 32 KB
 constexpr int V2_ATOM_STRIDE = V2_SN * 128;             // 2 KB between 64-feature atoms
 constexpr int V2_BOX_BYTES = V2_SN * 128 * 4;           // 8 KB: one raw source box
 constexpr int V2_RAW_SLOT = 5 * V2_BOX_BYTES;           // A, mask, B0, B1, B2
-constexpr int V2_NRAW = 3;
+// An even ring: slot q % 4 is then always consumed by the same converter group (q % 2).  With three slots the groups
+// alternated on a slot and a group waiting for fill m could be satisfied by the parity of fill m - 2 while fill m - 1
+// (the other group's) was still in flight -- it read the wrong stage, released the slot early and the copy issuer
+// re-armed a barrier whose phase was still open (illegal-instruction trap at B*N >= ~10^5 rows).
+constexpr int V2_NRAW = 4;
 constexpr int V2_NOP = 2;
 constexpr int V2_GROUP = 256;
 constexpr int V2_MMA_WARP = 16, V2_TMA_WARP = 17, V2_THREADS = 18 * 32;
 constexpr int V2_RED_BYTES = 16 * MI * 4;
-constexpr size_t V2_SMEM_BYTES = (size_t)V2_NOP * V2_OP_BYTES + (size_t)V2_NRAW * V2_RAW_SLOT + V2_RED_BYTES + 1024 + 256;
+// the column-sum staging (V2_RED_BYTES) reuses raw slot 0 once every stage has been converted
+constexpr size_t V2_SMEM_BYTES = (size_t)V2_NOP * V2_OP_BYTES + (size_t)V2_NRAW * V2_RAW_SLOT + 1024 + 256;
+static_assert(V2_RED_BYTES <= V2_RAW_SLOT, "column-sum staging must fit a raw slot");
+static_assert(V2_SMEM_BYTES <= 227 * 1024, "k_wgrad_tc2 shared memory");
 
 struct Wgrad2Params {
   alignas(64) CUtensorMap tm_a;       // A source rows (dY or x)
@@ -325,14 +332,14 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_wgrad_tc2(const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* raw = smem + (size_t)V2_NOP * V2_OP_BYTES;
-  float* red = reinterpret_cast<float*>(raw + (size_t)V2_NRAW * V2_RAW_SLOT);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(red) + V2_RED_BYTES);
+  float* red = reinterpret_cast<float*>(raw);          // valid only after the last stage (see the column sums below)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(raw + (size_t)V2_NRAW * V2_RAW_SLOT);
   uint64_t* op_full = bars;            // [2]
   uint64_t* op_empty = bars + 2;       // [2]
-  uint64_t* raw_full = bars + 4;       // [3]
-  uint64_t* raw_empty = bars + 7;      // [3]
-  uint64_t* done = bars + 10;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* raw_full = bars + 4;       // [4]
+  uint64_t* raw_empty = bars + 8;      // [4]
+  uint64_t* done = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int z = blockIdx.x % p.Z;
@@ -440,6 +447,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_wgrad_tc2(const __grid_consta
     }
     // column sums (dbias): 16 warps x 128 features -> smem -> fixed-order sum
     if (p.colsum_partial != nullptr) {
+      tc::named_bar_sync(2, 2 * V2_GROUP);       // every stage converted: the raw ring is free to hold the sums
       *reinterpret_cast<float4*>(red + warp * MI + lane * 4) = cs;
       tc::named_bar_sync(2, 2 * V2_GROUP);
       if (threadIdx.x < MI) {
