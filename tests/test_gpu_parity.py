@@ -252,6 +252,40 @@ def test_tc_path_oracle(mode, concat, G, F, K, P, B, N):
     assert (torch.from_numpy(layer.aij) - aij_ref).abs().max() < TOL
 
 
+@pytest.mark.parametrize("B,N,K,P", [(160, 1000, 3, 4), (130, 777, 2, 2)])
+def test_tc_path_matches_simt_at_scale(B, N, K, P):
+    """The tcgen05 pipelines (TMA rings, converter groups, persistent CTAs) against the fp32 SIMT kernels of the
+    same library at a size where every CTA wraps its rings many times (>= 10^5 node rows; the oracle's dense
+    [B,P,N,N] temporaries do not fit there).  The SIMT path itself is pinned to the oracle / golden vectors above.
+    A ring-parity bug in the weight-gradient kernel only showed from ~10^5 rows up."""
+    dev = torch.device("cuda:0")
+    G = F = 128
+    gen = torch.Generator().manual_seed(99 + N)
+    params = orc.init_params(G, F, K, P, mode="KeyQuery", generator=gen, weight_bias_std=0.1)
+    from bench import synth_gso
+    gdev = torch.Generator(device=dev).manual_seed(7 + N)
+    S = synth_gso(B, N, int(round((N / 0.025) ** 0.5)), dev, gdev)
+    x_mem = torch.relu(torch.randn(B, N, G, generator=gen)).to(dev)
+    dy_mem = torch.randn(B, N, P * F, generator=gen).to(dev)
+    meta = dict(G=G, F=F, K=K, P=P, concat=True, mode="KeyQuery")
+    out = {}
+    for path in ("simt", "tcgen05"):
+        layer = make_layer(meta, {"param." + k: v for k, v in params.items() if v is not None}, dev, path=path)
+        for rep in range(2):                     # twice back to back: kernels of consecutive steps overlap at the seams
+            for p_ in layer.parameters():
+                p_.grad = None
+            xd = x_mem.permute(0, 2, 1).detach().requires_grad_(True)
+            layer.addGSO(S)
+            y = layer(xd)
+            y.backward(dy_mem.permute(0, 2, 1))
+        torch.cuda.synchronize()
+        out[path] = dict(y=y.detach(), dx=xd.grad, dH=layer.filterWeight.grad, dW=layer.weight.grad, db=layer.bias.grad)
+    for k in out["simt"]:
+        e = rel_err(out["tcgen05"][k], out["simt"][k])
+        print(f"{k}: tcgen05 vs simt {e:.2e}")
+        assert e < TOL, k
+
+
 def test_tc_path_rejects_uncovered_shape(golden):
     from magat_pathplanning_b200._cabi import MagatError
     d, meta = golden.case("kq_concat_n10")          # G = 16
