@@ -268,6 +268,14 @@ def test_tc_path_matches_simt_at_scale(B, N, K, P):
     x_mem = torch.relu(torch.randn(B, N, G, generator=gen)).to(dev)
     dy_mem = torch.randn(B, N, P * F, generator=gen).to(dev)
     meta = dict(G=G, F=F, K=K, P=P, concat=True, mode="KeyQuery")
+    # The two paths differ by ~5e-6 in y, which flips relu'(y) for the few hundred outputs that sit that close to
+    # zero; their gradient would then differ by a whole dy entry.  No gradient flows into outputs below 1e-3.
+    probe = make_layer(meta, {"param." + k: v for k, v in params.items() if v is not None}, dev, path="simt")
+    probe.addGSO(S)
+    with torch.no_grad():
+        y0 = probe(x_mem.permute(0, 2, 1))
+    dy_mem = dy_mem * (y0.permute(0, 2, 1) > 1e-3)
+    del probe, y0
     out = {}
     for path in ("simt", "tcgen05"):
         layer = make_layer(meta, {"param." + k: v for k, v in params.items() if v is not None}, dev, path=path)
@@ -280,10 +288,9 @@ def test_tc_path_matches_simt_at_scale(B, N, K, P):
             y.backward(dy_mem.permute(0, 2, 1))
         torch.cuda.synchronize()
         out[path] = dict(y=y.detach(), dx=xd.grad, dH=layer.filterWeight.grad, dW=layer.weight.grad, db=layer.bias.grad)
-    for k in out["simt"]:
-        e = rel_err(out["tcgen05"][k], out["simt"][k])
-        print(f"{k}: tcgen05 vs simt {e:.2e}")
-        assert e < TOL, k
+    errs = {k: rel_err(out["tcgen05"][k], out["simt"][k]) for k in out["simt"]}
+    print("tcgen05 vs simt: " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()))
+    assert all(v < TOL for v in errs.values()), errs
 
 
 def test_tc_path_rejects_uncovered_shape(golden):
