@@ -239,8 +239,8 @@ __device__ __forceinline__ void stp(float* p, const float* a) {
 }
 
 // tap recursion backward, level k: one warp per sender row, lane l owns features 4l..4l+3 and out-slot l.
-template <int PT>
-__global__ void __launch_bounds__(256, 3) k_tap_bwd_v(const float* __restrict__ x, long x_sb, long x_sn,
+template <int PT, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_tap_bwd_v(const float* __restrict__ x, long x_sb, long x_sn,
                                                    const float* __restrict__ taps, const float* __restrict__ att,
                                                    const int32_t* __restrict__ nbr_out, long rows, int N, int K, int D,
                                                    int k, int first, float* __restrict__ gz, float* __restrict__ datt,
@@ -676,9 +676,19 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
   for (int k = K - 1; k >= 1; --k) {
     const int first = k == K - 1 ? 1 : 0;
     float* g0sum = (k == 1 && g0_in_dx) ? a->dx : nullptr;
+    static const int tb_occ = getenv("MAGAT_TB_OCC") ? atoi(getenv("MAGAT_TB_OCC")) : 3;
 #define MAGAT_TB(PT) \
-  k_tap_bwd_v<PT><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->taps, a->att, a->nbr_out, rows, N, K, D, k, \
-                                              first, a->gz, a->datt, g0sum)
+  do {                                                                                                              \
+    if (tb_occ == 4)                                                                                                \
+      k_tap_bwd_v<PT, 4><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->taps, a->att, a->nbr_out, rows, N, K, D, \
+                                                     k, first, a->gz, a->datt, g0sum);                              \
+    else if (tb_occ == 2)                                                                                           \
+      k_tap_bwd_v<PT, 2><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->taps, a->att, a->nbr_out, rows, N, K, D, \
+                                                     k, first, a->gz, a->datt, g0sum);                              \
+    else                                                                                                            \
+      k_tap_bwd_v<PT, 3><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->taps, a->att, a->nbr_out, rows, N, K, D, \
+                                                     k, first, a->gz, a->datt, g0sum);                              \
+  } while (0)
     if (vec && P == 4) MAGAT_TB(4);
     else if (vec && P == 2) MAGAT_TB(2);
     else if (vec && P == 1) MAGAT_TB(1);

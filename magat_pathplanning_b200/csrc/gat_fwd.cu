@@ -157,8 +157,8 @@ __device__ __forceinline__ float warp_max(float v) {
 // every 128-feature slab; lane s fetches the attention values of in-edge s (all heads) and they are
 // broadcast by shuffle.  When `ain` is given the in-edge values are also stored receiver-major,
 // ain[j][p][s] = A_p[nbr_in[j][s], j] (0 beyond the degree), which is what the fused tcgen05 kernel reads.
-template <int PT>
-__global__ void __launch_bounds__(256, 4) k_tap_gather_v(const float* __restrict__ x, long x_sb, long x_sn,
+template <int PT, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_tap_gather_v(const float* __restrict__ x, long x_sb, long x_sn,
                                                       const float* __restrict__ att,
                                                       const int32_t* __restrict__ nbr_in,
                                                       const int32_t* __restrict__ slot_in, long rows, int N,
@@ -258,8 +258,8 @@ __global__ void __launch_bounds__(256, 4) k_tap_gather_v(const float* __restrict
 }
 
 // KeyQuery scores + row softmax, D <= 32: lane s owns slot s; G = 128 * GV.
-template <int PT, int GV>
-__global__ void __launch_bounds__(256) k_attention_kq_v(const float* __restrict__ x, long x_sb, long x_sn,
+template <int PT, int GV, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_attention_kq_v(const float* __restrict__ x, long x_sb, long x_sn,
                                                         const float* __restrict__ sproj,
                                                         const int32_t* __restrict__ nbr_out, long rows, int N,
                                                         int D, float* __restrict__ att,
@@ -419,9 +419,19 @@ int run_tap_gather(const float* x, long x_sb, long x_sn, const float* att, const
   const int row_blocks = cdiv(rows, 8);
   const bool vec_ok = (G % 4 == 0) && (x_sn % 4 == 0) && (x_sb % 4 == 0) && (((uintptr_t)x) % 16 == 0) &&
                       (((uintptr_t)att) % 16 == 0) && (((uintptr_t)taps) % 16 == 0) && rows < (1l << 31);
+  static const int occ = getenv("MAGAT_GATHER_OCC") ? atoi(getenv("MAGAT_GATHER_OCC")) : 4;
 #define MAGAT_GATHER(PT) \
-  k_tap_gather_v<PT><<<row_blocks, 256, 0, st>>>(x, x_sb, x_sn, att, nbr_in, slot_in, rows, N, G, K, D, k, taps, ain, \
-                                                 ain_ready)
+  do {                                                                                                              \
+    if (occ == 3)                                                                                                   \
+      k_tap_gather_v<PT, 3><<<row_blocks, 256, 0, st>>>(x, x_sb, x_sn, att, nbr_in, slot_in, rows, N, G, K, D, k, taps, \
+                                                        ain, ain_ready);                                            \
+    else if (occ == 5)                                                                                              \
+      k_tap_gather_v<PT, 5><<<row_blocks, 256, 0, st>>>(x, x_sb, x_sn, att, nbr_in, slot_in, rows, N, G, K, D, k, taps, \
+                                                        ain, ain_ready);                                            \
+    else                                                                                                            \
+      k_tap_gather_v<PT, 4><<<row_blocks, 256, 0, st>>>(x, x_sb, x_sn, att, nbr_in, slot_in, rows, N, G, K, D, k, taps, \
+                                                        ain, ain_ready);                                            \
+  } while (0)
   if (vec_ok && P == 4) MAGAT_GATHER(4);
   else if (vec_ok && P == 2) MAGAT_GATHER(2);
   else if (vec_ok && P == 1) MAGAT_GATHER(1);
@@ -474,9 +484,16 @@ static int forward_impl(const magat_gat_fwd_args* a, cudaStream_t st, bool use_t
       if ((rc = check_launch("k_node_gemm(score projection)", st))) return rc;
     }
     bool fast = vec_ok && D <= 32 && (G == 128 || G == 256);
+    static const int att_occ = getenv("MAGAT_ATT_OCC") ? atoi(getenv("MAGAT_ATT_OCC")) : 1;
 #define MAGAT_ATT(PT, GV) \
-  k_attention_kq_v<PT, GV><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj, a->nbr_out, rows, N, D, a->att, \
-                                                       so, ain_w)
+  do {                                                                                                             \
+    if (att_occ == 8)                                                                                              \
+      k_attention_kq_v<PT, GV, 8><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj, a->nbr_out, rows, N, D, \
+                                                              a->att, so, ain_w);                                  \
+    else                                                                                                           \
+      k_attention_kq_v<PT, GV, 1><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj, a->nbr_out, rows, N, D, \
+                                                              a->att, so, ain_w);                                  \
+  } while (0)
     if (fast && P == 4 && G == 128) MAGAT_ATT(4, 1);
     else if (fast && P == 4 && G == 256) MAGAT_ATT(4, 2);
     else if (fast && P == 2 && G == 128) MAGAT_ATT(2, 1);
