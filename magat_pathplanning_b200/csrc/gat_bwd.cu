@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(256, MINB) k_tap_bwd_v(const float* __restrict
                                                    const float* __restrict__ taps, const float* __restrict__ att,
                                                    const int32_t* __restrict__ nbr_out, long rows, int N, int K, int D,
                                                    int k, int first, float* __restrict__ gz, float* __restrict__ datt,
-                                                   float* __restrict__ g0sum) {
+                                                   float* __restrict__ g0sum, float* __restrict__ rc_out) {
   constexpr int G = 128;
   const int lane = threadIdx.x & 31;
   const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -254,7 +254,12 @@ __global__ void __launch_bounds__(256, MINB) k_tap_bwd_v(const float* __restrict
   const int my_j = lane < D ? nbr_out[row * D + lane] : -1;
   const int deg = __popc(__ballot_sync(0xffffffffu, my_j >= 0));
   if (deg == 0) {
-    if (first && lane < D) {
+    if (rc_out != nullptr) {                // fused softmax backward of an empty row: de = 0, dR = 0
+#pragma unroll
+      for (int q = 0; q < PT; ++q)
+        *reinterpret_cast<float4*>(rc_out + ((size_t)row * PT + q) * G + g0) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if ((first || rc_out != nullptr) && lane < D) {
       float z[PT];
 #pragma unroll
       for (int q = 0; q < PT; ++q) z[q] = 0.f;
@@ -325,9 +330,11 @@ __global__ void __launch_bounds__(256, MINB) k_tap_bwd_v(const float* __restrict
       *dst = o;
     }
   }
+  float o[PT];
+#pragma unroll
+  for (int q = 0; q < PT; ++q) o[q] = 0.f;
+  float* da = datt + ((size_t)row * D + lane) * PT;
   if (lane < D) {
-    float* da = datt + ((size_t)row * D + lane) * PT;
-    float o[PT];
     if (first) {
 #pragma unroll
       for (int q = 0; q < PT; ++q) o[q] = dsum[q];
@@ -336,8 +343,41 @@ __global__ void __launch_bounds__(256, MINB) k_tap_bwd_v(const float* __restrict
 #pragma unroll
       for (int q = 0; q < PT; ++q) o[q] += dsum[q];
     }
-    stp<PT>(da, o);
   }
+  if (rc_out == nullptr) {
+    if (lane < D) stp<PT>(da, o);
+    return;
+  }
+  // Last level, KeyQuery: dA of this row is complete, so its softmax backward and dR_i = sum_j de[i,j] x_j follow
+  // here (same arithmetic as k_softmax_bwd_kq_v, which then need not run).  datt <- de.
+  float de[PT];
+#pragma unroll
+  for (int q = 0; q < PT; ++q) {
+    const float dot = warp_sum(am[q] * o[q]);
+    de[q] = am[q] * (o[q] - dot);
+  }
+  if (lane < D) stp<PT>(da, de);
+  float4 racc[PT];
+#pragma unroll
+  for (int q = 0; q < PT; ++q) racc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < deg; s += 4) {
+    float4 xv[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int j = __shfl_sync(0xffffffffu, my_j, (s + w) & 31);
+      xv[w] = (s + w < deg) ? __ldg(reinterpret_cast<const float4*>(x + b * x_sb + (long)j * x_sn + g0))
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int w = 0; w < 4; ++w)
+#pragma unroll
+      for (int q = 0; q < PT; ++q) {
+        const float d = __shfl_sync(0xffffffffu, de[q], (s + w) & 31);
+        bfma4(racc[q], s + w < deg ? d : 0.f, xv[w]);
+      }
+  }
+#pragma unroll
+  for (int q = 0; q < PT; ++q) *reinterpret_cast<float4*>(rc_out + ((size_t)row * PT + q) * G + g0) = racc[q];
 }
 
 // KeyQuery softmax backward + dR_i = sum_j de[i,j] x_j.  datt <- de in place.
@@ -673,21 +713,24 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
   // KeyQuery, vector kernels: g_0 is only ever read as its head sum (for dx), so the last level of the recursion
   // writes that sum straight into dx and the column kernel picks it up there
   const bool g0_in_dx = vec && !gm && K > 1 && a->need_dx && getenv("MAGAT_BWD_NO_G0SUM") == nullptr;
+  // ... and the row softmax backward (+ dR) rides on the same last level
+  const bool fuse_softmax = vec && !gm && K > 1 && getenv("MAGAT_BWD_NO_FUSED_SOFTMAX") == nullptr;
   for (int k = K - 1; k >= 1; --k) {
     const int first = k == K - 1 ? 1 : 0;
     float* g0sum = (k == 1 && g0_in_dx) ? a->dx : nullptr;
+    float* rc_fused = (k == 1 && fuse_softmax) ? a->rc : nullptr;
     static const int tb_occ = getenv("MAGAT_TB_OCC") ? atoi(getenv("MAGAT_TB_OCC")) : 3;
 #define MAGAT_TB(PT) \
   do {                                                                                                              \
     if (tb_occ == 4)                                                                                                \
       k_tap_bwd_v<PT, 4><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->taps, a->att, a->nbr_out, rows, N, K, D, \
-                                                     k, first, a->gz, a->datt, g0sum);                              \
+                                                     k, first, a->gz, a->datt, g0sum, rc_fused);                    \
     else if (tb_occ == 2)                                                                                           \
       k_tap_bwd_v<PT, 2><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->taps, a->att, a->nbr_out, rows, N, K, D, \
-                                                     k, first, a->gz, a->datt, g0sum);                              \
+                                                     k, first, a->gz, a->datt, g0sum, rc_fused);                    \
     else                                                                                                            \
       k_tap_bwd_v<PT, 3><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->taps, a->att, a->nbr_out, rows, N, K, D, \
-                                                     k, first, a->gz, a->datt, g0sum);                              \
+                                                     k, first, a->gz, a->datt, g0sum, rc_fused);                    \
   } while (0)
     if (vec && P == 4) MAGAT_TB(4);
     else if (vec && P == 2) MAGAT_TB(2);
@@ -702,7 +745,8 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
 #define MAGAT_SB(PT) \
   k_softmax_bwd_kq_v<PT><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->att, a->nbr_out, rows, N, D, has_datt, \
                                                      a->datt, a->rc)
-    if (vec && P == 4) MAGAT_SB(4);
+    if (fuse_softmax) {
+    } else if (vec && P == 4) MAGAT_SB(4);
     else if (vec && P == 2) MAGAT_SB(2);
     else if (vec && P == 1) MAGAT_SB(1);
     else
@@ -710,7 +754,7 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
                                                                       a->nbr_out, rows, N, G, P, D, has_datt,
                                                                       a->datt, a->rc);
 #undef MAGAT_SB
-    if ((rc = check_launch("k_softmax_bwd", st))) return rc;
+    if (!fuse_softmax && (rc = check_launch("k_softmax_bwd", st))) return rc;
 #define MAGAT_CB(PT) \
   k_col_bwd_kq_v<PT><<<row_blocks, 256, 0, st>>>(a->gz, a->datt, a->sproj, a->nbr_in, a->slot_in, rows, N, K, D, \
                                                  g0_in_dx ? 1 : 0, a->dx)

@@ -484,7 +484,7 @@ static int forward_impl(const magat_gat_fwd_args* a, cudaStream_t st, bool use_t
       if ((rc = check_launch("k_node_gemm(score projection)", st))) return rc;
     }
     bool fast = vec_ok && D <= 32 && (G == 128 || G == 256);
-    static const int att_occ = getenv("MAGAT_ATT_OCC") ? atoi(getenv("MAGAT_ATT_OCC")) : 1;
+    static const int att_occ = getenv("MAGAT_ATT_OCC") ? atoi(getenv("MAGAT_ATT_OCC")) : 8;
 #define MAGAT_ATT(PT, GV) \
   do {                                                                                                             \
     if (att_occ == 8)                                                                                              \
