@@ -294,7 +294,7 @@ __global__ void __launch_bounds__((17 + EW) * 32, 1) k_tap_tc(const __grid_const
       // Flat output rows: lane f of the warp holds feature f of 32 consecutive nodes, so one scalar store per node
       // is a full 128 B line of that node's row -- no transposition, no shared memory, no barrier between the
       // epilogue warps.  (The staged variant below paced every use of this kernel: the MMA issuer spent its
-      // time waiting for acc_empty, profiles/r01b_ncu_tap_tc_roles.md.)
+      // time waiting for acc_empty, profiles/r01b_tap_tc_lsu.md.)
       for (long tile = slot; tile < tiles; tile += nslots) {
         const long m0 = tile * TN;
         tc::mbar_wait(&acc_full[acc], acc_phase);

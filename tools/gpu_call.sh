@@ -26,6 +26,15 @@ for what in "$@"; do
       timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
         --profile-from-start off --csv --log-file "$out/launches_train.csv" python tools/profile_step.py --what train \
         > "$out/launches.log" 2>&1; echo "launches rc=$?" | tee -a "$out/rc.txt";;
+    sweep)
+      for w in c1_n10 c2_n10 c3_n100 c4_n10 c4_n50 c4_n200 c5_n1000; do
+        timeout 200 python bench.py --workload $w --no-cpu-baseline --no-e2e --steps 20 > "$out/bench_$w.json" 2> "$out/bench_$w.err"
+        echo "== $w rc=$?"; python tools/bench_summary.py "$out/bench_$w.json" 2>/dev/null | head -1
+      done;;
+    launches_fwd)
+      timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
+        --csv --log-file "$out/launches_bench.csv" python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e \
+        > "$out/launches_bench.log" 2>&1; echo "launches_bench rc=$?" | tee -a "$out/rc.txt";;
     ab:*)
       # A/B of one environment knob: tools/gpu_call.sh tag ab:MAGAT_X=1
       kv=${what#ab:}
