@@ -251,8 +251,8 @@ def main():
     if dist_on:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         import datetime
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"            # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: whatever NCCL logs (its version banner at VERSION / WARN level) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         torch.distributed.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     from magat_pathplanning_b200 import _cabi
     from magat_pathplanning_b200.dist import allreduce_gradients
