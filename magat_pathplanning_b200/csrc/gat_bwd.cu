@@ -481,6 +481,125 @@ __global__ void __launch_bounds__(256) k_col_bwd_kq_v(const float* __restrict__ 
   *reinterpret_cast<float4*>(dx + (size_t)row * G + g0) = acc;
 }
 
+// ---- GAT_modified vector kernels (G == 128, D <= 32, P in {1,2,4}) -------------------------------------------
+// softmax + LeakyReLU backward of a sender row: datt <- ds, rc[row][p][1] = sum_j ds[i,j] (the a2 / row term)
+template <int PT>
+__global__ void __launch_bounds__(256) k_softmax_bwd_gm_v(const float* __restrict__ sproj, const float* __restrict__ att,
+                                                          const int32_t* __restrict__ nbr_out, long rows, int N, int D,
+                                                          int has_datt, float* __restrict__ datt,
+                                                          float* __restrict__ rc) {
+  const int lane = threadIdx.x & 31;
+  const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  const long b = batch_of32(row, N);
+  const int my_j = lane < D ? nbr_out[row * D + lane] : -1;
+  float a[PT], da[PT], ds[PT];
+#pragma unroll
+  for (int q = 0; q < PT; ++q) { a[q] = 0.f; da[q] = 0.f; }
+  if (my_j >= 0) {
+    ldp<PT>(att + ((size_t)row * D + lane) * PT, a);
+    if (has_datt) ldp<PT>(datt + ((size_t)row * D + lane) * PT, da);
+  }
+#pragma unroll
+  for (int q = 0; q < PT; ++q) {
+    const float dot = warp_sum(a[q] * da[q]);
+    float de = a[q] * (da[q] - dot);
+    if (my_j >= 0) {
+      const float sr = sproj[((size_t)row * PT + q) * 2 + 1] + sproj[((size_t)(b * N + my_j) * PT + q) * 2 + 0];
+      de *= sr > 0.f ? 1.f : kLeaky;
+    }
+    ds[q] = de;
+    const float rsum = warp_sum(de);
+    if (lane == 0) rc[((size_t)row * PT + q) * 2 + 1] = rsum;
+  }
+  if (lane < D) stp<PT>(datt + ((size_t)row * D + lane) * PT, ds);
+}
+
+// column side: rc[row][p][0] = sum_{i in in(row)} ds[i,row]; dx_row = sum_p gU_0 + sum_p (c_p cvec[p][0] + r_p cvec[p][1])
+template <int PT>
+__global__ void __launch_bounds__(256) k_col_bwd_gm_v(const float* __restrict__ gz, const float* __restrict__ datt,
+                                                      const float* __restrict__ cvec,
+                                                      const int32_t* __restrict__ nbr_in,
+                                                      const int32_t* __restrict__ slot_in, long rows, int N, int K,
+                                                      int D, int g0_in_dx, float* __restrict__ rc,
+                                                      float* __restrict__ dx) {
+  constexpr int G = 128;
+  const int lane = threadIdx.x & 31;
+  const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  const long b = batch_of32(row, N);
+  const int g0 = lane * 4;
+  const int my_i = lane < D ? nbr_in[row * D + lane] : -1;
+  float ds[PT], c[PT], r[PT];
+#pragma unroll
+  for (int q = 0; q < PT; ++q) ds[q] = 0.f;
+  if (my_i >= 0) ldp<PT>(datt + ((size_t)(b * N + my_i) * D + slot_in[row * D + lane]) * PT, ds);
+#pragma unroll
+  for (int q = 0; q < PT; ++q) {
+    c[q] = warp_sum(ds[q]);
+    r[q] = rc[((size_t)row * PT + q) * 2 + 1];
+    if (lane == 0) rc[((size_t)row * PT + q) * 2 + 0] = c[q];
+  }
+  if (dx == nullptr) return;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (g0_in_dx) {
+    acc = *reinterpret_cast<const float4*>(dx + (size_t)row * G + g0);
+  } else {
+#pragma unroll
+    for (int q = 0; q < PT; ++q) {
+      const float4 v = *reinterpret_cast<const float4*>(gz + (((size_t)row * PT + q) * K + 0) * G + g0);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < PT; ++q) {
+    bfma4(acc, c[q], __ldg(reinterpret_cast<const float4*>(cvec + ((size_t)q * 2 + 0) * G + g0)));
+    bfma4(acc, r[q], __ldg(reinterpret_cast<const float4*>(cvec + ((size_t)q * 2 + 1) * G + g0)));
+  }
+  *reinterpret_cast<float4*>(dx + (size_t)row * G + g0) = acc;
+}
+
+// dc[n][g] = sum_m rc[m][n] x[m][g] (g < G) and dc[n][G] = sum_m rc[m][n], n = 2p + t.  Every warp walks a contiguous
+// run of nodes with 2P float4 accumulators per lane; blocks write one partial [2P][G+1] each (summed in block order).
+template <int PT>
+__global__ void __launch_bounds__(256) k_gm_dcvec_v(const float* __restrict__ x, long x_sb, long x_sn,
+                                                    const float* __restrict__ rc, long rows, int N, long per_block,
+                                                    float* __restrict__ partial) {
+  constexpr int G = 128, NV = 2 * PT;
+  __shared__ float red[8][NV][G + 4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long m0 = (long)blockIdx.x * per_block;
+  const long m1 = min(rows, m0 + per_block);
+  float4 acc[NV];
+  float cs[NV];
+#pragma unroll
+  for (int n = 0; n < NV; ++n) { acc[n] = make_float4(0.f, 0.f, 0.f, 0.f); cs[n] = 0.f; }
+  for (long m = m0 + warp; m < m1; m += 8) {
+    const long b = batch_of32(m, N);
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + b * x_sb + (m - b * N) * x_sn + lane * 4));
+#pragma unroll
+    for (int n = 0; n < NV; ++n) {
+      const float w = __ldg(rc + (size_t)m * NV + n);
+      bfma4(acc[n], w, xv);
+      cs[n] += w;                          // identical in every lane; lane 0 reports it
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < NV; ++n) {
+    *reinterpret_cast<float4*>(&red[warp][n][lane * 4]) = acc[n];
+    if (lane == 0) red[warp][n][G] = cs[n];
+  }
+  __syncthreads();
+  float* out = partial + (size_t)blockIdx.x * NV * (G + 1);
+  for (int e = threadIdx.x; e < NV * (G + 1); e += blockDim.x) {
+    const int n = e / (G + 1), g = e - n * (G + 1);
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][n][g];
+    out[e] = s;
+  }
+}
+
 // dbias partials: each block sums `chunk` rows of dP for every channel (coalesced, 8 rows in flight per
 // thread), one partial row per block
 __global__ void __launch_bounds__(256) k_dbias_partial(DPre dp, long rows, int C, int P, int F, int chunk,
@@ -712,7 +831,8 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
                    (K == 1 || ((uintptr_t)a->taps % 16) == 0) && (P == 1 || P == 2 || P == 4) && rows < (1l << 31);
   // KeyQuery, vector kernels: g_0 is only ever read as its head sum (for dx), so the last level of the recursion
   // writes that sum straight into dx and the column kernel picks it up there
-  const bool g0_in_dx = vec && !gm && K > 1 && a->need_dx && getenv("MAGAT_BWD_NO_G0SUM") == nullptr;
+  const bool gm_vec = gm && vec && getenv("MAGAT_GM_GENERIC") == nullptr;      // GAT_modified vector kernels
+  const bool g0_in_dx = vec && (!gm || gm_vec) && K > 1 && a->need_dx && getenv("MAGAT_BWD_NO_G0SUM") == nullptr;
   // ... and the row softmax backward (+ dR) rides on the same last level
   const bool fuse_softmax = vec && !gm && K > 1 && getenv("MAGAT_BWD_NO_FUSED_SOFTMAX") == nullptr;
   for (int k = K - 1; k >= 1; --k) {
@@ -794,20 +914,50 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
     }
   } else {
     const float* cvec = a->wprep;
-    k_softmax_bwd<MAGAT_MODE_GAT_MODIFIED><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj, a->att,
-                                                                        a->nbr_out, rows, N, G, P, D, has_datt,
-                                                                        a->datt, a->rc);
-    if ((rc = check_launch("k_softmax_bwd", st))) return rc;
-    k_col_bwd<MAGAT_MODE_GAT_MODIFIED><<<row_blocks, 256, 0, st>>>(a->gz, a->datt, a->sproj, cvec, a->nbr_in,
-                                                                    a->slot_in, rows, N, G, P, K, D, a->rc,
-                                                                    a->need_dx ? a->dx : nullptr);
-    if ((rc = check_launch("k_col_bwd", st))) return rc;
+    if (gm_vec) {
+#define MAGAT_GSB(PT) \
+  k_softmax_bwd_gm_v<PT><<<row_blocks, 256, 0, st>>>(a->sproj, a->att, a->nbr_out, rows, N, D, has_datt, a->datt, a->rc)
+      if (P == 4) MAGAT_GSB(4);
+      else if (P == 2) MAGAT_GSB(2);
+      else MAGAT_GSB(1);
+#undef MAGAT_GSB
+      if ((rc = check_launch("k_softmax_bwd", st))) return rc;
+#define MAGAT_GCB(PT) \
+  k_col_bwd_gm_v<PT><<<row_blocks, 256, 0, st>>>(a->gz, a->datt, cvec, a->nbr_in, a->slot_in, rows, N, K, D, \
+                                                 g0_in_dx ? 1 : 0, a->rc, a->need_dx ? a->dx : nullptr)
+      if (P == 4) MAGAT_GCB(4);
+      else if (P == 2) MAGAT_GCB(2);
+      else MAGAT_GCB(1);
+#undef MAGAT_GCB
+      if ((rc = check_launch("k_col_bwd", st))) return rc;
+    } else {
+      k_softmax_bwd<MAGAT_MODE_GAT_MODIFIED><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj, a->att,
+                                                                          a->nbr_out, rows, N, G, P, D, has_datt,
+                                                                          a->datt, a->rc);
+      if ((rc = check_launch("k_softmax_bwd", st))) return rc;
+      k_col_bwd<MAGAT_MODE_GAT_MODIFIED><<<row_blocks, 256, 0, st>>>(a->gz, a->datt, a->sproj, cvec, a->nbr_in,
+                                                                      a->slot_in, rows, N, G, P, K, D, a->rc,
+                                                                      a->need_dx ? a->dx : nullptr);
+      if ((rc = check_launch("k_col_bwd", st))) return rc;
+    }
     if (a->need_dweight || a->need_dmixer) {
       // dc [2P][G+1] lives at the tail of `partial`
       const size_t head = (size_t)magat_gat_bwd_partial_floats(B, N, G, F, K, P, a->mode) - (size_t)2 * P * (G + 1);
       float* dc = a->partial + head;
-      if ((rc = rowred(rows, 2 * P, G + 1, 1, RcRed2{a->rc, 2 * P}, XRed1{XRed{a->x, a->x_sb, a->x_sn, N}, G},
-                       a->partial, dc, st, "k_rowred_gemm(dcvec)")))
+      const int nblk = 2 * 148;
+      if (gm_vec && (size_t)nblk * 2 * P * (G + 1) <= head) {
+        const long per_block = (rows + nblk - 1) / nblk;
+#define MAGAT_GDC(PT) k_gm_dcvec_v<PT><<<nblk, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->rc, rows, N, per_block, a->partial)
+        if (P == 4) MAGAT_GDC(4);
+        else if (P == 2) MAGAT_GDC(2);
+        else MAGAT_GDC(1);
+#undef MAGAT_GDC
+        if ((rc = check_launch("k_gm_dcvec", st))) return rc;
+        const long per = 2l * P * (G + 1);
+        k_reduce_partials<<<cdiv(per, 256), 256, 0, st>>>(a->partial, nblk, per, per, dc);
+        if ((rc = check_launch("k_reduce_partials", st))) return rc;
+      } else if ((rc = rowred(rows, 2 * P, G + 1, 1, RcRed2{a->rc, 2 * P}, XRed1{XRed{a->x, a->x_sb, a->x_sn, N}, G},
+                              a->partial, dc, st, "k_rowred_gemm(dcvec)")))
         return rc;
       k_gm_param_bwd<<<P, 128, 0, st>>>(a->weight, a->mixer, a->weight_bias, dc, G, F, P,
                                         a->need_dweight ? a->dweight : nullptr,

@@ -323,6 +323,98 @@ __global__ void __launch_bounds__(256, MINB) k_attention_kq_v(const float* __res
   }
 }
 
+// ---- GAT_modified fast path (G = 128, P in {1,2,4}, D <= 32) ----------------------------------------
+// Sum NV per-lane values over the warp at once: every step halves the number of live values and doubles the lanes
+// each has absorbed (NV - 1 + 5 - log2 NV shuffles instead of 5 NV).  The lane's result is the sum with index
+// lane >> (5 - log2 NV).
+template <int NV>
+__device__ __forceinline__ float warp_multi_sum(float (&v)[NV], int lane) {
+  int off = 16;
+#pragma unroll
+  for (int n = NV; n > 1; n >>= 1, off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float keep = hi ? v[i + n / 2] : v[i];
+      const float send = hi ? v[i] : v[i + n / 2];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+#pragma unroll
+  for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+  return v[0];
+}
+
+// sproj[m][2p + t] = cvec[p][t] . x_m + dvec[p][t]: the whole "projection" of this mode is 2P dot products per node.
+// A warp keeps its slice of the 2P vectors in registers and walks over `per_warp` consecutive nodes, one 512 B row
+// load each -- the generic 64 x 64 tile GEMM spent 0.40 ms on an 8-column output.
+template <int PT>
+__global__ void __launch_bounds__(256) k_gm_mixer_v(const float* __restrict__ x, long x_sb, long x_sn,
+                                                    const float* __restrict__ cvec, const float* __restrict__ dvec,
+                                                    long rows, int N, int per_warp, float* __restrict__ sproj) {
+  constexpr int G = 128, NV = 2 * PT;
+  constexpr int SH = NV == 8 ? 2 : NV == 4 ? 3 : 4;            // 5 - log2 NV
+  const int lane = threadIdx.x & 31;
+  const long w = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  float4 c[NV];
+#pragma unroll
+  for (int n = 0; n < NV; ++n) c[n] = __ldg(reinterpret_cast<const float4*>(cvec + (size_t)n * G + lane * 4));
+  const int mine = lane >> SH;                                   // output this lane ends up holding
+  const float dv = __ldg(dvec + mine);
+  const long m_end = min(rows, (w + 1) * per_warp);
+  for (long m = w * per_warp; m < m_end; ++m) {
+    const long b = batch_of32(m, N);
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + b * x_sb + (m - b * N) * x_sn + lane * 4));
+    float d[NV];
+#pragma unroll
+    for (int n = 0; n < NV; ++n) d[n] = dot4(c[n], xv);
+    const float tot = warp_multi_sum<NV>(d, lane);
+    if ((lane & ((1 << SH) - 1)) == 0) sproj[(size_t)m * NV + mine] = tot + dv;
+  }
+}
+
+// scores e = LeakyReLU(a2.z_i + a1.z_j) from the two scalars per (node, head), row softmax, att + receiver-major ain
+template <int PT>
+__global__ void __launch_bounds__(256) k_attention_gm_v(const float* __restrict__ sproj,
+                                                        const int32_t* __restrict__ nbr_out, long rows, int N, int D,
+                                                        float* __restrict__ att, const int32_t* __restrict__ slot_out,
+                                                        float* __restrict__ ain) {
+  const int lane = threadIdx.x & 31;
+  const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  const long b = batch_of32(row, N);
+  const int my_j = lane < D ? __ldg(nbr_out + row * D + lane) : -1;
+  const bool v = my_j >= 0;
+  float a[PT];
+#pragma unroll
+  for (int p = 0; p < PT; ++p) {
+    const float si = __ldg(sproj + ((size_t)row * PT + p) * 2 + 1);
+    float e = -INFINITY;
+    if (v) {
+      e = si + __ldg(sproj + ((size_t)(b * N + my_j) * PT + p) * 2 + 0);
+      e = e > 0.f ? e : kLeaky * e;
+    }
+    const float mx = warp_max(e);
+    const float ex = v ? expf(e - mx) : 0.f;
+    const float sum = warp_sum(ex);
+    a[p] = v ? ex / sum : 0.f;
+  }
+  if (lane < D) {
+    float* dst = att + ((size_t)row * D + lane) * PT;
+    if (PT == 4) {
+      *reinterpret_cast<float4*>(dst) = make_float4(a[0], a[1 % PT], a[2 % PT], a[3 % PT]);
+    } else {
+#pragma unroll
+      for (int p = 0; p < PT; ++p) dst[p] = a[p];
+    }
+    if (ain != nullptr && v) {
+      float* r = ain + ((size_t)(b * N + my_j) * PT) * D + slot_out[row * D + lane];
+#pragma unroll
+      for (int p = 0; p < PT; ++p) r[(size_t)p * D] = a[p];
+    }
+  }
+}
+
 // ---- functors for the tile GEMMs ----------------------------------------------------------
 struct XLoad {   // A(m, g): node features
   const float* x; long x_sb, x_sn; int N;
@@ -509,11 +601,29 @@ static int forward_impl(const magat_gat_fwd_args* a, cudaStream_t st, bool use_t
     float* dvec = a->wprep + (size_t)P * 2 * G;
     k_gm_prep<<<P * 2, 128, 0, st>>>(a->weight, a->mixer, a->weight_bias, G, F, P, cvec, dvec);
     if ((rc = check_launch("k_gm_prep", st))) return rc;
-    dim3 grid(cdiv(rows, 64), cdiv(2l * P, 64), 1);
-    k_node_gemm<<<grid, 256, 0, st>>>(rows, 2 * P, G, xl, GmCLoad{cvec, G}, GmEpi{a->sproj, dvec, 2 * P});
-    if ((rc = check_launch("k_node_gemm(mixer projection)", st))) return rc;
-    k_attention<MAGAT_MODE_GAT_MODIFIED><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj,
-                                                                      a->nbr_out, rows, N, G, P, D, a->att, so, ain_w);
+    const bool gm_fast = vec_ok && G == 128 && D <= 32 && (P == 1 || P == 2 || P == 4) &&
+                         (((uintptr_t)cvec) % 16 == 0) && getenv("MAGAT_GM_GENERIC") == nullptr;
+    if (gm_fast) {
+      const int per_warp = 16;
+      const int blocks = cdiv(cdiv(rows, per_warp), 8);
+#define MAGAT_GMX(PT) k_gm_mixer_v<PT><<<blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, cvec, dvec, rows, N, per_warp, a->sproj)
+      if (P == 4) MAGAT_GMX(4);
+      else if (P == 2) MAGAT_GMX(2);
+      else MAGAT_GMX(1);
+#undef MAGAT_GMX
+      if ((rc = check_launch("k_gm_mixer", st))) return rc;
+#define MAGAT_GMA(PT) k_attention_gm_v<PT><<<row_blocks, 256, 0, st>>>(a->sproj, a->nbr_out, rows, N, D, a->att, so, ain_w)
+      if (P == 4) MAGAT_GMA(4);
+      else if (P == 2) MAGAT_GMA(2);
+      else MAGAT_GMA(1);
+#undef MAGAT_GMA
+    } else {
+      dim3 grid(cdiv(rows, 64), cdiv(2l * P, 64), 1);
+      k_node_gemm<<<grid, 256, 0, st>>>(rows, 2 * P, G, xl, GmCLoad{cvec, G}, GmEpi{a->sproj, dvec, 2 * P});
+      if ((rc = check_launch("k_node_gemm(mixer projection)", st))) return rc;
+      k_attention<MAGAT_MODE_GAT_MODIFIED><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj,
+                                                                        a->nbr_out, rows, N, G, P, D, a->att, so, ain_w);
+    }
   }
   if ((rc = check_launch("k_attention", st))) return rc;
   // 2. taps (the fused tcgen05 kernel gathers the second tap itself and only needs u_1 in memory)
