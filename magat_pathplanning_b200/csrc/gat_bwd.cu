@@ -437,7 +437,8 @@ __global__ void __launch_bounds__(256) k_col_bwd_kq_v(const float* __restrict__ 
                                                       const float* __restrict__ sproj,
                                                       const int32_t* __restrict__ nbr_in,
                                                       const int32_t* __restrict__ slot_in, long rows, int N, int K,
-                                                      int D, int g0_in_dx, float* __restrict__ dx) {
+                                                      int D, int g0_in_dx, const float* __restrict__ dxp, int ndxp,
+                                                      float* __restrict__ dx) {
   constexpr int G = 128;
   const int lane = threadIdx.x & 31;
   const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -459,6 +460,10 @@ __global__ void __launch_bounds__(256) k_col_bwd_kq_v(const float* __restrict__ 
       const float4 v = *reinterpret_cast<const float4*>(gz + (((size_t)row * PT + q) * K + 0) * G + g0);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
+  }
+  for (int h = 0; h < ndxp; ++h) {         // dense part sum_p dR_p W_p^T, one partial row per head pair
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(dxp + ((size_t)row * ndxp + h) * G + g0));
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
   for (int s = 0; s < deg; s += 2) {
     float4 rv[2][PT];
@@ -709,7 +714,7 @@ bool gz_tc_supported(const magat_gat_bwd_args* a);
 int gz_tc_backward(const magat_gat_bwd_args* a, float* ht, cudaStream_t st);
 bool dx_tc_supported(const magat_gat_bwd_args* a);
 bool dx_tap_supported(const magat_gat_bwd_args* a);                 // gat_tap_tc.cu
-int dx_tap_accumulate(const magat_gat_bwd_args* a, float* wcat, cudaStream_t st);
+int dx_tap_partials(const magat_gat_bwd_args* a, float* wcat, float* dxp, cudaStream_t st);
 int tc_dx_accumulate(const magat_gat_bwd_args* a, const __nv_bfloat16* w_hi, const __nv_bfloat16* w_lo,
                      cudaStream_t st);
 int tc_split_weights(const float* src, long n, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st);
@@ -875,9 +880,18 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
                                                                       a->datt, a->rc);
 #undef MAGAT_SB
     if (!fuse_softmax && (rc = check_launch("k_softmax_bwd", st))) return rc;
+    // dense part of dx first (needs only dR): head-pair partials into the dead planes of gz, added by the column kernel
+    int dx_done = 0;
+    const float* dxp = nullptr;
+    if (vec && g0_in_dx && a->need_dx && a->path != MAGAT_PATH_SIMT && dx_tap_supported(a) &&
+        (size_t)(P / 2) * G <= (size_t)P * K * G) {
+      rc = dx_tap_partials(a, a->partial, a->gz, st);
+      if (rc > 0) return rc;
+      if (rc == 0) { dx_done = 1; dxp = a->gz; }
+    }
 #define MAGAT_CB(PT) \
   k_col_bwd_kq_v<PT><<<row_blocks, 256, 0, st>>>(a->gz, a->datt, a->sproj, a->nbr_in, a->slot_in, rows, N, K, D, \
-                                                 g0_in_dx ? 1 : 0, a->dx)
+                                                 g0_in_dx ? 1 : 0, dxp, dxp ? P / 2 : 0, a->dx)
     if (vec && a->need_dx && P == 4) MAGAT_CB(4);
     else if (vec && a->need_dx && P == 2) MAGAT_CB(2);
     else if (vec && a->need_dx && P == 1) MAGAT_CB(1);
@@ -887,12 +901,6 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
                                                                   a->need_dx ? a->dx : nullptr);
 #undef MAGAT_CB
     if ((rc = check_launch("k_col_bwd", st))) return rc;
-    int dx_done = 0;
-    if (a->need_dx && a->path != MAGAT_PATH_SIMT && dx_tap_supported(a)) {
-      rc = dx_tap_accumulate(a, a->partial, st);
-      if (rc > 0) return rc;
-      dx_done = rc == 0;
-    }
     if (dx_done) {
     } else if (a->need_dx && a->path != MAGAT_PATH_SIMT && dx_tc_supported(a)) {
       __nv_bfloat16* w_hi = reinterpret_cast<__nv_bfloat16*>(a->partial);

@@ -861,42 +861,36 @@ __global__ void __launch_bounds__(256) k_pack_wcat(const float* __restrict__ W, 
   wcat[(size_t)h * G * 2 * G + (size_t)g * (G * nsl) + pl * G + gp] = W[i];
 }
 
+// KeyQuery: the dense part of dx, sum_p dR_p W_p^T, as head-PAIR partial products on the TMA-fed kernel:
+//   dxp[m][h][g] = sum_{pl < 2, g'} dR[m][2h + pl][g'] W[2h + pl][g][g']
+// (four heads of weights do not fit TMEM next to the accumulators; two do).  One launch, plain stores -- the
+// accumulating variant stalled its four epilogue warps on the read-modify-write latency (1.00 ms for two launches).
+// The column kernel, which runs next and owns dx anyway, adds the P/2 partial rows.
 bool dx_tap_supported(const magat_gat_bwd_args* a) {
-  // opt-in: measured 1.00 ms (two launches, read-modify-write epilogue) against 0.66 ms for k_tc_gemm at c4_n1000
-  if (a->mode != MAGAT_MODE_KEYQUERY || a->G != FT || getenv("MAGAT_DX_TAP") == nullptr) return false;
-  if (((uintptr_t)a->rc % 16) != 0 || ((uintptr_t)a->dx % 16) != 0 || ((uintptr_t)a->partial % 16) != 0) return false;
+  if (a->mode != MAGAT_MODE_KEYQUERY || a->G != FT || a->P % 2 != 0 || getenv("MAGAT_DX_GEMM") != nullptr) return false;
+  if (((uintptr_t)a->rc % 16) != 0 || ((uintptr_t)a->gz % 16) != 0 || ((uintptr_t)a->partial % 16) != 0) return false;
   if ((long)a->B * a->N >= (1l << 31)) return false;
   return true;
 }
 
-// KeyQuery: dx[m][g] += sum_{p,g'} dR[m][p][g'] W[p][g][g'] on the TMA-fed kernel, two heads (K slices) per launch --
-// four heads of weights do not fit TMEM next to the accumulators.  wcat: P*G*G floats of scratch.
-// Returns -1 when the v2 kernel cannot take the shapes (caller falls back to k_tc_gemm).
-int dx_tap_accumulate(const magat_gat_bwd_args* a, float* wcat, cudaStream_t st) {
+// wcat: P*G*G floats of scratch; dxp: rows * (P/2) * G floats.  Returns -1 when the v2 kernel cannot take the shapes.
+int dx_tap_partials(const magat_gat_bwd_args* a, float* wcat, float* dxp, cudaStream_t st) {
   const int G = a->G, P = a->P;
   TapParams tp{};
   tp.rows = (long)a->B * a->N;
-  tp.N = a->N; tp.K = 1; tp.P = 1; tp.D = a->D; tp.nout = 1;
-  tp.x_sn = (long)P * G; tp.x_sb = (long)a->N * tp.x_sn;
-  tp.x_hdiv = 1; tp.x_hmul = 0;
-  tp.y = a->dx; tp.y_sn = G; tp.y_sb = (long)a->N * G;
-  tp.accum = 1;
-  {  // probe with the first launch's shape before touching the scratch
+  tp.N = a->N; tp.G = 2 * G; tp.K = 1; tp.P = P / 2; tp.D = a->D; tp.nout = 1;
+  tp.x = a->rc; tp.x_sn = (long)P * G; tp.x_sb = (long)a->N * tp.x_sn;
+  tp.x_hdiv = 1; tp.x_hmul = 2 * G;
+  tp.H = wcat;
+  tp.y = dxp; tp.y_sn = (long)(P / 2) * G; tp.y_sb = (long)a->N * tp.y_sn;
+  {
     TapParams t0 = tp;
-    t0.G = G * (P >= 2 ? 2 : 1); t0.x = a->rc; t0.H = wcat;
-    if (!tap_tc2_prepare(t0, t0.G)) return -1;
+    if (!tap_tc2_prepare(t0, P * G)) return -1;
   }
   k_pack_wcat<<<cdiv((long)P * G * G, 256), 256, 0, st>>>(a->weight, G, P, wcat);
   int rc = check_launch("k_pack_wcat", st);
   if (rc) return rc;
-  for (int h = 0; 2 * h < P; ++h) {
-    const int nsl = (P - 2 * h) >= 2 ? 2 : 1;
-    tp.G = G * nsl;
-    tp.x = a->rc + (long)h * 2 * G;
-    tp.H = wcat + (size_t)h * G * 2 * G;
-    if ((rc = launch_tap_tc(tp, 1, st, "k_tap_tc(dx += dR W^T)", true))) return rc;
-  }
-  return MAGAT_OK;
+  return launch_tap_tc(tp, tp.P, st, "k_tap_tc(dx partials = dR W^T)", true);
 }
 
 // MAGAT_FUSE_U2=1 keeps the second tap out of HBM (gathered by the producer warps); measured slower than
