@@ -69,6 +69,16 @@ def synth_gso(B, N, width, device, gen, chunk=64):
     return S
 
 
+def synth_positions(B, N, width, device, gen, chunk=64):
+    """The agent cells synth_gso draws (same generator calls, so the same graphs), as [B,N,2] fp32 (row, column)."""
+    out = torch.empty((B, N, 2), dtype=torch.float32, device=device)
+    for b0 in range(0, B, chunk):
+        nb = min(chunk, B - b0)
+        cells = torch.rand((nb, width * width), device=device, generator=gen).argsort(dim=1)[:, :N]
+        out[b0:b0 + nb] = torch.stack((cells // width, cells % width), dim=2).to(torch.float32)
+    return out
+
+
 def make_problem(w, device, seed):
     from magat_pathplanning_b200 import GraphFilterBatchAttentional
     gen = torch.Generator(device=device).manual_seed(seed)
@@ -380,6 +390,63 @@ def main():
                        "H2D of chunk c+1 overlaps the layer call on chunk c"}
         del S_h, x_h, S_d, x_d
 
+    # ---- the same step fed with agent positions instead of the dense GSO -------------------------
+    # (reported next to the contract's numbers, never instead of them: `value`, `fwd`, `roofline` and `e2e` keep
+    # the reference's dense-GSO interface)
+    positions = None
+    if world == 1 and not args.no_e2e and N <= 3072:
+        try:
+            pos = synth_positions(B, N, w["width"], dev, torch.Generator(device=dev).manual_seed(SEED + rank))
+            from magat_pathplanning_b200 import build_adjacency, build_adjacency_from_positions
+            a_d, a_p = build_adjacency(S), build_adjacency_from_positions(pos, COMM_RADIUS)
+            same = all(torch.equal(getattr(a_d, k), getattr(a_p, k)) for k in ("nbr_out", "nbr_in", "slot_in", "slot_out"))
+            del a_d, a_p
+
+            def step_train_pos():
+                for p in params:
+                    p.grad = None
+                xg = x.detach().requires_grad_(True)
+                layer.addGSOFromPositions(pos, COMM_RADIUS)
+                y = layer(xg)
+                y.backward(dy)
+                return y
+
+            def step_fwd_pos():
+                with torch.no_grad():
+                    layer.addGSOFromPositions(pos, COMM_RADIUS)
+                    return layer(x)
+            ms_tp = timed(step_train_pos, max(2, args.steps // 2), 2, False)
+            ms_fp = timed(step_fwd_pos, max(2, args.steps // 2), 2, False)
+            pos_h = torch.empty(pos.shape, dtype=pos.dtype, pin_memory=True)
+            x_h2 = torch.empty(x_mem.shape, dtype=x_mem.dtype, pin_memory=True)
+            pos_h.copy_(pos)
+            x_h2.copy_(x_mem)
+            pos_d, x_d2 = torch.empty_like(pos), torch.empty_like(x_mem)
+
+            def step_e2e_pos():
+                pos_d.copy_(pos_h, non_blocking=True)
+                x_d2.copy_(x_h2, non_blocking=True)
+                for p in params:
+                    p.grad = None
+                xg = x_d2.permute(0, 2, 1).requires_grad_(True)
+                layer.addGSOFromPositions(pos_d, COMM_RADIUS)
+                y = layer(xg)
+                loss = (y * dy).sum()
+                loss.backward()
+                return float(loss.item())
+            ms_ep = timed(step_e2e_pos, max(2, min(args.steps, 5)), 1, False)
+            positions = {"lists_equal_dense_gso": bool(same),
+                         "train": {"value": units / (ms_tp * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms_tp},
+                         "fwd": {"value": units / (ms_fp * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms_fp},
+                         "e2e": {"value": units / (ms_ep * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms_ep,
+                                 "h2d_bytes_per_step": pos_h.numel() * 4 + x_h2.numel() * 4, "d2h_bytes_per_step": 4},
+                         "note": "addGSOFromPositions(pos [B,N,2], commR): neighbour lists built on the device from "
+                                 "positions (utils/new_simulator.py:823-827); no N x N GSO exists or crosses PCIe"}
+            del pos_h, x_h2, pos_d, x_d2
+            layer.addGSO(S)
+        except Exception as exc:                      # an extra, never a reason to lose the contract line
+            positions = {"error": str(exc)[-200:]}
+
     if rank != 0:
         if dist_on:
             torch.distributed.destroy_process_group()
@@ -430,6 +497,7 @@ def main():
                    "parallelism": f"batch-sharded x{world}, grad all-reduce (NCCL)" if dist_on else "1 GPU"},
         "fwd": {"value": units / (ms_fwd * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms_fwd},
         "roofline": roofline, "train_kernels": train_kernels, "cpu_baseline": cpu_baseline, "e2e": e2e,
+        "positions_input": positions,
         "gpu_launches": int(launches_per_step) * args.steps, "gpu_launches_per_step": int(launches_per_step),
         "clocks": clocks,
     }

@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define MAGAT_ABI_VERSION 6
+#define MAGAT_ABI_VERSION 7
 
 enum {
   MAGAT_OK = 0,
@@ -81,6 +81,14 @@ int magat_gso_scan(const void* S, int s_dtype, int B, int N,
 int magat_gso_build_ell(const uint32_t* rowbits, const uint32_t* colbits, int B, int N, int D,
                         int32_t* nbr_out, int32_t* nbr_in, int32_t* slot_in, int32_t* slot_out /* may be NULL */,
                         void* stream);
+
+/* ---- the step BEFORE the path.  Edge mask straight from agent positions, replacing the CPU
+ * squareform(pdist(pos)) < commR + zero diagonal of utils/new_simulator.py:823-827 and the 4N^2-byte dense GSO that
+ * then crosses PCIe.  pos: [B][N][2] fp32 or fp64 (device); the predicate is evaluated in fp64 like scipy's.  Writes the
+ * same rowbits / colbits / stats as magat_gso_scan (stats zero-initialised by the caller except stats[3] = 1);
+ * continue with magat_gso_build_ell.  N <= 3072. */
+int magat_gso_from_positions(const void* pos, int pos_dtype, int B, int N, double comm_radius,
+                             uint32_t* rowbits, uint32_t* colbits, int32_t* stats, void* stream);
 
 /* ---- forward (replaces GraphFilterBatchAttentional.forward, graphML.py:4636-4667) ---- */
 typedef struct magat_gat_fwd_args {

@@ -6,9 +6,10 @@ reference's own module interface.  See DESIGN.md / INTEGRATION.md.
 """
 from .graphML import (GraphFilterBatchAttentional, graphAttentionLSIGFBatch_KeyQuery,  # noqa: F401
                       graphAttentionLSIGFBatch_modified, learnAttentionGSOBatch_KeyQuery,
-                      learnAttentionGSOBatch, build_adjacency, gat_layer, attention_dense)
+                      learnAttentionGSOBatch, build_adjacency, build_adjacency_from_positions, gat_layer,
+                      attention_dense)
 from .integration import install_into_reference  # noqa: F401
 
 __all__ = ["GraphFilterBatchAttentional", "graphAttentionLSIGFBatch_KeyQuery",
            "graphAttentionLSIGFBatch_modified", "learnAttentionGSOBatch_KeyQuery", "learnAttentionGSOBatch",
-           "build_adjacency", "gat_layer", "attention_dense", "install_into_reference"]
+           "build_adjacency", "build_adjacency_from_positions", "gat_layer", "attention_dense", "install_into_reference"]

@@ -12,7 +12,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmagat_gat.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 MODE_KEYQUERY, MODE_GAT_MODIFIED = 0, 1
 DT_F32, DT_F64 = 0, 1
@@ -23,7 +23,7 @@ EXPORTS = (
     "magat_gso_build_ell", "magat_gat_wprep_floats", "magat_gat_forward", "magat_gat_forward_taps_valid",
     "magat_gat_bwd_partial_floats", "magat_gat_backward", "magat_gat_attention_dense",
     "magat_launch_count", "magat_profile_enable", "magat_profile_collect",
-    "magat_gat_small_supported", "magat_gat_forward_small",
+    "magat_gat_small_supported", "magat_gat_forward_small", "magat_gso_from_positions",
 )
 
 _i32, _i64, _ptr = C.c_int32, C.c_int64, C.c_void_p
@@ -85,6 +85,8 @@ def lib():
         L.magat_device_check.restype = C.c_int
         L.magat_gso_scan.argtypes = [_ptr, C.c_int, C.c_int, C.c_int, _ptr, _ptr, _ptr, _ptr]
         L.magat_gso_build_ell.argtypes = [_ptr, _ptr, C.c_int, C.c_int, C.c_int, _ptr, _ptr, _ptr, _ptr, _ptr]
+        L.magat_gso_from_positions.argtypes = [_ptr, C.c_int, C.c_int, C.c_int, C.c_double, _ptr, _ptr, _ptr, _ptr]
+        L.magat_gso_from_positions.restype = C.c_int
         L.magat_gat_wprep_floats.argtypes = [C.c_int] * 5
         L.magat_gat_wprep_floats.restype = C.c_size_t
         L.magat_gat_forward.argtypes = [C.POINTER(FwdArgs), _ptr]

@@ -252,6 +252,42 @@ __global__ void __launch_bounds__((kScanWarps + 1) * 32, 1) k_gso_scan_tma(const
   }
 }
 
+// ---- f1: edge mask straight from agent positions ------------------------------------------------
+// utils/new_simulator.py:823-827 builds the GSO as squareform(pdist(pos)) < commR with a zeroed diagonal (the
+// normalisation that follows only scales it, and the layer only tests |S| > 1e-9).  Same predicate here, in fp64 as
+// scipy computes it: sqrt(dx^2 + dy^2) < R, i != j.  One block = 32 rows of one instance, positions staged in shared
+// memory; a warp emits the W words of its rows with one ballot each.  The mask is symmetric: colbits = rowbits.
+template <typename T>
+__global__ void __launch_bounds__(256) k_gso_from_positions(const T* __restrict__ pos, int N, int W, double radius,
+                                                            uint32_t* __restrict__ rowbits,
+                                                            uint32_t* __restrict__ colbits) {
+  extern __shared__ double pos_s[];                    // [N][2]
+  const int b = blockIdx.y;
+  const T* pb = pos + (size_t)b * N * 2;
+  for (int e = threadIdx.x; e < 2 * N; e += blockDim.x) pos_s[e] = (double)pb[e];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int rr = warp; rr < 32; rr += 8) {
+    const int i = blockIdx.x * 32 + rr;
+    if (i >= N) break;
+    const double xi = pos_s[2 * i], yi = pos_s[2 * i + 1];
+    const size_t base = ((size_t)b * N + i) * W;
+    for (int w = 0; w < W; ++w) {
+      const int j = w * 32 + lane;
+      bool e = false;
+      if (j < N && j != i) {
+        const double dx = xi - pos_s[2 * j], dy = yi - pos_s[2 * j + 1];
+        e = sqrt(dx * dx + dy * dy) < radius;
+      }
+      const uint32_t word = __ballot_sync(0xffffffffu, e);
+      if (lane == 0) {
+        rowbits[base + w] = word;
+        colbits[base + w] = word;
+      }
+    }
+  }
+}
+
 // stats[0] max out-degree, [1] max in-degree, [2] number of edges, [3] symmetric flag.
 __global__ void __launch_bounds__(256) k_gso_stats(const uint32_t* __restrict__ rowbits,
                                                    const uint32_t* __restrict__ colbits, long rows,
@@ -543,6 +579,31 @@ __global__ void __launch_bounds__(256) k_att_dense(const float* __restrict__ att
 
 using namespace magat;
 
+static int launch_gso_stats(const uint32_t* rowbits, const uint32_t* colbits, int B, int N, int W, int32_t* stats,
+                            cudaStream_t st) {
+  const long rows = (long)B * N;
+  const int lpr = W / 4;
+  if (W % 4 == 0 && lpr <= 32 && (lpr & (lpr - 1)) == 0 && ((uintptr_t)rowbits % 16) == 0 &&
+      ((uintptr_t)colbits % 16) == 0) {
+    const long n4 = rows * lpr;
+    const int blocks = (int)min((long)148 * 8, (n4 + 255) / 256);
+    const uint4* r4 = reinterpret_cast<const uint4*>(rowbits);
+    const uint4* c4 = reinterpret_cast<const uint4*>(colbits);
+    switch (lpr) {
+      case 1: k_gso_stats_v<1><<<blocks, 256, 0, st>>>(r4, c4, n4, stats); break;
+      case 2: k_gso_stats_v<2><<<blocks, 256, 0, st>>>(r4, c4, n4, stats); break;
+      case 4: k_gso_stats_v<4><<<blocks, 256, 0, st>>>(r4, c4, n4, stats); break;
+      case 8: k_gso_stats_v<8><<<blocks, 256, 0, st>>>(r4, c4, n4, stats); break;
+      case 16: k_gso_stats_v<16><<<blocks, 256, 0, st>>>(r4, c4, n4, stats); break;
+      default: k_gso_stats_v<32><<<blocks, 256, 0, st>>>(r4, c4, n4, stats); break;
+    }
+  } else {
+    int blocks = (int)min((long)148 * 8, (rows + 7) / 8);
+    k_gso_stats<<<blocks, 256, 0, st>>>(rowbits, colbits, rows, W, stats);
+  }
+  return check_launch("k_gso_stats", st);
+}
+
 extern "C" int magat_gso_scan(const void* S, int s_dtype, int B, int N, uint32_t* rowbits,
                               uint32_t* colbits, int32_t* stats, void* stream) {
   MAGAT_REQUIRE(S && rowbits && colbits && stats, MAGAT_E_BAD_ARG, "magat_gso_scan: null pointer");
@@ -602,27 +663,7 @@ extern "C" int magat_gso_scan(const void* S, int s_dtype, int B, int N, uint32_t
   }
   int rc = check_launch("k_gso_scan", (cudaStream_t)stream);
   if (rc) return rc;
-  const long rows = (long)B * N;
-  const int lpr = W / 4;
-  if (W % 4 == 0 && lpr <= 32 && (lpr & (lpr - 1)) == 0 && ((uintptr_t)rowbits % 16) == 0 &&
-      ((uintptr_t)colbits % 16) == 0) {
-    const long n4 = rows * lpr;
-    const int blocks = (int)min((long)148 * 8, (n4 + 255) / 256);
-    const uint4* r4 = reinterpret_cast<const uint4*>(rowbits);
-    const uint4* c4 = reinterpret_cast<const uint4*>(colbits);
-    switch (lpr) {
-      case 1: k_gso_stats_v<1><<<blocks, 256, 0, st>>>(r4, c4, n4, stats); break;
-      case 2: k_gso_stats_v<2><<<blocks, 256, 0, st>>>(r4, c4, n4, stats); break;
-      case 4: k_gso_stats_v<4><<<blocks, 256, 0, st>>>(r4, c4, n4, stats); break;
-      case 8: k_gso_stats_v<8><<<blocks, 256, 0, st>>>(r4, c4, n4, stats); break;
-      case 16: k_gso_stats_v<16><<<blocks, 256, 0, st>>>(r4, c4, n4, stats); break;
-      default: k_gso_stats_v<32><<<blocks, 256, 0, st>>>(r4, c4, n4, stats); break;
-    }
-  } else {
-    int blocks = (int)min((long)148 * 8, (rows + 7) / 8);
-    k_gso_stats<<<blocks, 256, 0, st>>>(rowbits, colbits, rows, W, stats);
-  }
-  return check_launch("k_gso_stats", (cudaStream_t)stream);
+  return launch_gso_stats(rowbits, colbits, B, N, W, stats, st);
 }
 
 extern "C" int magat_gso_build_ell(const uint32_t* rowbits, const uint32_t* colbits, int B, int N,
@@ -658,6 +699,28 @@ extern "C" int magat_gso_build_ell(const uint32_t* rowbits, const uint32_t* colb
   if ((rc = check_launch("k_build_lists", st))) return rc;
   k_build_slots<<<cdiv(rows * D, 256), 256, 0, st>>>(nbr_out, nbr_in, rows, N, D, slot_in, slot_out);
   return check_launch("k_build_slots", st);
+}
+
+extern "C" int magat_gso_from_positions(const void* pos, int pos_dtype, int B, int N, double comm_radius,
+                                        uint32_t* rowbits, uint32_t* colbits, int32_t* stats, void* stream) {
+  MAGAT_REQUIRE(pos && rowbits && colbits && stats, MAGAT_E_BAD_ARG, "magat_gso_from_positions: null pointer");
+  MAGAT_REQUIRE(B >= 1 && N >= 1 && B <= 65535, MAGAT_E_BAD_ARG, "magat_gso_from_positions: B=%d N=%d", B, N);
+  MAGAT_REQUIRE(pos_dtype == MAGAT_DT_F32 || pos_dtype == MAGAT_DT_F64, MAGAT_E_BAD_ARG,
+                "magat_gso_from_positions: positions must be fp32 or fp64");
+  MAGAT_REQUIRE(comm_radius == comm_radius, MAGAT_E_BAD_ARG, "magat_gso_from_positions: radius is NaN");
+  const size_t smem = (size_t)N * 2 * sizeof(double);
+  MAGAT_REQUIRE(smem <= 48 * 1024, MAGAT_E_UNSUPPORTED, "magat_gso_from_positions: N=%d exceeds 3072 agents", N);
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin(st);
+  const int W = (N + 31) / 32;
+  dim3 grid(cdiv(N, 32), B);
+  if (pos_dtype == MAGAT_DT_F32)
+    k_gso_from_positions<float><<<grid, 256, smem, st>>>((const float*)pos, N, W, comm_radius, rowbits, colbits);
+  else
+    k_gso_from_positions<double><<<grid, 256, smem, st>>>((const double*)pos, N, W, comm_radius, rowbits, colbits);
+  int rc = check_launch("k_gso_from_positions", st);
+  if (rc) return rc;
+  return launch_gso_stats(rowbits, colbits, B, N, W, stats, st);
 }
 
 extern "C" int magat_gat_attention_dense(const float* att, const int32_t* nbr_out, int B, int N,

@@ -83,19 +83,52 @@ def build_adjacency(S: torch.Tensor) -> Adjacency:
         stats[3] = 1
         _cabi.check(L.magat_gso_scan(S.data_ptr(), _cabi.DT_F32 if S.dtype == torch.float32 else _cabi.DT_F64,
                                      B, N, rowbits.data_ptr(), colbits.data_ptr(), stats.data_ptr(), st))
-        if N <= _NOSYNC_N:
-            D = N
-        else:
-            h = stats.cpu()
-            D = max(int(h[0]), int(h[1]), 1)
-        D = (D + 3) // 4 * 4             # 16 B aligned neighbour rows (int4 / float4 loads in the kernels)
-        nbr_out = torch.empty((B, N, D), dtype=torch.int32, device=dev)
-        nbr_in = torch.empty((B, N, D), dtype=torch.int32, device=dev)
-        slot_in = torch.empty((B, N, D), dtype=torch.int32, device=dev)
-        slot_out = torch.empty((B, N, D), dtype=torch.int32, device=dev)
-        _cabi.check(L.magat_gso_build_ell(rowbits.data_ptr(), colbits.data_ptr(), B, N, D, nbr_out.data_ptr(),
-                                          nbr_in.data_ptr(), slot_in.data_ptr(), slot_out.data_ptr(), st))
+        return _lists_from_masks(rowbits, colbits, stats, B, N, dev, st)
+
+
+def _lists_from_masks(rowbits, colbits, stats, B, N, dev, st):
+    L = _cabi.lib()
+    if N <= _NOSYNC_N:
+        D = N
+    else:
+        h = stats.cpu()
+        D = max(int(h[0]), int(h[1]), 1)
+    D = (D + 3) // 4 * 4             # 16 B aligned neighbour rows (int4 / float4 loads in the kernels)
+    nbr_out = torch.empty((B, N, D), dtype=torch.int32, device=dev)
+    nbr_in = torch.empty((B, N, D), dtype=torch.int32, device=dev)
+    slot_in = torch.empty((B, N, D), dtype=torch.int32, device=dev)
+    slot_out = torch.empty((B, N, D), dtype=torch.int32, device=dev)
+    _cabi.check(L.magat_gso_build_ell(rowbits.data_ptr(), colbits.data_ptr(), B, N, D, nbr_out.data_ptr(),
+                                      nbr_in.data_ptr(), slot_in.data_ptr(), slot_out.data_ptr(), st))
     return Adjacency(B, N, D, nbr_out, nbr_in, slot_in, slot_out)
+
+
+def build_adjacency_from_positions(pos: torch.Tensor, comm_radius: float) -> Adjacency:
+    """neighbour lists straight from agent positions [B,N,2] (fp32 / fp64, CUDA), edge iff
+    the Euclidean distance is < comm_radius, no self loops -- the mask utils/new_simulator.py:823-827 builds on the
+    CPU before shipping a dense N x N GSO.  Equal to ``build_adjacency`` of that GSO."""
+    _require_cuda(pos, "the positions")
+    assert len(pos.shape) == 3 and pos.shape[2] == 2
+    pos = pos.detach()
+    if pos.dtype not in (torch.float32, torch.float64):
+        pos = pos.to(torch.float64)
+    if not pos.is_contiguous():
+        pos = pos.contiguous()
+    B, N = pos.shape[0], pos.shape[1]
+    dev = pos.device
+    L = _cabi.lib()
+    W = (N + 31) // 32
+    with torch.cuda.device(dev):
+        st = _stream(dev)
+        rowbits = torch.empty((B, N, W), dtype=torch.int32, device=dev)
+        colbits = torch.empty((B, N, W), dtype=torch.int32, device=dev)
+        stats = torch.zeros(4, dtype=torch.int32, device=dev)
+        stats[3] = 1
+        _cabi.check(L.magat_gso_from_positions(pos.data_ptr(),
+                                               _cabi.DT_F32 if pos.dtype == torch.float32 else _cabi.DT_F64, B, N,
+                                               float(comm_radius), rowbits.data_ptr(), colbits.data_ptr(),
+                                               stats.data_ptr(), st))
+        return _lists_from_masks(rowbits, colbits, stats, B, N, dev, st)
 
 
 def _node_major(x: torch.Tensor):
@@ -414,6 +447,7 @@ class GraphFilterBatchAttentional(nn.Module):
         self.path = "auto"
         self._last = None
         self._aij = None
+        self._adj = None
         if E != 1:
             raise NotImplementedError("edge_features E != 1 is not supported")
         self.mixer = nn.parameter.Parameter(torch.Tensor(P, E, 2 * F))
@@ -444,6 +478,16 @@ class GraphFilterBatchAttentional(nn.Module):
         self.N = S.shape[2]
         assert S.shape[3] == self.N
         self.S = S                       # borrowed, read at forward time like the reference
+        self._adj = None
+
+    def addGSOFromPositions(self, pos, comm_radius):
+        """Not in the reference: give the layer the agents' positions [B,N,2] instead of
+        the dense GSO the simulator derives from them (utils/new_simulator.py:823-827).  The neighbour lists are built
+        on the device, no N x N matrix exists anywhere, and 8N bytes per instance cross PCIe instead of 4N^2."""
+        assert len(pos.shape) == 3 and pos.shape[2] == 2
+        self.N = pos.shape[1]
+        self.S = None
+        self._adj = build_adjacency_from_positions(pos, comm_radius)
 
     # ``aij`` is what graphML.py:4650 stores eagerly; here the dense copy is made on first use.
     @property
@@ -475,7 +519,7 @@ class GraphFilterBatchAttentional(nn.Module):
         fused_relu = self.nonlinearity in (nn.functional.relu, torch.relu)
         y, att = gat_layer(x, self.S, self.filterWeight, self.mixer, self.weight, self.weight_bias,
                            self.bias, mode=_mode_of(self.attentionMode), concatenate=self.concatenate,
-                           relu=fused_relu, path=self.path)
+                           relu=fused_relu, path=self.path, adjacency=getattr(self, "_adj", None))
         self._last, self._aij = att, None
         if not fused_relu:
             y = self.nonlinearity(y)
@@ -502,4 +546,5 @@ class GraphFilterBatchAttentional(nn.Module):
         state = self.__dict__.copy()
         state["_last"] = None
         state["_aij"] = None
+        state["_adj"] = None
         return state

@@ -196,3 +196,17 @@ def random_geometric_gso(B, N, *, comm_radius=7.0, density=0.025, width=None,
             A = A / torch.linalg.eigvalsh(A).abs().max().clamp_min(1e-12)
         out[b, 0] = A.to(dtype)
     return out
+
+
+def gso_from_positions(pos, comm_radius):
+    """SURVEY 8f row f1 -- the simulator's adjacency from agent positions, utils/new_simulator.py:823-827:
+    ``distances = squareform(pdist(pos, 'euclidean')); W = (distances < commR); W -= diag(diag(W))``.
+    pos: [B,N,2]; returns the 0/1 mask [B,1,N,N] in fp64 (the normalisation of :829-839 only rescales it and the
+    attention layer only tests |S| > 1e-9)."""
+    pos = pos.to(torch.float64)
+    diff = pos[:, :, None, :] - pos[:, None, :, :]
+    d = diff.pow(2).sum(dim=-1).sqrt()                  # what pdist computes, pair by pair, in fp64
+    N = pos.shape[1]
+    A = (d < float(comm_radius)) & ~torch.eye(N, dtype=torch.bool)
+    return A.to(torch.float64).unsqueeze(1)
+

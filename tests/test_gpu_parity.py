@@ -342,6 +342,52 @@ def test_gso_scan_and_neighbour_lists(N, dtype):
 
 # ---- single-launch small-graph inference kernel (the simulator's B = 1, N <= 64 use) --------------------
 
+@pytest.mark.parametrize("N,width,R", [(1, 4, 7.0), (10, 20, 7.0), (37, 30, 7.0), (100, 50, 7.0), (1000, 200, 7.0),
+                                       (130, 40, 3.5)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_adjacency_from_positions(N, width, R, dtype):
+    """lists built on the device from positions == lists of the dense GSO the simulator formula
+    gives (oracle.gso_from_positions, pinned to scipy's pdist in the CPU suite)."""
+    from magat_pathplanning_b200 import build_adjacency, build_adjacency_from_positions
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(N * 7 + 1)
+    B = 5
+    pos = torch.empty(B, N, 2, dtype=torch.float64)
+    for b in range(B):
+        cells = torch.randperm(width * width, generator=gen)[:N]
+        pos[b] = torch.stack((cells // width, cells % width), dim=1).to(torch.float64)
+    if N == 130:
+        pos += torch.rand(pos.shape, generator=gen, dtype=torch.float64)       # off-lattice
+    pos = pos.to(dtype)
+    S = orc.gso_from_positions(pos, R)
+    a = build_adjacency(S.to(dev))
+    p_ = build_adjacency_from_positions(pos.to(dev), R)
+    assert a.D == p_.D
+    for name in ("nbr_out", "nbr_in", "slot_in", "slot_out"):
+        assert torch.equal(getattr(a, name), getattr(p_, name)), name
+
+
+def test_layer_from_positions_matches_dense_gso(golden):
+    from magat_pathplanning_b200 import GraphFilterBatchAttentional
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(11)
+    B, N, G, K, P = 3, 90, 128, 3, 4
+    cells = torch.stack([torch.randperm(50 * 50, generator=gen)[:N] for _ in range(B)])
+    pos = torch.stack((cells // 50, cells % 50), dim=2).to(torch.float32)
+    S = orc.gso_from_positions(pos, 7.0).to(torch.float32)
+    x = torch.relu(torch.randn(B, N, G, generator=gen)).permute(0, 2, 1).to(dev)
+    torch.manual_seed(3)
+    layer = GraphFilterBatchAttentional(G, G, K, P, 1, True, concatenate=True, attentionMode="KeyQuery").to(dev)
+    with torch.no_grad():
+        layer.addGSO(S.to(dev))
+        y_dense = layer(x)
+        layer.addGSOFromPositions(pos.to(dev), 7.0)
+        y_pos = layer(x)
+        att = layer.returnAttentionGSO()
+    assert torch.equal(y_dense, y_pos)
+    assert att.shape == (B, 1, N, N)
+
+
 SMALL_CASES = [n for n in golden_case_names() if n not in ("kq_b32p4_n100", "kq_n130_g128", "gm_n70_g64")]
 
 

@@ -63,3 +63,22 @@ def test_structural_facts(golden):
 def test_keyquery_requires_f_eq_g():
     with pytest.raises(ValueError):
         orc.init_params(8, 16, 2, 2, mode="KeyQuery")
+
+
+def test_gso_from_positions_matches_the_simulator_formula():
+    """oracle.gso_from_positions against the reference's own lines (utils/new_simulator.py:823-827) restated with the
+    scipy calls it uses: squareform(pdist(pos, 'euclidean')) < commR, diagonal removed."""
+    import numpy as np
+    from scipy.spatial.distance import pdist, squareform
+    from oracle import gat_oracle as orc
+    rng = np.random.default_rng(5)
+    for N, width, R in ((10, 20, 7.0), (57, 40, 7.0), (130, 70, 5.0), (9, 6, 2.5)):
+        cells = rng.permutation(width * width)[:N]
+        pos = np.stack((cells // width, cells % width), axis=1).astype(np.float64)
+        if N == 9:
+            pos = pos + rng.random(pos.shape)              # non-integer positions, and a radius on no lattice distance
+        W = (squareform(pdist(pos, "euclidean")) < R).astype(np.float64)
+        W = W - np.diag(np.diag(W))
+        got = orc.gso_from_positions(torch.from_numpy(pos)[None], R)[0, 0].numpy()
+        assert np.array_equal(got, W)
+
