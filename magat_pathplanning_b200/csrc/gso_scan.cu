@@ -1,6 +1,7 @@
 // GSO -> adjacency.  The dense graph-shift operator is only ever used as an edge mask
 // (|S| > 1e-9, graphML.py:1274-1276 and :808-809); this file reads it exactly once and
 // turns it into bit masks and padded neighbour lists.
+#include <math.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -255,10 +256,13 @@ __global__ void __launch_bounds__((kScanWarps + 1) * 32, 1) k_gso_scan_tma(const
 // ---- f1: edge mask straight from agent positions ------------------------------------------------
 // utils/new_simulator.py:823-827 builds the GSO as squareform(pdist(pos)) < commR with a zeroed diagonal (the
 // normalisation that follows only scales it, and the layer only tests |S| > 1e-9).  Same predicate here, in fp64 as
-// scipy computes it: sqrt(dx^2 + dy^2) < R, i != j.  One block = 32 rows of one instance, positions staged in shared
-// memory; a warp emits the W words of its rows with one ballot each.  The mask is symmetric: colbits = rowbits.
+// scipy computes it: sqrt(dx^2 + dy^2) < R, i != j -- evaluated as d2 < T with T the smallest double whose (correctly
+// rounded, monotone) square root reaches R, found on the host, so no fp64 sqrt runs per pair (it made this kernel
+// slower than scanning the dense GSO); squares and sum are rounded separately like the x86 build of scipy does.
+// One block = 32 rows of one instance, positions staged in shared memory; a warp emits the W words of its rows with
+// one ballot each.  The mask is symmetric: colbits = rowbits.
 template <typename T>
-__global__ void __launch_bounds__(256) k_gso_from_positions(const T* __restrict__ pos, int N, int W, double radius,
+__global__ void __launch_bounds__(256) k_gso_from_positions(const T* __restrict__ pos, int N, int W, double thr2,
                                                             uint32_t* __restrict__ rowbits,
                                                             uint32_t* __restrict__ colbits) {
   extern __shared__ double pos_s[];                    // [N][2]
@@ -272,18 +276,17 @@ __global__ void __launch_bounds__(256) k_gso_from_positions(const T* __restrict_
     if (i >= N) break;
     const double xi = pos_s[2 * i], yi = pos_s[2 * i + 1];
     const size_t base = ((size_t)b * N + i) * W;
+#pragma unroll 4
     for (int w = 0; w < W; ++w) {
       const int j = w * 32 + lane;
       bool e = false;
       if (j < N && j != i) {
         const double dx = xi - pos_s[2 * j], dy = yi - pos_s[2 * j + 1];
-        e = sqrt(dx * dx + dy * dy) < radius;
+        e = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < thr2;
       }
       const uint32_t word = __ballot_sync(0xffffffffu, e);
-      if (lane == 0) {
-        rowbits[base + w] = word;
-        colbits[base + w] = word;
-      }
+      if (lane == 0) rowbits[base + w] = word;
+      if (lane == 1) colbits[base + w] = word;
     }
   }
 }
@@ -713,11 +716,20 @@ extern "C" int magat_gso_from_positions(const void* pos, int pos_dtype, int B, i
   cudaStream_t st = (cudaStream_t)stream;
   prof_begin(st);
   const int W = (N + 31) / 32;
+  // smallest double T with sqrt(T) >= R: then sqrt(d2) < R  <=>  d2 < T for every d2 >= 0 (sqrt is monotone)
+  double thr2 = 0.0;
+  if (comm_radius > 0.0) {
+    thr2 = comm_radius * comm_radius;
+    if (thr2 < INFINITY) {
+      while (thr2 > 0.0 && sqrt(nextafter(thr2, 0.0)) >= comm_radius) thr2 = nextafter(thr2, 0.0);
+      while (sqrt(thr2) < comm_radius) thr2 = nextafter(thr2, INFINITY);
+    }
+  }
   dim3 grid(cdiv(N, 32), B);
   if (pos_dtype == MAGAT_DT_F32)
-    k_gso_from_positions<float><<<grid, 256, smem, st>>>((const float*)pos, N, W, comm_radius, rowbits, colbits);
+    k_gso_from_positions<float><<<grid, 256, smem, st>>>((const float*)pos, N, W, thr2, rowbits, colbits);
   else
-    k_gso_from_positions<double><<<grid, 256, smem, st>>>((const double*)pos, N, W, comm_radius, rowbits, colbits);
+    k_gso_from_positions<double><<<grid, 256, smem, st>>>((const double*)pos, N, W, thr2, rowbits, colbits);
   int rc = check_launch("k_gso_from_positions", st);
   if (rc) return rc;
   return launch_gso_stats(rowbits, colbits, B, N, W, stats, st);
