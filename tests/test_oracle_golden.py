@@ -82,3 +82,16 @@ def test_gso_from_positions_matches_the_simulator_formula():
         got = orc.gso_from_positions(torch.from_numpy(pos)[None], R)[0, 0].numpy()
         assert np.array_equal(got, W)
 
+
+def test_bench_positions_describe_the_bench_graphs():
+    """bench.synth_positions replays the generator calls of bench.synth_gso: the positions it returns give, through
+    the simulator formula (oracle.gso_from_positions), exactly the edge mask of the GSO batch the bench times."""
+    import bench
+    from oracle import gat_oracle as orc
+    dev = torch.device("cpu")
+    for B, N, width in ((3, 10, 20), (70, 50, 45)):            # 70 > one generator chunk of 64
+        S = bench.synth_gso(B, N, width, dev, torch.Generator().manual_seed(9))
+        pos = bench.synth_positions(B, N, width, dev, torch.Generator().manual_seed(9))
+        mask = orc.gso_from_positions(pos, bench.COMM_RADIUS)
+        assert torch.equal(S.abs() > 1e-9, mask > 0)
+
