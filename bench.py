@@ -220,7 +220,7 @@ def run_reference(args, w, rank):
     steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
     v, ms, cores = cpu_oracle_run(w, sample_B, steps, warmup)
     sample = f"{sample_B} of {w['B']} instances per step (dense [B,P,N,N] temporaries bound the batch), fwd+bwd"
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "agent-steps/sec GAT fwd+bwd", "value": v, "unit": "agent-steps/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -228,6 +228,30 @@ def run_reference(args, w, rank):
         "cpu_baseline": {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Keep the process's real stdout for the ONE JSON line: native libraries print there too (NCCL's version banner
+    at NCCL_DEBUG >= VERSION is a plain printf), so file descriptor 1 is pointed at stderr for everything else."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is not None:
+        return
+    try:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+        sys.stdout = sys.stderr
+    except OSError:
+        _REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.__stdout__
+    out.write(line + "\n")
+    out.flush()
 
 
 def main():
@@ -243,6 +267,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    claim_stdout()
 
     w = dict(WORKLOADS[args.workload])
     if args.batch:
@@ -501,7 +526,7 @@ def main():
         "gpu_launches": int(launches_per_step) * args.steps, "gpu_launches_per_step": int(launches_per_step),
         "clocks": clocks,
     }
-    print(json.dumps(out))
+    emit(json.dumps(out))
     if dist_on:
         torch.distributed.destroy_process_group()
 
