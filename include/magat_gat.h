@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define MAGAT_ABI_VERSION 7
+#define MAGAT_ABI_VERSION 8
 
 enum {
   MAGAT_OK = 0,
@@ -124,6 +124,37 @@ int magat_gat_forward(const magat_gat_fwd_args* a, void* stream);
 /* How many tap planes (k = 1..) of a->taps the forward call leaves valid for these arguments: K-1, or 1
  * when the fused tcgen05 kernel gathers the second tap on the fly.  Pass it on as bwd.taps_valid. */
 int magat_gat_forward_taps_valid(const magat_gat_fwd_args* a);
+
+
+/* ---- fused forward: ONE launch from the dense GSO to y (graphML.py:4636-4667 over :1724-1827, :1180-1286, :713-823) ----
+ * Covers G = F = 128, K <= 3, P in {1,2,4}, heads concatenated, N % 4 == 0, N >= 64, both attention modes
+ * (magat_gat_fused_supported).  Reads S once and never materialises anything N x N; the per-instance intermediates
+ * (bit masks, operand images, receiver-major attention, and -- unless save = 1 -- R and the taps) live in a per-team
+ * scratch inside `workspace` that stays in L2.  D is the caller's cap on the in/out degree (multiple of 4, <= 32):
+ * after the call workspace[0..3] (int32, device) hold {max out-degree, max in-degree, number of (node, direction)
+ * lists longer than D, 0}; when the third is non-zero the outputs are INVALID and the caller must redo the call with a
+ * larger D or through magat_gso_scan / magat_gso_build_ell / magat_gat_forward.
+ * Always written: y, the four neighbour lists [B][N][D] and att [B][N][D][P] (what returnAttentionGSO and
+ * magat_gat_backward need).  save = 1 (training) additionally writes taps [B][N][P][K-1][G], sproj and wprep
+ * (GAT_modified: magat_gat_wprep_floats floats) exactly as magat_gat_forward leaves them for magat_gat_backward. */
+typedef struct magat_gat_fused_args {
+  int32_t B, N, G, F, K, P, D;
+  int32_t mode, concat, relu;
+  int32_t s_dtype;            /* MAGAT_DT_* of S */
+  int32_t save;               /* 1: keep taps / sproj / wprep for magat_gat_backward */
+  const void* S;              /* [B][1][N][N] */
+  const float* x; int64_t x_sb, x_sn;
+  const float* weight; const float* mixer; const float* weight_bias; const float* filterWeight; const float* bias;
+  float* y; int64_t y_sb, y_sn, y_sc;
+  int32_t* nbr_out; int32_t* nbr_in; int32_t* slot_in; int32_t* slot_out;
+  float* att;
+  float* taps; float* sproj; float* wprep;      /* save = 1 only; may be NULL otherwise */
+  void* workspace; size_t ws_bytes;             /* magat_gat_fused_workspace_bytes(...), 1024 B aligned */
+} magat_gat_fused_args;
+
+int magat_gat_fused_supported(int N, int G, int F, int K, int P, int D, int mode, int concat);
+size_t magat_gat_fused_workspace_bytes(int B, int N, int K, int P, int D, int mode, int save);
+int magat_gat_forward_fused(const magat_gat_fused_args* a, void* stream);
 
 /* ---- backward (what autograd does over graphML.py:1180-1286,713-823,1724-1827) ---- */
 typedef struct magat_gat_bwd_args {

@@ -12,7 +12,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmagat_gat.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 MODE_KEYQUERY, MODE_GAT_MODIFIED = 0, 1
 DT_F32, DT_F64 = 0, 1
@@ -24,6 +24,7 @@ EXPORTS = (
     "magat_gat_bwd_partial_floats", "magat_gat_backward", "magat_gat_attention_dense",
     "magat_launch_count", "magat_profile_enable", "magat_profile_collect",
     "magat_gat_small_supported", "magat_gat_forward_small", "magat_gso_from_positions",
+    "magat_gat_fused_supported", "magat_gat_fused_workspace_bytes", "magat_gat_forward_fused",
 )
 
 _i32, _i64, _ptr = C.c_int32, C.c_int64, C.c_void_p
@@ -53,6 +54,18 @@ class BwdArgs(C.Structure):
         ("dx", _ptr), ("dweight", _ptr), ("dmixer", _ptr), ("dweight_bias", _ptr),
         ("dfilterWeight", _ptr), ("dbias", _ptr),
         ("gz", _ptr), ("datt", _ptr), ("rc", _ptr), ("partial", _ptr),
+    ]
+
+
+class FusedArgs(C.Structure):
+    _fields_ = [(n, _i32) for n in ("B", "N", "G", "F", "K", "P", "D", "mode", "concat", "relu", "s_dtype",
+                                    "save")] + [
+        ("S", _ptr), ("x", _ptr), ("x_sb", _i64), ("x_sn", _i64),
+        ("weight", _ptr), ("mixer", _ptr), ("weight_bias", _ptr), ("filterWeight", _ptr), ("bias", _ptr),
+        ("y", _ptr), ("y_sb", _i64), ("y_sn", _i64), ("y_sc", _i64),
+        ("nbr_out", _ptr), ("nbr_in", _ptr), ("slot_in", _ptr), ("slot_out", _ptr),
+        ("att", _ptr), ("taps", _ptr), ("sproj", _ptr), ("wprep", _ptr),
+        ("workspace", _ptr), ("ws_bytes", C.c_size_t),
     ]
 
 
@@ -105,6 +118,12 @@ def lib():
         L.magat_gat_forward_small.argtypes = ([_ptr, C.c_int, _ptr, _i64, _i64] + [_ptr] * 5 + [_ptr, _i64, _i64, _i64, _ptr]
                                               + [C.c_int] * 9 + [_ptr])
         L.magat_gat_forward_small.restype = C.c_int
+        L.magat_gat_fused_supported.argtypes = [C.c_int] * 8
+        L.magat_gat_fused_supported.restype = C.c_int
+        L.magat_gat_fused_workspace_bytes.argtypes = [C.c_int] * 7
+        L.magat_gat_fused_workspace_bytes.restype = C.c_size_t
+        L.magat_gat_forward_fused.argtypes = [C.POINTER(FusedArgs), _ptr]
+        L.magat_gat_forward_fused.restype = C.c_int
         L.magat_launch_count.restype = C.c_long
         L.magat_profile_enable.argtypes = [C.c_int]
         L.magat_profile_enable.restype = None

@@ -30,7 +30,27 @@ infiniteNumber = 1e12    # graphML.py:46
 #: no host sync for the ELL width below this node count (width = N)
 _NOSYNC_N = 48
 
-_PATH = {"auto": _cabi.PATH_AUTO, "simt": _cabi.PATH_SIMT, "tcgen05": _cabi.PATH_TCGEN05}
+_PATH = {"auto": _cabi.PATH_AUTO, "simt": _cabi.PATH_SIMT, "tcgen05": _cabi.PATH_TCGEN05, "fused": _cabi.PATH_AUTO}
+
+#: "auto" takes the single-launch fused forward (csrc/gat_fused.cu) from this many agents up; below it the work per
+#: instance is too small to give a team of 8 CTAs anything to do
+_FUSED_MIN_N = 128
+#: degree cap D the fused kernel is first tried with (its lists are [B][N][D]); a graph that exceeds it is redone
+#: with 32 and then through the general path
+_FUSED_D0 = 16
+
+_ws_cache = {}
+
+
+def _workspace(dev, nbytes):
+    """Scratch of the fused forward, one per (device, stream): reused call after call so it stays L2 resident."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    t = _ws_cache.get(key)
+    if t is None or t.numel() < nbytes + 1024:
+        t = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        _ws_cache[key] = t
+    off = (-t.data_ptr()) % 1024
+    return t[off:off + nbytes]
 
 
 def _stream(device):
@@ -152,14 +172,25 @@ def _sb(xt):
 
 
 class _Meta:
-    __slots__ = ("mode", "concat", "relu", "path", "G", "F", "K", "P", "has_bias")
+    __slots__ = ("mode", "concat", "relu", "path", "G", "F", "K", "P", "has_bias", "needs_grad")
+
+
+class _FusedGSO:
+    """The dense GSO on its way into the fused forward (which builds the neighbour lists itself); ``adj`` holds the
+    lists the kernel wrote."""
+    __slots__ = ("S", "D", "trusted", "adj", "overflow")
+
+    def __init__(self, S, D, trusted):
+        self.S, self.D, self.trusted, self.adj, self.overflow = S, D, trusted, None, False
 
 
 class _GATFunction(torch.autograd.Function):
     """x[B,G,N] -> y (concat: [B,P*F,N] view over [B,N,P*F]; mean: [B,F,N]) plus the sparse attention."""
 
     @staticmethod
-    def forward(ctx, x, weight, mixer, weight_bias, filterWeight, bias, adj: Adjacency, meta: _Meta):
+    def forward(ctx, x, weight, mixer, weight_bias, filterWeight, bias, adj, meta: _Meta):
+        if isinstance(adj, _FusedGSO):
+            return _GATFunction._forward_fused(ctx, x, weight, mixer, weight_bias, filterWeight, bias, adj, meta)
         L = _cabi.lib()
         dev = x.device
         B, G, N = x.shape
@@ -196,6 +227,67 @@ class _GATFunction(torch.autograd.Function):
                               sproj=sproj.data_ptr())
             _cabi.check(L.magat_gat_forward(a, _stream(dev)))
             ctx.taps_valid = L.magat_gat_forward_taps_valid(a)
+        ctx.meta, ctx.adj = meta, adj
+        ctx.save_for_backward(xt, weight_c, mixer_c, wb_c, filt_c, y, att, taps, wprep, sproj)
+        ctx.mark_non_differentiable(att)
+        return y, att
+
+    @staticmethod
+    def _forward_fused(ctx, x, weight, mixer, weight_bias, filterWeight, bias, gso, meta):
+        """ONE launch from the dense GSO to y (magat_gat_forward_fused); leaves for backward exactly what the
+        multi-launch forward leaves."""
+        L = _cabi.lib()
+        dev = x.device
+        B, G, N = x.shape
+        F, K, P = meta.F, meta.K, meta.P
+        S = gso.S
+        xt = _node_major(x.detach())
+        weight_c = weight.detach().contiguous()
+        filt_c = filterWeight.detach().contiguous()
+        mixer_c = None if mixer is None else mixer.detach().contiguous()
+        wb_c = None if weight_bias is None else weight_bias.detach().contiguous()
+        bias_c = None if bias is None else bias.detach().contiguous()
+        save = bool(meta.needs_grad)
+        kq = meta.mode == _cabi.MODE_KEYQUERY
+        with torch.cuda.device(dev):
+            y_mem = torch.empty((B, N, P * F), dtype=torch.float32, device=dev)
+            y = y_mem.permute(0, 2, 1)
+            taps = sproj = wprep = None
+            if save:
+                taps = torch.empty((B, N, P, max(K - 1, 1), G), dtype=torch.float32, device=dev) if K > 1 else None
+                sproj = torch.empty((B, N, P, G if kq else 2), dtype=torch.float32, device=dev)
+                wprep = torch.empty(L.magat_gat_wprep_floats(G, F, K, P, meta.mode), dtype=torch.float32, device=dev)
+            D = gso.D
+            while True:
+                lists = torch.empty((4, B, N, D), dtype=torch.int32, device=dev)
+                att = torch.empty((B, N, D, P), dtype=torch.float32, device=dev)
+                nbytes = L.magat_gat_fused_workspace_bytes(B, N, K, P, D, meta.mode, int(save))
+                ws = _workspace(dev, nbytes)
+                a = _cabi.FusedArgs(B=B, N=N, G=G, F=F, K=K, P=P, D=D, mode=meta.mode, concat=1, relu=int(meta.relu),
+                                    s_dtype=_cabi.DT_F32 if S.dtype == torch.float32 else _cabi.DT_F64, save=int(save),
+                                    S=S.data_ptr(), x=xt.data_ptr(), x_sb=_sb(xt), x_sn=_sn(xt),
+                                    weight=weight_c.data_ptr(), mixer=_p(mixer_c), weight_bias=_p(wb_c),
+                                    filterWeight=filt_c.data_ptr(), bias=_p(bias_c),
+                                    y=y_mem.data_ptr(), y_sb=y.stride(0), y_sn=y.stride(2), y_sc=y.stride(1),
+                                    nbr_out=lists[0].data_ptr(), nbr_in=lists[1].data_ptr(),
+                                    slot_in=lists[2].data_ptr(), slot_out=lists[3].data_ptr(),
+                                    att=att.data_ptr(), taps=_p(taps), sproj=_p(sproj), wprep=_p(wprep),
+                                    workspace=ws.data_ptr(), ws_bytes=nbytes)
+                _cabi.check(L.magat_gat_forward_fused(a, _stream(dev)))
+                if D >= N or gso.trusted:
+                    break                        # no list can be longer than D: nothing to check
+                st = ws[:16].view(torch.int32).tolist()          # {max out-degree, max in-degree, overflows, watchdog}
+                if st[2] == 0:
+                    break
+                need = (max(st[0], st[1]) + 3) // 4 * 4
+                if need > 32:
+                    gso.overflow = True          # a vertex with more than 32 neighbours: general path
+                    gso.adj = build_adjacency(S)
+                    return _GATFunction.forward(ctx, x, weight, mixer, weight_bias, filterWeight, bias, gso.adj, meta)
+                D = need
+        adj = Adjacency(B, N, D, lists[0], lists[1], lists[2], lists[3])
+        gso.adj = adj
+        ctx.taps_valid = K - 1
         ctx.meta, ctx.adj = meta, adj
         ctx.save_for_backward(xt, weight_c, mixer_c, wb_c, filt_c, y, att, taps, wprep, sproj)
         ctx.mark_non_differentiable(att)
@@ -324,8 +416,33 @@ def _small_forward(x, S, filterWeight, mixer, weight, weight_bias, bias, mode, c
     return y, DenseAttention(aij)
 
 
+def _fused_gso(x, S, G, F, K, P, mode, concatenate, path, max_degree):
+    """The dense GSO wrapped for the fused forward, or None when that kernel does not cover the call."""
+    B, N = x.shape[0], x.shape[2]
+    if not (S.is_cuda and len(S.shape) == 4 and S.shape[0] == B and S.shape[1] == 1 and S.shape[2] == N
+            and S.shape[3] == N):
+        return None
+    if path == "auto" and N < _FUSED_MIN_N:
+        return None
+    D = min(32, (min(N, max_degree if max_degree else _FUSED_D0) + 3) // 4 * 4)
+    if not _cabi.lib().magat_gat_fused_supported(N, G, F, K, P, D, mode, int(bool(concatenate))):
+        return None
+    if B * N * D * P >= 2 ** 31:
+        return None
+    S = S.detach()
+    if S.dtype not in (torch.float32, torch.float64):
+        S = S.to(torch.float32)
+    if not S.is_contiguous():
+        S = S.contiguous()
+    xt = _node_major(x.detach())
+    if S.data_ptr() % 16 or xt.data_ptr() % 16 or _sn(xt) % 4 or _sb(xt) % 4 or xt.dtype != torch.float32:
+        return None
+    return _FusedGSO(S, D, bool(max_degree))
+
+
 def gat_layer(x, S, filterWeight, mixer, weight, weight_bias, bias, *, mode: int, concatenate: bool,
-              relu: bool = True, path: str = "auto", adjacency: Optional[Adjacency] = None):
+              relu: bool = True, path: str = "auto", adjacency: Optional[Adjacency] = None,
+              max_degree: Optional[int] = None):
     """One call of the fused layer.  Returns ``(y, attention)``; ``attention.dense()`` / ``.dense_mean()`` give
     ``aij`` [B,P,1,N,N] / its head mean on demand."""
     _require_cuda(x, "x")
@@ -346,8 +463,16 @@ def gat_layer(x, S, filterWeight, mixer, weight, weight_bias, bias, *, mode: int
         assert len(S.shape) == 4 and S.shape[1] == 1 and S.shape[3] == N_ and S.shape[0] == B_
         return _small_forward(x, S, filterWeight, mixer if mode != _cabi.MODE_KEYQUERY else None, weight,
                               weight_bias if mode != _cabi.MODE_KEYQUERY else None, bias, mode, concatenate, relu)
-    adj = adjacency if adjacency is not None else build_adjacency(S)
-    assert adj.B == x.shape[0] and adj.N == x.shape[2]
+    fused = None
+    if adjacency is None and path in ("auto", "fused") and S is not None:
+        fused = _fused_gso(x, S, G, F, K, P, mode, concatenate, path, max_degree)
+    if path == "fused" and fused is None:
+        raise RuntimeError("path='fused': shape / layout not covered by the fused forward (magat_gat_fused_supported)")
+    if fused is not None:
+        adj = fused
+    else:
+        adj = adjacency if adjacency is not None else build_adjacency(S)
+        assert adj.B == x.shape[0] and adj.N == x.shape[2]
     if mode == _cabi.MODE_KEYQUERY:
         assert tuple(weight.shape) == (P, E, G, G)
         if F != G:
@@ -359,11 +484,14 @@ def gat_layer(x, S, filterWeight, mixer, weight, weight_bias, bias, *, mode: int
     meta = _Meta()
     meta.mode, meta.concat, meta.relu, meta.path = mode, bool(concatenate), bool(relu), _PATH[path]
     meta.G, meta.F, meta.K, meta.P, meta.has_bias = G, F, K, P, bias is not None
+    meta.needs_grad = needs_grad
     if mode == _cabi.MODE_KEYQUERY:
         mixer_in, wb_in = None, None             # unused by the math; grads stay None (graphML.py:1265-1266)
     else:
         mixer_in, wb_in = mixer, weight_bias
     y, att = _GATFunction.apply(x, weight, mixer_in, wb_in, filterWeight, bias, adj, meta)
+    if fused is not None:
+        adj = fused.adj
     return y, SparseAttention(att.detach(), adj)
 
 
@@ -445,6 +573,9 @@ class GraphFilterBatchAttentional(nn.Module):
         self.concatenate = concatenate
         self.attentionMode = attentionMode
         self.path = "auto"
+        #: optional promise that no agent has more than this many in- or out-neighbours: lets the fused forward size
+        #: its neighbour lists without reading the degree statistics back (no host synchronisation in forward)
+        self.max_degree = None
         self._last = None
         self._aij = None
         self._adj = None
@@ -519,7 +650,8 @@ class GraphFilterBatchAttentional(nn.Module):
         fused_relu = self.nonlinearity in (nn.functional.relu, torch.relu)
         y, att = gat_layer(x, self.S, self.filterWeight, self.mixer, self.weight, self.weight_bias,
                            self.bias, mode=_mode_of(self.attentionMode), concatenate=self.concatenate,
-                           relu=fused_relu, path=self.path, adjacency=getattr(self, "_adj", None))
+                           relu=fused_relu, path=self.path, adjacency=getattr(self, "_adj", None),
+                           max_degree=getattr(self, "max_degree", None))
         self._last, self._aij = att, None
         if not fused_relu:
             y = self.nonlinearity(y)
