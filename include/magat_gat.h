@@ -134,8 +134,8 @@ int magat_gat_forward_taps_valid(const magat_gat_fwd_args* a);
  * after the call workspace[0..3] (int32, device) hold {max out-degree, max in-degree, number of (node, direction)
  * lists longer than D, 0}; when the third is non-zero the outputs are INVALID and the caller must redo the call with a
  * larger D or through magat_gso_scan / magat_gso_build_ell / magat_gat_forward.
- * Always written: y, the four neighbour lists [B][N][D] and att [B][N][D][P] (what returnAttentionGSO and
- * magat_gat_backward need).  save = 1 (training) additionally writes taps [B][N][P][K-1][G], sproj and wprep
+ * Always written: y, nbr_out / nbr_in / slot_in [B][N][D] and att [B][N][D][P] (what returnAttentionGSO and
+ * magat_gat_backward need; slot_out is not used by this path and may be NULL).  save = 1 (training) additionally writes taps [B][N][P][K-1][G], sproj and wprep
  * (GAT_modified: magat_gat_wprep_floats floats) exactly as magat_gat_forward leaves them for magat_gat_backward. */
 typedef struct magat_gat_fused_args {
   int32_t B, N, G, F, K, P, D;

@@ -58,14 +58,13 @@ struct FusedParams {
   const float* x; long x_sb, x_sn;
   const float* weight; const float* mixer; const float* wb; const float* H; const float* bias;
   float* y; long y_sb, y_sn;
-  int32_t* nbr_out; int32_t* nbr_in; int32_t* slot_in; int32_t* slot_out;     // [B][N][D]
+  int32_t* nbr_out; int32_t* nbr_in; int32_t* slot_in;                         // [B][N][D]
   float* att;                                // [B][N][D][P]
   float* taps; long taps_inst, taps_team;    // fp32 taps for backward (save) -- [N][P][K-1][G] per instance
   float* sproj; long sproj_inst, sproj_team; // KeyQuery R [N][P][G] / GAT_modified [N][P][2]
   float* wprep_out;                          // GAT_modified, save: folded mixer vectors [2P][G] + [2P] for backward
-  uint32_t* rowbits; uint32_t* colbits;      // [team][N][WS]
+  uint32_t* rowbits; uint32_t* colbits;      // [team][2][N][WS] (double buffered by instance parity)
   uint16_t* ximg; uint16_t* uimg;            // images as above
-  float* ain;                                // [team][N][P][D] receiver-major attention
   unsigned* bar;                             // [team][32] barrier counters (128 B apart)
   int32_t* status;                           // [0] max out-degree [1] max in-degree [2] rows over the cap D [3] watchdog
   long long* prof;                           // [CTA][16] cycles per phase (work / barrier wait), see PROF_* below
@@ -93,12 +92,9 @@ __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
 // generic-proxy writes (global or shared) <-> async-proxy accesses (TMA, UMMA)
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-// one lane of the (converged) warp; the compiler keeps what the elected region consumes in uniform registers
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
+struct ScanJob {                              // one instance's GSO on its way into one parity of the mask buffers
+  const void* S; uint32_t* rowbits; uint32_t* colbits;
+};
 
 __device__ __forceinline__ void tensor_g2s_3d(uint32_t dst_smem, uint64_t tmap, int c0, int c1, int c2, uint64_t* bar) {
   asm volatile(
@@ -187,6 +183,11 @@ __device__ __forceinline__ void team_barrier(unsigned* cnt, unsigned& target, in
   __syncthreads();
 }
 
+// ---- phase: GSO scan (graphML.py:1274-1276: only |S| > 1e-9 matters; NaN is "no edge") --------------------
+// One warp per (32-row band, 128-column segment): 512 B row pieces, 8 rows in flight per lane.  Most row pieces of a
+// sparse GSO hold no edge at all: one vote per row piece decides that, and only pieces with an edge pay for the three
+// xor-shuffles that assemble the row words and for the column-word updates (bit r of a column word = row r of the
+// band).
 template <typename T> struct Nib4;
 template <> struct Nib4<float> {
   static __device__ __forceinline__ uint32_t edges(const float* p) {
@@ -204,44 +205,52 @@ template <> struct Nib4<double> {
   }
 };
 
-// ---- phase: GSO scan (graphML.py:1274-1276: only |S| > 1e-9 matters; NaN is "no edge") --------------------
-// One warp per (32-row band, 128-column segment): 512 B row pieces, 8 rows in flight per lane; row words by three
-// xor-shuffles, column words (bit r = row r of the band) accumulate in registers.
+// The units of an instance are dealt out to the team's CTAs round robin (unit u belongs to CTA u % TEAM); inside the
+// CTA the warps draw from a shared counter, so whoever has nothing else to do -- every warp in the scan phase, the
+// warps without a tensor-core role during the two projection phases of the PREVIOUS instance -- takes the next one.
 template <typename T>
-__device__ __forceinline__ void phase_scan(const FusedParams& p, const T* Sb, int r, int warp, int lane,
-                                           uint32_t* rowbits, uint32_t* colbits) {
+__device__ __forceinline__ void scan_units(const FusedParams& p, const T* Sb, int r, int lane, uint32_t* rowbits,
+                                           uint32_t* colbits, int* counter, const volatile int* stop, int stop_at) {
   const int N = p.N, W = p.W, WS = p.WS;
   const int segs = (N + 127) >> 7;
   const int units = W * segs;
-  for (int u = r * NWARPS + warp; u < units; u += TEAM * NWARPS) {
+  for (;;) {
+    int kq = 0;
+    if (lane == 0) kq = (stop != nullptr && *stop >= stop_at) ? -1 : atomicAdd(counter, 1);   // background pass: until the tensor-core roles are through
+    kq = __shfl_sync(0xffffffffu, kq, 0);
+    const int u = r + TEAM * kq;
+    if (kq < 0 || kq >= units || u >= units) break;
     const int seg = u % segs, band = u / segs;
     const int j0 = seg * 128 + lane * 4;
     const bool jin = j0 < N;                     // N % 4 == 0: a lane is entirely inside or outside
     const T* Sc = Sb + j0;
     uint32_t col0 = 0, col1 = 0, col2 = 0, col3 = 0;
     const int i0 = band * 32;
+    const int w = seg * 4 + (lane >> 3);
+    uint32_t* rb = rowbits + (size_t)i0 * WS + w;
+    const bool rw = (lane & 7) == 0 && w < WS;
 #pragma unroll
     for (int rr = 0; rr < 32; rr += 8) {
       uint32_t nib[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int i = i0 + rr + q;
-        nib[q] = (jin && i < N) ? Nib4<T>::edges(Sc + (size_t)i * N) : 0u;
-      }
+      for (int q = 0; q < 8; ++q)
+        nib[q] = (jin && i0 + rr + q < N) ? Nib4<T>::edges(Sc + (size_t)(i0 + rr + q) * N) : 0u;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const int rw = rr + q;
-        col0 |= (nib[q] & 1u) << rw;
-        col1 |= ((nib[q] >> 1) & 1u) << rw;
-        col2 |= ((nib[q] >> 2) & 1u) << rw;
-        col3 |= ((nib[q] >> 3) & 1u) << rw;
-        uint32_t v = nib[q] << (4 * (lane & 7));
-        v |= __shfl_xor_sync(0xffffffffu, v, 1);
-        v |= __shfl_xor_sync(0xffffffffu, v, 2);
-        v |= __shfl_xor_sync(0xffffffffu, v, 4);
-        const int i = i0 + rw;
-        const int w = seg * 4 + (lane >> 3);
-        if ((lane & 7) == 0 && i < N && w < WS) rowbits[(size_t)i * WS + w] = v;
+        const int rw_i = rr + q;
+        uint32_t v = 0u;
+        if (__any_sync(0xffffffffu, nib[q] != 0u)) {
+          const uint32_t nb = nib[q];
+          col0 |= (nb & 1u) << rw_i;
+          col1 |= ((nb >> 1) & 1u) << rw_i;
+          col2 |= ((nb >> 2) & 1u) << rw_i;
+          col3 |= ((nb >> 3) & 1u) << rw_i;
+          v = nb << (4 * (lane & 7));
+          v |= __shfl_xor_sync(0xffffffffu, v, 1);
+          v |= __shfl_xor_sync(0xffffffffu, v, 2);
+          v |= __shfl_xor_sync(0xffffffffu, v, 4);
+        }
+        if (rw && i0 + rw_i < N) rb[(size_t)rw_i * WS] = v;
       }
     }
     if (jin) {
@@ -252,6 +261,14 @@ __device__ __forceinline__ void phase_scan(const FusedParams& p, const T* Sb, in
       cb[3 * (size_t)WS] = col3;
     }
   }
+}
+
+__device__ __forceinline__ void scan_job(const FusedParams& p, const ScanJob& jb, int r, int lane, int* counter,
+                                         const volatile int* stop = nullptr, int stop_at = 0) {
+  if (p.s_f64)
+    scan_units<double>(p, reinterpret_cast<const double*>(jb.S), r, lane, jb.rowbits, jb.colbits, counter, stop, stop_at);
+  else
+    scan_units<float>(p, reinterpret_cast<const float*>(jb.S), r, lane, jb.rowbits, jb.colbits, counter, stop, stop_at);
 }
 
 // number of set bits of a mask row strictly below position n
@@ -271,8 +288,9 @@ __device__ __forceinline__ int rank_below(const uint32_t* __restrict__ bits, int
 // ---- phase: neighbour lists of this CTA's nodes ---------------------------------------------------------------
 // One task per (node, direction), a quarter warp (8 lanes) each -- lane l of the group owns mask words 4l .. 4l+3 of a
 // 32-word pass:
-//   direction 0: out-list of n from its row bits; slot_out = position of n in the in-list of each receiver
-//   direction 1: in-list of n from its column bits; slot_in = position of n in the out-list of each sender
+//   direction 0: out-list of n from its row bits
+//   direction 1: in-list of n from its column bits; slot_in = position of n in the out-list of each sender (where the
+//                sender's softmax leaves A[i, n] in att[i][:])
 // The position of n in the list of m is the number of set bits below n in the other mask's row m (one 16 B load per
 // lane and three shuffles per edge).  scratch: 2 x 32 ints per group in shared memory.
 __device__ __forceinline__ int rank_partial(const uint32_t* __restrict__ row, int wi, int sw, uint32_t below) {
@@ -339,7 +357,7 @@ __device__ __forceinline__ void phase_lists(const FusedParams& p, long rowbase, 
       deg += __shfl_sync(0xffffffffu, incl, 7, 8);
     }
     __syncwarp();
-    const int dcap = min(deg, D);
+    const int dcap = dir ? min(deg, D) : 0;      // only in-edges carry a slot (position in the sender's out-list)
     const int sw = n >> 5;
     const uint32_t below = (1u << (n & 31)) - 1u;
     if (W <= 32) {
@@ -372,10 +390,10 @@ __device__ __forceinline__ void phase_lists(const FusedParams& p, long rowbase, 
     __syncwarp(gmask);
     if (live) {
       int32_t* lst = (dir ? p.nbr_in : p.nbr_out) + (rowbase + n) * D;
-      int32_t* slt = (dir ? p.slot_in : p.slot_out) + (rowbase + n) * D;
       if (gl * 4 < D) {
         *reinterpret_cast<int4*>(lst + gl * 4) = *reinterpret_cast<const int4*>(my + gl * 4);
-        *reinterpret_cast<int4*>(slt + gl * 4) = *reinterpret_cast<const int4*>(my + 32 + gl * 4);
+        if (dir)
+          *reinterpret_cast<int4*>(p.slot_in + (rowbase + n) * D + gl * 4) = *reinterpret_cast<const int4*>(my + 32 + gl * 4);
       }
       if (dir) mi = max(mi, deg); else mo = max(mo, deg);
       if (deg > D) over = 1;
@@ -392,55 +410,96 @@ __device__ __forceinline__ void phase_lists(const FusedParams& p, long rowbase, 
   }
 }
 
-// ---- phase: KeyQuery scores + row softmax (graphML.py:1246-1286), warp per sender row, lane per slot ----------
+// ---- row softmax over the out-neighbours + store, shared by both attention modes ------------------------------
+// The raw scores of the row sit in shared memory, e_s[slot * PT + head].  Lane = (slot within a chunk of 32 / PT
+// slots, head): the max and the sum over the slots are xor-shuffles over the upper lane bits, all heads at once, and
+// att[row][slot][head] leaves with one coalesced store per chunk (zeros beyond the degree).
+template <int PT>
+__device__ __forceinline__ void softmax_store(float* att_row, int D, int lane, int deg, const float* e_s) {
+  constexpr int LOGP = PT == 4 ? 2 : PT == 2 ? 1 : 0;
+  constexpr int SPC = 32 / PT;
+  const int sl = lane >> LOGP;
+  float m = -INFINITY;
+  for (int c0 = 0; c0 < deg; c0 += SPC)
+    if (c0 + sl < deg) m = fmaxf(m, e_s[c0 * PT + lane]);
+#pragma unroll
+  for (int o = PT; o < 32; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float sum = 0.f;
+  for (int c0 = 0; c0 < deg; c0 += SPC)
+    if (c0 + sl < deg) sum += expf(e_s[c0 * PT + lane] - m);
+#pragma unroll
+  for (int o = PT; o < 32; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  for (int c0 = 0; c0 < D; c0 += SPC) {
+    const int sidx = c0 + sl;
+    if (sidx < D) att_row[c0 * PT + lane] = sidx < deg ? expf(e_s[c0 * PT + lane] - m) / sum : 0.f;
+  }
+}
+
+// Sum NV per-lane values over the 16 lanes of a half warp at once: every step halves the number of live values and
+// doubles the lanes each has absorbed.  Lane t of the half ends up with the total of value t >> (4 - log2 NV).
+template <int NV>
+__device__ __forceinline__ float half_multi_sum(float (&v)[NV], int t) {
+  int off = 8;
+#pragma unroll
+  for (int n = NV; n > 1; n >>= 1, off >>= 1) {
+    const bool hi = (t & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float keep = hi ? v[i + n / 2] : v[i];
+      const float send = hi ? v[i] : v[i + n / 2];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+#pragma unroll
+  for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+  return v[0];
+}
+
+// ---- phase: KeyQuery scores + row softmax (graphML.py:1246-1286) -----------------------------------------------
+// Warp per sender row i, HALF a warp per edge: lane t of a half owns features 8t .. 8t+7 of R_i (all heads, in
+// registers for the whole row) and of x_j, so the two halves score two edges per step and the cross-lane sum of the PT
+// head dots is one joint reduction (16 instructions for 4 heads instead of 40).
 template <int PT>
 __device__ __forceinline__ void phase_attention_kq(const FusedParams& p, long rowbase, const float* xb, int n0, int n1,
-                                                   int warp, int lane, const float* sproj, float* ain) {
+                                                   int warp, int lane, const float* sproj, float* esc) {
+  constexpr int LOGP = PT == 4 ? 2 : PT == 2 ? 1 : 0;
   const int D = p.D;
+  const int half = lane >> 4, t = lane & 15;
+  float* e_s = esc + warp * 32 * PT;
+  const int32_t* nbo = p.nbr_out + rowbase * D;
+  float* att_b = p.att + (size_t)rowbase * D * PT;
   for (int i = n0 + warp; i < n1; i += NWARPS) {
-    const long row = rowbase + i;
-    const int my_j = lane < D ? __ldcg(p.nbr_out + row * D + lane) : -1;
+    const int my_j = lane < D ? __ldcg(nbo + (unsigned)(i * D + lane)) : -1;
     const int deg = __popc(__ballot_sync(0xffffffffu, my_j >= 0));
-    float e[PT];
-#pragma unroll
-    for (int h = 0; h < PT; ++h) e[h] = -INFINITY;
     if (deg > 0) {
-      float4 rv[PT];
+      float4 rv[PT][2];
+      const float* rp = sproj + (unsigned)(i * PT * FT + t * 8);
 #pragma unroll
-      for (int h = 0; h < PT; ++h) rv[h] = ldcg4(sproj + ((size_t)i * PT + h) * FT + lane * 4);
-      for (int s = 0; s < deg; ++s) {
-        const int j = __shfl_sync(0xffffffffu, my_j, s);
-        const float4 xv = __ldg(reinterpret_cast<const float4*>(xb + (long)j * p.x_sn + lane * 4));
+      for (int h = 0; h < PT; ++h) {
+        rv[h][0] = ldcg4(rp + h * FT);
+        rv[h][1] = ldcg4(rp + h * FT + 4);
+      }
+      for (int s0 = 0; s0 < deg; s0 += 2) {
+        const int sidx = s0 + half;
+        const int j = __shfl_sync(0xffffffffu, my_j, sidx & 31);
+        float d[PT];
+        if (sidx < deg) {
+          const float* xr = xb + (long)j * p.x_sn + t * 8;
+          const float4 x0 = __ldg(reinterpret_cast<const float4*>(xr));
+          const float4 x1 = __ldg(reinterpret_cast<const float4*>(xr + 4));
 #pragma unroll
-        for (int h = 0; h < PT; ++h) {
-          float d = dot4(rv[h], xv);
-          d = warp_sum(d);
-          if (lane == s) e[h] = d;
+          for (int h = 0; h < PT; ++h) d[h] = dot4(rv[h][0], x0) + dot4(rv[h][1], x1);
+        } else {
+#pragma unroll
+          for (int h = 0; h < PT; ++h) d[h] = 0.f;
         }
+        const float tot = half_multi_sum<PT>(d, t);
+        if (sidx < deg && (t & (16 / PT - 1)) == 0) e_s[sidx * PT + (t >> (4 - LOGP))] = tot;
       }
     }
-    float a[PT];
-#pragma unroll
-    for (int h = 0; h < PT; ++h) {
-      const float mx = warp_max(e[h]);
-      const float ex = lane < deg ? expf(e[h] - mx) : 0.f;
-      const float sum = warp_sum(ex);
-      a[h] = lane < deg ? ex / sum : 0.f;
-    }
-    if (lane < D) {
-      float* dst = p.att + ((size_t)row * D + lane) * PT;
-      if (PT == 4) {
-        __stcs(reinterpret_cast<float4*>(dst), make_float4(a[0], a[1 % PT], a[2 % PT], a[3 % PT]));
-      } else {
-#pragma unroll
-        for (int h = 0; h < PT; ++h) __stcs(dst + h, a[h]);
-      }
-      if (lane < deg) {      // receiver-major copy: A_p[i, j] at the slot of i inside j's in-list
-        float* q = ain + ((size_t)my_j * PT) * D + __ldcg(p.slot_out + row * D + lane);
-#pragma unroll
-        for (int h = 0; h < PT; ++h) q[(size_t)h * D] = a[h];
-      }
-    }
+    __syncwarp();
+    softmax_store<PT>(att_b + (unsigned)(i * D * PT), D, lane, deg, e_s);
+    __syncwarp();
   }
 }
 
@@ -486,112 +545,120 @@ __device__ __forceinline__ void phase_mixer_gm(const FusedParams& p, const float
 
 template <int PT>
 __device__ __forceinline__ void phase_attention_gm(const FusedParams& p, long rowbase, int n0, int n1, int warp, int lane,
-                                                   const float* sproj, float* ain) {
+                                                   const float* sproj, float* esc) {
   const int D = p.D;
+  float* e_s = esc + warp * 32 * PT;
+  float* att_b = p.att + (size_t)rowbase * D * PT;
   for (int i = n0 + warp; i < n1; i += NWARPS) {
     const long row = rowbase + i;
     const int my_j = lane < D ? __ldcg(p.nbr_out + row * D + lane) : -1;
-    const bool v = my_j >= 0;
-    float a[PT];
+    const int deg = __popc(__ballot_sync(0xffffffffu, my_j >= 0));
+    if (my_j >= 0) {                         // lane = slot: e = LeakyReLU(a2.z_i + a1.z_j), graphML.py:785-796
 #pragma unroll
-    for (int h = 0; h < PT; ++h) {
-      const float si = __ldcg(sproj + ((size_t)i * PT + h) * 2 + 1);
-      float e = -INFINITY;
-      if (v) {
-        e = si + __ldcg(sproj + ((size_t)my_j * PT + h) * 2 + 0);
+      for (int h = 0; h < PT; ++h) {
+        float e = __ldcg(sproj + ((size_t)i * PT + h) * 2 + 1) + __ldcg(sproj + ((size_t)my_j * PT + h) * 2 + 0);
         e = e > 0.f ? e : kLeaky * e;
-      }
-      const float mx = warp_max(e);
-      const float ex = v ? expf(e - mx) : 0.f;
-      const float sum = warp_sum(ex);
-      a[h] = v ? ex / sum : 0.f;
-    }
-    if (lane < D) {
-      float* dst = p.att + ((size_t)row * D + lane) * PT;
-      if (PT == 4) {
-        __stcs(reinterpret_cast<float4*>(dst), make_float4(a[0], a[1 % PT], a[2 % PT], a[3 % PT]));
-      } else {
-#pragma unroll
-        for (int h = 0; h < PT; ++h) __stcs(dst + h, a[h]);
-      }
-      if (v) {
-        float* q = ain + ((size_t)my_j * PT) * D + __ldcg(p.slot_out + row * D + lane);
-#pragma unroll
-        for (int h = 0; h < PT; ++h) q[(size_t)h * D] = a[h];
+        e_s[lane * PT + h] = e;
       }
     }
+    __syncwarp();
+    softmax_store<PT>(att_b + (unsigned)(i * D * PT), D, lane, deg, e_s);
+    __syncwarp();
   }
 }
 
 // ---- phase: one level of the tap recursion, u_k[j] = sum_{i in in(j)} A_p[i,j] u_{k-1}[i] (graphML.py:1756-1759) ----
-// Warp per receiver, all heads at once; lane l owns features 4l .. 4l+3.  k = 1 gathers rows of x (one row feeds every
-// head), k = 2 gathers the heads' u_1 rows from the bf16 hi/lo image.  Output: image row (+ fp32 copy for backward).
+// Warp per receiver, all heads at once; lane l owns features 4l .. 4l+3.  Lane s keeps in-edge s (sender id and the
+// PT attention values, one 16 B load); the edge loop broadcasts them by shuffle, two edges in flight.  k = 1 gathers
+// rows of x (one row feeds every head), k = 2 the heads' fp32 u_1 rows.  Output: bf16 hi/lo image row for the
+// projection (+ the fp32 copy the next level and backward read).
+template <int PT>
+__device__ __forceinline__ void gather_edge(const float* xb, unsigned x_sn, const float* tsrc, int k, unsigned trow,
+                                            int lane, int i, float4 (&v)[PT]) {
+  if (k == 1) {
+    v[0] = __ldg(reinterpret_cast<const float4*>(xb + (unsigned)i * x_sn + lane * 4));
+  } else {
+#pragma unroll
+    for (int h = 0; h < PT; ++h) v[h] = ldcg4(tsrc + ((unsigned)i * PT + h) * trow + lane * 4);
+  }
+}
+
 template <int PT>
 __device__ __forceinline__ void phase_gather(const FusedParams& p, long rowbase, const float* xb, int n0, int n1,
-                                             int warp, int lane, int k, const float* ain, uint16_t* uimg, float* taps) {
+                                             int warp, int lane, int k, uint16_t* uimg, float* taps) {
   const int D = p.D, Km1 = p.K - 1;
+  const int32_t* nbi = p.nbr_in + rowbase * D;
+  const int32_t* sli = p.slot_in + rowbase * D;
+  const float* att_b = p.att + (size_t)rowbase * D * PT;
+  const unsigned trow = (unsigned)(Km1 * FT);                  // floats between the heads of a node in the taps buffer
+  const float* tsrc = taps + (k >= 2 ? (k - 2) * FT : 0);       // plane k-1 of every (node, head)
+  const bool keep32 = p.save || k < Km1;                       // fp32 copy: for backward, and as the source of the next level
+  const bool flat_x = p.x_sn < (1l << 24);
+  const unsigned x_sn = flat_x ? (unsigned)p.x_sn : 0u;
   for (int j = n0 + warp; j < n1; j += NWARPS) {
-    const long row = rowbase + j;
-    const int my_i = lane < D ? __ldcg(p.nbr_in + row * D + lane) : -1;
+    const int my_i = lane < D ? __ldcg(nbi + (unsigned)(j * D + lane)) : -1;
+    const int my_sl = lane < D ? __ldcg(sli + (unsigned)(j * D + lane)) : 0;
+    // in-edge `lane`: A_p[i, j] sits at slot my_sl of sender i's softmax row
     float am[PT];
+    if (PT == 4) {
+      const float4 wv = my_i >= 0 ? ldcg4(att_b + (unsigned)((my_i * D + my_sl) * PT)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      am[0] = wv.x; am[1 % PT] = wv.y; am[2 % PT] = wv.z; am[3 % PT] = wv.w;
+    } else {
 #pragma unroll
-    for (int h = 0; h < PT; ++h) am[h] = my_i >= 0 ? __ldcg(ain + ((size_t)j * PT + h) * D + lane) : 0.f;
+      for (int h = 0; h < PT; ++h) am[h] = my_i >= 0 ? __ldcg(att_b + (unsigned)((my_i * D + my_sl) * PT + h)) : 0.f;
+    }
     const int cnt = __popc(__ballot_sync(0xffffffffu, my_i >= 0));
     float4 acc[PT];
 #pragma unroll
     for (int h = 0; h < PT; ++h) acc[h] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (k == 1) {
-      for (int s = 0; s < cnt; s += 4) {
-        int iu[4];
-        float au[4][PT];
+    int s = 0;
+    for (; k == 1 && s + 1 < cnt; s += 2) {    // (level 2 loads PT rows per edge: one edge at a time keeps them in registers)
+      const int i0 = __shfl_sync(0xffffffffu, my_i, s), i1 = __shfl_sync(0xffffffffu, my_i, s + 1);
+      float4 v0[PT], v1[PT];
+      gather_edge<PT>(xb, x_sn, tsrc, 1, trow, lane, i0, v0);
+      gather_edge<PT>(xb, x_sn, tsrc, 1, trow, lane, i1, v1);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          iu[u] = __shfl_sync(0xffffffffu, my_i, (s + u) & 31);
-#pragma unroll
-          for (int h = 0; h < PT; ++h) au[u][h] = __shfl_sync(0xffffffffu, am[h], (s + u) & 31);
-          if (s + u >= cnt) iu[u] = -1;
-        }
-        float4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          v[u] = iu[u] >= 0 ? __ldg(reinterpret_cast<const float4*>(xb + (long)iu[u] * p.x_sn + lane * 4))
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-          for (int h = 0; h < PT; ++h) fma4(acc[h], au[u][h], v[u]);
-      }
-    } else {
-      // rows of u_{k-1}, all heads: fp32 copy in the taps buffer (a 16 B load per head and lane; the bf16 image would
-      // cost two loads and the hi + lo reassembly)
-      for (int s = 0; s < cnt; s += 2) {
-        int iu[2];
-        float au[2][PT];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          iu[u] = __shfl_sync(0xffffffffu, my_i, (s + u) & 31);
-#pragma unroll
-          for (int h = 0; h < PT; ++h) au[u][h] = __shfl_sync(0xffffffffu, am[h], (s + u) & 31);
-          if (s + u >= cnt) iu[u] = -1;
-        }
-        float4 v[2][PT];
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-#pragma unroll
-          for (int h = 0; h < PT; ++h)
-            v[u][h] = iu[u] >= 0 ? ldcg4(taps + (((size_t)iu[u] * PT + h) * Km1 + (k - 2)) * FT + lane * 4)
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-#pragma unroll
-          for (int h = 0; h < PT; ++h) fma4(acc[h], au[u][h], v[u][h]);
+      for (int h = 0; h < PT; ++h) {
+        fma4(acc[h], __shfl_sync(0xffffffffu, am[h], s), v0[0]);
+        fma4(acc[h], __shfl_sync(0xffffffffu, am[h], s + 1), v1[0]);
       }
     }
+    for (; s < cnt; ++s) {
+      const int i0 = __shfl_sync(0xffffffffu, my_i, s);
+      float4 v0[PT];
+      gather_edge<PT>(xb, x_sn, tsrc, k, trow, lane, i0, v0);
+#pragma unroll
+      for (int h = 0; h < PT; ++h) fma4(acc[h], __shfl_sync(0xffffffffu, am[h], s), k == 1 ? v0[0] : v0[h]);
+    }
+    uint16_t* irow = uimg + (unsigned)((j * PT * Km1 + (k - 1)) * 256);
+    float* trow_out = taps + (unsigned)(j * PT) * trow + (k - 1) * FT + lane * 4;
 #pragma unroll
     for (int h = 0; h < PT; ++h) {
-      image_store(uimg + (((size_t)j * PT + h) * Km1 + (k - 1)) * 256, lane, acc[h]);
-      if (p.save || k < Km1)                  // fp32 copy: for backward, and as the source of the next level
-        *reinterpret_cast<float4*>(taps + (((size_t)j * PT + h) * Km1 + (k - 1)) * FT + lane * 4) = acc[h];
+      image_store(irow + h * Km1 * 256, lane, acc[h]);
+      if (keep32) *reinterpret_cast<float4*>(trow_out + h * trow) = acc[h];
+    }
+  }
+}
+
+// ---- epilogue stores: lane f of the warp holds feature f of 32 consecutive nodes, one 128 B line per node -----------
+// STRIDE = floats between consecutive node rows, a compile-time constant so every store carries its offset as an
+// immediate (one FADD, one FMNMX and one STG per node instead of a 64-bit multiply-add chain); 0 = runtime stride.
+template <int STRIDE, bool ACT, bool STREAM>
+__device__ __forceinline__ void epi_store(float* dst, long stride_rt, const float (&v)[32], int left, float bias,
+                                          float floor_) {
+  if (left >= 32) {
+#pragma unroll
+    for (int n = 0; n < 32; ++n) {
+      const float o = ACT ? fmaxf(v[n] + bias, floor_) : v[n];
+      float* q = STRIDE ? dst + n * STRIDE : dst + n * stride_rt;
+      if (STREAM) __stcs(q, o); else *q = o;
+    }
+  } else {
+#pragma unroll
+    for (int n = 0; n < 32; ++n) {
+      const float o = ACT ? fmaxf(v[n] + bias, floor_) : v[n];
+      float* q = STRIDE ? dst + n * STRIDE : dst + n * stride_rt;
+      if (n < left) { if (STREAM) __stcs(q, o); else *q = o; }
     }
   }
 }
@@ -607,6 +674,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gat_fused(const __grid_constant
   uint64_t* acc_full = bars + 2 * NST;       // [2]
   uint64_t* acc_empty = acc_full + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  int* scan_ctr = reinterpret_cast<int*>(tmem_slot + 1);     // next scan unit of this CTA (of the instance being scanned)
+  volatile int* gemm_done = reinterpret_cast<volatile int*>(tmem_slot + 2);   // tensor-core phases this CTA has finished
+  int gphase = 0;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int team = blockIdx.x / TEAM, r = blockIdx.x % TEAM;
@@ -624,6 +694,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gat_fused(const __grid_constant
       tc::mbar_init(&acc_full[a], 1);
       tc::mbar_init(&acc_empty[a], 4 * 32);
     }
+    *scan_ctr = 0;
+    *gemm_done = 0;
     tc::fence_barrier_init();
   }
   if (warp == MMA_WARP) tc::tmem_alloc<512>(tmem_slot);
@@ -680,6 +752,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gat_fused(const __grid_constant
   __syncthreads();
   tc::tc_fence_after();
 
+  float* esc = reinterpret_cast<float*>(smem);       // sparse phases: per-warp score scratch in the (idle) stage ring
   unsigned* bar = p.bar + (size_t)team * 32;
   unsigned bar_target = 0;
   long long* prof = p.prof + (size_t)blockIdx.x * 16;
@@ -687,9 +760,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gat_fused(const __grid_constant
   long long wait_a = 0, wait_b = 0;          // role-private mbarrier wait clocks (slots 12..15 at exit)
   uint32_t q = 0, oc = 0;                    // running stage / accumulator counters of the tensor-core roles
   const int n0 = min(N, r * p.chunk), n1 = min(N, n0 + p.chunk);
-  uint32_t* rowbits = p.rowbits + (size_t)team * N * p.WS;
-  uint32_t* colbits = p.colbits + (size_t)team * N * p.WS;
-  float* ain = p.ain + (size_t)team * N * P * p.D;
+  const size_t esz = p.s_f64 ? 8 : 4;
+  const bool bg_warp = warp != TMA_WARP && warp != MMA_WARP && !(warp >= EPI_WARP0 && warp < EPI_WARP0 + 4);
   uint16_t* uimg = p.uimg + (size_t)team * N * P * (K > 1 ? K - 1 : 1) * 256;
   const uint64_t tmx = reinterpret_cast<uint64_t>(&p.tm_x);
   const uint64_t tmu = reinterpret_cast<uint64_t>(&p.tm_u);
@@ -708,11 +780,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gat_fused(const __grid_constant
     for (int n = n0 + warp; n < n1; n += NWARPS)
       image_store(ximg + (size_t)n * 256, lane,
                   __ldg(reinterpret_cast<const float4*>(xb + (long)n * p.x_sn + lane * 4)));
-    if (p.s_f64)
-      phase_scan<double>(p, reinterpret_cast<const double*>(p.S) + (size_t)b * N * N, r, warp, lane, rowbits, colbits);
-    else
-      phase_scan<float>(p, reinterpret_cast<const float*>(p.S) + (size_t)b * N * N, r, warp, lane, rowbits, colbits);
+    // mask buffers are double buffered by instance parity: the next instance is scanned in the background while this
+    // one is still being read by the list builders of slower CTAs
+    uint32_t* rowbits = p.rowbits + ((size_t)team * 2 + par) * N * p.WS;
+    uint32_t* colbits = p.colbits + ((size_t)team * 2 + par) * N * p.WS;
+    const ScanJob cur{reinterpret_cast<const uint8_t*>(p.S) + (size_t)b * N * N * esz, rowbits, colbits};
+    const int bn = b + p.nteams;
+    const ScanJob nxt{reinterpret_cast<const uint8_t*>(p.S) + (size_t)(bn < p.B ? bn : b) * N * N * esz,
+                      p.rowbits + ((size_t)team * 2 + (par ^ 1)) * N * p.WS,
+                      p.colbits + ((size_t)team * 2 + (par ^ 1)) * N * p.WS};
+    const bool bg = bn < p.B && bg_warp;
+    scan_job(p, cur, r, lane, scan_ctr);                       // whatever the background passes left over (all of it for it = 0)
     team_barrier(bar, bar_target, p.status, prof, prof_t, 0);
+    if (threadIdx.x == 0) *scan_ctr = 0;                        // (published by the __syncthreads below)
 
     // ================= neighbour lists of my nodes =========================================================
     phase_lists(p, rowbase, n0, n1, rowbits, colbits, reinterpret_cast<int32_t*>(smem), warp, lane);
@@ -722,8 +802,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gat_fused(const __grid_constant
     // ================= scores ==================================================================================
     if (kq) {
       // R_p[tile] = W_p^T x^T on tcgen05 (SS form): D[128 features x 64 nodes]
+      ++gphase;
       if (warp == TMA_WARP) {
-        if (elect_one()) {
+        if (tc::elect_one()) {
           for (int t = split; t < p.tiles; t += p.nsplit) {
             const int st = (int)(q % NST);
             mbar_wait_timed(&empty[st], ((q / NST) & 1u) ^ 1u, p.status, 1, wait_a);
@@ -745,7 +826,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gat_fused(const __grid_constant
           if (lane == 0) mbar_wait_timed(&full[st], (q / NST) & 1u, p.status, 3, wait_a);
           __syncwarp();
           tc::tc_fence_after();
-          if (elect_one()) {
+          if (tc::elect_one()) {
             const uint32_t tmem_d = tmem_base + (uint32_t)(ACC_COL0 + acc * TN);
             const uint32_t sb = tc::smem_u32(smem + (size_t)st * STAGE_BYTES);
             const uint32_t wb = tc::smem_u32(wimg);
@@ -789,14 +870,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gat_fused(const __grid_constant
               tc::mbar_arrive(&acc_empty[acc]);
             }
             const int m0 = t * TN + 32 * hh;
-            float* dst = sproj + ((size_t)m0 * P + head) * FT + f;
+            float* dst = sproj + (unsigned)((m0 * P + head) * FT + f);
             const int left = N - m0;
-#pragma unroll
-            for (int n = 0; n < 32; ++n)
-              if (n < left) dst[(size_t)n * P * FT] = v[n];
+            if (P == 4) epi_store<4 * FT, false, false>(dst, 0, v, left, 0.f, 0.f);
+            else if (P == 2) epi_store<2 * FT, false, false>(dst, 0, v, left, 0.f, 0.f);
+            else epi_store<FT, false, false>(dst, 0, v, left, 0.f, 0.f);
           }
           ++oc;
         }
+        if (warp == EPI_WARP0 && lane == 0) *gemm_done = gphase;
+      } else if (bg) {
+        scan_job(p, nxt, r, lane, scan_ctr, gemm_done, gphase);
       }
     } else {
       if (P == 4) phase_mixer_gm<4>(p, xb, n0, n1, warp, lane, gm_cd, sproj);
@@ -807,27 +891,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gat_fused(const __grid_constant
 
     // ================= attention ===================================================================================
     if (kq) {
-      if (P == 4) phase_attention_kq<4>(p, rowbase, xb, n0, n1, warp, lane, sproj, ain);
-      else if (P == 2) phase_attention_kq<2>(p, rowbase, xb, n0, n1, warp, lane, sproj, ain);
-      else phase_attention_kq<1>(p, rowbase, xb, n0, n1, warp, lane, sproj, ain);
+      if (P == 4) phase_attention_kq<4>(p, rowbase, xb, n0, n1, warp, lane, sproj, esc);
+      else if (P == 2) phase_attention_kq<2>(p, rowbase, xb, n0, n1, warp, lane, sproj, esc);
+      else phase_attention_kq<1>(p, rowbase, xb, n0, n1, warp, lane, sproj, esc);
     } else {
-      if (P == 4) phase_attention_gm<4>(p, rowbase, n0, n1, warp, lane, sproj, ain);
-      else if (P == 2) phase_attention_gm<2>(p, rowbase, n0, n1, warp, lane, sproj, ain);
-      else phase_attention_gm<1>(p, rowbase, n0, n1, warp, lane, sproj, ain);
+      if (P == 4) phase_attention_gm<4>(p, rowbase, n0, n1, warp, lane, sproj, esc);
+      else if (P == 2) phase_attention_gm<2>(p, rowbase, n0, n1, warp, lane, sproj, esc);
+      else phase_attention_gm<1>(p, rowbase, n0, n1, warp, lane, sproj, esc);
     }
 
     // ================= taps ========================================================================================
     for (int k = 1; k < K; ++k) {
       team_barrier(bar, bar_target, p.status, prof, prof_t, 3 + 2 * k);
-      if (P == 4) phase_gather<4>(p, rowbase, xb, n0, n1, warp, lane, k, ain, uimg, taps);
-      else if (P == 2) phase_gather<2>(p, rowbase, xb, n0, n1, warp, lane, k, ain, uimg, taps);
-      else phase_gather<1>(p, rowbase, xb, n0, n1, warp, lane, k, ain, uimg, taps);
+      if (P == 4) phase_gather<4>(p, rowbase, xb, n0, n1, warp, lane, k, uimg, taps);
+      else if (P == 2) phase_gather<2>(p, rowbase, xb, n0, n1, warp, lane, k, uimg, taps);
+      else phase_gather<1>(p, rowbase, xb, n0, n1, warp, lane, k, uimg, taps);
     }
     if (K > 1) team_barrier(bar, bar_target, p.status, prof, prof_t, 3 + 2 * K);
 
     // ================= projection: Y_p[tile] = H_p [x | u_1 | u_2]^T + b, ReLU (TS form, H_p in TMEM) ==========
+    ++gphase;
     if (warp == TMA_WARP) {
-      if (elect_one()) {
+      if (tc::elect_one()) {
         for (int t = split; t < p.tiles; t += p.nsplit) {
           for (int s = 0; s < K; ++s) {
             const int st = (int)(q % NST);
@@ -859,7 +944,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gat_fused(const __grid_constant
           if (lane == 0) mbar_wait_timed(&full[st], (q / NST) & 1u, p.status, 7, wait_a);
           __syncwarp();
           tc::tc_fence_after();
-          if (elect_one()) {
+          if (tc::elect_one()) {
             const uint32_t sb = tc::smem_u32(smem + (size_t)st * STAGE_BYTES);
             const uint32_t h_hi = tmem_base + (uint32_t)(s * (SK / 2));
             const uint32_t h_lo = h_hi + (uint32_t)(KG / 2);
@@ -888,6 +973,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gat_fused(const __grid_constant
       const int qd = warp & 3;
       const int f = qd * 32 + lane;
       const float bias = p.bias ? __ldg(p.bias + f) : 0.f;
+      const float yfloor = p.relu ? 0.f : -INFINITY;
+      const bool y_dense = p.y_sn == (long)P * FT;
       float* yb = p.y + (long)b * p.y_sb + (long)head * FT + f;
       for (int t = split; t < p.tiles; t += p.nsplit) {
         const int acc = (int)(oc & 1u);
@@ -907,15 +994,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gat_fused(const __grid_constant
           const int m0 = t * TN + 32 * hh;
           float* dst = yb + (long)m0 * p.y_sn;
           const int left = N - m0;
-#pragma unroll
-          for (int n = 0; n < 32; ++n) {
-            float o = v[n] + bias;
-            if (p.relu) o = fmaxf(o, 0.f);
-            if (n < left) __stcs(dst + (long)n * p.y_sn, o);
-          }
+          if (!y_dense) epi_store<0, true, true>(dst, p.y_sn, v, left, bias, yfloor);
+          else if (P == 4) epi_store<4 * FT, true, true>(dst, 0, v, left, bias, yfloor);
+          else if (P == 2) epi_store<2 * FT, true, true>(dst, 0, v, left, bias, yfloor);
+          else epi_store<FT, true, true>(dst, 0, v, left, bias, yfloor);
         }
         ++oc;
       }
+      if (warp == EPI_WARP0 && lane == 0) *gemm_done = gphase;
+    } else if (bg) {
+      scan_job(p, nxt, r, lane, scan_ctr, gemm_done, gphase);
     }
     // no barrier here: the next instance's scan only writes buffers nobody reads any more (the x image is double
     // buffered), and every later phase of it sits behind a team barrier all CTAs reach after this projection
@@ -953,7 +1041,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
   int nteams;
-  size_t off_bar, off_prof, off_rowbits, off_colbits, off_ximg, off_uimg, off_ain, off_sproj, off_taps, total;
+  size_t off_bar, off_prof, off_rowbits, off_colbits, off_ximg, off_uimg, off_sproj, off_taps, total;
 };
 
 // status (64 B) | team counters | per-team scratch
@@ -971,11 +1059,10 @@ WsLayout ws_layout(int B, int N, int K, int P, int D, int mode, int save) {
   size_t o = 64;
   L.off_bar = o; o = align_up(o + T * 128, 1024);
   L.off_prof = o; o = align_up(o + T * TEAM * 16 * 8, 1024);
-  L.off_rowbits = o; o = align_up(o + T * N * WS * 4, 1024);
-  L.off_colbits = o; o = align_up(o + T * N * WS * 4, 1024);
+  L.off_rowbits = o; o = align_up(o + T * 2 * N * WS * 4, 1024);
+  L.off_colbits = o; o = align_up(o + T * 2 * N * WS * 4, 1024);
   L.off_ximg = o; o = align_up(o + T * 2 * N * 512, 1024);
   L.off_uimg = o; o = align_up(o + T * N * P * (size_t)(K > 1 ? K - 1 : 1) * 512, 1024);
-  L.off_ain = o; o = align_up(o + T * N * P * D * 4, 1024);
   L.off_sproj = o;
   if (!save) o = align_up(o + T * N * P * (mode == MAGAT_MODE_KEYQUERY ? FT : 2) * 4, 1024);
   L.off_taps = o;
@@ -1011,7 +1098,7 @@ extern "C" int magat_gat_forward_fused(const magat_gat_fused_args* a, void* stre
                 "magat_gat_forward_fused: shape not covered (needs G=F=128, K<=3, P in {1,2,4}, concat, N%%4==0, "
                 "N>=64, D%%4==0, D<=32; got N=%d G=%d F=%d K=%d P=%d D=%d)", a->N, a->G, a->F, a->K, a->P, a->D);
   MAGAT_REQUIRE(a->S && a->x && a->weight && a->filterWeight && a->y && a->nbr_out && a->nbr_in && a->slot_in &&
-                    a->slot_out && a->att && a->workspace,
+                    a->att && a->workspace,
                 MAGAT_E_BAD_ARG, "magat_gat_forward_fused: null pointer");
   MAGAT_REQUIRE(a->s_dtype == MAGAT_DT_F32 || a->s_dtype == MAGAT_DT_F64, MAGAT_E_BAD_ARG,
                 "magat_gat_forward_fused: GSO dtype must be fp32 or fp64");
@@ -1021,12 +1108,13 @@ extern "C" int magat_gat_forward_fused(const magat_gat_fused_args* a, void* stre
                 "magat_gat_forward_fused: save = 1 needs the taps and sproj buffers");
   auto al16 = [](const void* q) { return ((uintptr_t)q % 16) == 0; };
   MAGAT_REQUIRE(al16(a->S) && al16(a->x) && al16(a->y) && al16(a->att) && al16(a->nbr_out) && al16(a->nbr_in) &&
-                    al16(a->slot_in) && al16(a->slot_out) && (a->x_sn % 4) == 0 && (a->x_sb % 4) == 0 &&
+                    al16(a->slot_in) && (a->x_sn % 4) == 0 && (a->x_sb % 4) == 0 &&
                     (a->y_sn % 4) == 0 && (a->y_sb % 4) == 0 && a->y_sc == 1 && a->x_sn >= FT &&
                     (!a->taps || al16(a->taps)) && (!a->sproj || al16(a->sproj)) && ((uintptr_t)a->workspace % 1024) == 0,
                 MAGAT_E_ALIGN, "magat_gat_forward_fused: pointers must be 16 B aligned (workspace 1024 B), strides "
                 "multiples of 4 floats, unit channel stride");
-  MAGAT_REQUIRE((long)a->B * a->N * a->D * a->P < (1l << 31), MAGAT_E_UNSUPPORTED, "magat_gat_forward_fused: batch too large");
+  MAGAT_REQUIRE((long)a->B * a->N * a->D * a->P < (1l << 31) && (long)a->N * a->x_sn < (1l << 31), MAGAT_E_UNSUPPORTED,
+                "magat_gat_forward_fused: batch or row stride too large for the 32-bit index math");
   const WsLayout L = ws_layout(a->B, a->N, a->K, a->P, a->D, a->mode, a->save);
   MAGAT_REQUIRE(a->ws_bytes >= L.total, MAGAT_E_BAD_ARG, "magat_gat_forward_fused: workspace %zu B < %zu B", a->ws_bytes,
                 L.total);
@@ -1046,7 +1134,7 @@ extern "C" int magat_gat_forward_fused(const magat_gat_fused_args* a, void* stre
   fp.S = a->S; fp.x = a->x; fp.x_sb = a->x_sb; fp.x_sn = a->x_sn;
   fp.weight = a->weight; fp.mixer = a->mixer; fp.wb = a->weight_bias; fp.H = a->filterWeight; fp.bias = a->bias;
   fp.y = a->y; fp.y_sb = a->y_sb; fp.y_sn = a->y_sn;
-  fp.nbr_out = a->nbr_out; fp.nbr_in = a->nbr_in; fp.slot_in = a->slot_in; fp.slot_out = a->slot_out;
+  fp.nbr_out = a->nbr_out; fp.nbr_in = a->nbr_in; fp.slot_in = a->slot_in;
   fp.att = a->att;
   const int sw = a->mode == MAGAT_MODE_KEYQUERY ? FT : 2;
   if (a->save) {
@@ -1063,7 +1151,6 @@ extern "C" int magat_gat_forward_fused(const magat_gat_fused_args* a, void* stre
   fp.colbits = reinterpret_cast<uint32_t*>(ws + L.off_colbits);
   fp.ximg = reinterpret_cast<uint16_t*>(ws + L.off_ximg);
   fp.uimg = reinterpret_cast<uint16_t*>(ws + L.off_uimg);
-  fp.ain = reinterpret_cast<float*>(ws + L.off_ain);
   fp.bar = reinterpret_cast<unsigned*>(ws + L.off_bar);
   fp.status = reinterpret_cast<int32_t*>(ws);
   fp.prof = reinterpret_cast<long long*>(ws + L.off_prof);

@@ -395,7 +395,7 @@ __global__ void __launch_bounds__((17 + EW) * 32, 1) k_tap_tc(const __grid_const
         const uint32_t phase = (q >> 2) & 1u;
         tc::mbar_wait(&full[stage], phase);
         tc::tc_fence_after();
-        if (lane == 0) {
+        if (tc::elect_one()) {
           const uint32_t sb = tc::smem_u32(smem + (size_t)stage * STAGE_BYTES);
           const uint32_t h_hi = tmem_base + (uint32_t)(s * (SK / 2));
           const uint32_t h_lo = h_hi + (uint32_t)(KG / 2);
@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_tap_tc2(const __grid_constant
     // ===== copy issuer ====================================================================================
     // One tensor copy (cp.async.bulk.tensor.2d) per 64-row x 128-float box; rows past the end are zero filled by
     // the TMA unit, so every stage carries the same byte count.
-    if (lane == 0) {
+    if (tc::elect_one()) {
       const int x_c0 = p.x_hmul ? (int)(((hg * nout) / p.x_hdiv) * p.x_hmul) : 0;
       const int u_c0 = (hg * nout) * (p.K - 1) * p.G;
       const uint64_t tmx = reinterpret_cast<uint64_t>(&p.tm_x);
@@ -672,7 +672,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_tap_tc2(const __grid_constant
             tc::mbar_wait(&op_full[stage], (qq >> 1) & 1u);
             tc::tc_fence_after();
           }
-          if (lane == 0) {
+          if (tc::elect_one()) {
             const uint32_t sb = tc::smem_u32(smem + (size_t)stage * STAGE_BYTES);
             const uint32_t h_hi = tmem_base + (uint32_t)((o * nst + s) * (SK / 2));
             const uint32_t h_lo = h_hi + (uint32_t)(KGtot / 2);

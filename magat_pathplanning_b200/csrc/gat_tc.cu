@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) k_tc_gemm(const __grid_constan
       for (int ch = 0; ch < chunks; ++ch) {
         tc::mbar_wait(&full[stage], phase);
         tc::tc_fence_after();
-        if (lane == 0) {
+        if (tc::elect_one()) {
           const uint32_t sa = tc::smem_u32(smem + (size_t)stage * STAGE_BYTES);
           const uint64_t a_hi = tc::make_sw128_desc(sa), a_lo = tc::make_sw128_desc(sa + TILE_BYTES);
           const uint64_t b_hi = tc::make_sw128_desc(sa + 2 * TILE_BYTES), b_lo = tc::make_sw128_desc(sa + 3 * TILE_BYTES);

@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const __grid_constant__
     for (long sidx = slot; sidx < nstages; sidx += nslots) {
       tc::mbar_wait(&full[stage], phase);
       tc::tc_fence_after();
-      if (lane == 0) {
+      if (tc::elect_one()) {
         const uint32_t sb = tc::smem_u32(smem + (size_t)stage * STAGE_BYTES);
         const uint32_t a_hi = sb, a_lo = sb + A_BYTES, b_hi = sb + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
 #pragma unroll
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const __grid_constant__
       __syncwarp();
       if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
-    if (lane == 0) tc::umma_commit(done);
+    if (tc::elect_one()) tc::umma_commit(done);
     __syncwarp();
   }
   tc::tc_fence_before();
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_wgrad_tc2(const __grid_consta
 
   if (warp == V2_TMA_WARP) {
     // ===== copy issuer ====================================================================================
-    if (lane == 0) {
+    if (tc::elect_one()) {
       const uint64_t tma_ = reinterpret_cast<uint64_t>(&p.tm_a), tmm = reinterpret_cast<uint64_t>(&p.tm_m);
       const uint64_t tmb = reinterpret_cast<uint64_t>(&p.tm_b0), tmu = reinterpret_cast<uint64_t>(&p.tm_u);
       const uint32_t bytes = (uint32_t)V2_BOX_BYTES * (uint32_t)(nsrc + (p.has_mask ? 1 : 0));
@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_wgrad_tc2(const __grid_consta
       const int stage = (int)(q & 1u);
       tc::mbar_wait(&op_full[stage], (q >> 1) & 1u);
       tc::tc_fence_after();
-      if (lane == 0) {
+      if (tc::elect_one()) {
         const uint32_t sb = tc::smem_u32(smem + (size_t)stage * V2_OP_BYTES);
         const uint32_t a_hi = sb, a_lo = sb + V2_A_BYTES, b_hi = sb + 2 * V2_A_BYTES, b_lo = b_hi + V2_B_BYTES;
 #pragma unroll
@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_wgrad_tc2(const __grid_consta
       }
       __syncwarp();
     }
-    if (lane == 0) tc::umma_commit(done);
+    if (tc::elect_one()) tc::umma_commit(done);
     __syncwarp();
   }
   tc::tc_fence_before();

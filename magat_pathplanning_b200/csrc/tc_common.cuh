@@ -11,6 +11,16 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of the (converged) warp.  Inside `if (elect_one())` the compiler keeps UMMA / TMA operands in uniform
+// registers; behind `if (lane == 0)` it cannot prove uniformity and wraps EVERY tcgen05.mma in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall (~10 extra issue slots per MMA on the one issuing thread: the issuer,
+// not HBM or the tensor pipe, then paces the kernel -- profiles/r02_mma_issue.md).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier ------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -67,6 +67,22 @@ def _require_cuda(t: torch.Tensor, what: str):
                            "this package has no CPU path")
 
 
+def _check_params(x, filterWeight, mixer, weight, weight_bias, bias, need_cuda=True):
+    """Every parameter must be fp32 on x's device: the kernels get raw device pointers (the reference would raise a
+    dtype / device error from its first matmul)."""
+    for name, t in (("filterWeight", filterWeight), ("mixer", mixer), ("weight", weight),
+                    ("weight_bias", weight_bias), ("bias", bias)):
+        if t is None:
+            continue
+        if need_cuda:
+            _require_cuda(t, name)
+        if t.device != x.device:
+            raise RuntimeError(f"magat_pathplanning_b200: {name} is on {t.device}, x on {x.device}")
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"magat_pathplanning_b200: {name} is {t.dtype}; the layer computes in float32 "
+                               "(call .float() on the module)")
+
+
 class Adjacency:
     """Neighbour lists of one GSO batch (device tensors; layouts in include/magat_gat.h)."""
 
@@ -259,7 +275,7 @@ class _GATFunction(torch.autograd.Function):
                 wprep = torch.empty(L.magat_gat_wprep_floats(G, F, K, P, meta.mode), dtype=torch.float32, device=dev)
             D = gso.D
             while True:
-                lists = torch.empty((4, B, N, D), dtype=torch.int32, device=dev)
+                lists = torch.empty((3, B, N, D), dtype=torch.int32, device=dev)
                 att = torch.empty((B, N, D, P), dtype=torch.float32, device=dev)
                 nbytes = L.magat_gat_fused_workspace_bytes(B, N, K, P, D, meta.mode, int(save))
                 ws = _workspace(dev, nbytes)
@@ -270,7 +286,7 @@ class _GATFunction(torch.autograd.Function):
                                     filterWeight=filt_c.data_ptr(), bias=_p(bias_c),
                                     y=y_mem.data_ptr(), y_sb=y.stride(0), y_sn=y.stride(2), y_sc=y.stride(1),
                                     nbr_out=lists[0].data_ptr(), nbr_in=lists[1].data_ptr(),
-                                    slot_in=lists[2].data_ptr(), slot_out=lists[3].data_ptr(),
+                                    slot_in=lists[2].data_ptr(), slot_out=None,
                                     att=att.data_ptr(), taps=_p(taps), sproj=_p(sproj), wprep=_p(wprep),
                                     workspace=ws.data_ptr(), ws_bytes=nbytes)
                 _cabi.check(L.magat_gat_forward_fused(a, _stream(dev)))
@@ -285,7 +301,7 @@ class _GATFunction(torch.autograd.Function):
                     gso.adj = build_adjacency(S)
                     return _GATFunction.forward(ctx, x, weight, mixer, weight_bias, filterWeight, bias, gso.adj, meta)
                 D = need
-        adj = Adjacency(B, N, D, lists[0], lists[1], lists[2], lists[3])
+        adj = Adjacency(B, N, D, lists[0], lists[1], lists[2], None)      # (nothing downstream needs slot_out)
         gso.adj = adj
         ctx.taps_valid = K - 1
         ctx.meta, ctx.adj = meta, adj
@@ -452,6 +468,8 @@ def gat_layer(x, S, filterWeight, mixer, weight, weight_bias, bias, *, mode: int
     assert x.shape[1] == G                       # graphML.py:1735
     if x.dtype != torch.float32:
         x = x.float()
+    _check_params(x, filterWeight, mixer if mode != _cabi.MODE_KEYQUERY else None, weight,
+                  weight_bias if mode != _cabi.MODE_KEYQUERY else None, bias)
     B_, N_ = x.shape[0], x.shape[2]
     needs_grad = torch.is_grad_enabled() and any(
         t is not None and t.requires_grad for t in (x, filterWeight, mixer, weight, weight_bias, bias))
@@ -517,13 +535,21 @@ def _functional(h, x, a, W, W_b, S, b, mode):
     return y, att.dense()
 
 
-def graphAttentionLSIGFBatch_KeyQuery(h, x, a, W, W_b, S, b=None):
+def _check_slope(negative_slope):
+    if negative_slope != 0.2:
+        raise NotImplementedError("only the reference's default negative_slope = 0.2 is built in "
+                                  "(graphML.py:713; no caller overrides it)")
+
+
+def graphAttentionLSIGFBatch_KeyQuery(h, x, a, W, W_b, S, b=None, negative_slope=0.2):
     """graphML.py:1724-1775: returns (y [B,P,F,N] before the nonlinearity, aij [B,P,E,N,N])."""
+    _check_slope(negative_slope)
     return _functional(h, x, a, W, W_b, S, b, _cabi.MODE_KEYQUERY)
 
 
-def graphAttentionLSIGFBatch_modified(h, x, a, W, W_b, S, b=None):
+def graphAttentionLSIGFBatch_modified(h, x, a, W, W_b, S, b=None, negative_slope=0.2):
     """graphML.py:1777-1827."""
+    _check_slope(negative_slope)
     return _functional(h, x, a, W, W_b, S, b, _cabi.MODE_GAT_MODIFIED)
 
 
@@ -536,15 +562,15 @@ def _attention_only(x, a, W, W_b, S, mode):
     return att.dense()
 
 
-def learnAttentionGSOBatch_KeyQuery(x, a, W, S, negative_slope=0.2):
-    """graphML.py:1180-1286 (the reference ignores ``a`` and ``negative_slope`` in this mode)."""
+def learnAttentionGSOBatch_KeyQuery(x, a, W, W_b, S, negative_slope=0.2):
+    """graphML.py:1180-1286, same argument order (the reference ignores ``a``, ``W_b`` and ``negative_slope`` in
+    this mode: no LeakyReLU on the scores, :1265-1266)."""
     return _attention_only(x, a, W, None, S, _cabi.MODE_KEYQUERY)
 
 
 def learnAttentionGSOBatch(x, a, W, W_b, S, negative_slope=0.2):
     """graphML.py:713-823."""
-    if negative_slope != 0.2:
-        raise NotImplementedError("only the reference's default negative_slope = 0.2 is built in")
+    _check_slope(negative_slope)
     return _attention_only(x, a, W, W_b, S, _cabi.MODE_GAT_MODIFIED)
 
 
@@ -648,6 +674,9 @@ class GraphFilterBatchAttentional(nn.Module):
         if Nin < self.N:                 # graphML.py:4642-4646
             x = torch.cat((x, torch.zeros(B, F, self.N - Nin).type(x.dtype).to(x.device)), dim=2)
         fused_relu = self.nonlinearity in (nn.functional.relu, torch.relu)
+        if self.S is None and getattr(self, "_adj", None) is None:
+            raise RuntimeError("GraphFilterBatchAttentional.forward: no GSO stored -- call addGSO(S) (or "
+                               "addGSOFromPositions) first; device-side neighbour lists do not survive pickling")
         y, att = gat_layer(x, self.S, self.filterWeight, self.mixer, self.weight, self.weight_bias,
                            self.bias, mode=_mode_of(self.attentionMode), concatenate=self.concatenate,
                            relu=fused_relu, path=self.path, adjacency=getattr(self, "_adj", None),

@@ -39,6 +39,8 @@ def test_struct_sizes_match_header(built):
     # 12 x int32 + 21 x 8 bytes ; 18 x int32 + 32 x 8 bytes
     assert ctypes.sizeof(built.FwdArgs) == 12 * 4 + 21 * 8
     assert ctypes.sizeof(built.BwdArgs) == 18 * 4 + 32 * 8
+    # 12 x int32 + 23 x 8 bytes
+    assert ctypes.sizeof(built.FusedArgs) == 12 * 4 + 23 * 8
 
 
 def test_sizes_helpers_need_no_gpu(built):
@@ -56,6 +58,55 @@ def test_bad_arguments_return_codes_not_crash(built):
     assert L.magat_gat_forward(a, None) == 1                        # MAGAT_E_BAD_ARG
     assert L.magat_gat_forward(None, None) == 1
     assert L.magat_gso_scan(None, 0, 1, 4, None, None, None, None) == 1
+
+
+def test_fused_entry_point_rejects_without_crashing(built):
+    L = built.lib()
+    assert L.magat_gat_forward_fused(None, None) == 1
+    a = built.FusedArgs(B=2, N=100, G=128, F=128, K=3, P=4, D=16, mode=built.MODE_KEYQUERY, concat=0)
+    assert L.magat_gat_forward_fused(a, None) == 2 and b"not covered" in L.magat_last_error()
+    assert L.magat_gat_fused_supported(1000, 128, 128, 3, 4, 16, built.MODE_KEYQUERY, 1) == 1
+    assert L.magat_gat_fused_supported(1000, 128, 128, 3, 4, 36, built.MODE_KEYQUERY, 1) == 0     # D > 32
+    assert L.magat_gat_fused_supported(1001, 128, 128, 3, 4, 16, built.MODE_KEYQUERY, 1) == 0     # N % 4
+    assert L.magat_gat_fused_supported(1000, 64, 64, 3, 4, 16, built.MODE_KEYQUERY, 1) == 0
+    n = L.magat_gat_fused_workspace_bytes(512, 1000, 3, 4, 16, built.MODE_KEYQUERY, 0)
+    assert 0 < n < 1 << 30
+    assert L.magat_gat_fused_workspace_bytes(512, 1000, 3, 4, 16, built.MODE_KEYQUERY, 1) < n
+
+
+def test_functional_signatures_match_reference():
+    """The functionals are rebound by name inside the reference module (integration.install_into_reference): same
+    parameter names, order and defaults (graphML.py:713, :1180, :1724, :1777)."""
+    import inspect
+    from oracle.ref_loader import load_reference_graphml, reference_available
+    if not reference_available():
+        pytest.skip("reference checkout not present")
+    gml = load_reference_graphml()
+    import magat_pathplanning_b200 as ours
+    for name in ("learnAttentionGSOBatch", "learnAttentionGSOBatch_KeyQuery", "graphAttentionLSIGFBatch_KeyQuery",
+                 "graphAttentionLSIGFBatch_modified"):
+        assert str(inspect.signature(getattr(ours, name))) == str(inspect.signature(getattr(gml, name))), name
+    ref_init = inspect.signature(gml.GraphFilterBatchAttentional.__init__)
+    our_init = inspect.signature(ours.GraphFilterBatchAttentional.__init__)
+    assert list(ref_init.parameters) == list(our_init.parameters)
+    for k, v in ref_init.parameters.items():
+        if k != "nonlinearity":
+            assert our_init.parameters[k].default == v.default, k
+
+
+def test_parameters_are_validated_before_the_kernels_see_them():
+    """A layer left on the CPU, or cast to another dtype, must raise instead of handing raw pointers to CUDA."""
+    from magat_pathplanning_b200 import graphML
+    m = graphML.GraphFilterBatchAttentional(16, 16, 2, 2, 1, True, concatenate=True, attentionMode="KeyQuery")
+    x = torch.zeros(1, 16, 5)
+    for bad in (m.double(),):
+        with pytest.raises(RuntimeError):
+            graphML._check_params(x.float(), bad.filterWeight, bad.mixer, bad.weight, bad.weight_bias, bad.bias,
+                                  need_cuda=False)
+    m = m.float()
+    graphML._check_params(x, m.filterWeight, m.mixer, m.weight, m.weight_bias, m.bias, need_cuda=False)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        graphML._check_params(x, m.filterWeight, m.mixer, m.weight, m.weight_bias, m.bias)
 
 
 def test_module_surface_matches_reference():

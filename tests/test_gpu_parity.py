@@ -140,10 +140,7 @@ def test_functional_surface(golden):
                                                 mode=meta["mode"], concatenate=True, return_pre=True)
         assert y.shape == pre.shape and rel_err(y, pre) < TOL
         assert aij.shape == aij_ref.shape and (aij.cpu() - aij_ref).abs().max() < TOL
-        if meta["mode"] == "KeyQuery":
-            a2 = att_fn(x, p["mixer"], p["weight"], S)
-        else:
-            a2 = att_fn(x, p["mixer"], p["weight"], p["weight_bias"], S)
+        a2 = att_fn(x, p["mixer"], p["weight"], p["weight_bias"], S)      # the reference's argument order for both
         assert (a2.cpu() - aij_ref).abs().max() < TOL
 
 
