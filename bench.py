@@ -211,21 +211,61 @@ def cpu_oracle_run(w, sample_B, steps, warmup, what="fwdbwd"):
     return sample_B * N / dt, dt * 1e3, cores
 
 
+def reference_layer_run(w, sample_B, steps, warmup):
+    """The UNMODIFIED reference layer (utils/graphUtils/graphML.py, loaded by oracle/ref_loader.py from /root/reference
+    or baseline/_ref) on the host cores: addGSO + forward + backward on sample_B instances per step."""
+    from oracle.ref_loader import load_reference_graphml
+    gml = load_reference_graphml()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    gen = torch.Generator().manual_seed(SEED)
+    N, G, P, K = w["N"], w["G"], w["P"], w["K"]
+    S = synth_gso(sample_B, N, w["width"], torch.device("cpu"), gen, chunk=8)
+    x = torch.relu(torch.randn(sample_B, N, G, generator=gen)).permute(0, 2, 1)
+    C = P * G if w["concat"] else G
+    dy = torch.randn(sample_B, C, N, generator=gen)
+    torch.manual_seed(SEED)
+    layer = gml.GraphFilterBatchAttentional(G, G, K, P, 1, True, concatenate=w["concat"], attentionMode=w["mode"])
+    params = list(layer.parameters())
+
+    def run():
+        for p in params:
+            p.grad = None
+        xg = x.detach().requires_grad_(True)
+        layer.addGSO(S)
+        layer(xg).backward(dy)
+    for _ in range(warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run()
+    dt = (time.perf_counter() - t0) / steps
+    return sample_B * N / dt, dt * 1e3, cores
+
+
 def run_reference(args, w, rank):
-    """`--impl reference`: the reference's CPU algorithm (oracle port; the Python reference itself cannot
-    travel to the GPU box) with every host thread, each step a bounded sample of the workload."""
+    """`--impl reference`: the reference's own CPU implementation of the path with every host thread, each step a
+    bounded sample of the workload (the dense [B,P,N,N] temporaries bound the batch).  The unmodified reference
+    layer when its files are present (kind "reference"), else the oracle port (kind "port")."""
     if rank != 0:
         return
+    from oracle.ref_loader import reference_available
     sample_B = 8 if w["N"] >= 500 else min(w["B"], 64)
-    steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
-    v, ms, cores = cpu_oracle_run(w, sample_B, steps, warmup)
-    sample = f"{sample_B} of {w['B']} instances per step (dense [B,P,N,N] temporaries bound the batch), fwd+bwd"
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    if reference_available():
+        kind = "reference"
+        v, ms, cores = reference_layer_run(w, sample_B, steps, warmup)
+    else:
+        kind = "port"
+        v, ms, cores = cpu_oracle_run(w, sample_B, steps, warmup)
+    sample = (f"{sample_B} of {w['B']} instances per step (the reference's dense [B,P,N,N] temporaries bound the "
+              f"batch; agent-steps/s does not depend on B at this size), addGSO + forward + backward")
     emit(json.dumps({
         "impl": "reference", "metric": "agent-steps/sec GAT fwd+bwd", "value": v, "unit": "agent-steps/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(w), "sample": sample},
-        "cpu_baseline": {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -507,10 +547,16 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         sample_B = 8 if N >= 500 else min(B, 64)
         reps = 3 if N >= 500 else 5
-        v, ms, cores = cpu_oracle_run(w, sample_B, reps, 1)
-        cpu_baseline = {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": "port",
-                        "sample": f"{sample_B} of {B} instances x {reps} steps, fwd+bwd, torch CPU fp32, "
-                                  f"{ms:.0f} ms/step (oracle/gat_oracle.py)"}
+        from oracle.ref_loader import reference_available
+        if reference_available():
+            v, ms, cores = reference_layer_run(w, sample_B, reps, 1)
+            kind, src = "reference", "unmodified reference layer, baseline/_ref"
+        else:
+            v, ms, cores = cpu_oracle_run(w, sample_B, reps, 1)
+            kind, src = "port", "oracle/gat_oracle.py"
+        cpu_baseline = {"value": v, "unit": "agent-steps/s", "cores": cores, "kind": kind,
+                        "sample": f"{sample_B} of {B} instances x {reps} steps, addGSO + fwd + bwd, torch CPU fp32, "
+                                  f"{ms:.0f} ms/step ({src})"}
 
     out = {
         "metric": "agent-steps/sec GAT fwd+bwd", "value": units / (ms_train * 1e-3), "unit": "agent-steps/s",

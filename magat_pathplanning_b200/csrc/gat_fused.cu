@@ -645,18 +645,24 @@ __device__ __forceinline__ void phase_gather(const FusedParams& p, long rowbase,
 // immediate (one FADD, one FMNMX and one STG per node instead of a 64-bit multiply-add chain); 0 = runtime stride.
 template <int STRIDE, bool ACT, bool STREAM>
 __device__ __forceinline__ void epi_store(float* dst, long stride_rt, const float (&v)[32], int left, float bias,
-                                          float floor_) {
-  if (left >= 32) {
+                                          bool relu) {
+  if (ACT && !relu) {                          // bias only (a caller-supplied nonlinearity follows in torch)
 #pragma unroll
     for (int n = 0; n < 32; ++n) {
-      const float o = ACT ? fmaxf(v[n] + bias, floor_) : v[n];
+      float* q = STRIDE ? dst + n * STRIDE : dst + n * stride_rt;
+      if (n < left) __stcs(q, v[n] + bias);
+    }
+  } else if (left >= 32) {
+#pragma unroll
+    for (int n = 0; n < 32; ++n) {
+      const float o = ACT ? fmaxf(v[n] + bias, 0.f) : v[n];
       float* q = STRIDE ? dst + n * STRIDE : dst + n * stride_rt;
       if (STREAM) __stcs(q, o); else *q = o;
     }
   } else {
 #pragma unroll
     for (int n = 0; n < 32; ++n) {
-      const float o = ACT ? fmaxf(v[n] + bias, floor_) : v[n];
+      const float o = ACT ? fmaxf(v[n] + bias, 0.f) : v[n];
       float* q = STRIDE ? dst + n * STRIDE : dst + n * stride_rt;
       if (n < left) { if (STREAM) __stcs(q, o); else *q = o; }
     }
@@ -872,9 +878,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gat_fused(const __grid_constant
             const int m0 = t * TN + 32 * hh;
             float* dst = sproj + (unsigned)((m0 * P + head) * FT + f);
             const int left = N - m0;
-            if (P == 4) epi_store<4 * FT, false, false>(dst, 0, v, left, 0.f, 0.f);
-            else if (P == 2) epi_store<2 * FT, false, false>(dst, 0, v, left, 0.f, 0.f);
-            else epi_store<FT, false, false>(dst, 0, v, left, 0.f, 0.f);
+            if (P == 4) epi_store<4 * FT, false, false>(dst, 0, v, left, 0.f, false);
+            else if (P == 2) epi_store<2 * FT, false, false>(dst, 0, v, left, 0.f, false);
+            else epi_store<FT, false, false>(dst, 0, v, left, 0.f, false);
           }
           ++oc;
         }
@@ -973,7 +979,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gat_fused(const __grid_constant
       const int qd = warp & 3;
       const int f = qd * 32 + lane;
       const float bias = p.bias ? __ldg(p.bias + f) : 0.f;
-      const float yfloor = p.relu ? 0.f : -INFINITY;
       const bool y_dense = p.y_sn == (long)P * FT;
       float* yb = p.y + (long)b * p.y_sb + (long)head * FT + f;
       for (int t = split; t < p.tiles; t += p.nsplit) {
@@ -994,10 +999,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gat_fused(const __grid_constant
           const int m0 = t * TN + 32 * hh;
           float* dst = yb + (long)m0 * p.y_sn;
           const int left = N - m0;
-          if (!y_dense) epi_store<0, true, true>(dst, p.y_sn, v, left, bias, yfloor);
-          else if (P == 4) epi_store<4 * FT, true, true>(dst, 0, v, left, bias, yfloor);
-          else if (P == 2) epi_store<2 * FT, true, true>(dst, 0, v, left, bias, yfloor);
-          else epi_store<FT, true, true>(dst, 0, v, left, bias, yfloor);
+          if (!y_dense) epi_store<0, true, true>(dst, p.y_sn, v, left, bias, p.relu != 0);
+          else if (P == 4) epi_store<4 * FT, true, true>(dst, 0, v, left, bias, p.relu != 0);
+          else if (P == 2) epi_store<2 * FT, true, true>(dst, 0, v, left, bias, p.relu != 0);
+          else epi_store<FT, true, true>(dst, 0, v, left, bias, p.relu != 0);
         }
         ++oc;
       }

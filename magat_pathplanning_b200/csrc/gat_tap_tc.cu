@@ -453,6 +453,30 @@ constexpr int V2_EPI_WARP0 = 16, V2_EPI_WARPS = 4, V2_MMA_WARP = 20, V2_TMA_WARP
 constexpr size_t V2_SMEM_BYTES = (size_t)V2_NOP * STAGE_BYTES + V2_RAW_BYTES + 1024 + 256;
 
 
+template <int STRIDE>
+__device__ __forceinline__ void v2_store(float* dst, long stride_rt, const float (&v)[32], long left, float bias,
+                                         bool relu) {
+  if (relu) {
+    if (left >= 32) {
+#pragma unroll
+      for (int n = 0; n < 32; ++n) __stcs(STRIDE ? dst + n * STRIDE : dst + n * stride_rt, fmaxf(v[n] + bias, 0.f));
+    } else {
+#pragma unroll
+      for (int n = 0; n < 32; ++n)
+        if (n < left) __stcs(STRIDE ? dst + n * STRIDE : dst + n * stride_rt, fmaxf(v[n] + bias, 0.f));
+    }
+  } else {
+    if (left >= 32) {
+#pragma unroll
+      for (int n = 0; n < 32; ++n) __stcs(STRIDE ? dst + n * STRIDE : dst + n * stride_rt, v[n] + bias);
+    } else {
+#pragma unroll
+      for (int n = 0; n < 32; ++n)
+        if (n < left) __stcs(STRIDE ? dst + n * STRIDE : dst + n * stride_rt, v[n] + bias);
+    }
+  }
+}
+
 template <bool MASKED>
 __global__ void __launch_bounds__(V2_THREADS, 1) k_tap_tc2(const __grid_constant__ TapParams p) {
   constexpr int NRAW = MASKED ? 2 : 4;
@@ -637,21 +661,13 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_tap_tc2(const __grid_constant
             for (int n = 0; n < 32; ++n)
               if (n < left) v[n] += dst[(long)n * p.y_sn];
           }
-          if (left >= 32) {
-#pragma unroll
-            for (int n = 0; n < 32; ++n) {
-              float ov = v[n] + bias;
-              if (p.relu) ov = fmaxf(ov, 0.f);
-              __stcs(dst + (long)n * p.y_sn, ov);
-            }
-          } else {
-#pragma unroll
-            for (int n = 0; n < 32; ++n) {
-              float ov = v[n] + bias;
-              if (p.relu) ov = fmaxf(ov, 0.f);
-              if (n < left) __stcs(dst + (long)n * p.y_sn, ov);
-            }
-          }
+          // the usual row strides as compile-time constants: every store then carries its offset as an immediate
+          // (FADD + FMNMX + STG per node instead of a 64-bit multiply-add chain -- the four epilogue warps pace the
+          // one-slice uses of this kernel)
+          if (p.y_sn == 512) v2_store<512>(dst, 0, v, left, bias, p.relu != 0);
+          else if (p.y_sn == 1536) v2_store<1536>(dst, 0, v, left, bias, p.relu != 0);
+          else if (p.y_sn == 256) v2_store<256>(dst, 0, v, left, bias, p.relu != 0);
+          else v2_store<0>(dst, p.y_sn, v, left, bias, p.relu != 0);
         }
       }
     }

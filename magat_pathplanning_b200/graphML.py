@@ -16,6 +16,7 @@ There is no CPU path: CPU tensors raise.
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import numpy as np
@@ -32,8 +33,10 @@ _NOSYNC_N = 48
 
 _PATH = {"auto": _cabi.PATH_AUTO, "simt": _cabi.PATH_SIMT, "tcgen05": _cabi.PATH_TCGEN05, "fused": _cabi.PATH_AUTO}
 
-#: "auto" takes the single-launch fused forward (csrc/gat_fused.cu) from this many agents up; below it the work per
-#: instance is too small to give a team of 8 CTAs anything to do
+#: path="fused" takes the single-launch fused forward (csrc/gat_fused.cu).  "auto" only does so when this switch is on
+#: (MAGAT_FUSED_AUTO=1) and the graphs have at least _FUSED_MIN_N agents: on B200 the multi-launch path is currently the
+#: faster of the two, so it stays the default
+_FUSED_AUTO = os.environ.get("MAGAT_FUSED_AUTO", "0") not in ("", "0")
 _FUSED_MIN_N = 128
 #: degree cap D the fused kernel is first tried with (its lists are [B][N][D]); a graph that exceeds it is redone
 #: with 32 and then through the general path
@@ -438,7 +441,7 @@ def _fused_gso(x, S, G, F, K, P, mode, concatenate, path, max_degree):
     if not (S.is_cuda and len(S.shape) == 4 and S.shape[0] == B and S.shape[1] == 1 and S.shape[2] == N
             and S.shape[3] == N):
         return None
-    if path == "auto" and N < _FUSED_MIN_N:
+    if path == "auto" and (not _FUSED_AUTO or N < _FUSED_MIN_N):
         return None
     D = min(32, (min(N, max_degree if max_degree else _FUSED_D0) + 3) // 4 * 4)
     if not _cabi.lib().magat_gat_fused_supported(N, G, F, K, P, D, mode, int(bool(concatenate))):

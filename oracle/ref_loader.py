@@ -1,10 +1,10 @@
-"""Load the UNMODIFIED reference ``graphML.py`` by file path.  TEST INFRASTRUCTURE ONLY.
+"""Load the UNMODIFIED reference ``graphML.py`` (and planner model files) by file path.  TEST INFRASTRUCTURE ONLY.
 
-Only usable where the reference checkout exists (the build container, /root/reference);
-it does not exist on the GPU box, so nothing in the ``-m gpu`` tests, ``smoke()`` or
-``bench.py`` calls this.  It is used by ``tests/golden/make_golden.py`` to produce the
-committed golden vectors and by the optional CPU tests that compare the oracle against
-the live reference when it is present.
+Looks for the reference in ``$MAGAT_REFERENCE``, then ``/root/reference`` (the build container's read-only checkout),
+then ``baseline/_ref/`` -- the git-ignored copy of the few files the path needs that ``baseline/fetch_reference.py``
+makes and that travels to the GPU box with the snapshot.  Used by ``tests/golden/make_golden.py`` (golden vectors), by
+the tests that compare the oracle / the CUDA layer with the live reference, and by ``bench.py --impl reference``.
+Nothing under ``magat_pathplanning_b200/`` imports it.
 
 ``utils/__init__.py`` of the reference auto-imports every module (matplotlib, easydict,
 ... are absent here), so the packages are stubbed and the one file is exec'd directly
@@ -18,7 +18,17 @@ import sys
 import types
 import warnings
 
-DEFAULT_REF = os.environ.get("MAGAT_REFERENCE", "/root/reference")
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_reference():
+    for cand in (os.environ.get("MAGAT_REFERENCE"), "/root/reference", os.path.join(_ROOT, "baseline", "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "utils", "graphUtils", "graphML.py")):
+            return cand
+    return "/root/reference"
+
+
+DEFAULT_REF = _find_reference()
 
 
 def reference_available(ref: str = DEFAULT_REF) -> bool:
@@ -82,7 +92,12 @@ def load_reference_planner(name: str = "decentralplanner_GAT", ref: str = DEFAUL
 
 class PlannerConfig(dict):
     """Attribute dict with the fields the planners read (graphs/models/decentralplanner_GAT.py)."""
-    __getattr__ = dict.__getitem__
+
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError:
+            raise AttributeError(name) from None
 
     @classmethod
     def default(cls, **kw):

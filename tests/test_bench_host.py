@@ -26,13 +26,16 @@ def test_only_the_json_line_reaches_stdout():
 
 
 def test_reference_arm_prints_one_json_line():
+    sys.path.insert(0, ROOT)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c2_n10",
                         "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
-    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port"
+    from oracle.ref_loader import reference_available
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == ("reference" if reference_available() else "port")
+    assert d["steps"] == 1 and d["warmup"] == 1                      # the arm honours --steps / --warmup
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["metric"].startswith("agent-steps/sec") and d["higher_is_better"] is True
 

@@ -154,7 +154,8 @@ def test_fused_is_one_launch():
     params = orc.init_params(G, F, 3, 4, mode="KeyQuery", generator=gen)
     S = orc.random_geometric_gso(6, 256, generator=gen).to(dev)
     x = torch.relu(torch.randn(6, 256, G, generator=gen)).permute(0, 2, 1).to(dev)
-    layer = _layer(params, dict(G=G, F=F, K=3, P=4, concat=True, mode="KeyQuery"), dev, "auto")
+    layer = _layer(params, dict(G=G, F=F, K=3, P=4, concat=True, mode="KeyQuery"), dev, "fused")
+    layer.max_degree = 16                  # promised bound: not even the degree read-back remains
     L = _cabi.lib()
     with torch.no_grad():
         layer.addGSO(S)

@@ -33,11 +33,12 @@ def make_layer(meta, d, dev, path="simt"):
     return layer.to(dev)
 
 
+@pytest.mark.parametrize("path", ["simt", "auto"])
 @pytest.mark.parametrize("name", golden_case_names())
-def test_golden_forward_backward(golden, name):
+def test_golden_forward_backward(golden, name, path):
     d, meta = golden.case(name)
     dev = torch.device("cuda:0")
-    layer = make_layer(meta, d, dev)
+    layer = make_layer(meta, d, dev, path=path)
     x = d["x"].to(dev).requires_grad_(True)
     layer.addGSO(d["S"].to(dev))
     y = layer(x)
@@ -230,23 +231,81 @@ def test_tc_path_golden(golden, name):
     ("KeyQuery", True, 256, 256, 2, 1, 2, 50),
 ])
 def test_tc_path_oracle(mode, concat, G, F, K, P, B, N):
+    """Forward AND backward of the tcgen05 path (both attention modes) against the CPU oracle."""
     dev = torch.device("cuda:0")
     gen = torch.Generator().manual_seed(4242 + N + G)
     params = orc.init_params(G, F, K, P, mode=mode, generator=gen, weight_bias_std=0.1)
     S = orc.random_geometric_gso(B, N, generator=gen)
     x = torch.relu(torch.randn(B, N, G, generator=gen)).permute(0, 2, 1)
-    y_ref, aij_ref = orc.gat_layer_forward(x, S, params, mode=mode, concatenate=concat)
+    dy = torch.randn(B, P * F if concat else F, N, generator=gen)
+    # no gradient into outputs next to the ReLU kink (a 5e-6 difference in y would flip relu'(y) there)
+    _, _, pre = orc.gat_layer_forward(x, S, params, mode=mode, concatenate=concat, return_pre=True)
+    pre_out = pre.reshape(B, P * F, N) if concat else pre.mean(dim=1)
+    dy = dy * (pre_out.abs() > 1e-3)
+    y_ref, aij_ref, g_ref = orc.gat_layer_fwd_bwd(x, S, params, dy, mode=mode, concatenate=concat)
     meta = dict(G=G, F=F, K=K, P=P, concat=concat, mode=mode)
     layer = make_layer(meta, {"param." + k: v for k, v in params.items() if v is not None}, dev, path="tcgen05")
     layer.addGSO(S.to(dev))
+    xd = x.to(dev).requires_grad_(True)
+    y = layer(xd)
+    y.backward(dy.to(dev))
     with torch.no_grad():
-        y = layer(x.to(dev))
         layer.path = "simt"
         y_simt = layer(x.to(dev))
     e_tc, e_simt = rel_err(y, y_ref), rel_err(y_simt, y_ref)
     print(f"tcgen05 err {e_tc:.2e}  simt err {e_simt:.2e}")
     assert e_tc < TOL
     assert (torch.from_numpy(layer.aij) - aij_ref).abs().max() < TOL
+    assert rel_err(xd.grad, g_ref["x"]) < TOL
+    for k in PARAMS:
+        if g_ref[k] is not None:
+            assert rel_err(getattr(layer, k).grad, g_ref[k]) < TOL, k
+
+
+@pytest.mark.parametrize("path", ["auto", "fused"])
+def test_oracle_at_the_graded_shape(path):
+    """B x N = 160 x 1000, G = F = 128, K = 3, P = 4, concat, KeyQuery -- the north-star shape, persistent CTAs wrapping
+    their rings many times -- against the ORACLE: instances are independent, so the oracle runs on three of them (its
+    dense [P,N,N] temporaries fit) and, with dy zero everywhere else, pins y, aij, dx AND every parameter gradient of
+    the whole at-scale run."""
+    from magat_pathplanning_b200.graphML import Adjacency, attention_dense
+    from bench import synth_gso
+    dev = torch.device("cuda:0")
+    G = F = 128
+    B, N, K, P = 160, 1000, 3, 4
+    gen = torch.Generator().manual_seed(2024)
+    params = orc.init_params(G, F, K, P, mode="KeyQuery", generator=gen, weight_bias_std=0.1)
+    S = synth_gso(B, N, 200, dev, torch.Generator(device=dev).manual_seed(17))
+    x_mem = torch.relu(torch.randn(B, N, G, generator=gen))
+    pick = [0, 77, 159]
+    xs, Ss = x_mem[pick].permute(0, 2, 1), S[pick].cpu()
+    dys = torch.randn(len(pick), P * F, N, generator=gen)
+    _, _, pre = orc.gat_layer_forward(xs, Ss, params, mode="KeyQuery", concatenate=True, return_pre=True)
+    dys = dys * (pre.reshape(len(pick), P * F, N).abs() > 1e-3)
+    y_ref, aij_ref, g_ref = orc.gat_layer_fwd_bwd(xs, Ss, params, dys, mode="KeyQuery", concatenate=True)
+    dy = torch.zeros(B, P * F, N)
+    dy[pick] = dys
+    layer = make_layer(dict(G=G, F=F, K=K, P=P, concat=True, mode="KeyQuery"),
+                       {"param." + k: v for k, v in params.items() if v is not None}, dev, path=path)
+    xd = x_mem.to(dev).permute(0, 2, 1).requires_grad_(True)
+    layer.addGSO(S)
+    y = layer(xd)
+    y.backward(dy.to(dev))
+    assert rel_err(y[pick], y_ref) < TOL
+    last = layer._last
+    idx = torch.tensor(pick, device=dev)
+    adj = last.adj
+    sub = Adjacency(len(pick), N, adj.D, adj.nbr_out[idx].contiguous(), adj.nbr_in[idx].contiguous(),
+                    adj.slot_in[idx].contiguous(), None)
+    aij = attention_dense(last.att[idx].contiguous(), sub).cpu()
+    assert (aij - aij_ref).abs().max() < TOL
+    assert rel_err(xd.grad[pick], g_ref["x"]) < TOL
+    rest = torch.ones(B, dtype=torch.bool)
+    rest[pick] = False
+    assert float(xd.grad[rest.to(dev)].abs().max()) == 0.0
+    for k in PARAMS:
+        if g_ref[k] is not None:
+            assert rel_err(getattr(layer, k).grad, g_ref[k]) < TOL, k
 
 
 @pytest.mark.parametrize("B,N,K,P", [(160, 1000, 3, 4), (130, 777, 2, 2)])
