@@ -28,8 +28,9 @@ from . import _cabi
 zeroTolerance = 1e-9     # graphML.py:45
 infiniteNumber = 1e12    # graphML.py:46
 
-#: no host sync for the ELL width below this node count (width = N)
-_NOSYNC_N = 48
+#: no host sync for the ELL width up to this node count (width = N: no list can overflow, and the lane-per-slot
+#: kernels still apply)
+_NOSYNC_N = 32
 
 _PATH = {"auto": _cabi.PATH_AUTO, "simt": _cabi.PATH_SIMT, "tcgen05": _cabi.PATH_TCGEN05, "fused": _cabi.PATH_AUTO}
 
@@ -89,16 +90,41 @@ def _check_params(x, filterWeight, mixer, weight, weight_bias, bias, need_cuda=T
 class Adjacency:
     """Neighbour lists of one GSO batch (device tensors; layouts in include/magat_gat.h)."""
 
-    __slots__ = ("B", "N", "D", "nbr_out", "nbr_in", "slot_in", "slot_out")
+    __slots__ = ("B", "N", "D", "nbr_out", "nbr_in", "slot_in", "slot_out", "stats")
 
-    def __init__(self, B, N, D, nbr_out, nbr_in, slot_in, slot_out):
+    def __init__(self, B, N, D, nbr_out, nbr_in, slot_in, slot_out, stats=None):
         self.B, self.N, self.D = B, N, D
         self.nbr_out, self.nbr_in, self.slot_in, self.slot_out = nbr_out, nbr_in, slot_in, slot_out
+        self.stats = stats          # device int32 {max out-degree, max in-degree, edges, symmetric} of the scan, or None
+
+    def check_degree(self):
+        """Synchronising check of a ``max_degree`` promise: raises when a neighbour list did not fit its D slots."""
+        if self.stats is not None:
+            h = self.stats.cpu()
+            if max(int(h[0]), int(h[1])) > self.D:
+                raise RuntimeError(f"max_degree promise broken: a node has {max(int(h[0]), int(h[1]))} neighbours, "
+                                   f"the lists hold {self.D}")
 
 
-def build_adjacency(S: torch.Tensor) -> Adjacency:
+_stats0 = {}
+
+
+def _stats_init(dev):
+    """{0, 0, 0, 1}: the scan's statistics block before the call (one device-to-device copy of a cached constant, so
+    the layer stays capturable in a CUDA graph)."""
+    t = _stats0.get(dev.index)
+    if t is None:
+        t = torch.tensor([0, 0, 0, 1], dtype=torch.int32, device=dev)
+        _stats0[dev.index] = t
+    return t.clone()
+
+
+def build_adjacency(S: torch.Tensor, max_degree: Optional[int] = None) -> Adjacency:
     """[B,1,N,N] dense GSO -> neighbour lists.  Only ``|S| > 1e-9`` matters (graphML.py:1274-1276):
-    NaN is "no edge", negative weights are edges.  S is read once, by one kernel."""
+    NaN is "no edge", negative weights are edges.  S is read once, by one kernel.
+
+    The list width D comes from N (N <= 32), from the caller's ``max_degree`` promise, or -- the only case with a
+    host synchronisation -- from the degree statistics of the scan."""
     _require_cuda(S, "the GSO")
     assert len(S.shape) == 4
     B, E, N = S.shape[0], S.shape[1], S.shape[2]
@@ -118,17 +144,18 @@ def build_adjacency(S: torch.Tensor) -> Adjacency:
         st = _stream(dev)
         rowbits = torch.empty((B, N, W), dtype=torch.int32, device=dev)
         colbits = torch.empty((B, N, W), dtype=torch.int32, device=dev)
-        stats = torch.zeros(4, dtype=torch.int32, device=dev)
-        stats[3] = 1
+        stats = _stats_init(dev)
         _cabi.check(L.magat_gso_scan(S.data_ptr(), _cabi.DT_F32 if S.dtype == torch.float32 else _cabi.DT_F64,
                                      B, N, rowbits.data_ptr(), colbits.data_ptr(), stats.data_ptr(), st))
-        return _lists_from_masks(rowbits, colbits, stats, B, N, dev, st)
+        return _lists_from_masks(rowbits, colbits, stats, B, N, dev, st, max_degree)
 
 
-def _lists_from_masks(rowbits, colbits, stats, B, N, dev, st):
+def _lists_from_masks(rowbits, colbits, stats, B, N, dev, st, max_degree=None):
     L = _cabi.lib()
     if N <= _NOSYNC_N:
         D = N
+    elif max_degree:
+        D = max(1, min(int(max_degree), N))
     else:
         h = stats.cpu()
         D = max(int(h[0]), int(h[1]), 1)
@@ -139,10 +166,10 @@ def _lists_from_masks(rowbits, colbits, stats, B, N, dev, st):
     slot_out = torch.empty((B, N, D), dtype=torch.int32, device=dev)
     _cabi.check(L.magat_gso_build_ell(rowbits.data_ptr(), colbits.data_ptr(), B, N, D, nbr_out.data_ptr(),
                                       nbr_in.data_ptr(), slot_in.data_ptr(), slot_out.data_ptr(), st))
-    return Adjacency(B, N, D, nbr_out, nbr_in, slot_in, slot_out)
+    return Adjacency(B, N, D, nbr_out, nbr_in, slot_in, slot_out, stats)
 
 
-def build_adjacency_from_positions(pos: torch.Tensor, comm_radius: float) -> Adjacency:
+def build_adjacency_from_positions(pos: torch.Tensor, comm_radius: float, max_degree: Optional[int] = None) -> Adjacency:
     """neighbour lists straight from agent positions [B,N,2] (fp32 / fp64, CUDA), edge iff
     the Euclidean distance is < comm_radius, no self loops -- the mask utils/new_simulator.py:823-827 builds on the
     CPU before shipping a dense N x N GSO.  Equal to ``build_adjacency`` of that GSO."""
@@ -161,13 +188,12 @@ def build_adjacency_from_positions(pos: torch.Tensor, comm_radius: float) -> Adj
         st = _stream(dev)
         rowbits = torch.empty((B, N, W), dtype=torch.int32, device=dev)
         colbits = torch.empty((B, N, W), dtype=torch.int32, device=dev)
-        stats = torch.zeros(4, dtype=torch.int32, device=dev)
-        stats[3] = 1
+        stats = _stats_init(dev)
         _cabi.check(L.magat_gso_from_positions(pos.data_ptr(),
                                                _cabi.DT_F32 if pos.dtype == torch.float32 else _cabi.DT_F64, B, N,
                                                float(comm_radius), rowbits.data_ptr(), colbits.data_ptr(),
                                                stats.data_ptr(), st))
-        return _lists_from_masks(rowbits, colbits, stats, B, N, dev, st)
+        return _lists_from_masks(rowbits, colbits, stats, B, N, dev, st, max_degree)
 
 
 def _node_major(x: torch.Tensor):
@@ -492,7 +518,7 @@ def gat_layer(x, S, filterWeight, mixer, weight, weight_bias, bias, *, mode: int
     if fused is not None:
         adj = fused
     else:
-        adj = adjacency if adjacency is not None else build_adjacency(S)
+        adj = adjacency if adjacency is not None else build_adjacency(S, max_degree)
         assert adj.B == x.shape[0] and adj.N == x.shape[2]
     if mode == _cabi.MODE_KEYQUERY:
         assert tuple(weight.shape) == (P, E, G, G)
@@ -647,7 +673,7 @@ class GraphFilterBatchAttentional(nn.Module):
         assert len(pos.shape) == 3 and pos.shape[2] == 2
         self.N = pos.shape[1]
         self.S = None
-        self._adj = build_adjacency_from_positions(pos, comm_radius)
+        self._adj = build_adjacency_from_positions(pos, comm_radius, getattr(self, "max_degree", None))
 
     # ``aij`` is what graphML.py:4650 stores eagerly; here the dense copy is made on first use.
     @property

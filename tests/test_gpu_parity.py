@@ -480,3 +480,48 @@ def test_small_graph_kernel_not_used_when_training(golden):
     assert L.magat_launch_count() - c0 > 1
     y.backward(d["dy"].to(dev))
     assert rel_err(layer.filterWeight.grad, d["grad.filterWeight"]) < TOL
+
+
+@pytest.mark.parametrize("N,promise", [(10, None), (100, 24)])
+def test_layer_is_cuda_graph_capturable(N, promise):
+    """No host synchronisation in addGSO / forward / backward when the list width is known up front (N <= 32, or a
+    max_degree promise): the whole training step replays as one CUDA graph and reproduces the eager result."""
+    dev = torch.device("cuda:0")
+    G = F = 128
+    K, P, B = 3, 4, 6
+    gen = torch.Generator().manual_seed(40 + N)
+    params = orc.init_params(G, F, K, P, mode="KeyQuery", generator=gen, weight_bias_std=0.1)
+    S = orc.random_geometric_gso(B, N, generator=gen).to(dev)
+    x = torch.relu(torch.randn(B, N, G, generator=gen)).permute(0, 2, 1).to(dev)
+    dy = torch.randn(B, P * F, N, generator=gen).to(dev)
+    layer = make_layer(dict(G=G, F=F, K=K, P=P, concat=True, mode="KeyQuery"),
+                       {"param." + k: v for k, v in params.items() if v is not None}, dev, path="auto")
+    layer.max_degree = promise
+    out = {}
+
+    def step():
+        for p_ in layer.parameters():
+            p_.grad = None
+        xg = x.detach().requires_grad_(True)
+        layer.addGSO(S)
+        y = layer(xg)
+        y.backward(dy)
+        out["y"], out["dx"] = y.detach(), xg.grad
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            step()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize()
+    eager = {k: v.clone() for k, v in out.items()}
+    eager["dH"] = layer.filterWeight.grad.clone()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        step()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out["y"], eager["y"]) and torch.equal(out["dx"], eager["dx"])
+    assert rel_err(layer.filterWeight.grad, eager["dH"]) < 1e-6
+    layer._last.adj.check_degree()                      # the promise held
