@@ -59,7 +59,10 @@ enum {
   MAGAT_E_DEVICE = 5        /* not an sm_100 device */
 };
 
-enum { MAGAT_MODE_KEYQUERY = 0, MAGAT_MODE_GAT_MODIFIED = 1 };
+/* MAGAT_MODE_GSO_VALUES: the non-attentional graph filter GraphFilterBatch / BatchLSIGF (graphML.py:5485-5700, SURVEY 8f
+ * row f2): the caller fills att[B][N][D][1] with the GSO's own values (magat_gso_edge_values) and magat_gat_forward /
+ * magat_gat_backward skip the score, softmax and attention-parameter parts; P must be 1. */
+enum { MAGAT_MODE_KEYQUERY = 0, MAGAT_MODE_GAT_MODIFIED = 1, MAGAT_MODE_GSO_VALUES = 2 };
 enum { MAGAT_DT_F32 = 0, MAGAT_DT_F64 = 1 };
 /* which implementation magat_gat_forward uses for the dense projections */
 enum { MAGAT_PATH_AUTO = 0, MAGAT_PATH_SIMT = 1, MAGAT_PATH_TCGEN05 = 2 };
@@ -76,6 +79,16 @@ int magat_device_check(void);
  * zero-initialised by the caller except stats[3] = 1. */
 int magat_gso_scan(const void* S, int s_dtype, int B, int N,
                    uint32_t* rowbits, uint32_t* colbits, int32_t* stats, void* stream);
+
+/* The same scan with the predicate of the NON-attentional filter: BatchLSIGF multiplies by S itself
+ * (graphML.py:5569-5572), so every entry that is not exactly zero is an edge (NaN included). */
+int magat_gso_scan_nonzero(const void* S, int s_dtype, int B, int N,
+                           uint32_t* rowbits, uint32_t* colbits, int32_t* stats, void* stream);
+
+/* att[b][i][s] = (float) S[b][i][nbr_out[b][i][s]] (0 beyond the degree): the edge weights MAGAT_MODE_GSO_VALUES uses in
+ * place of an attention. */
+int magat_gso_edge_values(const void* S, int s_dtype, const int32_t* nbr_out, int B, int N, int D, float* att,
+                          void* stream);
 
 /* Bit masks -> padded neighbour lists of width D (D >= max(stats[0], stats[1]), D >= 1). */
 int magat_gso_build_ell(const uint32_t* rowbits, const uint32_t* colbits, int B, int N, int D,

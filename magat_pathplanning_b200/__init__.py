@@ -2,14 +2,16 @@
 
 Only the hot path is here: ``GraphFilterBatchAttentional`` and the functionals it calls
 (reference: utils/graphUtils/graphML.py:4506-4685, :1724-1827, :1180-1286, :713-823), behind the
-reference's own module interface.  See DESIGN.md / INTEGRATION.md.
+reference's own module interface, plus the non-attentional ``GraphFilterBatch`` / ``BatchLSIGF`` (:5485-5700) on
+the same kernels.  See DESIGN.md / INTEGRATION.md.
 """
 from .graphML import (GraphFilterBatchAttentional, graphAttentionLSIGFBatch_KeyQuery,  # noqa: F401
                       graphAttentionLSIGFBatch_modified, learnAttentionGSOBatch_KeyQuery,
                       learnAttentionGSOBatch, build_adjacency, build_adjacency_from_positions, gat_layer,
-                      attention_dense)
+                      attention_dense, GraphFilterBatch, BatchLSIGF)
 from .integration import install_into_reference  # noqa: F401
 
 __all__ = ["GraphFilterBatchAttentional", "graphAttentionLSIGFBatch_KeyQuery",
            "graphAttentionLSIGFBatch_modified", "learnAttentionGSOBatch_KeyQuery", "learnAttentionGSOBatch",
-           "build_adjacency", "build_adjacency_from_positions", "gat_layer", "attention_dense", "install_into_reference"]
+           "build_adjacency", "build_adjacency_from_positions", "gat_layer", "attention_dense", "install_into_reference",
+           "GraphFilterBatch", "BatchLSIGF"]

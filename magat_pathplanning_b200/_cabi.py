@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmagat_gat.so")
 ABI_VERSION = 8
 
-MODE_KEYQUERY, MODE_GAT_MODIFIED = 0, 1
+MODE_KEYQUERY, MODE_GAT_MODIFIED, MODE_GSO_VALUES = 0, 1, 2
 DT_F32, DT_F64 = 0, 1
 PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
 
@@ -25,6 +25,7 @@ EXPORTS = (
     "magat_launch_count", "magat_profile_enable", "magat_profile_collect",
     "magat_gat_small_supported", "magat_gat_forward_small", "magat_gso_from_positions",
     "magat_gat_fused_supported", "magat_gat_fused_workspace_bytes", "magat_gat_forward_fused",
+    "magat_gso_scan_nonzero", "magat_gso_edge_values",
 )
 
 _i32, _i64, _ptr = C.c_int32, C.c_int64, C.c_void_p
@@ -97,6 +98,10 @@ def lib():
         L.magat_last_error.restype = C.c_char_p
         L.magat_device_check.restype = C.c_int
         L.magat_gso_scan.argtypes = [_ptr, C.c_int, C.c_int, C.c_int, _ptr, _ptr, _ptr, _ptr]
+        L.magat_gso_scan_nonzero.argtypes = [_ptr, C.c_int, C.c_int, C.c_int, _ptr, _ptr, _ptr, _ptr]
+        L.magat_gso_scan_nonzero.restype = C.c_int
+        L.magat_gso_edge_values.argtypes = [_ptr, C.c_int, _ptr, C.c_int, C.c_int, C.c_int, _ptr, _ptr]
+        L.magat_gso_edge_values.restype = C.c_int
         L.magat_gso_build_ell.argtypes = [_ptr, _ptr, C.c_int, C.c_int, C.c_int, _ptr, _ptr, _ptr, _ptr, _ptr]
         L.magat_gso_from_positions.argtypes = [_ptr, C.c_int, C.c_int, C.c_int, C.c_double, _ptr, _ptr, _ptr, _ptr]
         L.magat_gso_from_positions.restype = C.c_int

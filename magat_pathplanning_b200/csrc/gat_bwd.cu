@@ -699,6 +699,18 @@ __global__ void __launch_bounds__(128) k_gm_param_bwd(const float* __restrict__ 
   }
 }
 
+// dx[m][g] = sum_p gz[m][p][0][g]
+__global__ void __launch_bounds__(256) k_gz0_to_dx(const float* __restrict__ gz, long rows, int G, int P, int K,
+                                                   float* __restrict__ dx) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rows * G) return;
+  const long m = t / G;
+  const int g = (int)(t - m * G);
+  float s = 0.f;
+  for (int p = 0; p < P; ++p) s += gz[((m * P + p) * K + 0) * G + g];
+  dx[t] = s;
+}
+
 int run_tap_gather(const float* x, long x_sb, long x_sn, const float* att, const int32_t* nbr_in,
                    const int32_t* slot_in, int B, int N, int G, int K, int P, int D, int k, float* taps,
                    float* ain, int ain_ready, cudaStream_t st);   // gat_fwd.cu
@@ -769,8 +781,10 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
   const int B = a->B, N = a->N, G = a->G, F = a->F, K = a->K, P = a->P, D = a->D;
   MAGAT_REQUIRE(B >= 1 && N >= 1 && G >= 1 && F >= 1 && K >= 1 && P >= 1 && D >= 1, MAGAT_E_BAD_ARG,
                 "magat_gat_backward: bad shape");
-  MAGAT_REQUIRE(a->mode == MAGAT_MODE_KEYQUERY || a->mode == MAGAT_MODE_GAT_MODIFIED, MAGAT_E_BAD_ARG,
-                "magat_gat_backward: unknown mode %d", a->mode);
+  MAGAT_REQUIRE(a->mode == MAGAT_MODE_KEYQUERY || a->mode == MAGAT_MODE_GAT_MODIFIED || a->mode == MAGAT_MODE_GSO_VALUES,
+                MAGAT_E_BAD_ARG, "magat_gat_backward: unknown mode %d", a->mode);
+  const bool plain = a->mode == MAGAT_MODE_GSO_VALUES;       // non-attentional filter: no score / softmax part
+  MAGAT_REQUIRE(!plain || P == 1, MAGAT_E_BAD_ARG, "magat_gat_backward: MAGAT_MODE_GSO_VALUES needs P == 1");
   MAGAT_REQUIRE(a->mode != MAGAT_MODE_KEYQUERY || F == G, MAGAT_E_UNSUPPORTED, "KeyQuery needs F == G");
   MAGAT_REQUIRE(a->x && a->nbr_out && a->nbr_in && a->slot_in && a->weight && a->filterWeight && a->y && a->att &&
                     a->sproj && a->dy && a->gz && a->datt && a->rc && a->partial,
@@ -794,7 +808,7 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
   const DPre dp{a->y, a->y_sb, a->y_sn, a->y_sc, a->dy, a->dy_sb, a->dy_sn, a->dy_sc,
                 N, F, a->concat, a->relu, a->concat ? 1.f : 1.f / (float)P};
   const ZNode zn{a->x, a->x_sb, a->x_sn, a->taps, N, G, K, P};
-  const bool need_scores = a->need_dx || a->need_dweight || (gm && a->need_dmixer);
+  const bool need_scores = plain ? (a->need_dx != 0) : (a->need_dx || a->need_dweight || (gm && a->need_dmixer));
   // the fused forward keeps only u_1 in memory: rebuild the later taps before anything reads them
   for (int k = (a->taps_valid < 1 ? 1 : a->taps_valid + 1); k < K; ++k)
     if ((rc = run_tap_gather(a->x, a->x_sb, a->x_sn, a->att, a->nbr_in, a->slot_in, B, N, G, K, P, D, k,
@@ -839,7 +853,7 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
   const bool gm_vec = gm && vec && getenv("MAGAT_GM_GENERIC") == nullptr;      // GAT_modified vector kernels
   const bool g0_in_dx = vec && (!gm || gm_vec) && K > 1 && a->need_dx && getenv("MAGAT_BWD_NO_G0SUM") == nullptr;
   // ... and the row softmax backward (+ dR) rides on the same last level
-  const bool fuse_softmax = vec && !gm && K > 1 && getenv("MAGAT_BWD_NO_FUSED_SOFTMAX") == nullptr;
+  const bool fuse_softmax = vec && !gm && !plain && K > 1 && getenv("MAGAT_BWD_NO_FUSED_SOFTMAX") == nullptr;
   for (int k = K - 1; k >= 1; --k) {
     const int first = k == K - 1 ? 1 : 0;
     float* g0sum = (k == 1 && g0_in_dx) ? a->dx : nullptr;
@@ -866,6 +880,14 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
     if ((rc = check_launch("k_tap_bwd", st))) return rc;
   }
   const int has_datt = K > 1 ? 1 : 0;
+  if (plain) {
+    // dx = gU_0 (one head): already in dx when the last recursion level wrote the head sum there
+    if (!g0_in_dx) {
+      k_gz0_to_dx<<<cdiv(rows * G, 256), 256, 0, st>>>(a->gz, rows, G, P, K, a->dx);
+      if ((rc = check_launch("k_gz0_to_dx", st))) return rc;
+    }
+    return MAGAT_OK;
+  }
   if (!gm) {
 #define MAGAT_SB(PT) \
   k_softmax_bwd_kq_v<PT><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->att, a->nbr_out, rows, N, D, has_datt, \

@@ -479,8 +479,9 @@ struct YEpi {
 static int validate_common(int B, int N, int G, int F, int K, int P, int D, int mode) {
   MAGAT_REQUIRE(B >= 1 && N >= 1 && G >= 1 && F >= 1 && K >= 1 && P >= 1 && D >= 1, MAGAT_E_BAD_ARG,
                 "bad shape B=%d N=%d G=%d F=%d K=%d P=%d D=%d", B, N, G, F, K, P, D);
-  MAGAT_REQUIRE(mode == MAGAT_MODE_KEYQUERY || mode == MAGAT_MODE_GAT_MODIFIED, MAGAT_E_BAD_ARG,
-                "unknown attention mode %d", mode);
+  MAGAT_REQUIRE(mode == MAGAT_MODE_KEYQUERY || mode == MAGAT_MODE_GAT_MODIFIED || mode == MAGAT_MODE_GSO_VALUES,
+                MAGAT_E_BAD_ARG, "unknown attention mode %d", mode);
+  MAGAT_REQUIRE(mode != MAGAT_MODE_GSO_VALUES || P == 1, MAGAT_E_BAD_ARG, "MAGAT_MODE_GSO_VALUES needs P == 1 (got %d)", P);
   MAGAT_REQUIRE(mode != MAGAT_MODE_KEYQUERY || F == G, MAGAT_E_UNSUPPORTED,
                 "KeyQuery needs F == G (got F=%d G=%d; graphML.py:1728,1765)", F, G);
   MAGAT_REQUIRE(P <= 65535 && (long)P * K * G < (1l << 31), MAGAT_E_UNSUPPORTED, "P/K/G too large");
@@ -562,10 +563,12 @@ static int forward_impl(const magat_gat_fwd_args* a, cudaStream_t st, bool use_t
     if (!fused && (rc = tc_split_weights(a->filterWeight, (long)nH, h_hi, h_lo, st))) return rc;
   }
   // the attention kernel also scatters the receiver-major copy `ain` when the caller provides it
-  const int32_t* so = (a->ain && a->slot_out) ? a->slot_out : nullptr;
+  const int32_t* so = (a->ain && a->slot_out && a->mode != MAGAT_MODE_GSO_VALUES) ? a->slot_out : nullptr;
   float* ain_w = so ? a->ain : nullptr;
   // 1. score projection
-  if (a->mode == MAGAT_MODE_KEYQUERY) {
+  if (a->mode == MAGAT_MODE_GSO_VALUES) {
+    // non-attentional filter: att already holds the GSO values of the edges (magat_gso_edge_values)
+  } else if (a->mode == MAGAT_MODE_KEYQUERY) {
     if (score_fused) {
       if ((rc = score_tc_forward(a, wt_f32, st))) return rc;
     } else if (use_tc) {
@@ -625,7 +628,7 @@ static int forward_impl(const magat_gat_fwd_args* a, cudaStream_t st, bool use_t
                                                                         a->nbr_out, rows, N, G, P, D, a->att, so, ain_w);
     }
   }
-  if ((rc = check_launch("k_attention", st))) return rc;
+  if (a->mode != MAGAT_MODE_GSO_VALUES && (rc = check_launch("k_attention", st))) return rc;
   // 2. taps (the fused tcgen05 kernel gathers the second tap itself and only needs u_1 in memory)
   const int k_last = (fused && tap_tc_gathers_u2()) ? (K - 1 < 1 ? K - 1 : 1) : K - 1;
   for (int k = 1; k <= k_last; ++k)

@@ -16,7 +16,9 @@ template <> __device__ __forceinline__ bool is_edge<double>(double v) { return f
 // One warp owns a band of 32 sender rows and sweeps it in 32x32 blocks: every load is a full
 // 128 B (fp32) row segment, ballots give the row words, each lane accumulates the transposed
 // (column) word of its own column.  A CTA is 8 consecutive bands.
-template <typename T>
+// NZ = true: the predicate of the non-attentional graph filter (BatchLSIGF multiplies by S itself, graphML.py:5571:
+// every entry that is not exactly zero takes part, NaN included).
+template <typename T, bool NZ = false>
 __global__ void __launch_bounds__(256) k_gso_scan(const T* __restrict__ S, int N, int W,
                                                   uint32_t* __restrict__ rowbits,
                                                   uint32_t* __restrict__ colbits) {
@@ -35,7 +37,7 @@ __global__ void __launch_bounds__(256) k_gso_scan(const T* __restrict__ S, int N
       const int i = rb * 32 + r;
       T v = T(0);
       if (jin && i < N) v = __ldg(Sb + (size_t)i * N + j);
-      const bool e = is_edge<T>(v);
+      const bool e = NZ ? (v != T(0)) : is_edge<T>(v);
       const uint32_t word = __ballot_sync(0xffffffffu, e);
       if (lane == r) myrow = word;
       mycol |= (uint32_t)e << r;
@@ -667,6 +669,51 @@ extern "C" int magat_gso_scan(const void* S, int s_dtype, int B, int N, uint32_t
   int rc = check_launch("k_gso_scan", (cudaStream_t)stream);
   if (rc) return rc;
   return launch_gso_stats(rowbits, colbits, B, N, W, stats, st);
+}
+
+// att[b][i][s][0] = (float) S[b][i][nbr_out[b][i][s]], 0 beyond the degree: the "attention" of the non-attentional
+// filter is the GSO itself (graphML.py:5569-5572)
+template <typename T>
+__global__ void __launch_bounds__(256) k_gso_edge_values(const T* __restrict__ S, const int32_t* __restrict__ nbr_out,
+                                                         long total, int N, int D, float* __restrict__ att) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const long row = t / D;
+  const int j = nbr_out[t];
+  att[t] = j >= 0 ? (float)S[row * N + j] : 0.f;
+}
+
+extern "C" int magat_gso_scan_nonzero(const void* S, int s_dtype, int B, int N, uint32_t* rowbits, uint32_t* colbits,
+                                      int32_t* stats, void* stream) {
+  MAGAT_REQUIRE(S && rowbits && colbits && stats, MAGAT_E_BAD_ARG, "magat_gso_scan_nonzero: null pointer");
+  MAGAT_REQUIRE(B >= 1 && N >= 1 && B <= 65535, MAGAT_E_BAD_ARG, "magat_gso_scan_nonzero: B=%d N=%d", B, N);
+  MAGAT_REQUIRE(s_dtype == MAGAT_DT_F32 || s_dtype == MAGAT_DT_F64, MAGAT_E_BAD_ARG,
+                "magat_gso_scan_nonzero: GSO dtype must be fp32 or fp64");
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin(st);
+  const int W = (N + 31) / 32;
+  dim3 grid(cdiv(W, 8), B);
+  if (s_dtype == MAGAT_DT_F32) k_gso_scan<float, true><<<grid, 256, 0, st>>>((const float*)S, N, W, rowbits, colbits);
+  else k_gso_scan<double, true><<<grid, 256, 0, st>>>((const double*)S, N, W, rowbits, colbits);
+  int rc = check_launch("k_gso_scan(nonzero)", st);
+  if (rc) return rc;
+  return launch_gso_stats(rowbits, colbits, B, N, W, stats, st);
+}
+
+extern "C" int magat_gso_edge_values(const void* S, int s_dtype, const int32_t* nbr_out, int B, int N, int D, float* att,
+                                     void* stream) {
+  MAGAT_REQUIRE(S && nbr_out && att, MAGAT_E_BAD_ARG, "magat_gso_edge_values: null pointer");
+  MAGAT_REQUIRE(B >= 1 && N >= 1 && D >= 1, MAGAT_E_BAD_ARG, "magat_gso_edge_values: B=%d N=%d D=%d", B, N, D);
+  MAGAT_REQUIRE(s_dtype == MAGAT_DT_F32 || s_dtype == MAGAT_DT_F64, MAGAT_E_BAD_ARG,
+                "magat_gso_edge_values: GSO dtype must be fp32 or fp64");
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin(st);
+  const long total = (long)B * N * D;
+  if (s_dtype == MAGAT_DT_F32)
+    k_gso_edge_values<float><<<cdiv(total, 256), 256, 0, st>>>((const float*)S, nbr_out, total, N, D, att);
+  else
+    k_gso_edge_values<double><<<cdiv(total, 256), 256, 0, st>>>((const double*)S, nbr_out, total, N, D, att);
+  return check_launch("k_gso_edge_values", st);
 }
 
 extern "C" int magat_gso_build_ell(const uint32_t* rowbits, const uint32_t* colbits, int B, int N,

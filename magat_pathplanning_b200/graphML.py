@@ -119,7 +119,7 @@ def _stats_init(dev):
     return t.clone()
 
 
-def build_adjacency(S: torch.Tensor, max_degree: Optional[int] = None) -> Adjacency:
+def build_adjacency(S: torch.Tensor, max_degree: Optional[int] = None, nonzero: bool = False) -> Adjacency:
     """[B,1,N,N] dense GSO -> neighbour lists.  Only ``|S| > 1e-9`` matters (graphML.py:1274-1276):
     NaN is "no edge", negative weights are edges.  S is read once, by one kernel.
 
@@ -145,8 +145,9 @@ def build_adjacency(S: torch.Tensor, max_degree: Optional[int] = None) -> Adjace
         rowbits = torch.empty((B, N, W), dtype=torch.int32, device=dev)
         colbits = torch.empty((B, N, W), dtype=torch.int32, device=dev)
         stats = _stats_init(dev)
-        _cabi.check(L.magat_gso_scan(S.data_ptr(), _cabi.DT_F32 if S.dtype == torch.float32 else _cabi.DT_F64,
-                                     B, N, rowbits.data_ptr(), colbits.data_ptr(), stats.data_ptr(), st))
+        scan = L.magat_gso_scan_nonzero if nonzero else L.magat_gso_scan    # nonzero: BatchLSIGF's "S itself" predicate
+        _cabi.check(scan(S.data_ptr(), _cabi.DT_F32 if S.dtype == torch.float32 else _cabi.DT_F64,
+                         B, N, rowbits.data_ptr(), colbits.data_ptr(), stats.data_ptr(), st))
         return _lists_from_masks(rowbits, colbits, stats, B, N, dev, st, max_degree)
 
 
@@ -601,6 +602,174 @@ def learnAttentionGSOBatch(x, a, W, W_b, S, negative_slope=0.2):
     """graphML.py:713-823."""
     _check_slope(negative_slope)
     return _attention_only(x, a, W, W_b, S, _cabi.MODE_GAT_MODIFIED)
+
+
+# ---- SURVEY 8f row f2: the non-attentional graph filter on the same kernels ------------------------------------
+
+class _LSIGFFunction(torch.autograd.Function):
+    """BatchLSIGF (graphML.py:5485-5579): y = sum_k H_k (x S^k) + b.  The tap recursion and the K-tap projection are
+    the attention layer's kernels with one head whose "attention" is the GSO's own edge values."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, adj: Adjacency, vals, path):
+        L = _cabi.lib()
+        dev = x.device
+        B, G, N = x.shape
+        F, _, K, _ = weight.shape
+        D = adj.D
+        xt = _node_major(x.detach())
+        filt_c = weight.detach().contiguous()                   # [F,1,K,G] is [P=1][F][1][K][G]
+        bias_c = None if bias is None else bias.detach().contiguous()
+        with torch.cuda.device(dev):
+            y_mem = torch.empty((B, N, F), dtype=torch.float32, device=dev)
+            y = y_mem.permute(0, 2, 1)                          # the reference returns this permuted view too (:5573-5575)
+            ain = torch.empty((B, N, 1, D), dtype=torch.float32, device=dev) if K > 1 else None
+            taps = torch.empty((B, N, 1, max(K - 1, 1), G), dtype=torch.float32, device=dev) if K > 1 else None
+            wprep = torch.empty(L.magat_gat_wprep_floats(G, F, K, 1, _cabi.MODE_GSO_VALUES), dtype=torch.float32, device=dev)
+            dummy = torch.empty(4, dtype=torch.float32, device=dev)
+            a = _cabi.FwdArgs(B=B, N=N, G=G, F=F, K=K, P=1, D=D, mode=_cabi.MODE_GSO_VALUES, concat=1, relu=0,
+                              path=_PATH[path], reserved=0, x=xt.data_ptr(), x_sb=_sb(xt), x_sn=_sn(xt),
+                              nbr_out=adj.nbr_out.data_ptr(), nbr_in=adj.nbr_in.data_ptr(),
+                              slot_in=adj.slot_in.data_ptr(), slot_out=_p(adj.slot_out),
+                              weight=filt_c.data_ptr(), mixer=None, weight_bias=None,
+                              filterWeight=filt_c.data_ptr(), bias=_p(bias_c),
+                              y=y_mem.data_ptr(), y_sb=y.stride(0), y_sn=y.stride(2), y_sc=y.stride(1),
+                              att=vals.data_ptr(), ain=_p(ain), taps=_p(taps), wprep=wprep.data_ptr(),
+                              sproj=dummy.data_ptr())
+            _cabi.check(L.magat_gat_forward(a, _stream(dev)))
+            ctx.taps_valid = L.magat_gat_forward_taps_valid(a)
+        ctx.adj, ctx.path, ctx.has_bias = adj, path, bias is not None
+        ctx.save_for_backward(xt, filt_c, y, vals, taps, wprep)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        L = _cabi.lib()
+        adj = ctx.adj
+        xt, filt_c, y, vals, taps, wprep = ctx.saved_tensors
+        dev = xt.device
+        B, N, G = xt.shape
+        F, _, K, _ = filt_c.shape
+        D = adj.D
+        need_dx, need_df, need_db = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2] and ctx.has_bias
+        if dy.dtype != torch.float32:
+            dy = dy.float()
+        with torch.cuda.device(dev):
+            def buf(*shape):
+                return torch.empty(shape, dtype=torch.float32, device=dev)
+            dx = buf(B, N, G) if need_dx else None
+            df = torch.empty_like(filt_c) if need_df else None
+            db = buf(F, 1) if need_db else None
+            gz, datt = buf(B, N, 1, K, G), buf(B, N, D, 1)
+            dummy = buf(B * N * 2 + 4)
+            partial = buf(L.magat_gat_bwd_partial_floats(B, N, G, F, K, 1, _cabi.MODE_GSO_VALUES))
+            a = _cabi.BwdArgs(B=B, N=N, G=G, F=F, K=K, P=1, D=D, mode=_cabi.MODE_GSO_VALUES, concat=1, relu=0,
+                              path=_PATH[ctx.path], need_dx=int(need_dx), need_dweight=0, need_dfilter=int(need_df),
+                              need_dbias=int(need_db), need_dmixer=0, taps_valid=int(ctx.taps_valid), reserved=0,
+                              x=xt.data_ptr(), x_sb=_sb(xt), x_sn=_sn(xt),
+                              nbr_out=adj.nbr_out.data_ptr(), nbr_in=adj.nbr_in.data_ptr(), slot_in=adj.slot_in.data_ptr(),
+                              weight=filt_c.data_ptr(), mixer=None, weight_bias=None, filterWeight=filt_c.data_ptr(),
+                              y=y.data_ptr(), y_sb=y.stride(0), y_sn=y.stride(2), y_sc=y.stride(1),
+                              att=vals.data_ptr(), taps=_p(taps), wprep=wprep.data_ptr(), sproj=dummy.data_ptr(),
+                              dy=dy.data_ptr(), dy_sb=dy.stride(0), dy_sn=dy.stride(2), dy_sc=dy.stride(1),
+                              dx=_p(dx), dweight=None, dmixer=None, dweight_bias=None,
+                              dfilterWeight=_p(df), dbias=_p(db),
+                              gz=gz.data_ptr(), datt=datt.data_ptr(), rc=dummy.data_ptr(), partial=partial.data_ptr())
+            _cabi.check(L.magat_gat_backward(a, _stream(dev)))
+        return (dx.permute(0, 2, 1) if need_dx else None), df, db, None, None, None
+
+
+def BatchLSIGF(h, S, x, b=None):
+    """graphML.py:5485-5579, same signature: h [F,E,K,G], S [B,E,N,N], x [B,G,N], b [F,1] -> y [B,F,N]."""
+    return _lsigf(h, S, x, b)
+
+
+def _lsigf(h, S, x, b=None, path="auto", max_degree=None):
+    _require_cuda(x, "x")
+    F, E, K, G = h.shape
+    assert S.shape[1] == E
+    N = S.shape[2]
+    assert S.shape[3] == N
+    B = x.shape[0]
+    assert x.shape[1] == G
+    assert x.shape[2] == N
+    if E != 1:
+        raise NotImplementedError("edge_features E != 1 is not supported (the planners use E = 1)")
+    if b is not None and (b.shape[-1] != 1):
+        raise NotImplementedError("per-node bias [F,N] is not supported (the planners use [F,1])")
+    if x.dtype != torch.float32:
+        x = x.float()
+    _check_params(x, h, None, None, None, b)
+    adj = build_adjacency(S, max_degree, nonzero=True)
+    Sd = S.detach()
+    if Sd.dtype not in (torch.float32, torch.float64):
+        Sd = Sd.to(torch.float32)
+    if not Sd.is_contiguous():
+        Sd = Sd.contiguous()
+    dev = x.device
+    with torch.cuda.device(dev):
+        vals = torch.empty((B, N, adj.D, 1), dtype=torch.float32, device=dev)
+        _cabi.check(_cabi.lib().magat_gso_edge_values(
+            Sd.data_ptr(), _cabi.DT_F32 if Sd.dtype == torch.float32 else _cabi.DT_F64, adj.nbr_out.data_ptr(), B, N, adj.D,
+            vals.data_ptr(), _stream(dev)))
+    return _LSIGFFunction.apply(x, h, b, adj, vals, path)
+
+
+class GraphFilterBatch(nn.Module):
+    """Drop-in for ``utils.graphUtils.graphML.GraphFilterBatch`` (graphML.py:5581-5700), the graph convolution of the
+    GNN baseline planners (graphs/models/decentralplanner.py:280): same constructor, parameters (``weight`` [F,E,K,G],
+    ``bias`` [F,1]), ``addGSO``, ``forward`` and ``extra_repr``.  No nonlinearity inside (the planner appends its own)."""
+
+    def __init__(self, G, F, K, E=1, bias=True):
+        super().__init__()
+        self.G = G
+        self.F = F
+        self.K = K
+        self.E = E
+        self.S = None
+        self.path = "auto"
+        self.max_degree = None
+        if E != 1:
+            raise NotImplementedError("edge_features E != 1 is not supported")
+        self.weight = nn.parameter.Parameter(torch.Tensor(F, E, K, G))
+        if bias:
+            self.bias = nn.parameter.Parameter(torch.Tensor(F, 1))
+        else:
+            self.register_parameter('bias', None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        stdv = 1. / math.sqrt(self.G * self.K)
+        self.weight.data.uniform_(-stdv, stdv)
+        if self.bias is not None:
+            self.bias.data.uniform_(-stdv, stdv)
+
+    def addGSO(self, S):
+        assert len(S.shape) == 4
+        assert S.shape[1] == self.E
+        self.N = S.shape[2]
+        assert S.shape[3] == self.N
+        self.S = S
+
+    def forward(self, x):
+        B = x.shape[0]
+        F = x.shape[1]
+        Nin = x.shape[2]
+        if Nin < self.N:
+            x = torch.cat((x, torch.zeros(B, F, self.N - Nin).type(x.dtype).to(x.device)), dim=2)
+        u = _lsigf(self.weight, self.S, x, self.bias, path=self.path, max_degree=self.max_degree)
+        if Nin < self.N:
+            u = torch.index_select(u, 2, torch.arange(Nin).to(u.device))
+        return u
+
+    def extra_repr(self):
+        reprString = "in_features=%d, out_features=%d, " % (self.G, self.F) + "filter_taps=%d, " % (self.K) + \
+            "edge_features=%d, " % (self.E) + "bias=%s, " % (self.bias is not None)
+        if self.S is not None:
+            reprString += "GSO stored"
+        else:
+            reprString += "no GSO stored"
+        return reprString
 
 
 # ---- the module ------------------------------------------------------------------------------

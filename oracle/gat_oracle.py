@@ -210,3 +210,36 @@ def gso_from_positions(pos, comm_radius):
     A = (d < float(comm_radius)) & ~torch.eye(N, dtype=torch.bool)
     return A.to(torch.float64).unsqueeze(1)
 
+
+
+# ---- the non-attentional graph filter ------------------------------------------------------------
+
+def lsigf_forward(x, S, weight, bias=None):
+    """BatchLSIGF, graphML.py:5485-5579, restated densely:  u_0 = x, u_k = u_{k-1} S (the values of S, cast to fp32,
+    :5569-5571),  y[b,f,n] = sum_{k,g} h[f,0,k,g] u_k[b,g,n] + bias[f]  (:5573-5577).
+
+    x [B,G,N]; S [B,1,N,N] (fp32 or fp64); weight [F,1,K,G]; bias [F,1] or None -> y [B,F,N].  Parity pinned by
+    tests/golden/lsigf_golden.npz (outputs of the unmodified reference, tests/golden/make_golden_lsigf.py)."""
+    F, E, K, G = weight.shape
+    assert E == 1 and S.shape[1] == 1 and x.shape[1] == G
+    Sf = S[:, 0].float()
+    u = x
+    taps = [u]
+    for _ in range(1, K):
+        u = torch.matmul(u, Sf)
+        taps.append(u)
+    z = torch.stack(taps, dim=1)                              # [B,K,G,N]
+    y = torch.einsum("fkg,bkgn->bfn", weight[:, 0], z)
+    if bias is not None:
+        y = y + bias
+    return y
+
+
+def lsigf_fwd_bwd(x, S, weight, bias, dy):
+    """Forward + autograd backward of ``lsigf_forward``: (y, {"x", "weight", "bias"} gradients)."""
+    xg = x.detach().clone().requires_grad_(True)
+    w = weight.detach().clone().requires_grad_(True)
+    b = None if bias is None else bias.detach().clone().requires_grad_(True)
+    y = lsigf_forward(xg, S, w, b)
+    y.backward(dy)
+    return y.detach(), {"x": xg.grad, "weight": w.grad, "bias": None if b is None else b.grad}
