@@ -731,8 +731,14 @@ int tc_dx_accumulate(const magat_gat_bwd_args* a, const __nv_bfloat16* w_hi, con
                      cudaStream_t st);
 int tc_split_weights(const float* src, long n, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st);
 
+// SMs of the current device; the B200 count where there is none (size helpers called on a build box)
+static long sm_count_or_default() {
+  const int n = device_sm_count();
+  return n > 0 ? n : 148;
+}
+
 static int pick_splits(long R, int tiles) {
-  long s = (148l * 4 + tiles - 1) / tiles;
+  long s = (sm_count_or_default() * 4 + tiles - 1) / tiles;
   const long cap = (R + 255) / 256;
   if (s > cap) s = cap;
   if (s > 256) s = 256;
@@ -763,7 +769,7 @@ extern "C" size_t magat_gat_bwd_partial_floats(int B, int N, int G, int F, int K
   // every row-reduction writes at most Z * splits * Mi * Nj floats with Z*splits*tiles <= ~148*4 + Z*tiles
   auto need = [](long Mi, long Nj, long Z) {
     const long tiles = ((Mi + 63) / 64) * ((Nj + 63) / 64) * Z;
-    long s = (148l * 4 + tiles - 1) / tiles;
+    long s = (sm_count_or_default() * 4 + tiles - 1) / tiles;
     if (s > 256) s = 256;
     if (s < 1) s = 1;
     return (size_t)(Z * s * Mi * Nj);
@@ -819,7 +825,7 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
   const bool dbias_in_wgrad = a->need_dbias && a->need_dfilter && tc_wgrad;
   if (a->need_dbias && !dbias_in_wgrad) {
     const int C = a->concat ? P * F : F;
-    const int nblocks = 148 * 8;
+    const int nblocks = (int)sm_count_or_default() * 8;
     const int chunk = cdiv(rows, nblocks);
     k_dbias_partial<<<nblocks, 256, 0, st>>>(dp, rows, C, P, F, chunk, a->partial);
     if ((rc = check_launch("k_dbias_partial", st))) return rc;
@@ -850,10 +856,10 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
                    (K == 1 || ((uintptr_t)a->taps % 16) == 0) && (P == 1 || P == 2 || P == 4) && rows < (1l << 31);
   // KeyQuery, vector kernels: g_0 is only ever read as its head sum (for dx), so the last level of the recursion
   // writes that sum straight into dx and the column kernel picks it up there
-  const bool gm_vec = gm && vec && getenv("MAGAT_GM_GENERIC") == nullptr;      // GAT_modified vector kernels
-  const bool g0_in_dx = vec && (!gm || gm_vec) && K > 1 && a->need_dx && getenv("MAGAT_BWD_NO_G0SUM") == nullptr;
+  const bool gm_vec = gm && vec;      // GAT_modified vector kernels
+  const bool g0_in_dx = vec && (!gm || gm_vec) && K > 1 && a->need_dx;
   // ... and the row softmax backward (+ dR) rides on the same last level
-  const bool fuse_softmax = vec && !gm && !plain && K > 1 && getenv("MAGAT_BWD_NO_FUSED_SOFTMAX") == nullptr;
+  const bool fuse_softmax = vec && !gm && !plain && K > 1;
   for (int k = K - 1; k >= 1; --k) {
     const int first = k == K - 1 ? 1 : 0;
     float* g0sum = (k == 1 && g0_in_dx) ? a->dx : nullptr;
@@ -974,7 +980,7 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
       // dc [2P][G+1] lives at the tail of `partial`
       const size_t head = (size_t)magat_gat_bwd_partial_floats(B, N, G, F, K, P, a->mode) - (size_t)2 * P * (G + 1);
       float* dc = a->partial + head;
-      const int nblk = 2 * 148;
+      const int nblk = 2 * (int)sm_count_or_default();
       if (gm_vec && (size_t)nblk * 2 * P * (G + 1) <= head) {
         const long per_block = (rows + nblk - 1) / nblk;
 #define MAGAT_GDC(PT) k_gm_dcvec_v<PT><<<nblk, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->rc, rows, N, per_block, a->partial)

@@ -605,7 +605,7 @@ static int forward_impl(const magat_gat_fwd_args* a, cudaStream_t st, bool use_t
     k_gm_prep<<<P * 2, 128, 0, st>>>(a->weight, a->mixer, a->weight_bias, G, F, P, cvec, dvec);
     if ((rc = check_launch("k_gm_prep", st))) return rc;
     const bool gm_fast = vec_ok && G == 128 && D <= 32 && (P == 1 || P == 2 || P == 4) &&
-                         (((uintptr_t)cvec) % 16 == 0) && getenv("MAGAT_GM_GENERIC") == nullptr;
+                         (((uintptr_t)cvec) % 16 == 0);
     if (gm_fast) {
       const int per_warp = 16;
       const int blocks = cdiv(cdiv(rows, per_warp), 8);

@@ -737,7 +737,6 @@ __global__ void __launch_bounds__(256) k_transpose_w(const float* __restrict__ W
 // v2 needs flat inputs and outputs (one row stride over the whole batch), no on-the-fly second tap; nout > 1 only
 // with one K slice.  Fills the tensor maps of tq.
 bool tap_tc2_prepare(TapParams& tq, int x_width) {
-  if (getenv("MAGAT_TAP_V1") != nullptr) return false;
   if (tq.nout < 1 || tq.P % tq.nout != 0 || tq.rows >= (1l << 31)) return false;
   const int nst = tq.K * tq.G / SK;
   if (tq.G % SK != 0 || tq.nout * nst * SK > ACC_COL0 || (tq.nout > 1 && nst != 1)) return false;
@@ -757,8 +756,12 @@ bool tap_tc2_prepare(TapParams& tq, int x_width) {
 int launch_tap_tc(const TapParams& tp, int P, cudaStream_t st, const char* what, bool v2_only = false) {
   const int sm_count = device_sm_count();
   TapParams tq = tp;
+#ifdef MAGAT_DBG_KNOBS
   const char* dbg = getenv("MAGAT_DBG");
   tq.dbg = dbg ? atoi(dbg) : 0;
+#else
+  tq.dbg = 0;
+#endif
   const long tiles = (tp.rows + TN - 1) / TN;
   // logical width of an x row: every weight-block group reads its own 128-wide (G-wide) column window
   const int x_width = tp.x_hmul ? (int)(((tp.P - 1) / tp.x_hdiv) * tp.x_hmul) + tp.G : tp.G;
@@ -781,7 +784,7 @@ int launch_tap_tc(const TapParams& tp, int P, cudaStream_t st, const char* what,
   int rc0 = ensure_dyn_smem(KID_TAP_TC4, (const void*)k_tap_tc<4>, SMEM_BYTES, "k_tap_tc<4>");
   if (!rc0) rc0 = ensure_dyn_smem(KID_TAP_TC8, (const void*)k_tap_tc<8>, SMEM_BYTES, "k_tap_tc<8>");
   if (rc0) return rc0;
-  tq.epi_direct = (tp.y_sb == (long)tp.N * tp.y_sn && getenv("MAGAT_EPI_STAGED") == nullptr) ? 1 : 0;
+  tq.epi_direct = (tp.y_sb == (long)tp.N * tp.y_sn) ? 1 : 0;
   long slots = sm_count / P;
   if (slots < 1) slots = 1;
   if (slots > tiles) slots = tiles;
@@ -883,7 +886,7 @@ __global__ void __launch_bounds__(256) k_pack_wcat(const float* __restrict__ W, 
 // accumulating variant stalled its four epilogue warps on the read-modify-write latency (1.00 ms for two launches).
 // The column kernel, which runs next and owns dx anyway, adds the P/2 partial rows.
 bool dx_tap_supported(const magat_gat_bwd_args* a) {
-  if (a->mode != MAGAT_MODE_KEYQUERY || a->G != FT || a->P % 2 != 0 || getenv("MAGAT_DX_GEMM") != nullptr) return false;
+  if (a->mode != MAGAT_MODE_KEYQUERY || a->G != FT || a->P % 2 != 0) return false;
   if (((uintptr_t)a->rc % 16) != 0 || ((uintptr_t)a->gz % 16) != 0 || ((uintptr_t)a->partial % 16) != 0) return false;
   if ((long)a->B * a->N >= (1l << 31)) return false;
   return true;

@@ -544,7 +544,6 @@ int wgrad_nslots(int Z) {
 
 // v2 when every source is a flat [rows][stride] matrix; fills the tensor maps
 bool wgrad2_prepare(const WgradParams& wp, Wgrad2Params& q) {
-  if (getenv("MAGAT_WGRAD_V1") != nullptr) return false;
   if (wp.rows >= (1l << 31) || wp.NB % 128 != 0 || wp.NB > MAX_NB) return false;
   auto flat = [&](const Src& s) { return s.sb == (long)wp.N * s.sn; };
   const int nseg = wp.NB / 128;

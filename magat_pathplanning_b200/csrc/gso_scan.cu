@@ -591,7 +591,7 @@ static int launch_gso_stats(const uint32_t* rowbits, const uint32_t* colbits, in
   if (W % 4 == 0 && lpr <= 32 && (lpr & (lpr - 1)) == 0 && ((uintptr_t)rowbits % 16) == 0 &&
       ((uintptr_t)colbits % 16) == 0) {
     const long n4 = rows * lpr;
-    const int blocks = (int)min((long)148 * 8, (n4 + 255) / 256);
+    const int blocks = (int)min((long)(device_sm_count() > 0 ? device_sm_count() : 148) * 8, (n4 + 255) / 256);
     const uint4* r4 = reinterpret_cast<const uint4*>(rowbits);
     const uint4* c4 = reinterpret_cast<const uint4*>(colbits);
     switch (lpr) {
@@ -603,7 +603,7 @@ static int launch_gso_stats(const uint32_t* rowbits, const uint32_t* colbits, in
       default: k_gso_stats_v<32><<<blocks, 256, 0, st>>>(r4, c4, n4, stats); break;
     }
   } else {
-    int blocks = (int)min((long)148 * 8, (rows + 7) / 8);
+    int blocks = (int)min((long)(device_sm_count() > 0 ? device_sm_count() : 148) * 8, (rows + 7) / 8);
     k_gso_stats<<<blocks, 256, 0, st>>>(rowbits, colbits, rows, W, stats);
   }
   return check_launch("k_gso_stats", st);
@@ -622,8 +622,7 @@ extern "C" int magat_gso_scan(const void* S, int s_dtype, int B, int N, uint32_t
   const size_t esz = s_dtype == MAGAT_DT_F32 ? 4 : 8;
   int R = 32;
   while (R > 1 && (size_t)R * N * esz > 32 * 1024) R >>= 1;
-  const bool tma_ok = N % 4 == 0 && ((uintptr_t)S % 16) == 0 && N <= 2048 && (size_t)R * N * esz <= 48 * 1024 &&
-                      getenv("MAGAT_SCAN_NO_TMA") == nullptr;
+  const bool tma_ok = N % 4 == 0 && ((uintptr_t)S % 16) == 0 && N <= 2048 && (size_t)R * N * esz <= 48 * 1024;
   if (tma_ok) {
     const int sm_count = device_sm_count();
     const size_t chunk_bytes = (size_t)R * N * esz;
@@ -726,15 +725,10 @@ extern "C" int magat_gso_build_ell(const uint32_t* rowbits, const uint32_t* colb
   const int W = (N + 31) / 32;
   cudaStream_t st = (cudaStream_t)stream;
   prof_begin(st);
-  if (getenv("MAGAT_BUILD_ELL_V1") != nullptr) {       // the one-kernel builder (ranks by popcount), kept for A/B timing
-    k_build_ell<<<cdiv(rows, 8), 256, 0, st>>>(rowbits, colbits, rows, N, W, D, nbr_out, nbr_in, slot_in, slot_out);
-    return check_launch("k_build_ell", st);
-  }
   MAGAT_REQUIRE(rows * D < (1l << 40), MAGAT_E_UNSUPPORTED, "magat_gso_build_ell: B*N*D too large");
   auto al16 = [](const void* q) { return ((uintptr_t)q % 16) == 0; };
   const bool per_thread = W % 4 == 0 && D % 4 == 0 && D <= 32 && rows < (1l << 31) && al16(rowbits) && al16(colbits) &&
-                          al16(nbr_out) && al16(nbr_in) && al16(slot_in) && (slot_out == nullptr || al16(slot_out)) &&
-                          getenv("MAGAT_BUILD_WARP") == nullptr;
+                          al16(nbr_out) && al16(nbr_in) && al16(slot_in) && (slot_out == nullptr || al16(slot_out));
   int rc;
   if (per_thread) {
     k_build_lists_t<<<dim3(cdiv(rows, 128), 2), 128, 0, st>>>(reinterpret_cast<const uint4*>(rowbits),

@@ -43,6 +43,14 @@ def _worker(rank, world, port, q):
                 ok = ok and p.grad is None
             else:
                 ok = ok and bool(torch.all(p.grad == (1 + world) / 2.0))      # mean of 1..world
+        # uneven shards: weighted combination = gradient of the global-batch mean; a parameter only one rank has a
+        # gradient for (an empty shard elsewhere) still reduces like-for-like
+        lin = torch.nn.Linear(3, 2)
+        lin.weight.grad = torch.full_like(lin.weight, float(rank + 1))
+        lin.bias.grad = torch.ones_like(lin.bias) if rank == 0 else None
+        allreduce_gradients(lin.parameters(), local_weight=float(3 if rank == 0 else 1), uniform=False)
+        ok = ok and bool(torch.allclose(lin.weight.grad, torch.full_like(lin.weight, (3 * 1 + 1 * 2) / 4.0)))
+        ok = ok and lin.bias.grad is not None and bool(torch.allclose(lin.bias.grad, torch.full_like(lin.bias, 3 / 4.0)))
         full = torch.arange(10 * 3).reshape(10, 3)
         mine = shard_batch(full, rank, world)
         gathered = [torch.zeros(5, 3, dtype=full.dtype) for _ in range(world)]
