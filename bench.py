@@ -294,6 +294,33 @@ def emit(line):
     out.flush()
 
 
+def bind_to_gpu_numa(local_rank):
+    """Best effort: run this rank (and therefore first-touch its pinned host buffers) on the NUMA node its GPU hangs
+    off.  With 8 ranks each pushing 2.3 GB of dense GSO per step over its own PCIe link, pinned buffers that all sit
+    on one socket turn the end-to-end step into a host-memory contest (SCALE_r01: 53 GB/s per GPU at N=1, 23 GB/s
+    at N=8).  Returns a short description for the JSON line."""
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev_id = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return "numa: not reported"
+        cpus = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            lo, _, hi = part.partition("-")
+            ids.update(range(int(lo), int(hi or lo) + 1))
+        allowed = ids & os.sched_getaffinity(0)
+        if not allowed:
+            return f"numa: node {node} has no allowed cpus"
+        os.sched_setaffinity(0, allowed)
+        return f"numa: rank bound to node {node} ({len(allowed)} cpus)"
+    except Exception as exc:
+        return f"numa: unbound ({str(exc)[:60]})"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -325,6 +352,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist_on = world > 1
+    numa = bind_to_gpu_numa(local_rank) if dist_on else "numa: single rank, unbound"
     if dist_on:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         import datetime
@@ -449,7 +477,8 @@ def main():
         x_d = [torch.empty((cb,) + tuple(x_mem.shape[1:]), dtype=x_mem.dtype, device=dev) for _ in range(2)]
         copy_stream = torch.cuda.Stream(device=dev)
 
-        def step_e2e():
+        def step_e2e_dense():
+            """The GSO crosses PCIe as the dense fp32 tensor (2.3 GB per step at the default workload)."""
             main = torch.cuda.current_stream(dev)
             for p in params:
                 p.grad = None
@@ -478,28 +507,91 @@ def main():
                 loss_acc += loss.detach()
                 done[c] = main.record_event()
             return float(loss_acc.item())           # D2H read of the step's result
+
+        from concurrent.futures import ThreadPoolExecutor
+        from magat_pathplanning_b200 import build_adjacency_from_rowbits, pack_gso_host
+        packer = ThreadPoolExecutor(max_workers=1)
+
+        def step_e2e():
+            """The GSO stays in (pinned) host memory, where the reference's dataloader / simulator builds it: its edge
+            mask is packed on the host cores (pack_gso_host: one streaming pass, all cores, the packing of chunk c+1
+            under the GPU work on chunk c) and N^2 / 8 bytes per instance cross PCIe instead of 4 N^2."""
+            main = torch.cuda.current_stream(dev)
+            for p in params:
+                p.grad = None
+            loss_acc = torch.zeros((), device=dev)
+            ready, done = [None] * nchunk, [None] * nchunk
+
+            def enqueue_copy(c):
+                with torch.cuda.stream(copy_stream):
+                    if c >= 2:
+                        copy_stream.wait_event(done[c - 2])
+                    else:
+                        copy_stream.wait_stream(main)
+                    x_d[c % 2].copy_(x_h[c * cb:(c + 1) * cb], non_blocking=True)
+                    ready[c] = copy_stream.record_event()
+            fut = packer.submit(pack_gso_host, S_h[0:cb])
+            enqueue_copy(0)
+            for c in range(nchunk):
+                bits = fut.result()
+                if c + 1 < nchunk:
+                    fut = packer.submit(pack_gso_host, S_h[(c + 1) * cb:(c + 2) * cb])
+                    enqueue_copy(c + 1)
+                main.wait_event(ready[c])
+                layer.addAdjacency(build_adjacency_from_rowbits(bits, dev))
+                xg = x_d[c % 2].permute(0, 2, 1).requires_grad_(True)
+                y = layer(xg)
+                loss = (y * dy[c * cb:(c + 1) * cb]).sum()
+                loss.backward()
+                loss_acc += loss.detach()
+                done[c] = main.record_event()
+            return float(loss_acc.item())
         e2e_steps = max(2, min(args.steps, 5))
         ms_e2e = timed(step_e2e, e2e_steps, 1, dist_on)
+        ms_e2e_dense = timed(step_e2e_dense, e2e_steps, 1, dist_on)
+        layer.addGSO(S)
+        bits_bytes = B * N * ((N + 31) // 32) * 4
         e2e = {"value": units / (ms_e2e * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": (S_h.numel() * S_h.element_size() + x_h.numel() * 4) * world,
+               "h2d_bytes_per_step": (bits_bytes + x_h.numel() * 4) * world,
                "d2h_bytes_per_step": 4 * world, "steps": e2e_steps,
-               "chunks": nchunk,
-               "note": "dense fp32 GSO (4N^2 B per instance) crosses PCIe every step, as the reference API passes it; "
-                       "H2D of chunk c+1 overlaps the layer call on chunk c"}
+               "host_bytes_read_per_step": S_h.numel() * S_h.element_size() * world,
+               "dense_h2d": {"value": units / (ms_e2e_dense * 1e-3), "unit": "agent-steps/s",
+                             "ms_per_step": ms_e2e_dense,
+                             "h2d_bytes_per_step": (S_h.numel() * S_h.element_size() + x_h.numel() * 4) * world,
+                             "note": "same step with the dense fp32 GSO copied to the device (round-1 path)"},
+               "chunks": nchunk, "host_placement": numa,
+               "note": "inputs start in pinned HOST buffers every step: the dense fp32 GSO (4N^2 B per instance, as the "
+                       "reference builds it on the CPU) and x. The GSO's edge mask is packed on the host cores "
+                       "(pack_gso_host, inside the timed region) and N^2/8 B per instance cross PCIe; x is copied "
+                       "as is; the scalar loss is read back. Chunked: packing / copies of chunk c+1 overlap the "
+                       "layer call on chunk c"}
         del S_h, x_h, S_d, x_d
 
     # ---- SURVEY 8f row f1: the same step fed with agent positions instead of the dense GSO -------------------------
     # (reported next to the contract's numbers, never instead of them: `value`, `fwd`, `roofline` and `e2e` keep
     # the reference's dense-GSO interface)
     positions = None
-    if world == 1 and not args.no_e2e and N <= 3072:
+    if not args.no_e2e and N <= 3072:
+        # every rank takes the same branches (the timed regions hold barriers): agree on the set-up first
+        pos_ok, same, pos_err = 1, False, None
         try:
             pos = synth_positions(B, N, w["width"], dev, torch.Generator(device=dev).manual_seed(SEED + rank))
             from magat_pathplanning_b200 import build_adjacency, build_adjacency_from_positions
             a_d, a_p = build_adjacency(S), build_adjacency_from_positions(pos, COMM_RADIUS)
             same = all(torch.equal(getattr(a_d, k), getattr(a_p, k)) for k in ("nbr_out", "nbr_in", "slot_in", "slot_out"))
             del a_d, a_p
-
+            pos_h = torch.empty(pos.shape, dtype=pos.dtype, pin_memory=True)
+            x_h2 = torch.empty(x_mem.shape, dtype=x_mem.dtype, pin_memory=True)
+            pos_h.copy_(pos)
+            x_h2.copy_(x_mem)
+            pos_d, x_d2 = torch.empty_like(pos), torch.empty_like(x_mem)
+        except Exception as exc:                      # an extra, never a reason to lose the contract line
+            pos_ok, pos_err = 0, str(exc)[-200:]
+        if dist_on:
+            flag = torch.tensor([pos_ok], device=dev)
+            torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+            pos_ok = int(flag.item())
+        if pos_ok:
             def step_train_pos():
                 for p in params:
                     p.grad = None
@@ -507,19 +599,14 @@ def main():
                 layer.addGSOFromPositions(pos, COMM_RADIUS)
                 y = layer(xg)
                 y.backward(dy)
+                if dist_on:
+                    allreduce_gradients(params)
                 return y
 
             def step_fwd_pos():
                 with torch.no_grad():
                     layer.addGSOFromPositions(pos, COMM_RADIUS)
                     return layer(x)
-            ms_tp = timed(step_train_pos, max(2, args.steps // 2), 2, False)
-            ms_fp = timed(step_fwd_pos, max(2, args.steps // 2), 2, False)
-            pos_h = torch.empty(pos.shape, dtype=pos.dtype, pin_memory=True)
-            x_h2 = torch.empty(x_mem.shape, dtype=x_mem.dtype, pin_memory=True)
-            pos_h.copy_(pos)
-            x_h2.copy_(x_mem)
-            pos_d, x_d2 = torch.empty_like(pos), torch.empty_like(x_mem)
 
             def step_e2e_pos():
                 pos_d.copy_(pos_h, non_blocking=True)
@@ -531,19 +618,25 @@ def main():
                 y = layer(xg)
                 loss = (y * dy).sum()
                 loss.backward()
+                if dist_on:
+                    allreduce_gradients(params)
                 return float(loss.item())
-            ms_ep = timed(step_e2e_pos, max(2, min(args.steps, 5)), 1, False)
+            ms_tp = timed(step_train_pos, max(2, args.steps // 2), 2, dist_on)
+            ms_fp = timed(step_fwd_pos, max(2, args.steps // 2), 2, dist_on)
+            ms_ep = timed(step_e2e_pos, max(2, min(args.steps, 5)), 1, dist_on)
             positions = {"lists_equal_dense_gso": bool(same),
                          "train": {"value": units / (ms_tp * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms_tp},
                          "fwd": {"value": units / (ms_fp * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms_fp},
                          "e2e": {"value": units / (ms_ep * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms_ep,
-                                 "h2d_bytes_per_step": pos_h.numel() * 4 + x_h2.numel() * 4, "d2h_bytes_per_step": 4},
+                                 "h2d_bytes_per_step": (pos_h.numel() * 4 + x_h2.numel() * 4) * world,
+                                 "d2h_bytes_per_step": 4 * world},
                          "note": "addGSOFromPositions(pos [B,N,2], commR): neighbour lists built on the device from "
-                                 "positions (utils/new_simulator.py:823-827); no N x N GSO exists or crosses PCIe"}
+                                 "positions (utils/new_simulator.py:823-827); no N x N GSO exists or crosses PCIe; "
+                                 "all ranks, max over ranks, gradient all-reduce included"}
             del pos_h, x_h2, pos_d, x_d2
             layer.addGSO(S)
-        except Exception as exc:                      # an extra, never a reason to lose the contract line
-            positions = {"error": str(exc)[-200:]}
+        else:
+            positions = {"error": pos_err or "set-up failed on another rank"}
 
     if rank != 0:
         if dist_on:

@@ -90,6 +90,16 @@ int magat_gso_scan_nonzero(const void* S, int s_dtype, int B, int N,
 int magat_gso_edge_values(const void* S, int s_dtype, const int32_t* nbr_out, int B, int N, int D, float* att,
                           void* stream);
 
+/* ---- GSO in HOST memory ----
+ * The reference builds the GSO on the CPU (dataloader / simulator); testing 4 N^2 bytes per instance on the device means
+ * shipping them over PCIe first.  magat_gso_pack_host (plain C++, no CUDA; multi-threaded, AVX2 when the CPU has it) makes
+ * the row mask on the host cores -- rowbits_host[rows = B * N][W], same layout and predicate as magat_gso_scan -- so
+ * N^2 / 8 bytes cross the link; after the caller's H2D copy magat_gso_from_rowbits transposes it into colbits on the
+ * device and fills stats like magat_gso_scan (stats zero-initialised by the caller except stats[3] = 1).  Continue
+ * with magat_gso_build_ell.  threads <= 0: one per hardware thread. */
+int magat_gso_pack_host(const void* S_host, int s_dtype, long rows, int N, uint32_t* rowbits_host, int threads);
+int magat_gso_from_rowbits(const uint32_t* rowbits, int B, int N, uint32_t* colbits, int32_t* stats, void* stream);
+
 /* Bit masks -> padded neighbour lists of width D (D >= max(stats[0], stats[1]), D >= 1). */
 int magat_gso_build_ell(const uint32_t* rowbits, const uint32_t* colbits, int B, int N, int D,
                         int32_t* nbr_out, int32_t* nbr_in, int32_t* slot_in, int32_t* slot_out /* may be NULL */,

@@ -25,7 +25,7 @@ EXPORTS = (
     "magat_launch_count", "magat_profile_enable", "magat_profile_collect",
     "magat_gat_small_supported", "magat_gat_forward_small", "magat_gso_from_positions",
     "magat_gat_fused_supported", "magat_gat_fused_workspace_bytes", "magat_gat_forward_fused",
-    "magat_gso_scan_nonzero", "magat_gso_edge_values",
+    "magat_gso_scan_nonzero", "magat_gso_edge_values", "magat_gso_pack_host", "magat_gso_from_rowbits",
 )
 
 _i32, _i64, _ptr = C.c_int32, C.c_int64, C.c_void_p
@@ -102,6 +102,10 @@ def lib():
         L.magat_gso_scan_nonzero.restype = C.c_int
         L.magat_gso_edge_values.argtypes = [_ptr, C.c_int, _ptr, C.c_int, C.c_int, C.c_int, _ptr, _ptr]
         L.magat_gso_edge_values.restype = C.c_int
+        L.magat_gso_pack_host.argtypes = [_ptr, C.c_int, C.c_long, C.c_int, _ptr, C.c_int]
+        L.magat_gso_pack_host.restype = C.c_int
+        L.magat_gso_from_rowbits.argtypes = [_ptr, C.c_int, C.c_int, _ptr, _ptr, _ptr]
+        L.magat_gso_from_rowbits.restype = C.c_int
         L.magat_gso_build_ell.argtypes = [_ptr, _ptr, C.c_int, C.c_int, C.c_int, _ptr, _ptr, _ptr, _ptr, _ptr]
         L.magat_gso_from_positions.argtypes = [_ptr, C.c_int, C.c_int, C.c_int, C.c_double, _ptr, _ptr, _ptr, _ptr]
         L.magat_gso_from_positions.restype = C.c_int

@@ -125,22 +125,12 @@ __device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, 
 
 // Data produced inside this launch by another CTA: L2 is the point of coherence, so bypass L1 (ld.global.cg).
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ uint2 ldcg2u(const void* p) { return __ldcg(reinterpret_cast<const uint2*>(p)); }
 
 __device__ __forceinline__ void fma4(float4& acc, float a, const float4& v) {
   acc.x = fmaf(a, v.x, acc.x); acc.y = fmaf(a, v.y, acc.y); acc.z = fmaf(a, v.z, acc.z); acc.w = fmaf(a, v.w, acc.w);
 }
 __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
   return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
-}
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-// two packed bf16 -> two floats
-__device__ __forceinline__ float2 bf2_to_f2(uint32_t w) {
-  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
 }
 // one image row (256 bf16: hi[128] | lo[128]); lane l owns features 4l .. 4l+3
 __device__ __forceinline__ void image_store(uint16_t* row, int lane, const float4& v) {
@@ -150,12 +140,6 @@ __device__ __forceinline__ void image_store(uint16_t* row, int lane, const float
   *reinterpret_cast<uint2*>(row + lane * 4) = hi;
   *reinterpret_cast<uint2*>(row + 128 + lane * 4) = lo;
 }
-__device__ __forceinline__ float4 image_load(const uint16_t* row, int lane) {
-  const uint2 hi = ldcg2u(row + lane * 4), lo = ldcg2u(row + 128 + lane * 4);
-  const float2 h0 = bf2_to_f2(hi.x), h1 = bf2_to_f2(hi.y), l0 = bf2_to_f2(lo.x), l1 = bf2_to_f2(lo.y);
-  return make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
-}
-
 // Team barrier: every thread publishes its writes (also towards the TMA engine of the other CTAs), one thread per CTA
 // arrives on the team's counter and waits until all TEAM CTAs have.
 __device__ __forceinline__ void team_barrier(unsigned* cnt, unsigned& target, int32_t* status, long long* prof,
@@ -269,20 +253,6 @@ __device__ __forceinline__ void scan_job(const FusedParams& p, const ScanJob& jb
     scan_units<double>(p, reinterpret_cast<const double*>(jb.S), r, lane, jb.rowbits, jb.colbits, counter, stop, stop_at);
   else
     scan_units<float>(p, reinterpret_cast<const float*>(jb.S), r, lane, jb.rowbits, jb.colbits, counter, stop, stop_at);
-}
-
-// number of set bits of a mask row strictly below position n
-__device__ __forceinline__ int rank_below(const uint32_t* __restrict__ bits, int n) {
-  const int sw = n >> 5;
-  int rk = 0;
-  int w = 0;
-  for (; w + 4 <= sw; w += 4) {
-    const uint4 v = __ldcg(reinterpret_cast<const uint4*>(bits + w));
-    rk += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
-  }
-  for (; w < sw; ++w) rk += __popc(__ldcg(bits + w));
-  rk += __popc(__ldcg(bits + sw) & ((1u << (n & 31)) - 1u));
-  return rk;
 }
 
 // ---- phase: neighbour lists of this CTA's nodes ---------------------------------------------------------------

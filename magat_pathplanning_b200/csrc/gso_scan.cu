@@ -682,6 +682,42 @@ __global__ void __launch_bounds__(256) k_gso_edge_values(const T* __restrict__ S
   att[t] = j >= 0 ? (float)S[row * N + j] : 0.f;
 }
 
+// colbits = transpose of rowbits, one warp per 32 x 32 bit block: lane r holds word w of row i0 + r; ballot c collects
+// bit c of all 32 rows, i.e. the word (band i0 / 32) of column w * 32 + c.
+__global__ void __launch_bounds__(256) k_bits_transpose(const uint32_t* __restrict__ rowbits, int N, int W, long blocks,
+                                                        uint32_t* __restrict__ colbits) {
+  const int lane = threadIdx.x & 31;
+  const long blk = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (blk >= blocks) return;
+  const int w = (int)(blk % W);
+  const int band = (int)((blk / W) % W);
+  const long b = blk / ((long)W * W);
+  const int i = band * 32 + lane;
+  const uint32_t x = i < N ? rowbits[((size_t)b * N + i) * W + w] : 0u;
+  uint32_t mine = 0u;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    const uint32_t v = __ballot_sync(0xffffffffu, (x >> c) & 1u);
+    if (lane == c) mine = v;
+  }
+  const int j = w * 32 + lane;
+  if (j < N) colbits[((size_t)b * N + j) * W + band] = mine;
+}
+
+extern "C" int magat_gso_from_rowbits(const uint32_t* rowbits, int B, int N, uint32_t* colbits, int32_t* stats,
+                                      void* stream) {
+  MAGAT_REQUIRE(rowbits && colbits && stats, MAGAT_E_BAD_ARG, "magat_gso_from_rowbits: null pointer");
+  MAGAT_REQUIRE(B >= 1 && N >= 1, MAGAT_E_BAD_ARG, "magat_gso_from_rowbits: B=%d N=%d", B, N);
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin(st);
+  const int W = (N + 31) / 32;
+  const long blocks = (long)B * W * W;
+  k_bits_transpose<<<cdiv(blocks, 8), 256, 0, st>>>(rowbits, N, W, blocks, colbits);
+  int rc = check_launch("k_bits_transpose", st);
+  if (rc) return rc;
+  return launch_gso_stats(rowbits, colbits, B, N, W, stats, st);
+}
+
 extern "C" int magat_gso_scan_nonzero(const void* S, int s_dtype, int B, int N, uint32_t* rowbits, uint32_t* colbits,
                                       int32_t* stats, void* stream) {
   MAGAT_REQUIRE(S && rowbits && colbits && stats, MAGAT_E_BAD_ARG, "magat_gso_scan_nonzero: null pointer");

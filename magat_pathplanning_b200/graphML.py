@@ -151,6 +151,48 @@ def build_adjacency(S: torch.Tensor, max_degree: Optional[int] = None, nonzero: 
         return _lists_from_masks(rowbits, colbits, stats, B, N, dev, st, max_degree)
 
 
+def pack_gso_host(S: torch.Tensor, threads: int = 0) -> torch.Tensor:
+    """Edge mask of a GSO that lives in HOST memory, packed on the host cores: [B,1,N,N] fp32 / fp64 CPU tensor ->
+    pinned int32 [B,N,ceil(N/32)] (bit j % 32 of word j / 32 of row i set iff |S[i,j]| > 1e-9).  One streaming pass
+    (magat_gso_pack_host: threads + AVX2); 32x fewer bytes then cross PCIe than with the dense fp32 operator."""
+    assert len(S.shape) == 4 and S.shape[1] == 1 and S.shape[2] == S.shape[3]
+    if S.is_cuda:
+        raise RuntimeError("pack_gso_host: the GSO is already on the device; use build_adjacency")
+    S = S.detach()
+    if S.dtype not in (torch.float32, torch.float64):
+        S = S.to(torch.float32)
+    if not S.is_contiguous():
+        S = S.contiguous()
+    B, N = S.shape[0], S.shape[2]
+    pin = torch.cuda.is_available()
+    bits = torch.empty((B, N, (N + 31) // 32), dtype=torch.int32, pin_memory=pin)
+    _cabi.check(_cabi.lib().magat_gso_pack_host(S.data_ptr(), _cabi.DT_F32 if S.dtype == torch.float32 else _cabi.DT_F64,
+                                                B * N, N, bits.data_ptr(), int(threads)))
+    return bits
+
+
+def build_adjacency_from_rowbits(bits: torch.Tensor, device, max_degree: Optional[int] = None) -> Adjacency:
+    """Neighbour lists from a packed row mask [B,N,W] (``pack_gso_host``; host or device): H2D copy of the mask on the
+    current stream, transposition into the column mask and the usual list build on the device."""
+    dev = torch.device(device)
+    B, N, W = bits.shape
+    assert W == (N + 31) // 32 and bits.dtype == torch.int32
+    L = _cabi.lib()
+    with torch.cuda.device(dev):
+        st = _stream(dev)
+        rowbits = bits if bits.is_cuda else bits.to(dev, non_blocking=True)
+        rowbits = rowbits.contiguous()
+        colbits = torch.empty((B, N, W), dtype=torch.int32, device=dev)
+        stats = _stats_init(dev)
+        _cabi.check(L.magat_gso_from_rowbits(rowbits.data_ptr(), B, N, colbits.data_ptr(), stats.data_ptr(), st))
+        return _lists_from_masks(rowbits, colbits, stats, B, N, dev, st, max_degree)
+
+
+def build_adjacency_host(S: torch.Tensor, device, max_degree: Optional[int] = None, threads: int = 0) -> Adjacency:
+    """``build_adjacency`` for a GSO in host memory: mask packed on the host cores, N^2 / 8 bytes over PCIe."""
+    return build_adjacency_from_rowbits(pack_gso_host(S, threads), device, max_degree)
+
+
 def _lists_from_masks(rowbits, colbits, stats, B, N, dev, st, max_degree=None):
     L = _cabi.lib()
     if N <= _NOSYNC_N:
@@ -503,7 +545,7 @@ def gat_layer(x, S, filterWeight, mixer, weight, weight_bias, bias, *, mode: int
     B_, N_ = x.shape[0], x.shape[2]
     needs_grad = torch.is_grad_enabled() and any(
         t is not None and t.requires_grad for t in (x, filterWeight, mixer, weight, weight_bias, bias))
-    if (adjacency is None and path == "auto" and not needs_grad and S is not None and S.shape[2] == N_
+    if (adjacency is None and path == "auto" and not needs_grad and S is not None and S.is_cuda and S.shape[2] == N_
             and N_ <= _SMALL_N_MAX and B_ <= _SMALL_B
             and (mode != _cabi.MODE_KEYQUERY or F == G)
             and _cabi.lib().magat_gat_small_supported(N_, G, F, K, P, int(concatenate))):
@@ -512,9 +554,15 @@ def gat_layer(x, S, filterWeight, mixer, weight, weight_bias, bias, *, mode: int
         return _small_forward(x, S, filterWeight, mixer if mode != _cabi.MODE_KEYQUERY else None, weight,
                               weight_bias if mode != _cabi.MODE_KEYQUERY else None, bias, mode, concatenate, relu)
     fused = None
+    if adjacency is None and S is not None and not S.is_cuda:
+        # the GSO stayed in host memory (where the reference's dataloader / simulator builds it): pack the mask there
+        assert len(S.shape) == 4 and S.shape[0] == B_ and S.shape[2] == N_ and S.shape[3] == N_
+        if S.shape[1] != 1:
+            raise NotImplementedError("edge_features E != 1 is not supported")
+        adjacency = build_adjacency_host(S, x.device, max_degree)
     if adjacency is None and path in ("auto", "fused") and S is not None:
         fused = _fused_gso(x, S, G, F, K, P, mode, concatenate, path, max_degree)
-    if path == "fused" and fused is None:
+    if path == "fused" and fused is None and adjacency is None:
         raise RuntimeError("path='fused': shape / layout not covered by the fused forward (magat_gat_fused_supported)")
     if fused is not None:
         adj = fused
@@ -834,6 +882,13 @@ class GraphFilterBatchAttentional(nn.Module):
         assert S.shape[3] == self.N
         self.S = S                       # borrowed, read at forward time like the reference
         self._adj = None
+
+    def addAdjacency(self, adj: Adjacency):
+        """Not in the reference: hand the layer neighbour lists built ahead of time (``build_adjacency``,
+        ``build_adjacency_host``, ``build_adjacency_from_rowbits`` -- e.g. by a prefetching thread on a side stream)."""
+        self.N = adj.N
+        self.S = None
+        self._adj = adj
 
     def addGSOFromPositions(self, pos, comm_radius):
         """Not in the reference: give the layer the agents' positions [B,N,2] instead of

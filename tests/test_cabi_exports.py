@@ -141,3 +141,21 @@ def test_reference_state_dict_loads():
         assert list(ref.state_dict()) == list(ours.state_dict())
         ours.load_state_dict(ref.state_dict())
         assert repr(ours) == repr(ref)
+
+
+def test_host_mask_packer_matches_numpy(built):
+    """magat_gso_pack_host needs no GPU: |s| > 1e-9 per entry (NaN is no edge), bit j % 32 of word j / 32."""
+    import numpy as np
+    from magat_pathplanning_b200 import pack_gso_host
+    gen = torch.Generator().manual_seed(3)
+    for N, dtype in ((70, torch.float32), (64, torch.float64), (5, torch.float32)):
+        S = torch.randn(3, 1, N, N, generator=gen).to(dtype) * (torch.rand(3, 1, N, N, generator=gen) < 0.2)
+        S[0, 0, 0, 1] = float("nan")
+        S[1, 0, 1, 0] = 5e-10
+        S[2, 0, 2, 3] = -2e-9
+        bits = pack_gso_host(S, threads=3).numpy().view(np.uint32)
+        W = (N + 31) // 32
+        ref = np.zeros((3 * N, W * 32), dtype=bool)
+        ref[:, :N] = (S.abs() > 1e-9)[:, 0].reshape(3 * N, N).numpy()
+        want = np.packbits(ref, axis=1, bitorder="little").view(np.uint32).reshape(3, N, W)
+        assert np.array_equal(bits, want)

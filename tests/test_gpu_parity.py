@@ -525,3 +525,27 @@ def test_layer_is_cuda_graph_capturable(N, promise):
     assert torch.equal(out["y"], eager["y"]) and torch.equal(out["dx"], eager["dx"])
     assert rel_err(layer.filterWeight.grad, eager["dH"]) < 1e-6
     layer._last.adj.check_degree()                      # the promise held
+
+
+def test_gso_in_host_memory_gives_the_same_adjacency_and_output(golden):
+    """addGSO with a CPU tensor: the mask is packed on the host (magat_gso_pack_host), transposed on the device."""
+    from magat_pathplanning_b200 import build_adjacency, build_adjacency_host
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(12)
+    for N, dtype in ((1000, torch.float32), (77, torch.float64), (10, torch.float32)):
+        S = orc.random_geometric_gso(3, N, generator=gen).to(dtype)
+        S[0, 0, 1, 2] = float("nan")
+        S[1, 0, 2, 1] = -3e-9
+        S[2, 0, 0, 1] = 5e-10
+        a, b = build_adjacency(S.to(dev)), build_adjacency_host(S, dev)
+        assert a.D == b.D
+        for k in ("nbr_out", "nbr_in", "slot_in", "slot_out"):
+            assert torch.equal(getattr(a, k), getattr(b, k)), (N, k)
+    d, meta = golden.case("kq_concat_c2")
+    layer = make_layer(meta, d, dev)
+    layer.addGSO(d["S"])                                   # stays on the CPU
+    x = d["x"].to(dev).requires_grad_(True)
+    y = layer(x)
+    assert rel_err(y, d["y"]) < TOL
+    y.backward(d["dy"].to(dev))
+    assert rel_err(x.grad, d["grad.x"]) < TOL
