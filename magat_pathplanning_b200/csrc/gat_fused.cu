@@ -26,6 +26,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "gat_sparse.cuh"
 #include "tc_common.cuh"
 #include "tma_host.cuh"
 
@@ -124,14 +125,7 @@ __device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, 
 }
 
 // Data produced inside this launch by another CTA: L2 is the point of coherence, so bypass L1 (ld.global.cg).
-__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
-__device__ __forceinline__ void fma4(float4& acc, float a, const float4& v) {
-  acc.x = fmaf(a, v.x, acc.x); acc.y = fmaf(a, v.y, acc.y); acc.z = fmaf(a, v.z, acc.z); acc.w = fmaf(a, v.w, acc.w);
-}
-__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
-  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
-}
 // one image row (256 bf16: hi[128] | lo[128]); lane l owns features 4l .. 4l+3
 __device__ __forceinline__ void image_store(uint16_t* row, int lane, const float4& v) {
   uint2 hi, lo;
@@ -380,97 +374,17 @@ __device__ __forceinline__ void phase_lists(const FusedParams& p, long rowbase, 
   }
 }
 
-// ---- row softmax over the out-neighbours + store, shared by both attention modes ------------------------------
-// The raw scores of the row sit in shared memory, e_s[slot * PT + head].  Lane = (slot within a chunk of 32 / PT
-// slots, head): the max and the sum over the slots are xor-shuffles over the upper lane bits, all heads at once, and
-// att[row][slot][head] leaves with one coalesced store per chunk (zeros beyond the degree).
-template <int PT>
-__device__ __forceinline__ void softmax_store(float* att_row, int D, int lane, int deg, const float* e_s) {
-  constexpr int LOGP = PT == 4 ? 2 : PT == 2 ? 1 : 0;
-  constexpr int SPC = 32 / PT;
-  const int sl = lane >> LOGP;
-  float m = -INFINITY;
-  for (int c0 = 0; c0 < deg; c0 += SPC)
-    if (c0 + sl < deg) m = fmaxf(m, e_s[c0 * PT + lane]);
-#pragma unroll
-  for (int o = PT; o < 32; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  float sum = 0.f;
-  for (int c0 = 0; c0 < deg; c0 += SPC)
-    if (c0 + sl < deg) sum += expf(e_s[c0 * PT + lane] - m);
-#pragma unroll
-  for (int o = PT; o < 32; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  for (int c0 = 0; c0 < D; c0 += SPC) {
-    const int sidx = c0 + sl;
-    if (sidx < D) att_row[c0 * PT + lane] = sidx < deg ? expf(e_s[c0 * PT + lane] - m) / sum : 0.f;
-  }
-}
-
-// Sum NV per-lane values over the 16 lanes of a half warp at once: every step halves the number of live values and
-// doubles the lanes each has absorbed.  Lane t of the half ends up with the total of value t >> (4 - log2 NV).
-template <int NV>
-__device__ __forceinline__ float half_multi_sum(float (&v)[NV], int t) {
-  int off = 8;
-#pragma unroll
-  for (int n = NV; n > 1; n >>= 1, off >>= 1) {
-    const bool hi = (t & off) != 0;
-#pragma unroll
-    for (int i = 0; i < n / 2; ++i) {
-      const float keep = hi ? v[i + n / 2] : v[i];
-      const float send = hi ? v[i] : v[i + n / 2];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-#pragma unroll
-  for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
-  return v[0];
-}
-
-// ---- phase: KeyQuery scores + row softmax (graphML.py:1246-1286) -----------------------------------------------
-// Warp per sender row i, HALF a warp per edge: lane t of a half owns features 8t .. 8t+7 of R_i (all heads, in
-// registers for the whole row) and of x_j, so the two halves score two edges per step and the cross-lane sum of the PT
-// head dots is one joint reduction (16 instructions for 4 heads instead of 40).
+// ---- phase: KeyQuery scores + row softmax (graphML.py:1246-1286): warp per sender row (gat_sparse.cuh) ----------
 template <int PT>
 __device__ __forceinline__ void phase_attention_kq(const FusedParams& p, long rowbase, const float* xb, int n0, int n1,
                                                    int warp, int lane, const float* sproj, float* esc) {
-  constexpr int LOGP = PT == 4 ? 2 : PT == 2 ? 1 : 0;
   const int D = p.D;
-  const int half = lane >> 4, t = lane & 15;
   float* e_s = esc + warp * 32 * PT;
   const int32_t* nbo = p.nbr_out + rowbase * D;
   float* att_b = p.att + (size_t)rowbase * D * PT;
-  for (int i = n0 + warp; i < n1; i += NWARPS) {
-    const int my_j = lane < D ? __ldcg(nbo + (unsigned)(i * D + lane)) : -1;
-    const int deg = __popc(__ballot_sync(0xffffffffu, my_j >= 0));
-    if (deg > 0) {
-      float4 rv[PT][2];
-      const float* rp = sproj + (unsigned)(i * PT * FT + t * 8);
-#pragma unroll
-      for (int h = 0; h < PT; ++h) {
-        rv[h][0] = ldcg4(rp + h * FT);
-        rv[h][1] = ldcg4(rp + h * FT + 4);
-      }
-      for (int s0 = 0; s0 < deg; s0 += 2) {
-        const int sidx = s0 + half;
-        const int j = __shfl_sync(0xffffffffu, my_j, sidx & 31);
-        float d[PT];
-        if (sidx < deg) {
-          const float* xr = xb + (long)j * p.x_sn + t * 8;
-          const float4 x0 = __ldg(reinterpret_cast<const float4*>(xr));
-          const float4 x1 = __ldg(reinterpret_cast<const float4*>(xr + 4));
-#pragma unroll
-          for (int h = 0; h < PT; ++h) d[h] = dot4(rv[h][0], x0) + dot4(rv[h][1], x1);
-        } else {
-#pragma unroll
-          for (int h = 0; h < PT; ++h) d[h] = 0.f;
-        }
-        const float tot = half_multi_sum<PT>(d, t);
-        if (sidx < deg && (t & (16 / PT - 1)) == 0) e_s[sidx * PT + (t >> (4 - LOGP))] = tot;
-      }
-    }
-    __syncwarp();
-    softmax_store<PT>(att_b + (unsigned)(i * D * PT), D, lane, deg, e_s);
-    __syncwarp();
-  }
+  for (int i = n0 + warp; i < n1; i += NWARPS)
+    sparse::attention_kq_row<PT, true>(xb, (unsigned)p.x_sn, sproj + (unsigned)(i * PT * FT), nbo + (unsigned)(i * D),
+                                       att_b + (unsigned)(i * D * PT), D, lane, e_s);
 }
 
 // ---- GAT_modified (graphML.py:713-823) ---------------------------------------------------------------------
@@ -507,7 +421,7 @@ __device__ __forceinline__ void phase_mixer_gm(const FusedParams& p, const float
     const float4 xv = __ldg(reinterpret_cast<const float4*>(xb + (long)n * p.x_sn + lane * 4));
 #pragma unroll
     for (int q = 0; q < 2 * PT; ++q) {
-      const float d = warp_sum(dot4(c[q], xv));
+      const float d = warp_sum(sparse::dot4(c[q], xv));
       if (lane == q) sproj[(size_t)n * 2 * PT + q] = d + cd[2 * PT * FT + q];
     }
   }
@@ -532,7 +446,7 @@ __device__ __forceinline__ void phase_attention_gm(const FusedParams& p, long ro
       }
     }
     __syncwarp();
-    softmax_store<PT>(att_b + (unsigned)(i * D * PT), D, lane, deg, e_s);
+    sparse::softmax_store<PT>(att_b + (unsigned)(i * D * PT), D, lane, deg, e_s);
     __syncwarp();
   }
 }
@@ -543,17 +457,6 @@ __device__ __forceinline__ void phase_attention_gm(const FusedParams& p, long ro
 // rows of x (one row feeds every head), k = 2 the heads' fp32 u_1 rows.  Output: bf16 hi/lo image row for the
 // projection (+ the fp32 copy the next level and backward read).
 template <int PT>
-__device__ __forceinline__ void gather_edge(const float* xb, unsigned x_sn, const float* tsrc, int k, unsigned trow,
-                                            int lane, int i, float4 (&v)[PT]) {
-  if (k == 1) {
-    v[0] = __ldg(reinterpret_cast<const float4*>(xb + (unsigned)i * x_sn + lane * 4));
-  } else {
-#pragma unroll
-    for (int h = 0; h < PT; ++h) v[h] = ldcg4(tsrc + ((unsigned)i * PT + h) * trow + lane * 4);
-  }
-}
-
-template <int PT>
 __device__ __forceinline__ void phase_gather(const FusedParams& p, long rowbase, const float* xb, int n0, int n1,
                                              int warp, int lane, int k, uint16_t* uimg, float* taps) {
   const int D = p.D, Km1 = p.K - 1;
@@ -563,43 +466,14 @@ __device__ __forceinline__ void phase_gather(const FusedParams& p, long rowbase,
   const unsigned trow = (unsigned)(Km1 * FT);                  // floats between the heads of a node in the taps buffer
   const float* tsrc = taps + (k >= 2 ? (k - 2) * FT : 0);       // plane k-1 of every (node, head)
   const bool keep32 = p.save || k < Km1;                       // fp32 copy: for backward, and as the source of the next level
-  const bool flat_x = p.x_sn < (1l << 24);
-  const unsigned x_sn = flat_x ? (unsigned)p.x_sn : 0u;
   for (int j = n0 + warp; j < n1; j += NWARPS) {
-    const int my_i = lane < D ? __ldcg(nbi + (unsigned)(j * D + lane)) : -1;
-    const int my_sl = lane < D ? __ldcg(sli + (unsigned)(j * D + lane)) : 0;
-    // in-edge `lane`: A_p[i, j] sits at slot my_sl of sender i's softmax row
-    float am[PT];
-    if (PT == 4) {
-      const float4 wv = my_i >= 0 ? ldcg4(att_b + (unsigned)((my_i * D + my_sl) * PT)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      am[0] = wv.x; am[1 % PT] = wv.y; am[2 % PT] = wv.z; am[3 % PT] = wv.w;
-    } else {
-#pragma unroll
-      for (int h = 0; h < PT; ++h) am[h] = my_i >= 0 ? __ldcg(att_b + (unsigned)((my_i * D + my_sl) * PT + h)) : 0.f;
-    }
-    const int cnt = __popc(__ballot_sync(0xffffffffu, my_i >= 0));
     float4 acc[PT];
-#pragma unroll
-    for (int h = 0; h < PT; ++h) acc[h] = make_float4(0.f, 0.f, 0.f, 0.f);
-    int s = 0;
-    for (; k == 1 && s + 1 < cnt; s += 2) {    // (level 2 loads PT rows per edge: one edge at a time keeps them in registers)
-      const int i0 = __shfl_sync(0xffffffffu, my_i, s), i1 = __shfl_sync(0xffffffffu, my_i, s + 1);
-      float4 v0[PT], v1[PT];
-      gather_edge<PT>(xb, x_sn, tsrc, 1, trow, lane, i0, v0);
-      gather_edge<PT>(xb, x_sn, tsrc, 1, trow, lane, i1, v1);
-#pragma unroll
-      for (int h = 0; h < PT; ++h) {
-        fma4(acc[h], __shfl_sync(0xffffffffu, am[h], s), v0[0]);
-        fma4(acc[h], __shfl_sync(0xffffffffu, am[h], s + 1), v1[0]);
-      }
-    }
-    for (; s < cnt; ++s) {
-      const int i0 = __shfl_sync(0xffffffffu, my_i, s);
-      float4 v0[PT];
-      gather_edge<PT>(xb, x_sn, tsrc, k, trow, lane, i0, v0);
-#pragma unroll
-      for (int h = 0; h < PT; ++h) fma4(acc[h], __shfl_sync(0xffffffffu, am[h], s), k == 1 ? v0[0] : v0[h]);
-    }
+    if (k == 1)
+      sparse::gather_row<PT, true, true>(xb, (unsigned)p.x_sn, tsrc, trow, att_b, nbi + (unsigned)(j * D),
+                                         sli + (unsigned)(j * D), D, lane, acc);
+    else
+      sparse::gather_row<PT, false, true>(xb, (unsigned)p.x_sn, tsrc, trow, att_b, nbi + (unsigned)(j * D),
+                                          sli + (unsigned)(j * D), D, lane, acc);
     uint16_t* irow = uimg + (unsigned)((j * PT * Km1 + (k - 1)) * 256);
     float* trow_out = taps + (unsigned)(j * PT) * trow + (k - 1) * FT + lane * 4;
 #pragma unroll

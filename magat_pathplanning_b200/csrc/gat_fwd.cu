@@ -14,6 +14,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "gat_sparse.cuh"
 #include "simt_gemm.cuh"
 
 namespace magat {
@@ -415,6 +416,49 @@ __global__ void __launch_bounds__(256) k_attention_gm_v(const float* __restrict_
   }
 }
 
+// ---- lean sparse kernels (G = 128, D <= 32, P in {1,2,4}): the warp-level routines of gat_sparse.cuh, one row per warp ----
+// Attention: half a warp per edge, joint head reduction, softmax through shared memory; no receiver-major copy.
+template <int PT>
+__global__ void __launch_bounds__(256) k_attention_kq_h(const float* __restrict__ x, long x_sb, long x_sn,
+                                                        const float* __restrict__ sproj,
+                                                        const int32_t* __restrict__ nbr_out, long rows, int N, int D,
+                                                        float* __restrict__ att) {
+  __shared__ float esc[8 * 32 * PT];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long row = (long)blockIdx.x * 8 + warp;
+  if (row >= rows) return;
+  const long b = batch_of32(row, N);
+  sparse::attention_kq_row<PT, false>(x + b * x_sb, (unsigned)x_sn, sproj + (size_t)row * PT * 128, nbr_out + row * D,
+                                      att + (size_t)row * D * PT, D, lane, esc + warp * 32 * PT);
+}
+
+// Tap level k for all heads; the in-edge attention values come straight from the senders' softmax rows (slot_in).
+template <int PT, bool K1>
+__global__ void __launch_bounds__(256) k_tap_gather_s(const float* __restrict__ x, long x_sb, long x_sn,
+                                                      const float* __restrict__ att, const int32_t* __restrict__ nbr_in,
+                                                      const int32_t* __restrict__ slot_in, long rows, int N, int K, int D,
+                                                      int k, float* __restrict__ taps) {
+  const int lane = threadIdx.x & 31;
+  const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  const long b = batch_of32(row, N);
+  const unsigned trow = (unsigned)((K - 1) * 128);
+  const float* src = taps + (size_t)b * N * PT * trow + (k >= 2 ? (k - 2) * 128 : 0);
+  float4 acc[PT];
+  sparse::gather_row<PT, K1, false>(x + b * x_sb, (unsigned)x_sn, src, trow, att + (size_t)b * N * D * PT, nbr_in + row * D,
+                                    slot_in + row * D, D, lane, acc);
+  float* out = taps + (size_t)row * PT * trow + (k - 1) * 128 + lane * 4;
+#pragma unroll
+  for (int h = 0; h < PT; ++h) *reinterpret_cast<float4*>(out + h * trow) = acc[h];
+}
+
+// shapes the lean sparse kernels take (32-bit offsets inside an instance)
+static bool lean_sparse_ok(long x_sb, long x_sn, int N, int G, int K, int P, int D) {
+  return G == 128 && D <= 32 && D % 4 == 0 && (P == 1 || P == 2 || P == 4) && x_sn < (1l << 24) &&
+         (long)N * x_sn < (1l << 31) && (long)N * P * (K > 1 ? K - 1 : 1) * 128 < (1l << 31) && (x_sn % 4) == 0 &&
+         (x_sb % 4) == 0;
+}
+
 // ---- functors for the tile GEMMs ----------------------------------------------------------
 struct XLoad {   // A(m, g): node features
   const float* x; long x_sb, x_sn; int N;
@@ -512,6 +556,18 @@ int run_tap_gather(const float* x, long x_sb, long x_sn, const float* att, const
   const int row_blocks = cdiv(rows, 8);
   const bool vec_ok = (G % 4 == 0) && (x_sn % 4 == 0) && (x_sb % 4 == 0) && (((uintptr_t)x) % 16 == 0) &&
                       (((uintptr_t)att) % 16 == 0) && (((uintptr_t)taps) % 16 == 0) && rows < (1l << 31);
+  if (vec_ok && slot_in != nullptr && lean_sparse_ok(x_sb, x_sn, N, G, K, P, D) && ((uintptr_t)nbr_in % 16) == 0) {
+#define MAGAT_GS(PT)                                                                                                   \
+  do {                                                                                                                 \
+    if (k == 1) k_tap_gather_s<PT, true><<<row_blocks, 256, 0, st>>>(x, x_sb, x_sn, att, nbr_in, slot_in, rows, N, K, D, k, taps); \
+    else k_tap_gather_s<PT, false><<<row_blocks, 256, 0, st>>>(x, x_sb, x_sn, att, nbr_in, slot_in, rows, N, K, D, k, taps);       \
+  } while (0)
+    if (P == 4) MAGAT_GS(4);
+    else if (P == 2) MAGAT_GS(2);
+    else MAGAT_GS(1);
+#undef MAGAT_GS
+    return check_launch("k_tap_gather", st);
+  }
   static const int occ = getenv("MAGAT_GATHER_OCC") ? atoi(getenv("MAGAT_GATHER_OCC")) : 4;
 #define MAGAT_GATHER(PT) \
   do {                                                                                                              \
@@ -563,7 +619,10 @@ static int forward_impl(const magat_gat_fwd_args* a, cudaStream_t st, bool use_t
     if (!fused && (rc = tc_split_weights(a->filterWeight, (long)nH, h_hi, h_lo, st))) return rc;
   }
   // the attention kernel also scatters the receiver-major copy `ain` when the caller provides it
-  const int32_t* so = (a->ain && a->slot_out && a->mode != MAGAT_MODE_GSO_VALUES) ? a->slot_out : nullptr;
+  // (the lean gather kernels read the senders' softmax rows through slot_in and need no receiver-major copy)
+  const bool lean = vec_ok && !tap_tc_gathers_u2() && lean_sparse_ok(a->x_sb, a->x_sn, N, G, K, P, D) &&
+                    ((uintptr_t)a->nbr_in % 16) == 0 && ((uintptr_t)a->nbr_out % 16) == 0;
+  const int32_t* so = (a->ain && a->slot_out && a->mode != MAGAT_MODE_GSO_VALUES && !lean) ? a->slot_out : nullptr;
   float* ain_w = so ? a->ain : nullptr;
   // 1. score projection
   if (a->mode == MAGAT_MODE_GSO_VALUES) {
@@ -589,7 +648,10 @@ static int forward_impl(const magat_gat_fwd_args* a, cudaStream_t st, bool use_t
       k_attention_kq_v<PT, GV, 1><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj, a->nbr_out, rows, N, D, \
                                                               a->att, so, ain_w);                                  \
   } while (0)
-    if (fast && P == 4 && G == 128) MAGAT_ATT(4, 1);
+    if (lean && P == 4) k_attention_kq_h<4><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj, a->nbr_out, rows, N, D, a->att);
+    else if (lean && P == 2) k_attention_kq_h<2><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj, a->nbr_out, rows, N, D, a->att);
+    else if (lean && P == 1) k_attention_kq_h<1><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj, a->nbr_out, rows, N, D, a->att);
+    else if (fast && P == 4 && G == 128) MAGAT_ATT(4, 1);
     else if (fast && P == 4 && G == 256) MAGAT_ATT(4, 2);
     else if (fast && P == 2 && G == 128) MAGAT_ATT(2, 1);
     else if (fast && P == 2 && G == 256) MAGAT_ATT(2, 2);
