@@ -119,7 +119,8 @@ def _stats_init(dev):
     return t.clone()
 
 
-def build_adjacency(S: torch.Tensor, max_degree: Optional[int] = None, nonzero: bool = False) -> Adjacency:
+def build_adjacency(S: torch.Tensor, max_degree: Optional[int] = None, nonzero: bool = False,
+                    with_slot_out: bool = False) -> Adjacency:
     """[B,1,N,N] dense GSO -> neighbour lists.  Only ``|S| > 1e-9`` matters (graphML.py:1274-1276):
     NaN is "no edge", negative weights are edges.  S is read once, by one kernel.
 
@@ -148,7 +149,7 @@ def build_adjacency(S: torch.Tensor, max_degree: Optional[int] = None, nonzero: 
         scan = L.magat_gso_scan_nonzero if nonzero else L.magat_gso_scan    # nonzero: BatchLSIGF's "S itself" predicate
         _cabi.check(scan(S.data_ptr(), _cabi.DT_F32 if S.dtype == torch.float32 else _cabi.DT_F64,
                          B, N, rowbits.data_ptr(), colbits.data_ptr(), stats.data_ptr(), st))
-        return _lists_from_masks(rowbits, colbits, stats, B, N, dev, st, max_degree)
+        return _lists_from_masks(rowbits, colbits, stats, B, N, dev, st, max_degree, with_slot_out)
 
 
 def pack_gso_host(S: torch.Tensor, threads: int = 0) -> torch.Tensor:
@@ -193,7 +194,7 @@ def build_adjacency_host(S: torch.Tensor, device, max_degree: Optional[int] = No
     return build_adjacency_from_rowbits(pack_gso_host(S, threads), device, max_degree)
 
 
-def _lists_from_masks(rowbits, colbits, stats, B, N, dev, st, max_degree=None):
+def _lists_from_masks(rowbits, colbits, stats, B, N, dev, st, max_degree=None, with_slot_out=False):
     L = _cabi.lib()
     if N <= _NOSYNC_N:
         D = N
@@ -206,9 +207,11 @@ def _lists_from_masks(rowbits, colbits, stats, B, N, dev, st, max_degree=None):
     nbr_out = torch.empty((B, N, D), dtype=torch.int32, device=dev)
     nbr_in = torch.empty((B, N, D), dtype=torch.int32, device=dev)
     slot_in = torch.empty((B, N, D), dtype=torch.int32, device=dev)
-    slot_out = torch.empty((B, N, D), dtype=torch.int32, device=dev)
+    # slot_out (position of a sender in its receivers' in-lists) only fed the receiver-major attention copy of the
+    # round-1 kernels; nothing on the current path reads it, so it is built on request only
+    slot_out = torch.empty((B, N, D), dtype=torch.int32, device=dev) if with_slot_out else None
     _cabi.check(L.magat_gso_build_ell(rowbits.data_ptr(), colbits.data_ptr(), B, N, D, nbr_out.data_ptr(),
-                                      nbr_in.data_ptr(), slot_in.data_ptr(), slot_out.data_ptr(), st))
+                                      nbr_in.data_ptr(), slot_in.data_ptr(), _p(slot_out), st))
     return Adjacency(B, N, D, nbr_out, nbr_in, slot_in, slot_out, stats)
 
 
@@ -307,7 +310,7 @@ class _GATFunction(torch.autograd.Function):
                               relu=int(meta.relu), path=meta.path, reserved=0,
                               x=xt.data_ptr(), x_sb=_sb(xt), x_sn=_sn(xt),
                               nbr_out=adj.nbr_out.data_ptr(), nbr_in=adj.nbr_in.data_ptr(),
-                              slot_in=adj.slot_in.data_ptr(), slot_out=adj.slot_out.data_ptr(),
+                              slot_in=adj.slot_in.data_ptr(), slot_out=_p(adj.slot_out),
                               weight=weight_c.data_ptr(), mixer=_p(mixer_c), weight_bias=_p(wb_c),
                               filterWeight=filt_c.data_ptr(), bias=_p(bias_c),
                               y=y_mem.data_ptr(), y_sb=y.stride(0), y_sn=y.stride(2), y_sc=y.stride(1),

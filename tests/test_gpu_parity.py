@@ -376,7 +376,7 @@ def test_gso_scan_and_neighbour_lists(N, dtype):
         S[:, :, 4, 1] = -3e-9
         S[:, :, 0, :] = 0
     mask = (S.abs() > 1e-9)[:, 0]                               # [B,N,N]
-    adj = build_adjacency(S.to(dev))
+    adj = build_adjacency(S.to(dev), with_slot_out=True)
     out, inn, slot, sout = adj.nbr_out.cpu(), adj.nbr_in.cpu(), adj.slot_in.cpu(), adj.slot_out.cpu()
     D = adj.D
     assert D % 4 == 0 and D >= max(int(mask.sum(2).max()), int(mask.sum(1).max()), 1)
@@ -419,7 +419,7 @@ def test_adjacency_from_positions(N, width, R, dtype):
     a = build_adjacency(S.to(dev))
     p_ = build_adjacency_from_positions(pos.to(dev), R)
     assert a.D == p_.D
-    for name in ("nbr_out", "nbr_in", "slot_in", "slot_out"):
+    for name in ("nbr_out", "nbr_in", "slot_in"):
         assert torch.equal(getattr(a, name), getattr(p_, name)), name
 
 
@@ -539,7 +539,7 @@ def test_gso_in_host_memory_gives_the_same_adjacency_and_output(golden):
         S[2, 0, 0, 1] = 5e-10
         a, b = build_adjacency(S.to(dev)), build_adjacency_host(S, dev)
         assert a.D == b.D
-        for k in ("nbr_out", "nbr_in", "slot_in", "slot_out"):
+        for k in ("nbr_out", "nbr_in", "slot_in"):
             assert torch.equal(getattr(a, k), getattr(b, k)), (N, k)
     d, meta = golden.case("kq_concat_c2")
     layer = make_layer(meta, d, dev)
