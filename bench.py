@@ -329,7 +329,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override instances per GPU")
-    ap.add_argument("--path", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--path", default="auto", choices=["auto", "simt", "tcgen05", "fused"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -396,6 +396,27 @@ def main():
     ms_train = timed(step_train, args.steps, args.warmup, dist_on, sampler)
     clocks = sampler.summary()
     ms_fwd = timed(step_fwd, args.steps, args.warmup, dist_on)
+
+    # ---- the single-launch fused forward (path="fused"), beside the default multi-launch path ---------------------
+    fused_fwd = None
+    if N >= 64 and N % 4 == 0 and w["G"] == 128 and w["concat"] and w["K"] <= 3:
+        try:
+            fused_fwd = {}
+            layer.path = "fused"
+            for team in (8, 16):
+                layer.fused_team = team
+                c1 = L.magat_launch_count()
+                step_fwd()
+                n_l = L.magat_launch_count() - c1
+                ms_ff = timed(step_fwd, args.steps, 3, dist_on)
+                fused_fwd[f"team{team}"] = {"ms_per_step": ms_ff, "value": units / (ms_ff * 1e-3), "unit": "agent-steps/s",
+                                            "launches": int(n_l), "frac_of_hbm_roofline": None}
+            fused_fwd["note"] = ("magat_gat_forward_fused: ONE cooperative launch from the dense GSO to y, intermediates in "
+                                 "an L2-resident per-team scratch (ncu DRAM traffic: profiles/r02_ncu_fused.md); slower "
+                                 "than the multi-launch path on B200, hence opt-in")
+        except Exception as exc:
+            fused_fwd = {"error": str(exc)[-300:]}
+        layer.path, layer.fused_team = args.path, 0
 
     # ---- the same step captured in a CUDA graph (small graphs are launch-bound: ~20 launches of a few us each) ----
     # Needs a forward without host synchronisation: the list width comes from N (N <= 32) or from a max-degree promise
@@ -662,6 +683,10 @@ def main():
             traffic_src = "ncu dram__bytes_read+write.sum over the forward launches: profiles/" + tdb[args.workload]["source"]
     except Exception:
         pass
+    if fused_fwd and "error" not in fused_fwd:
+        for k in ("team8", "team16"):
+            if k in fused_fwd:
+                fused_fwd[k]["frac_of_hbm_roofline"] = bytes_fwd / (fused_fwd[k]["ms_per_step"] * 1e-3) / 1e9 / hbm_peak
     roofline = {
         "bound": "hbm", "kernel": f"forward path ({sum(k['launches_per_step'] for k in kernels)} launches: "
                                   "GSO scan + neighbour lists + attention + taps + projection)",
@@ -695,7 +720,7 @@ def main():
                    "parallelism": f"batch-sharded x{world}, grad all-reduce (NCCL)" if dist_on else "1 GPU"},
         "fwd": {"value": units / (ms_fwd * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms_fwd},
         "roofline": roofline, "train_kernels": train_kernels, "cpu_baseline": cpu_baseline, "e2e": e2e,
-        "positions_input": positions, "cuda_graph": graphed,
+        "positions_input": positions, "cuda_graph": graphed, "fused_forward": fused_fwd,
         "gpu_launches": int(launches_per_step) * args.steps, "gpu_launches_per_step": int(launches_per_step),
         "clocks": clocks,
     }

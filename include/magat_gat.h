@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define MAGAT_ABI_VERSION 8
+#define MAGAT_ABI_VERSION 9
 
 enum {
   MAGAT_OK = 0,
@@ -165,6 +165,10 @@ typedef struct magat_gat_fused_args {
   int32_t mode, concat, relu;
   int32_t s_dtype;            /* MAGAT_DT_* of S */
   int32_t save;               /* 1: keep taps / sproj / wprep for magat_gat_backward */
+  int32_t team;               /* CTAs per planning instance: 0 = default (8), or 8 / 16.  16 halves the instances in flight:
+                                 the per-team scratch then fits L2 with room to spare (DRAM traffic 4.0 instead of 8.0 GB at
+                                 B = 512, N = 1000) at ~25 % more time */
+  int32_t reserved;
   const void* S;              /* [B][1][N][N] */
   const float* x; int64_t x_sb, x_sn;
   const float* weight; const float* mixer; const float* weight_bias; const float* filterWeight; const float* bias;
@@ -176,7 +180,7 @@ typedef struct magat_gat_fused_args {
 } magat_gat_fused_args;
 
 int magat_gat_fused_supported(int N, int G, int F, int K, int P, int D, int mode, int concat);
-size_t magat_gat_fused_workspace_bytes(int B, int N, int K, int P, int D, int mode, int save);
+size_t magat_gat_fused_workspace_bytes(int B, int N, int K, int P, int D, int mode, int save, int team);
 int magat_gat_forward_fused(const magat_gat_fused_args* a, void* stream);
 
 /* ---- backward (what autograd does over graphML.py:1180-1286,713-823,1724-1827) ---- */

@@ -12,7 +12,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmagat_gat.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 MODE_KEYQUERY, MODE_GAT_MODIFIED, MODE_GSO_VALUES = 0, 1, 2
 DT_F32, DT_F64 = 0, 1
@@ -60,7 +60,7 @@ class BwdArgs(C.Structure):
 
 class FusedArgs(C.Structure):
     _fields_ = [(n, _i32) for n in ("B", "N", "G", "F", "K", "P", "D", "mode", "concat", "relu", "s_dtype",
-                                    "save")] + [
+                                    "save", "team", "reserved")] + [
         ("S", _ptr), ("x", _ptr), ("x_sb", _i64), ("x_sn", _i64),
         ("weight", _ptr), ("mixer", _ptr), ("weight_bias", _ptr), ("filterWeight", _ptr), ("bias", _ptr),
         ("y", _ptr), ("y_sb", _i64), ("y_sn", _i64), ("y_sc", _i64),
@@ -129,7 +129,7 @@ def lib():
         L.magat_gat_forward_small.restype = C.c_int
         L.magat_gat_fused_supported.argtypes = [C.c_int] * 8
         L.magat_gat_fused_supported.restype = C.c_int
-        L.magat_gat_fused_workspace_bytes.argtypes = [C.c_int] * 7
+        L.magat_gat_fused_workspace_bytes.argtypes = [C.c_int] * 8
         L.magat_gat_fused_workspace_bytes.restype = C.c_size_t
         L.magat_gat_forward_fused.argtypes = [C.POINTER(FusedArgs), _ptr]
         L.magat_gat_forward_fused.restype = C.c_int

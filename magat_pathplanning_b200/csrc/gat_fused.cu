@@ -2,7 +2,7 @@
 // :1724-1827, :1180-1286, :713-823 behind it) for the shapes the planners train at scale: G = F = 128, K <= 3,
 // P in {1,2,4}, heads concatenated.
 //
-// One cooperative, persistent launch.  A TEAM of 8 CTAs owns one planning instance at a time; everything the
+// One cooperative, persistent launch.  A TEAM of 8 (or 16) CTAs owns one planning instance at a time; everything the
 // instance needs between reading its dense GSO and writing y lives in a few MB of per-team scratch that is reused
 // for the team's next instance, i.e. stays in L2 and never travels to HBM:
 //
@@ -45,7 +45,7 @@ constexpr int WIMG_BYTES = 4 * WATOM;        // W_p^T image: hi atom 0/1, lo ato
 constexpr int ACC_COL0 = 384;                // TMEM: filter taps in columns [0, K*G), accumulators at 384 + 64 a
 constexpr int NTHREADS = 768, NWARPS = NTHREADS / 32;
 constexpr int TMA_WARP = 0, MMA_WARP = 1, EPI_WARP0 = 4;       // warps 4..7: TMEM lane quarter = warp % 4
-constexpr int TEAM = 8;
+constexpr int TEAM_DEFAULT = 8;              // CTAs per planning instance (a multiple of P; 16 halves the instances in flight)
 constexpr size_t SMEM_BYTES = (size_t)NST * STAGE_BYTES + WIMG_BYTES + 1024 + 256;
 constexpr long long WATCHDOG_CYCLES = 6000000000ll;            // ~3 s: a lost arrival traps instead of hanging the GPU
 
@@ -54,7 +54,7 @@ struct FusedParams {
   alignas(64) CUtensorMap tm_u;              // tap image [teams][N][P * (K-1) * 256] bf16, box 64 x 64
   int B, N, K, P, D, W, WS;                  // W = ceil(N / 32) mask words per row, WS = W rounded up to 4
   int mode, relu, save, s_f64;
-  int nteams, nsplit, chunk, tiles;
+  int nteams, team_size, nsplit, chunk, tiles;
   const void* S;
   const float* x; long x_sb, x_sn;
   const float* weight; const float* mixer; const float* wb; const float* H; const float* bias;
@@ -126,6 +126,15 @@ __device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, 
 
 // Data produced inside this launch by another CTA: L2 is the point of coherence, so bypass L1 (ld.global.cg).
 
+// Scratch that has been consumed is dead, but L2 does not know: left alone, its dirty lines are written back to HBM when
+// the next instances push them out (4.5 GB per forward at the default workload -- more than the layer's output).
+// discard.global.L2 drops the lines without a write-back.  All threads of the CTA; base and size multiples of 128 B.
+__device__ __forceinline__ void discard_lines(const void* base, size_t bytes) {
+  const char* q = reinterpret_cast<const char*>(base);
+  for (size_t off = (size_t)threadIdx.x * 128; off < bytes; off += (size_t)NTHREADS * 128)
+    asm volatile("discard.global.L2 [%0], 128;" ::"l"(q + off) : "memory");
+}
+
 // one image row (256 bf16: hi[128] | lo[128]); lane l owns features 4l .. 4l+3
 __device__ __forceinline__ void image_store(uint16_t* row, int lane, const float4& v) {
   uint2 hi, lo;
@@ -136,13 +145,13 @@ __device__ __forceinline__ void image_store(uint16_t* row, int lane, const float
 }
 // Team barrier: every thread publishes its writes (also towards the TMA engine of the other CTAs), one thread per CTA
 // arrives on the team's counter and waits until all TEAM CTAs have.
-__device__ __forceinline__ void team_barrier(unsigned* cnt, unsigned& target, int32_t* status, long long* prof,
-                                             long long& prof_t, int slot) {
+__device__ __forceinline__ void team_barrier(unsigned* cnt, unsigned& target, int team_size, int32_t* status,
+                                             long long* prof, long long& prof_t, int slot) {
   fence_proxy_async_all();
   __syncthreads();
   if (threadIdx.x == 0) {
     PROF_MARK(slot);                          // work of the phase that ends here
-    target += TEAM;
+    target += (unsigned)team_size;
     __threadfence();
     red_release_add(cnt, 1u);
     const long long t0 = clock64();
@@ -196,7 +205,7 @@ __device__ __forceinline__ void scan_units(const FusedParams& p, const T* Sb, in
     int kq = 0;
     if (lane == 0) kq = (stop != nullptr && *stop >= stop_at) ? -1 : atomicAdd(counter, 1);   // background pass: until the tensor-core roles are through
     kq = __shfl_sync(0xffffffffu, kq, 0);
-    const int u = r + TEAM * kq;
+    const int u = r + p.team_size * kq;
     if (kq < 0 || kq >= units || u >= units) break;
     const int seg = u % segs, band = u / segs;
     const int j0 = seg * 128 + lane * 4;
@@ -529,6 +538,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gat_fused(const __grid_constant
   int gphase = 0;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int TEAM = p.team_size;
   const int team = blockIdx.x / TEAM, r = blockIdx.x % TEAM;
   const int P = p.P, K = p.K, N = p.N;
   const int head = r % P, split = r / P;
@@ -641,8 +651,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gat_fused(const __grid_constant
                       p.colbits + ((size_t)team * 2 + (par ^ 1)) * N * p.WS};
     const bool bg = bn < p.B && bg_warp;
     scan_job(p, cur, r, lane, scan_ctr);                       // whatever the background passes left over (all of it for it = 0)
-    team_barrier(bar, bar_target, p.status, prof, prof_t, 0);
+    team_barrier(bar, bar_target, TEAM, p.status, prof, prof_t, 0);
     if (threadIdx.x == 0) *scan_ctr = 0;                        // (published by the __syncthreads below)
+    if (it > 0 && n1 > n0) {
+      // every CTA of the team is past the previous instance's projection: its operand images are dead
+      discard_lines(p.ximg + (((size_t)team * 2 + (par ^ 1)) * N + n0) * 256, (size_t)(n1 - n0) * 512);
+      if (K > 1) discard_lines(uimg + (size_t)n0 * P * (K - 1) * 256, (size_t)(n1 - n0) * P * (K - 1) * 512);
+    }
 
     // ================= neighbour lists of my nodes =========================================================
     phase_lists(p, rowbase, n0, n1, rowbits, colbits, reinterpret_cast<int32_t*>(smem), warp, lane);
@@ -737,7 +752,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gat_fused(const __grid_constant
       else if (P == 2) phase_mixer_gm<2>(p, xb, n0, n1, warp, lane, gm_cd, sproj);
       else phase_mixer_gm<1>(p, xb, n0, n1, warp, lane, gm_cd, sproj);
     }
-    team_barrier(bar, bar_target, p.status, prof, prof_t, 3);
+    team_barrier(bar, bar_target, TEAM, p.status, prof, prof_t, 3);
 
     // ================= attention ===================================================================================
     if (kq) {
@@ -752,12 +767,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gat_fused(const __grid_constant
 
     // ================= taps ========================================================================================
     for (int k = 1; k < K; ++k) {
-      team_barrier(bar, bar_target, p.status, prof, prof_t, 3 + 2 * k);
+      team_barrier(bar, bar_target, TEAM, p.status, prof, prof_t, 3 + 2 * k);
+      if (k == 1 && kq && !p.save && n1 > n0)        // R of my rows: read by this CTA's attention only, and that is over
+        discard_lines(sproj + (size_t)n0 * P * FT, (size_t)(n1 - n0) * P * FT * 4);
       if (P == 4) phase_gather<4>(p, rowbase, xb, n0, n1, warp, lane, k, uimg, taps);
       else if (P == 2) phase_gather<2>(p, rowbase, xb, n0, n1, warp, lane, k, uimg, taps);
       else phase_gather<1>(p, rowbase, xb, n0, n1, warp, lane, k, uimg, taps);
     }
-    if (K > 1) team_barrier(bar, bar_target, p.status, prof, prof_t, 3 + 2 * K);
+    if (K > 1) team_barrier(bar, bar_target, TEAM, p.status, prof, prof_t, 3 + 2 * K);
+    if (!p.save && K > 2 && n1 > n0)                 // fp32 u_1 of my rows: the last gather level has read it
+      discard_lines(taps + (size_t)n0 * P * (K - 1) * FT, (size_t)(n1 - n0) * P * (K - 1) * FT * 4);
 
     // ================= projection: Y_p[tile] = H_p [x | u_1 | u_2]^T + b, ReLU (TS form, H_p in TMEM) ==========
     ++gphase;
@@ -858,6 +877,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gat_fused(const __grid_constant
     // buffered), and every later phase of it sits behind a team barrier all CTAs reach after this projection
     __syncthreads();
     PROF_MARK(11);
+    if (K == 1 && kq && !p.save && n1 > n0) discard_lines(sproj + (size_t)n0 * P * FT, (size_t)(n1 - n0) * P * FT * 4);
   }
 
   if (lane == 0) {
@@ -894,13 +914,11 @@ struct WsLayout {
 };
 
 // status (64 B) | team counters | per-team scratch
-WsLayout ws_layout(int B, int N, int K, int P, int D, int mode, int save) {
+WsLayout ws_layout(int B, int N, int K, int P, int D, int mode, int save, int TEAM) {
   WsLayout L{};
   int sms = device_sm_count();
   if (sms <= 0) sms = 148;
   L.nteams = sms / TEAM;
-  static const int team_cap = getenv("MAGAT_FUSED_TEAMS") ? atoi(getenv("MAGAT_FUSED_TEAMS")) : 0;   // experiments
-  if (team_cap > 0 && L.nteams > team_cap) L.nteams = team_cap;
   if (L.nteams > B) L.nteams = B;
   if (L.nteams < 1) L.nteams = 1;
   const size_t T = (size_t)L.nteams;
@@ -935,9 +953,14 @@ extern "C" int magat_gat_fused_supported(int N, int G, int F, int K, int P, int 
   return 1;
 }
 
-extern "C" size_t magat_gat_fused_workspace_bytes(int B, int N, int K, int P, int D, int mode, int save) {
-  if (B < 1 || N < 1 || K < 1 || P < 1 || D < 1) return 0;
-  return ws_layout(B, N, K, P, D, mode, save).total;
+static int team_of(int requested, int P) {
+  const int t = requested > 0 ? requested : TEAM_DEFAULT;
+  return (t == 8 || t == 16) && t % P == 0 ? t : 0;
+}
+
+extern "C" size_t magat_gat_fused_workspace_bytes(int B, int N, int K, int P, int D, int mode, int save, int team) {
+  if (B < 1 || N < 1 || K < 1 || P < 1 || D < 1 || team_of(team, P) == 0) return 0;
+  return ws_layout(B, N, K, P, D, mode, save, team_of(team, P)).total;
 }
 
 extern "C" int magat_gat_forward_fused(const magat_gat_fused_args* a, void* stream) {
@@ -964,7 +987,9 @@ extern "C" int magat_gat_forward_fused(const magat_gat_fused_args* a, void* stre
                 "multiples of 4 floats, unit channel stride");
   MAGAT_REQUIRE((long)a->B * a->N * a->D * a->P < (1l << 31) && (long)a->N * a->x_sn < (1l << 31), MAGAT_E_UNSUPPORTED,
                 "magat_gat_forward_fused: batch or row stride too large for the 32-bit index math");
-  const WsLayout L = ws_layout(a->B, a->N, a->K, a->P, a->D, a->mode, a->save);
+  const int TEAM = team_of(a->team, a->P);
+  MAGAT_REQUIRE(TEAM != 0, MAGAT_E_BAD_ARG, "magat_gat_forward_fused: team must be 0 (default), 8 or 16 (got %d)", a->team);
+  const WsLayout L = ws_layout(a->B, a->N, a->K, a->P, a->D, a->mode, a->save, TEAM);
   MAGAT_REQUIRE(a->ws_bytes >= L.total, MAGAT_E_BAD_ARG, "magat_gat_forward_fused: workspace %zu B < %zu B", a->ws_bytes,
                 L.total);
   cudaStream_t st = (cudaStream_t)stream;
@@ -977,7 +1002,7 @@ extern "C" int magat_gat_forward_fused(const magat_gat_fused_args* a, void* stre
   fp.B = a->B; fp.N = a->N; fp.K = a->K; fp.P = a->P; fp.D = a->D;
   fp.W = (a->N + 31) / 32; fp.WS = (fp.W + 3) / 4 * 4;
   fp.mode = a->mode; fp.relu = a->relu; fp.save = a->save; fp.s_f64 = a->s_dtype == MAGAT_DT_F64;
-  fp.nteams = L.nteams; fp.nsplit = TEAM / a->P;
+  fp.nteams = L.nteams; fp.team_size = TEAM; fp.nsplit = TEAM / a->P;
   fp.chunk = (a->N + TEAM - 1) / TEAM;
   fp.tiles = (a->N + TN - 1) / TN;
   fp.S = a->S; fp.x = a->x; fp.x_sb = a->x_sb; fp.x_sn = a->x_sn;

@@ -269,10 +269,10 @@ class _Meta:
 class _FusedGSO:
     """The dense GSO on its way into the fused forward (which builds the neighbour lists itself); ``adj`` holds the
     lists the kernel wrote."""
-    __slots__ = ("S", "D", "trusted", "adj", "overflow")
+    __slots__ = ("S", "D", "trusted", "adj", "overflow", "team")
 
-    def __init__(self, S, D, trusted):
-        self.S, self.D, self.trusted, self.adj, self.overflow = S, D, trusted, None, False
+    def __init__(self, S, D, trusted, team=0):
+        self.S, self.D, self.trusted, self.adj, self.overflow, self.team = S, D, trusted, None, False, team
 
 
 class _GATFunction(torch.autograd.Function):
@@ -352,10 +352,11 @@ class _GATFunction(torch.autograd.Function):
             while True:
                 lists = torch.empty((3, B, N, D), dtype=torch.int32, device=dev)
                 att = torch.empty((B, N, D, P), dtype=torch.float32, device=dev)
-                nbytes = L.magat_gat_fused_workspace_bytes(B, N, K, P, D, meta.mode, int(save))
+                nbytes = L.magat_gat_fused_workspace_bytes(B, N, K, P, D, meta.mode, int(save), gso.team)
                 ws = _workspace(dev, nbytes)
                 a = _cabi.FusedArgs(B=B, N=N, G=G, F=F, K=K, P=P, D=D, mode=meta.mode, concat=1, relu=int(meta.relu),
                                     s_dtype=_cabi.DT_F32 if S.dtype == torch.float32 else _cabi.DT_F64, save=int(save),
+                                    team=gso.team, reserved=0,
                                     S=S.data_ptr(), x=xt.data_ptr(), x_sb=_sb(xt), x_sn=_sn(xt),
                                     weight=weight_c.data_ptr(), mixer=_p(mixer_c), weight_bias=_p(wb_c),
                                     filterWeight=filt_c.data_ptr(), bias=_p(bias_c),
@@ -507,7 +508,7 @@ def _small_forward(x, S, filterWeight, mixer, weight, weight_bias, bias, mode, c
     return y, DenseAttention(aij)
 
 
-def _fused_gso(x, S, G, F, K, P, mode, concatenate, path, max_degree):
+def _fused_gso(x, S, G, F, K, P, mode, concatenate, path, max_degree, team=0):
     """The dense GSO wrapped for the fused forward, or None when that kernel does not cover the call."""
     B, N = x.shape[0], x.shape[2]
     if not (S.is_cuda and len(S.shape) == 4 and S.shape[0] == B and S.shape[1] == 1 and S.shape[2] == N
@@ -528,12 +529,12 @@ def _fused_gso(x, S, G, F, K, P, mode, concatenate, path, max_degree):
     xt = _node_major(x.detach())
     if S.data_ptr() % 16 or xt.data_ptr() % 16 or _sn(xt) % 4 or _sb(xt) % 4 or xt.dtype != torch.float32:
         return None
-    return _FusedGSO(S, D, bool(max_degree))
+    return _FusedGSO(S, D, bool(max_degree), int(team or 0))
 
 
 def gat_layer(x, S, filterWeight, mixer, weight, weight_bias, bias, *, mode: int, concatenate: bool,
               relu: bool = True, path: str = "auto", adjacency: Optional[Adjacency] = None,
-              max_degree: Optional[int] = None):
+              max_degree: Optional[int] = None, fused_team: int = 0):
     """One call of the fused layer.  Returns ``(y, attention)``; ``attention.dense()`` / ``.dense_mean()`` give
     ``aij`` [B,P,1,N,N] / its head mean on demand."""
     _require_cuda(x, "x")
@@ -564,7 +565,7 @@ def gat_layer(x, S, filterWeight, mixer, weight, weight_bias, bias, *, mode: int
             raise NotImplementedError("edge_features E != 1 is not supported")
         adjacency = build_adjacency_host(S, x.device, max_degree)
     if adjacency is None and path in ("auto", "fused") and S is not None:
-        fused = _fused_gso(x, S, G, F, K, P, mode, concatenate, path, max_degree)
+        fused = _fused_gso(x, S, G, F, K, P, mode, concatenate, path, max_degree, fused_team)
     if path == "fused" and fused is None and adjacency is None:
         raise RuntimeError("path='fused': shape / layout not covered by the fused forward (magat_gat_fused_supported)")
     if fused is not None:
@@ -851,6 +852,8 @@ class GraphFilterBatchAttentional(nn.Module):
         #: optional promise that no agent has more than this many in- or out-neighbours: lets the fused forward size
         #: its neighbour lists without reading the degree statistics back (no host synchronisation in forward)
         self.max_degree = None
+        #: CTAs per planning instance of the fused forward (path="fused"): 0 = default (8), or 16
+        self.fused_team = 0
         self._last = None
         self._aij = None
         self._adj = None
@@ -936,7 +939,7 @@ class GraphFilterBatchAttentional(nn.Module):
         y, att = gat_layer(x, self.S, self.filterWeight, self.mixer, self.weight, self.weight_bias,
                            self.bias, mode=_mode_of(self.attentionMode), concatenate=self.concatenate,
                            relu=fused_relu, path=self.path, adjacency=getattr(self, "_adj", None),
-                           max_degree=getattr(self, "max_degree", None))
+                           max_degree=getattr(self, "max_degree", None), fused_team=getattr(self, "fused_team", 0))
         self._last, self._aij = att, None
         if not fused_relu:
             y = self.nonlinearity(y)

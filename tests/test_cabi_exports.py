@@ -39,8 +39,8 @@ def test_struct_sizes_match_header(built):
     # 12 x int32 + 21 x 8 bytes ; 18 x int32 + 32 x 8 bytes
     assert ctypes.sizeof(built.FwdArgs) == 12 * 4 + 21 * 8
     assert ctypes.sizeof(built.BwdArgs) == 18 * 4 + 32 * 8
-    # 12 x int32 + 23 x 8 bytes
-    assert ctypes.sizeof(built.FusedArgs) == 12 * 4 + 23 * 8
+    # 14 x int32 + 23 x 8 bytes
+    assert ctypes.sizeof(built.FusedArgs) == 14 * 4 + 23 * 8
 
 
 def test_sizes_helpers_need_no_gpu(built):
@@ -69,9 +69,11 @@ def test_fused_entry_point_rejects_without_crashing(built):
     assert L.magat_gat_fused_supported(1000, 128, 128, 3, 4, 36, built.MODE_KEYQUERY, 1) == 0     # D > 32
     assert L.magat_gat_fused_supported(1001, 128, 128, 3, 4, 16, built.MODE_KEYQUERY, 1) == 0     # N % 4
     assert L.magat_gat_fused_supported(1000, 64, 64, 3, 4, 16, built.MODE_KEYQUERY, 1) == 0
-    n = L.magat_gat_fused_workspace_bytes(512, 1000, 3, 4, 16, built.MODE_KEYQUERY, 0)
+    n = L.magat_gat_fused_workspace_bytes(512, 1000, 3, 4, 16, built.MODE_KEYQUERY, 0, 0)
     assert 0 < n < 1 << 30
-    assert L.magat_gat_fused_workspace_bytes(512, 1000, 3, 4, 16, built.MODE_KEYQUERY, 1) < n
+    assert L.magat_gat_fused_workspace_bytes(512, 1000, 3, 4, 16, built.MODE_KEYQUERY, 1, 0) < n
+    assert L.magat_gat_fused_workspace_bytes(512, 1000, 3, 4, 16, built.MODE_KEYQUERY, 0, 16) < n       # fewer teams
+    assert L.magat_gat_fused_workspace_bytes(512, 1000, 3, 4, 16, built.MODE_KEYQUERY, 0, 12) == 0
 
 
 def test_functional_signatures_match_reference():

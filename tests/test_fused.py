@@ -146,6 +146,27 @@ def test_fused_falls_back_when_a_vertex_has_more_than_32_neighbours():
     assert xd.grad is not None
 
 
+def test_fused_teams_of_sixteen():
+    """fused_team = 16: twice the CTAs per instance, half the instances in flight (the scratch then fits L2)."""
+    dev = torch.device("cuda:0")
+    G = F = 128
+    K, P, B, N = 3, 4, 11, 300
+    gen = torch.Generator().manual_seed(61)
+    params = orc.init_params(G, F, K, P, mode="KeyQuery", generator=gen, weight_bias_std=0.1)
+    S = orc.random_geometric_gso(B, N, generator=gen).to(dev)
+    x = torch.relu(torch.randn(B, N, G, generator=gen)).permute(0, 2, 1).to(dev)
+    layer = _layer(params, dict(G=G, F=F, K=K, P=P, concat=True, mode="KeyQuery"), dev, "fused")
+    with torch.no_grad():
+        layer.addGSO(S)
+        y8 = layer(x)
+        layer.fused_team = 16
+        layer.addGSO(S)
+        y16 = layer(x)
+    assert torch.equal(y8, y16)
+    y_ref, _ = orc.gat_layer_forward(x[:3].cpu(), S[:3].cpu(), params, mode="KeyQuery", concatenate=True)
+    assert rel_err(y16[:3], y_ref) < TOL
+
+
 def test_fused_is_one_launch():
     from magat_pathplanning_b200 import _cabi
     dev = torch.device("cuda:0")

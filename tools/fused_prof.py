@@ -19,6 +19,7 @@ def main():
     layer, S, x_mem, dy_mem = bench.make_problem(w, dev, bench.SEED)
     layer.path = "fused"
     layer.max_degree = 16
+    layer.fused_team = int(os.environ.get("MAGAT_TEAM", "8"))
     x = x_mem.permute(0, 2, 1)
     for _ in range(3):
         if train:
@@ -37,11 +38,10 @@ def main():
     ws = list(graphML._ws_cache.values())[0]
     off = (-ws.data_ptr()) % 1024
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    T = min(sms // 8, w["B"])
-    if os.environ.get("MAGAT_FUSED_TEAMS"):
-        T = min(T, int(os.environ["MAGAT_FUSED_TEAMS"]))
+    TEAM = int(os.environ.get("MAGAT_TEAM", "8"))
+    T = min(sms // TEAM, w["B"])
     off_prof = (64 + T * 128 + 1023) // 1024 * 1024
-    prof = ws[off + off_prof: off + off_prof + T * 8 * 16 * 8].view(torch.int64).view(T * 8, 16).cpu().double()
+    prof = ws[off + off_prof: off + off_prof + T * TEAM * 16 * 8].view(torch.int64).view(T * TEAM, 16).cpu().double()
     mhz = 1965.0
     per_inst = prof / (w["B"] / T) / mhz          # us per instance per CTA
     print(f"{name} B={w['B']} teams={T} {'train' if train else 'infer'}: per-instance us (mean over CTAs / max)")
