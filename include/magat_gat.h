@@ -134,8 +134,8 @@ typedef struct magat_gat_fwd_args {
   /* outputs */
   float* y; int64_t y_sb, y_sn, y_sc;
   float* att;                 /* [B][N][D][P] */
-  float* ain;                 /* [B][N][P][D] receiver-major copy of att (scratch of the fused tcgen05 kernel; may be
-                                 NULL, which disables that kernel); needs D % 4 == 0 */
+  float* ain;                 /* [B][N][P][D] receiver-major copy of att: only the general (non-vectorised) gather kernels
+                                 use it, and only when slot_out is given; may be NULL */
   float* taps;                /* [B][N][P][K-1][G] (unused when K == 1) */
   /* scratch (caller allocated) */
   float* wprep;               /* magat_gat_wprep_floats(...) floats */
@@ -144,8 +144,8 @@ typedef struct magat_gat_fwd_args {
 
 size_t magat_gat_wprep_floats(int G, int F, int K, int P, int mode);
 int magat_gat_forward(const magat_gat_fwd_args* a, void* stream);
-/* How many tap planes (k = 1..) of a->taps the forward call leaves valid for these arguments: K-1, or 1
- * when the fused tcgen05 kernel gathers the second tap on the fly.  Pass it on as bwd.taps_valid. */
+/* How many tap planes (k = 1..) of a->taps the forward call leaves valid for these arguments (K-1 today).  Pass it on
+ * as bwd.taps_valid; magat_gat_backward rebuilds the planes above it. */
 int magat_gat_forward_taps_valid(const magat_gat_fwd_args* a);
 
 

@@ -544,7 +544,6 @@ int tc_split_weights_t(const float* W, int G, int P, __nv_bfloat16* hi, __nv_bfl
 
 bool tap_tc_supported(const magat_gat_fwd_args* a);              // gat_tap_tc.cu
 bool score_tc_supported(const magat_gat_fwd_args* a);
-bool tap_tc_gathers_u2();
 int score_tc_forward(const magat_gat_fwd_args* a, float* wt, cudaStream_t st);
 int tap_tc_forward(const magat_gat_fwd_args* a, cudaStream_t st);
 
@@ -620,7 +619,7 @@ static int forward_impl(const magat_gat_fwd_args* a, cudaStream_t st, bool use_t
   }
   // the attention kernel also scatters the receiver-major copy `ain` when the caller provides it
   // (the lean gather kernels read the senders' softmax rows through slot_in and need no receiver-major copy)
-  const bool lean = vec_ok && !tap_tc_gathers_u2() && lean_sparse_ok(a->x_sb, a->x_sn, N, G, K, P, D) &&
+  const bool lean = vec_ok && lean_sparse_ok(a->x_sb, a->x_sn, N, G, K, P, D) &&
                     ((uintptr_t)a->nbr_in % 16) == 0 && ((uintptr_t)a->nbr_out % 16) == 0;
   const int32_t* so = (a->ain && a->slot_out && a->mode != MAGAT_MODE_GSO_VALUES && !lean) ? a->slot_out : nullptr;
   float* ain_w = so ? a->ain : nullptr;
@@ -691,11 +690,10 @@ static int forward_impl(const magat_gat_fwd_args* a, cudaStream_t st, bool use_t
     }
   }
   if (a->mode != MAGAT_MODE_GSO_VALUES && (rc = check_launch("k_attention", st))) return rc;
-  // 2. taps (the fused tcgen05 kernel gathers the second tap itself and only needs u_1 in memory)
-  const int k_last = (fused && tap_tc_gathers_u2()) ? (K - 1 < 1 ? K - 1 : 1) : K - 1;
-  for (int k = 1; k <= k_last; ++k)
+  // 2. taps
+  for (int k = 1; k < K; ++k)
     if ((rc = run_tap_gather(a->x, a->x_sb, a->x_sn, a->att, a->nbr_in, a->slot_in, B, N, G, K, P, D, k, a->taps,
-                             (ain_w || (fused && k == 1)) ? a->ain : nullptr, ain_w ? 1 : 0, st)))
+                             ain_w ? a->ain : nullptr, ain_w ? 1 : 0, st)))
       return rc;
   // 3. per-(head, tap) projection + bias + activation + concat / head mean
   if (fused) return tap_tc_forward(a, st);
@@ -720,8 +718,6 @@ extern "C" size_t magat_gat_wprep_floats(int G, int F, int K, int P, int mode) {
 // number of tap planes (k = 1 .. K-1) magat_gat_forward leaves valid in a->taps for these arguments
 extern "C" int magat_gat_forward_taps_valid(const magat_gat_fwd_args* a) {
   if (a == nullptr || a->K <= 1) return 0;
-  const bool use_tc = a->path == MAGAT_PATH_TCGEN05 || (a->path == MAGAT_PATH_AUTO && tc_supported(a));
-  if (use_tc && tc_supported(a) && tap_tc_supported(a) && tap_tc_gathers_u2()) return 1;
   return a->K - 1;
 }
 

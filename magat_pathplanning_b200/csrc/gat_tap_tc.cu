@@ -2,19 +2,13 @@
 //
 //   Y_p^T [F x nodes] = H_p [F x K*G] . Z_p^T,   Z_p[n] = [ x_n | u_1^p[n] | u_2^p[n] ]
 //
-// Each persistent CTA owns ONE head p.  Its filter taps H_p, split into bf16 hi/lo, are written once
-// into TMEM (K*G 32-bit columns: two K elements per column) and used as the A operand of every
-// tcgen05.mma (TS form); shared memory is therefore free for the node-side operand, which the
-// producer warps BUILD instead of load: x and u_1 rows straight from global, u_2 rows gathered on the
-// fly, u_2[j] = sum_{i in in(j)} A_p[i,j] u_1^p[i], so the second tap never exists in HBM.  Three MMAs
-// per 16-wide K step (hi.hi + lo.hi + hi.lo) give fp32-level accuracy.  The accumulator tile
-// [F=128 lanes x 64 nodes] is double buffered in the remaining 128 TMEM columns; the epilogue warps
-// add bias, apply ReLU, transpose through shared memory and store full 512 B rows of y.
-//
-//   warps 0-15  producers, four groups of four; group g builds every fourth 128-wide K slice
-//               ([64 nodes x 128 k] -> hi/lo tiles, SWIZZLE_128B K-major) into its own smem stage
-//   warps 16-23 epilogue (warp 16+e: TMEM lane quarter e%4, node half e/4)
-//   warp  24    MMA issuer (one thread): 24 MMAs per stage, then tcgen05.commit frees the stage
+// Each persistent CTA owns ONE weight-block group (a head, or `nout` blocks that share one operand tile).  Its weights,
+// split into bf16 hi/lo, are written once into TMEM (two K elements per 32-bit column) and used as the A operand of
+// every tcgen05.mma (TS form); shared memory is therefore free for the node-side operand, which arrives by TMA tensor
+// copies and is converted to bf16 hi/lo by shared-memory-only converter warps.  Three MMAs per 16-wide K step
+// (hi.hi + lo.hi + hi.lo) give fp32-level accuracy.  The accumulator tile [F=128 lanes x 64 nodes] is double buffered
+// in the remaining 128 TMEM columns; the epilogue warps add bias, apply ReLU and store 128 B lines straight from
+// registers.  Also used with K = 1 for the KeyQuery score projection, the backward gz = dP H and the dense part of dx.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
@@ -27,25 +21,12 @@ namespace magat {
 
 namespace {
 
-// MAGAT_DBG=<bits> switches parts of the kernel off for bottleneck experiments (1 loads, 2 smem stores,
-// 4 global stores, 16 epilogue math, 32 MMAs, 128 gather).  Compiled out unless -DMAGAT_DBG_KNOBS.
-#ifdef MAGAT_DBG_KNOBS
-#define DBGBIT(p, b) ((p).dbg & (b))
-#else
-#define DBGBIT(p, b) 0
-#endif
-
 constexpr int TN = 64;                       // nodes per tile = UMMA N
 constexpr int SK = 128;                      // K elements per stage = two 64-wide swizzle atoms
-constexpr int STAGES = 4;                    // one per producer group
 constexpr int ATOM_BYTES = TN * 64 * 2;      // 8 KB: bf16 [64 rows x 64 k], SWIZZLE_128B
 constexpr int STAGE_BYTES = 4 * ATOM_BYTES;  // hi atom 0/1, lo atom 0/1
 constexpr int FT = 128;                      // out-features = UMMA M = TMEM lanes
-constexpr int EPI_BYTES = TN * FT * 4;       // 32 KB transposition buffer
-constexpr int PROD_WARPS = 16, PROD_GROUP = 128;
-constexpr int EPI_WARP0 = 16;                 // epilogue warps 16 .. 16+EW-1, then the MMA warp
 constexpr int ACC_COL0 = 384;                // accumulators: columns 384 + 64 a
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
 
 struct TapParams {
   // v2 kernel: 2-D views [rows][row stride] of x, the optional mask and the taps buffer; one box = 64 rows x 128 floats
@@ -58,385 +39,18 @@ struct TapParams {
   int x_hdiv; long x_hmul;               // head h reads x + (h / x_hdiv) * x_hmul (0 in the forward)
   const float* mask; long m_sb, m_sn;    // optional: x is zeroed where mask <= 0 (same head offset rule)
   const float* u1;       // taps buffer, tap k = 1 of head p of node m at u1 + (m*P + p)*(K-1)*G
-  const float* ain; const int32_t* nbr_in;   // ain[m][p][s] = A_p[nbr_in[m][s], m]
   const float* H;        // filterWeight [P][F][K*G]
   const float* bias; int relu;
   float* y; long y_sb, y_sn;     // channel stride 1
-  int nout;                      // v2 kernel: P counts weight blocks; nout consecutive blocks share one operand tile
-  int accum;                     // v2 kernel: y += result (the caller guarantees one weight-block group, i.e. no two CTAs
-                                 // ever touch the same output row)
-  int epi_direct;                // 1: y rows are flat (y_sb == N * y_sn): the epilogue stores straight from registers
-  int gather_u2;                 // 1: tap k = 2 is gathered on the fly from u_1; 0: read from the taps buffer
-  int dbg;                       // experiment knobs; only read when built with -DMAGAT_DBG_KNOBS
+  int nout;                      // P counts weight blocks; nout consecutive blocks share one operand tile
+  int accum;                     // y += result (the caller guarantees one weight-block group, i.e. no two CTAs ever touch
+                                 // the same output row)
 };
 
-// hi_dst / lo_dst are shared-window addresses (tc::smem_u32): st.shared, not the generic ST the compiler emits for
-// pointers it cannot prove to be shared (the first source-level profile showed ST.E / LD.E on every smem access
-// of this kernel)
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ void split_store(uint32_t hi_dst, uint32_t lo_dst, const float4& a, const float4& b) {
-  uint4 hi, lo;
-  tc::split2(a.x, a.y, hi.x, lo.x);
-  tc::split2(a.z, a.w, hi.y, lo.y);
-  tc::split2(b.x, b.y, hi.z, lo.z);
-  tc::split2(b.z, b.w, hi.w, lo.w);
-  st_shared_v4(hi_dst, hi);
-  st_shared_v4(lo_dst, lo);
-}
-__device__ __forceinline__ void fma44(float4& acc, float a, const float4& v) {
-  acc.x = fmaf(a, v.x, acc.x); acc.y = fmaf(a, v.y, acc.y); acc.z = fmaf(a, v.z, acc.z); acc.w = fmaf(a, v.w, acc.w);
-}
-
-// EW = epilogue warps: 8 for the K = 1 uses (score projection, backward gU), which are paced by the epilogue,
-// 4 for the K-tap projection, which is paced by the producers and wants their 96-register budget.
-template <int EW>
-__global__ void __launch_bounds__((17 + EW) * 32, 1) k_tap_tc(const __grid_constant__ TapParams p) {
-  constexpr int EPI_WARPS = EW, MMA_WARP = EPI_WARP0 + EW;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  float* epi = reinterpret_cast<float*>(smem + (size_t)STAGES * STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES + EPI_BYTES);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + STAGES;
-  uint64_t* acc_full = bars + 2 * STAGES;
-  uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int head = blockIdx.x % p.P;
-  const int slot = blockIdx.x / p.P, nslots = gridDim.x / p.P;
-  const int KG = p.K * p.G;
-  const int nst = KG / SK;                   // stages (128-wide K slices) per tile
-  const int sps = p.G / SK;                  // stages per K segment
-  const long tiles = (p.rows + TN - 1) / TN;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      tc::mbar_init(&full[s], PROD_GROUP);
-      tc::mbar_init(&empty[s], 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      tc::mbar_init(&acc_full[a], 1);
-      tc::mbar_init(&acc_empty[a], EPI_WARPS * 32);
-    }
-    tc::fence_barrier_init();
-  }
-  if (warp == MMA_WARP) tc::tmem_alloc<512>(tmem_slot);
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  // ---- filter taps of this head -> TMEM (hi at columns [0, KG/2), lo at [KG/2, KG)) --------------
-  if (warp < 4) {
-    const int f = warp * 32 + lane;          // TMEM lane = output feature
-    const float* hrow = p.H + ((size_t)head * FT + f) * KG;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    for (int k0 = 0; k0 < KG; k0 += 32) {
-      uint32_t hi[16], lo[16];
-#pragma unroll
-      for (int j = 0; j < 16; j += 2) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(hrow + k0 + 2 * j));
-        tc::split2(v.x, v.y, hi[j], lo[j]);
-        tc::split2(v.z, v.w, hi[j + 1], lo[j + 1]);
-      }
-      tc::tmem_st16(lane_addr + (uint32_t)(k0 / 2), hi);
-      tc::tmem_st16(lane_addr + (uint32_t)(KG / 2 + k0 / 2), lo);
-    }
-    tc::tmem_st_wait();
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  tc::tc_fence_after();
-
-  if (warp < PROD_WARPS) {
-    // ===== producers ======================================================================
-    // Four groups of 128 threads; group g builds every stage-chunk q with q % 4 == g, always into smem stage g.
-    // A thread owns the 16 B column group c16 (+8 for the second atom) of rows r0 + 16 i.  32-bit index math
-    // (the host guarantees rows * P * D < 2^31).
-    const unsigned grp = warp >> 2;
-    const int tg = threadIdx.x & (PROD_GROUP - 1);
-    const int c16 = tg & 7;
-    const int r0 = tg >> 3;
-    const unsigned N = (unsigned)p.N, D = (unsigned)p.D;
-    const int rows = (int)p.rows;
-    const unsigned u1_row4 = (unsigned)(p.P * (p.K - 1) * p.G) >> 2;      // float4 per node in the taps buffer
-    const float4* u1h4 = reinterpret_cast<const float4*>(p.u1 + (long)head * (p.K - 1) * p.G);
-    const long x_hoff = p.x_hmul ? (long)(head / p.x_hdiv) * p.x_hmul : 0;
-    const float4* x4 = reinterpret_cast<const float4*>(p.x + x_hoff);
-    const float4* mk4 = p.mask ? reinterpret_cast<const float4*>(p.mask + x_hoff) : nullptr;
-    const uint32_t st = tc::smem_u32(smem + (size_t)grp * STAGE_BYTES);
-    uint32_t sw_off[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) sw_off[i] = tc::sw128_offset(r0 + 16 * i, c16);
-    unsigned q = 0;                           // running stage-chunk counter of the CTA
-    for (long tile = slot; tile < tiles; tile += nslots) {
-      const int m0 = (int)(tile * TN);
-      for (int s = 0; s < nst; ++s, ++q) {
-        if ((q & 3u) != grp) continue;
-        const uint32_t phase = (q >> 2) & 1u;
-        const int seg = s / sps;
-        const unsigned k4 = (unsigned)(((s - seg * sps) * SK + c16 * 8) >> 2);    // float4 offset inside the row
-        if (seg < 2 || !p.gather_u2) {
-          // x or a materialised tap: straight copy.  All 16 loads of the thread are in flight before the stage is awaited.
-          float4 va[2][4], vb[2][4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int m = m0 + r0 + 16 * i;
-            const float4* src = nullptr;
-            const float4* msk = nullptr;
-            if (m < rows && !DBGBIT(p, 1)) {
-              if (seg == 0) {
-                const unsigned b = (unsigned)m / N;
-                src = x4 + (((long)b * p.x_sb + (long)((unsigned)m - b * N) * p.x_sn) >> 2) + k4;
-                if (mk4) msk = mk4 + (((long)b * p.m_sb + (long)((unsigned)m - b * N) * p.m_sn) >> 2) + k4;
-              } else {
-                src = u1h4 + (size_t)(unsigned)m * u1_row4 + (unsigned)((seg - 1) * (p.G >> 2)) + k4;
-              }
-            }
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              if (src != nullptr) {
-                va[hh][i] = __ldg(src + hh * 16);
-                vb[hh][i] = __ldg(src + hh * 16 + 1);
-              } else {
-                va[hh][i] = vb[hh][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-              }
-              if (msk != nullptr) {
-                const float4 ma = __ldg(msk + hh * 16), mb = __ldg(msk + hh * 16 + 1);
-                float4& A = va[hh][i];
-                float4& Bv = vb[hh][i];
-                A.x = ma.x > 0.f ? A.x : 0.f; A.y = ma.y > 0.f ? A.y : 0.f;
-                A.z = ma.z > 0.f ? A.z : 0.f; A.w = ma.w > 0.f ? A.w : 0.f;
-                Bv.x = mb.x > 0.f ? Bv.x : 0.f; Bv.y = mb.y > 0.f ? Bv.y : 0.f;
-                Bv.z = mb.z > 0.f ? Bv.z : 0.f; Bv.w = mb.w > 0.f ? Bv.w : 0.f;
-              }
-            }
-          }
-          tc::mbar_wait(&empty[grp], phase ^ 1);
-          if (!DBGBIT(p, 2)) {
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh)
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-                split_store(st + hh * ATOM_BYTES + sw_off[i], st + (2 + hh) * ATOM_BYTES + sw_off[i], va[hh][i],
-                            vb[hh][i]);
-          }
-        } else {
-          // second tap gathered on the fly: u_2[j] = sum_i A_p[i,j] u_1^p[i].  One (row, atom) at a time, four
-          // neighbour rows (128 B) in flight per thread; index / weight lists are contiguous per receiver.
-          tc::mbar_wait(&empty[grp], phase ^ 1);
-#pragma unroll 1
-          for (int i = 0; i < 4; ++i) {
-            const int m = m0 + r0 + 16 * i;
-            const bool live = m < rows && !DBGBIT(p, 1) && !DBGBIT(p, 128);
-            const unsigned bN = live ? ((unsigned)m / N) * N : 0u;
-            const int32_t* nb = p.nbr_in + (unsigned)(live ? m : 0) * D;
-            const float* aw_p = p.ain + ((unsigned)(live ? m : 0) * (unsigned)p.P + head) * D;
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-              if (live) {
-                for (unsigned s0 = 0; s0 < D; s0 += 4) {
-                  const int4 id = __ldg(reinterpret_cast<const int4*>(nb + s0));
-                  if (id.x < 0) break;                       // lists are packed
-                  const float4 aw = __ldg(reinterpret_cast<const float4*>(aw_p + s0));
-                  const int ids[4] = {id.x, id.y, id.z, id.w};
-                  // weights of absent entries may be uninitialised memory: force 0 so 0 * garbage never makes a NaN
-                  const float aws[4] = {id.x >= 0 ? aw.x : 0.f, id.y >= 0 ? aw.y : 0.f, id.z >= 0 ? aw.z : 0.f,
-                                        id.w >= 0 ? aw.w : 0.f};
-                  float4 ta[4], tb[4];
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    if (ids[e] >= 0) {
-                      const float4* src = u1h4 + (size_t)(bN + (unsigned)ids[e]) * u1_row4 + k4 + hh * 16;
-                      ta[e] = __ldg(src);
-                      tb[e] = __ldg(src + 1);
-                    } else {
-                      ta[e] = tb[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                  }
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    fma44(a, aws[e], ta[e]);
-                    fma44(b, aws[e], tb[e]);
-                  }
-                }
-              }
-              if (!DBGBIT(p, 2))
-                split_store(st + hh * ATOM_BYTES + sw_off[i], st + (2 + hh) * ATOM_BYTES + sw_off[i], a, b);
-            }
-          }
-        }
-        tc::fence_proxy_async();
-        tc::mbar_arrive(&full[grp]);
-      }
-    }
-  } else if (warp < MMA_WARP) {
-    // ===== epilogue =======================================================================
-    // Eight warps: warp e reads TMEM lane quarter (e & 3) (the quarter a warp may touch is warp % 4) and the
-    // 32-node half (e >> 2) of the accumulator, then stores 8 of the 64 output rows.  The first profile showed
-    // this role, not the MMAs or the producers, pacing the K = 1 uses of the kernel (4 warps busy 100 % of the
-    // time, a third of their instructions the emulated integer division m / N per stored row), hence the
-    // incremental (batch, node) bookkeeping below.
-    const int e = warp - EPI_WARP0;
-    const int qd = e & 3, half = e >> 2;
-    constexpr int HALVES = 8 / EW;             // 32-node halves of the accumulator this warp drains
-    constexpr int ROWS = TN / EW;              // output rows this warp stores
-    const int f = qd * 32 + lane;
-    const float bias = p.bias ? __ldg(p.bias + f) : 0.f;
-    const unsigned N = (unsigned)p.N;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    if (p.epi_direct) {
-      // Flat output rows: lane f of the warp holds feature f of 32 consecutive nodes, so one scalar store per node
-      // is a full 128 B line of that node's row -- no transposition, no shared memory, no barrier between the
-      // epilogue warps.  (The staged variant below paced every use of this kernel: the MMA issuer spent its
-      // time waiting for acc_empty, profiles/r01b_tap_tc_lsu.md.)
-      for (long tile = slot; tile < tiles; tile += nslots) {
-        const long m0 = tile * TN;
-        tc::mbar_wait(&acc_full[acc], acc_phase);
-        tc::tc_fence_after();
-#pragma unroll
-        for (int hh = 0; hh < HALVES; ++hh) {
-          const int hsel = HALVES == 1 ? half : hh;
-          const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(ACC_COL0 + acc * TN + 32 * hsel);
-          float v[32];
-          tc::tmem_ld32(taddr, v);
-          tc::tmem_ld_wait();
-          if (hh == HALVES - 1) {
-            tc::tc_fence_before();
-            tc::mbar_arrive(&acc_empty[acc]);    // this warp's slice of the accumulator is in registers
-          }
-          const long mrow = m0 + 32 * hsel;
-          float* dst = p.y + mrow * p.y_sn + (long)head * FT + f;
-          const long left = p.rows - mrow;
-          if (left >= 32) {
-#pragma unroll
-            for (int n = 0; n < 32; ++n) {
-              float o = v[n] + bias;
-              if (p.relu) o = fmaxf(o, 0.f);
-              __stcs(dst + (long)n * p.y_sn, o);
-            }
-          } else {
-#pragma unroll
-            for (int n = 0; n < 32; ++n) {
-              float o = v[n] + bias;
-              if (p.relu) o = fmaxf(o, 0.f);
-              if (n < left) __stcs(dst + (long)n * p.y_sn, o);
-            }
-          }
-        }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      }
-    } else
-    for (long tile = slot; tile < tiles; tile += nslots) {
-      const long m0 = tile * TN;
-      tc::mbar_wait(&acc_full[acc], acc_phase);
-      tc::tc_fence_after();
-#pragma unroll
-      for (int hh = 0; hh < HALVES; ++hh) {
-        const int hsel = HALVES == 1 ? half : hh;
-        const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(ACC_COL0 + acc * TN + 32 * hsel);
-        float v[32];
-        tc::tmem_ld32(taddr, v);
-        tc::tmem_ld_wait();
-        if (hh == HALVES - 1) {
-          tc::tc_fence_before();
-          tc::mbar_arrive(&acc_empty[acc]);    // this warp's slice of the accumulator is in registers
-        }
-        if (!DBGBIT(p, 16)) {
-          float* col = epi + (32 * hsel) * FT + f;
-          if (p.relu) {
-#pragma unroll
-            for (int n = 0; n < 32; ++n) col[n * FT] = fmaxf(v[n] + bias, 0.f);
-          } else {
-#pragma unroll
-            for (int n = 0; n < 32; ++n) col[n * FT] = v[n] + bias;
-          }
-        }
-      }
-      tc::named_bar_sync(1, EPI_WARPS * 32);
-      // 64 rows x 512 B: each warp ROWS rows, one float4 per lane
-      if (!DBGBIT(p, 4)) {
-        const long mfirst = m0 + e * ROWS;
-        unsigned bq = (unsigned)mfirst / N;
-        unsigned r = (unsigned)mfirst - bq * N;
-        float* dst = p.y + (long)bq * p.y_sb + (long)r * p.y_sn + (long)head * FT + lane * 4;
-        const float* src = epi + (e * ROWS) * FT + lane * 4;
-        const long left = p.rows - mfirst;
-#pragma unroll
-        for (int i = 0; i < ROWS; ++i) {
-          if (i < left) __stcs(reinterpret_cast<float4*>(dst), *reinterpret_cast<const float4*>(src + i * FT));
-          dst += p.y_sn;
-          if (++r == N) {                       // next batch element
-            r = 0;
-            dst += p.y_sb - (long)N * p.y_sn;
-          }
-        }
-      }
-      tc::named_bar_sync(1, EPI_WARPS * 32);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-  } else {
-    // ===== MMA issuer =====================================================================
-    constexpr uint32_t idesc = tc::make_idesc_bf16(FT, TN);
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    unsigned q = 0;
-    for (long tile = slot; tile < tiles; tile += nslots) {
-      tc::mbar_wait(&acc_empty[acc], acc_phase ^ 1);
-      tc::tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(ACC_COL0 + acc * TN);
-      for (int s = 0; s < nst; ++s, ++q) {
-        const int stage = (int)(q & 3u);
-        const uint32_t phase = (q >> 2) & 1u;
-        tc::mbar_wait(&full[stage], phase);
-        tc::tc_fence_after();
-        if (tc::elect_one()) {
-          const uint32_t sb = tc::smem_u32(smem + (size_t)stage * STAGE_BYTES);
-          const uint32_t h_hi = tmem_base + (uint32_t)(s * (SK / 2));
-          const uint32_t h_lo = h_hi + (uint32_t)(KG / 2);
-          if (!DBGBIT(p, 32)) {
-#pragma unroll
-            for (int at = 0; at < 2; ++at) {
-              const uint64_t z_hi = tc::make_sw128_desc(sb + at * ATOM_BYTES);
-              const uint64_t z_lo = tc::make_sw128_desc(sb + (2 + at) * ATOM_BYTES);
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                const uint64_t adv = (uint64_t)((kk * 32) >> 4);
-                const uint32_t col = (uint32_t)(at * 32 + kk * 8);
-                tc::umma_bf16_ts(tmem_d, h_hi + col, z_hi + adv, idesc, (s | at | kk) != 0);
-                tc::umma_bf16_ts(tmem_d, h_lo + col, z_hi + adv, idesc, 1);
-                tc::umma_bf16_ts(tmem_d, h_hi + col, z_lo + adv, idesc, 1);
-              }
-            }
-          }
-          tc::umma_commit(&empty[stage]);
-          if (s == nst - 1) tc::umma_commit(&acc_full[acc]);
-        }
-        __syncwarp();
-      }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-    }
-  }
-  tc::tc_fence_before();
-  __syncthreads();
-  if (warp == MMA_WARP) {
-    tc::tc_fence_after();
-    tc::tmem_dealloc<512>(tmem_base);
-  }
-}
-
 // ================================================================================================================
-// v2: the same GEMM with a TMA-fed operand pipeline.
-//
-// The source-level profile of the kernel above (profiles/r01b_tap_tc_lsu.md) showed the LSU data pipe 71 % busy and
-// every role queueing behind it: producer threads holding 16 global loads each (spilling), generic-space shared
-// stores, the staged epilogue.  Here nothing but the unavoidable fp32 -> bf16 hi/lo conversion goes through the
-// LSU:
+// Roles.  (A first version built the operand with SIMT producer warps straight from global memory; its source-level
+// profile -- profiles/r01b_tap_tc_lsu.md -- showed the LSU data pipe 71 % busy and every role queueing behind it.)
+// Here nothing but the unavoidable fp32 -> bf16 hi/lo conversion goes through the LSU:
 //   warp 21      copy issuer: raw fp32 node rows -> shared-memory ring, one cp.async.bulk.tensor.2d per 64 x 128 box
 //                (per-row 512 B bulk copies capped the K-tap use at ~70 cycles per row), mbarrier completion;
 //                128 KB in flight
@@ -734,13 +348,13 @@ __global__ void __launch_bounds__(256) k_transpose_w(const float* __restrict__ W
   Wt[i] = W[(p * G + g) * G + gp];
 }
 
-// v2 needs flat inputs and outputs (one row stride over the whole batch), no on-the-fly second tap; nout > 1 only
-// with one K slice.  Fills the tensor maps of tq.
+// The kernel needs flat inputs and outputs (one row stride over the whole batch); nout > 1 only with one K slice.
+// Fills the tensor maps of tq.
 bool tap_tc2_prepare(TapParams& tq, int x_width) {
   if (tq.nout < 1 || tq.P % tq.nout != 0 || tq.rows >= (1l << 31)) return false;
   const int nst = tq.K * tq.G / SK;
   if (tq.G % SK != 0 || tq.nout * nst * SK > ACC_COL0 || (tq.nout > 1 && nst != 1)) return false;
-  if (tq.y_sb != (long)tq.N * tq.y_sn || tq.gather_u2) return false;
+  if (tq.y_sb != (long)tq.N * tq.y_sn) return false;
   if (tq.x_sb != (long)tq.N * tq.x_sn) return false;
   if (!tma::make_row_map(&tq.tm_x, tq.x, tq.rows, x_width, tq.x_sn, TN, SK)) return false;
   if (tq.mask) {
@@ -753,44 +367,32 @@ bool tap_tc2_prepare(TapParams& tq, int x_width) {
   return true;
 }
 
-int launch_tap_tc(const TapParams& tp, int P, cudaStream_t st, const char* what, bool v2_only = false) {
+// Returns -1 when the layout cannot be described to the kernel (the *_supported predicates below rule that out for
+// the callers that have no other route).
+int launch_tap_tc(const TapParams& tp, cudaStream_t st, const char* what) {
   const int sm_count = device_sm_count();
   TapParams tq = tp;
-#ifdef MAGAT_DBG_KNOBS
-  const char* dbg = getenv("MAGAT_DBG");
-  tq.dbg = dbg ? atoi(dbg) : 0;
-#else
-  tq.dbg = 0;
-#endif
   const long tiles = (tp.rows + TN - 1) / TN;
   // logical width of an x row: every weight-block group reads its own 128-wide (G-wide) column window
   const int x_width = tp.x_hmul ? (int)(((tp.P - 1) / tp.x_hdiv) * tp.x_hmul) + tp.G : tp.G;
-  if (tap_tc2_prepare(tq, x_width)) {
-    int rc0 = ensure_dyn_smem(KID_TAP_TC2, (const void*)k_tap_tc2<false>, V2_SMEM_BYTES, "k_tap_tc2<false>");
-    if (!rc0) rc0 = ensure_dyn_smem(KID_TAP_TC2M, (const void*)k_tap_tc2<true>, V2_SMEM_BYTES, "k_tap_tc2<true>");
-    if (rc0) return rc0;
-    const int ngroups = tp.P / tp.nout;
-    long slots = sm_count / ngroups;
-    if (slots < 1) slots = 1;
-    if (slots > tiles) slots = tiles;
-    tq.epi_direct = 1;
-    if (tp.mask) k_tap_tc2<true><<<(int)(slots * ngroups), V2_THREADS, V2_SMEM_BYTES, st>>>(tq);
-    else k_tap_tc2<false><<<(int)(slots * ngroups), V2_THREADS, V2_SMEM_BYTES, st>>>(tq);
-    return check_launch(what, st);
-  }
-  if (v2_only) return -1;
-  // v1: one weight block per CTA
-  tq.nout = 1;
-  int rc0 = ensure_dyn_smem(KID_TAP_TC4, (const void*)k_tap_tc<4>, SMEM_BYTES, "k_tap_tc<4>");
-  if (!rc0) rc0 = ensure_dyn_smem(KID_TAP_TC8, (const void*)k_tap_tc<8>, SMEM_BYTES, "k_tap_tc<8>");
+  if (!tap_tc2_prepare(tq, x_width)) return -1;
+  int rc0 = ensure_dyn_smem(KID_TAP_TC2, (const void*)k_tap_tc2<false>, V2_SMEM_BYTES, "k_tap_tc2<false>");
+  if (!rc0) rc0 = ensure_dyn_smem(KID_TAP_TC2M, (const void*)k_tap_tc2<true>, V2_SMEM_BYTES, "k_tap_tc2<true>");
   if (rc0) return rc0;
-  tq.epi_direct = (tp.y_sb == (long)tp.N * tp.y_sn) ? 1 : 0;
-  long slots = sm_count / P;
+  const int ngroups = tp.P / tp.nout;
+  long slots = sm_count / ngroups;
   if (slots < 1) slots = 1;
   if (slots > tiles) slots = tiles;
-  if (tq.K == 1) k_tap_tc<8><<<(int)(slots * P), (17 + 8) * 32, SMEM_BYTES, st>>>(tq);
-  else k_tap_tc<4><<<(int)(slots * P), (17 + 4) * 32, SMEM_BYTES, st>>>(tq);
+  if (tp.mask) k_tap_tc2<true><<<(int)(slots * ngroups), V2_THREADS, V2_SMEM_BYTES, st>>>(tq);
+  else k_tap_tc2<false><<<(int)(slots * ngroups), V2_THREADS, V2_SMEM_BYTES, st>>>(tq);
   return check_launch(what, st);
+}
+
+// -1 (layout not describable after the *_supported check passed: a tensor map could not be encoded) becomes an error
+int must_launch(int rc, const char* what) {
+  if (rc >= 0) return rc;
+  set_error("%s: cuTensorMapEncodeTiled rejected the operand layout", what);
+  return MAGAT_E_CUDA;
 }
 
 }  // namespace
@@ -802,6 +404,7 @@ bool score_tc_supported(const magat_gat_fwd_args* a) {
   if ((a->x_sn % 4) != 0 || (a->x_sb % 4) != 0 || ((uintptr_t)a->x % 16) != 0 || ((uintptr_t)a->sproj % 16) != 0)
     return false;
   if ((long)a->B * a->N * a->D * a->P >= (1l << 31)) return false;
+  if (a->x_sb != (long)a->N * a->x_sn) return false;                   // flat rows (one stride over the whole batch)
   return true;
 }
 
@@ -815,13 +418,13 @@ int score_tc_forward(const magat_gat_fwd_args* a, float* wt, cudaStream_t st) {
   tp.N = a->N; tp.G = a->G; tp.K = 1; tp.P = a->P; tp.D = a->D;
   tp.x = a->x; tp.x_sb = a->x_sb; tp.x_sn = a->x_sn;
   tp.x_hdiv = 1; tp.x_hmul = 0; tp.mask = nullptr;
-  tp.u1 = nullptr; tp.ain = nullptr; tp.nbr_in = nullptr;
+  tp.u1 = nullptr;
   tp.H = wt;
   tp.bias = nullptr; tp.relu = 0;
   tp.y = a->sproj; tp.y_sb = (long)a->N * a->P * a->G; tp.y_sn = (long)a->P * a->G;
   // heads that share one converted x tile (their W_p^T blocks sit side by side in TMEM)
   tp.nout = (a->P % 3 == 0) ? 3 : (a->P % 2 == 0) ? 2 : 1;
-  return launch_tap_tc(tp, a->P, st, "k_tap_tc(score projection)");
+  return must_launch(launch_tap_tc(tp, st, "k_tap_tc(score projection)"), "score projection");
 }
 
 // Ht[(p*K + k)][g][f] = H[p][f][k][g]: the backward projection gz = dP H as the same kernel
@@ -844,6 +447,7 @@ bool gz_tc_supported(const magat_gat_bwd_args* a) {
   if (a->relu && (a->y_sc != 1 || (a->y_sn % 4) || (a->y_sb % 4) || ((uintptr_t)a->y % 16))) return false;
   if (((uintptr_t)a->gz % 16) != 0) return false;
   if ((long)a->B * a->N * a->D * a->P >= (1l << 31)) return false;
+  if (a->dy_sb != (long)a->N * a->dy_sn || (a->relu && a->y_sb != (long)a->N * a->y_sn)) return false;   // flat rows
   return true;
 }
 
@@ -864,7 +468,7 @@ int gz_tc_backward(const magat_gat_bwd_args* a, float* ht, cudaStream_t st) {
   tp.H = ht;
   tp.bias = nullptr; tp.relu = 0;
   tp.y = a->gz; tp.y_sn = (long)a->P * a->K * a->G; tp.y_sb = (long)a->N * tp.y_sn;
-  return launch_tap_tc(tp, tp.P, st, "k_tap_tc(gz = dP H)");
+  return must_launch(launch_tap_tc(tp, st, "k_tap_tc(gz = dP H)"), "gz = dP H");
 }
 
 // Wcat[h][g][pl*G + g'] = W[2h + pl][g][g'] (block h starts at h * G * 2G; its rows are G * nsl long, nsl = heads in it)
@@ -909,18 +513,7 @@ int dx_tap_partials(const magat_gat_bwd_args* a, float* wcat, float* dxp, cudaSt
   k_pack_wcat<<<cdiv((long)P * G * G, 256), 256, 0, st>>>(a->weight, G, P, wcat);
   int rc = check_launch("k_pack_wcat", st);
   if (rc) return rc;
-  return launch_tap_tc(tp, tp.P, st, "k_tap_tc(dx partials = dR W^T)", true);
-}
-
-// MAGAT_FUSE_U2=1 keeps the second tap out of HBM (gathered by the producer warps); measured slower than
-// materialising it with k_tap_gather_v (0.87 ms of exposed gather against 0.47 + 0.15 ms), so it is opt-in.
-bool tap_tc_gathers_u2() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MAGAT_FUSE_U2");
-    v = (e && atoi(e) != 0) ? 1 : 0;
-  }
-  return v == 1;
+  return launch_tap_tc(tp, st, "k_tap_tc(dx partials = dR W^T)");
 }
 
 bool tap_tc_supported(const magat_gat_fwd_args* a) {
@@ -931,13 +524,11 @@ bool tap_tc_supported(const magat_gat_fwd_args* a) {
   if (a->K > 1 && ((uintptr_t)a->taps % 16) != 0) return false;
   if (a->P > 64) return false;
   if ((long)a->B * a->N * a->D * a->P >= (1l << 31)) return false;     // 32-bit index math in the kernel
-  if (a->K > 2 && tap_tc_gathers_u2() && (a->ain == nullptr || a->D % 4 != 0 || ((uintptr_t)a->ain % 16) != 0 ||
-                   ((uintptr_t)a->nbr_in % 16) != 0))
-    return false;
+  if (a->x_sb != (long)a->N * a->x_sn || a->y_sb != (long)a->N * a->y_sn) return false;   // flat rows
   return true;
 }
 
-// needs tap k = 1 (u_1) in a->taps when K >= 2; never reads or writes tap k = 2
+// needs the taps k = 1 .. K-1 in a->taps
 int tap_tc_forward(const magat_gat_fwd_args* a, cudaStream_t st) {
   TapParams tp{};
   tp.rows = (long)a->B * a->N;
@@ -945,13 +536,11 @@ int tap_tc_forward(const magat_gat_fwd_args* a, cudaStream_t st) {
   tp.x = a->x; tp.x_sb = a->x_sb; tp.x_sn = a->x_sn;
   tp.x_hdiv = 1; tp.x_hmul = 0; tp.mask = nullptr;
   tp.u1 = a->taps;
-  tp.gather_u2 = tap_tc_gathers_u2() ? 1 : 0;
-  tp.ain = a->ain; tp.nbr_in = a->nbr_in;
   tp.H = a->filterWeight;
   tp.bias = a->bias; tp.relu = a->relu;
   tp.y = a->y; tp.y_sb = a->y_sb; tp.y_sn = a->y_sn;
   tp.nout = 1;
-  return launch_tap_tc(tp, a->P, st, "k_tap_tc(fused taps + projection)");
+  return must_launch(launch_tap_tc(tp, st, "k_tap_tc(fused taps + projection)"), "K-tap projection");
 }
 
 }  // namespace magat
