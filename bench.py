@@ -492,96 +492,91 @@ def main():
         x_h.copy_(x_mem)
         # The batch crosses PCIe in chunks on a copy stream while the previous chunk is being processed (two device
         # buffers); parameter gradients accumulate over the chunks exactly as they do over one big batch.
-        nchunk = 8 if B % 8 == 0 and B >= 64 else 1
+        nchunk = 16 if B % 16 == 0 and B >= 256 else (8 if B % 8 == 0 and B >= 64 else 1)
         cb = B // nchunk
         S_d = [torch.empty((cb,) + tuple(S.shape[1:]), dtype=S.dtype, device=dev) for _ in range(2)]
         x_d = [torch.empty((cb,) + tuple(x_mem.shape[1:]), dtype=x_mem.dtype, device=dev) for _ in range(2)]
         copy_stream = torch.cuda.Stream(device=dev)
 
-        def step_e2e_dense():
-            """The GSO crosses PCIe as the dense fp32 tensor (2.3 GB per step at the default workload)."""
-            main = torch.cuda.current_stream(dev)
-            for p in params:
-                p.grad = None
-            loss_acc = torch.zeros((), device=dev)
-            ready, done = [None] * nchunk, [None] * nchunk
-
-            def enqueue_copy(c):
-                with torch.cuda.stream(copy_stream):
-                    if c >= 2:
-                        copy_stream.wait_event(done[c - 2])            # buffer c % 2 is free again
-                    else:
-                        copy_stream.wait_stream(main)
-                    S_d[c % 2].copy_(S_h[c * cb:(c + 1) * cb], non_blocking=True)
-                    x_d[c % 2].copy_(x_h[c * cb:(c + 1) * cb], non_blocking=True)
-                    ready[c] = copy_stream.record_event()
-            enqueue_copy(0)
-            for c in range(nchunk):
-                if c + 1 < nchunk:
-                    enqueue_copy(c + 1)
-                main.wait_event(ready[c])
-                xg = x_d[c % 2].permute(0, 2, 1).requires_grad_(True)
-                layer.addGSO(S_d[c % 2])
-                y = layer(xg)
-                loss = (y * dy[c * cb:(c + 1) * cb]).sum()
-                loss.backward()
-                loss_acc += loss.detach()
-                done[c] = main.record_event()
-            return float(loss_acc.item())           # D2H read of the step's result
-
         from concurrent.futures import ThreadPoolExecutor
         from magat_pathplanning_b200 import build_adjacency_from_rowbits, pack_gso_host
         packer = ThreadPoolExecutor(max_workers=1)
-        pack_threads = max(1, min(32, (os.cpu_count() or 1) // max(1, world)))      # the ranks of a box share its cores
+        # the ranks of a box share its cores; one core stays with the thread that feeds the GPU
+        pack_threads = max(1, min(32, (os.cpu_count() or 1) // max(1, world) - 1))
 
-        def step_e2e():
-            """The GSO stays in (pinned) host memory, where the reference's dataloader / simulator builds it: its edge
-            mask is packed on the host cores (pack_gso_host: one streaming pass, all cores, the packing of chunk c+1
-            under the GPU work on chunk c) and N^2 / 8 bytes per instance cross PCIe instead of 4 N^2."""
-            main = torch.cuda.current_stream(dev)
-            for p in params:
-                p.grad = None
-            loss_acc = torch.zeros((), device=dev)
-            ready, done = [None] * nchunk, [None] * nchunk
+        def make_step(dense_chunks):
+            """One end-to-end training step over the batch in `nchunk` chunks.  Every chunk's inputs start in pinned
+            HOST memory.  x is copied as is.  The GSO of a chunk in `dense_chunks` crosses PCIe as the dense fp32 tensor
+            (copy engine) and is scanned on the device; the GSO of the other chunks stays on the host, where its edge
+            mask is packed by the host cores (pack_gso_host) so that N^2 / 8 bytes cross PCIe.  The preparation of
+            chunk c+1 (copies, packing) runs under the GPU work on chunk c."""
+            dense_chunks = frozenset(dense_chunks)
+            order = {c: k for k, c in enumerate(sorted(dense_chunks))}       # dense chunk -> its S_d buffer turn
 
-            def enqueue_copy(c):
-                with torch.cuda.stream(copy_stream):
-                    if c >= 2:
-                        copy_stream.wait_event(done[c - 2])
+            def step():
+                main = torch.cuda.current_stream(dev)
+                for p in params:
+                    p.grad = None
+                loss_acc = torch.zeros((), device=dev)
+                ready, done = [None] * nchunk, [None] * nchunk
+                dense_sorted = sorted(dense_chunks)
+
+                def prepare(c):
+                    fut = None
+                    if c not in dense_chunks:
+                        fut = packer.submit(pack_gso_host, S_h[c * cb:(c + 1) * cb], pack_threads)
+                    with torch.cuda.stream(copy_stream):
+                        if c >= 2:
+                            copy_stream.wait_event(done[c - 2])            # x buffer c % 2 is free again
+                        else:
+                            copy_stream.wait_stream(main)
+                        x_d[c % 2].copy_(x_h[c * cb:(c + 1) * cb], non_blocking=True)
+                        if c in dense_chunks:
+                            k = order[c]
+                            if k >= 2:
+                                copy_stream.wait_event(done[dense_sorted[k - 2]])   # S buffer k % 2 is free again
+                            S_d[k % 2].copy_(S_h[c * cb:(c + 1) * cb], non_blocking=True)
+                        ready[c] = copy_stream.record_event()
+                    return fut
+                fut = prepare(0)
+                for c in range(nchunk):
+                    bits = fut.result() if fut is not None else None
+                    if c + 1 < nchunk:
+                        fut = prepare(c + 1)
+                    main.wait_event(ready[c])
+                    if bits is None:
+                        layer.addGSO(S_d[order[c] % 2])
                     else:
-                        copy_stream.wait_stream(main)
-                    x_d[c % 2].copy_(x_h[c * cb:(c + 1) * cb], non_blocking=True)
-                    ready[c] = copy_stream.record_event()
-            fut = packer.submit(pack_gso_host, S_h[0:cb], pack_threads)
-            enqueue_copy(0)
-            for c in range(nchunk):
-                bits = fut.result()
-                if c + 1 < nchunk:
-                    fut = packer.submit(pack_gso_host, S_h[(c + 1) * cb:(c + 2) * cb], pack_threads)
-                    enqueue_copy(c + 1)
-                main.wait_event(ready[c])
-                layer.addAdjacency(build_adjacency_from_rowbits(bits, dev))
-                xg = x_d[c % 2].permute(0, 2, 1).requires_grad_(True)
-                y = layer(xg)
-                loss = (y * dy[c * cb:(c + 1) * cb]).sum()
-                loss.backward()
-                loss_acc += loss.detach()
-                done[c] = main.record_event()
-            return float(loss_acc.item())
+                        layer.addAdjacency(build_adjacency_from_rowbits(bits, dev))
+                    xg = x_d[c % 2].permute(0, 2, 1).requires_grad_(True)
+                    y = layer(xg)
+                    loss = (y * dy[c * cb:(c + 1) * cb]).sum()
+                    loss.backward()
+                    loss_acc += loss.detach()
+                    done[c] = main.record_event()
+                return float(loss_acc.item())           # D2H read of the step's result
+            return step
+
+        # (Mixing the two ingest routes -- some chunks dense over the copy engine, the others packed on the host -- was
+        # measured and does not pay: both read the same host memory, 43.7 ms with half the chunks each way against 25.6 ms
+        # all packed and 42.8 ms all dense on the 16-core bench host.)
+        step_e2e = make_step(set())
+        step_e2e_dense = make_step(set(range(nchunk)))
         e2e_steps = max(2, min(args.steps, 5))
         ms_e2e = timed(step_e2e, e2e_steps, 1, dist_on)
         ms_e2e_dense = timed(step_e2e_dense, e2e_steps, 1, dist_on)
         layer.addGSO(S)
-        bits_bytes = B * N * ((N + 31) // 32) * 4
+        bits_chunk_bytes = cb * N * ((N + 31) // 32) * 4
+        h2d_gso = nchunk * bits_chunk_bytes
         e2e = {"value": units / (ms_e2e * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": (bits_bytes + x_h.numel() * 4) * world,
+               "h2d_bytes_per_step": (h2d_gso + x_h.numel() * 4) * world,
                "d2h_bytes_per_step": 4 * world, "steps": e2e_steps,
-               "host_bytes_read_per_step": S_h.numel() * S_h.element_size() * world, "host_pack_threads": pack_threads,
+               "chunks": nchunk, "host_pack_threads": pack_threads, "host_placement": numa,
+               "host_bytes_read_per_step": S_h.numel() * S_h.element_size() * world,
                "dense_h2d": {"value": units / (ms_e2e_dense * 1e-3), "unit": "agent-steps/s",
                              "ms_per_step": ms_e2e_dense,
                              "h2d_bytes_per_step": (S_h.numel() * S_h.element_size() + x_h.numel() * 4) * world,
-                             "note": "same step with the dense fp32 GSO copied to the device (round-1 path)"},
-               "chunks": nchunk, "host_placement": numa,
+                             "note": "every chunk's dense fp32 GSO copied to the device (round-1 path)"},
                "note": "inputs start in pinned HOST buffers every step: the dense fp32 GSO (4N^2 B per instance, as the "
                        "reference builds it on the CPU) and x. The GSO's edge mask is packed on the host cores "
                        "(pack_gso_host, inside the timed region) and N^2/8 B per instance cross PCIe; x is copied "
