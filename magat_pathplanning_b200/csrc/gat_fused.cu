@@ -391,9 +391,16 @@ __device__ __forceinline__ void phase_attention_kq(const FusedParams& p, long ro
   float* e_s = esc + warp * 32 * PT;
   const int32_t* nbo = p.nbr_out + rowbase * D;
   float* att_b = p.att + (size_t)rowbase * D * PT;
-  for (int i = n0 + warp; i < n1; i += NWARPS)
-    sparse::attention_kq_row<PT, true>(xb, (unsigned)p.x_sn, sproj + (unsigned)(i * PT * FT), nbo + (unsigned)(i * D),
+  int i = n0 + warp;
+  if (i >= n1) return;
+  int my_j = sparse::list_entry<true>(nbo + (unsigned)(i * D), D, lane, -1);
+  for (; i < n1; i += NWARPS) {                 // the next row's list entry is loaded one row ahead
+    const int nxt = i + NWARPS;
+    const int nxt_j = nxt < n1 ? sparse::list_entry<true>(nbo + (unsigned)(nxt * D), D, lane, -1) : -1;
+    sparse::attention_kq_row<PT, true>(xb, (unsigned)p.x_sn, sproj + (unsigned)(i * PT * FT), my_j,
                                        att_b + (unsigned)(i * D * PT), D, lane, e_s);
+    my_j = nxt_j;
+  }
 }
 
 // ---- GAT_modified (graphML.py:713-823) ---------------------------------------------------------------------
@@ -475,14 +482,20 @@ __device__ __forceinline__ void phase_gather(const FusedParams& p, long rowbase,
   const unsigned trow = (unsigned)(Km1 * FT);                  // floats between the heads of a node in the taps buffer
   const float* tsrc = taps + (k >= 2 ? (k - 2) * FT : 0);       // plane k-1 of every (node, head)
   const bool keep32 = p.save || k < Km1;                       // fp32 copy: for backward, and as the source of the next level
-  for (int j = n0 + warp; j < n1; j += NWARPS) {
+  int j = n0 + warp;
+  if (j >= n1) return;
+  // the next row's list entries are loaded one row ahead
+  int my_i = sparse::list_entry<true>(nbi + (unsigned)(j * D), D, lane, -1);
+  int my_sl = sparse::list_entry<true>(sli + (unsigned)(j * D), D, lane, 0);
+  for (; j < n1; j += NWARPS) {
+    const int nxt = j + NWARPS;
+    const int nxt_i = nxt < n1 ? sparse::list_entry<true>(nbi + (unsigned)(nxt * D), D, lane, -1) : -1;
+    const int nxt_sl = nxt < n1 ? sparse::list_entry<true>(sli + (unsigned)(nxt * D), D, lane, 0) : 0;
+    float am[PT];
+    sparse::edge_weights<PT, true>(att_b, my_i, my_sl, D, am);
     float4 acc[PT];
-    if (k == 1)
-      sparse::gather_row<PT, true, true>(xb, (unsigned)p.x_sn, tsrc, trow, att_b, nbi + (unsigned)(j * D),
-                                         sli + (unsigned)(j * D), D, lane, acc);
-    else
-      sparse::gather_row<PT, false, true>(xb, (unsigned)p.x_sn, tsrc, trow, att_b, nbi + (unsigned)(j * D),
-                                          sli + (unsigned)(j * D), D, lane, acc);
+    if (k == 1) sparse::gather_row<PT, true, true>(xb, (unsigned)p.x_sn, tsrc, trow, my_i, am, lane, acc);
+    else sparse::gather_row<PT, false, true>(xb, (unsigned)p.x_sn, tsrc, trow, my_i, am, lane, acc);
     uint16_t* irow = uimg + (unsigned)((j * PT * Km1 + (k - 1)) * 256);
     float* trow_out = taps + (unsigned)(j * PT) * trow + (k - 1) * FT + lane * 4;
 #pragma unroll
@@ -490,6 +503,8 @@ __device__ __forceinline__ void phase_gather(const FusedParams& p, long rowbase,
       image_store(irow + h * Km1 * 256, lane, acc[h]);
       if (keep32) *reinterpret_cast<float4*>(trow_out + h * trow) = acc[h];
     }
+    my_i = nxt_i;
+    my_sl = nxt_sl;
   }
 }
 

@@ -58,18 +58,23 @@ __device__ __forceinline__ float half_multi_sum(float (&v)[NV], int t) {
   return v[0];
 }
 
+template <bool CG>
+__device__ __forceinline__ int list_entry(const int32_t* __restrict__ list_row, int D, int lane, int fill) {
+  return lane < D ? (CG ? __ldcg(list_row + lane) : __ldg(list_row + lane)) : fill;
+}
+
 // KeyQuery scores + softmax of ONE sender row by one warp (graphML.py:1246-1286).  HALF a warp per edge: lane t of a
 // half owns features 8t .. 8t+7 of R_i (all heads, in registers for the whole row) and of x_j, so the two halves
 // score two edges per step and the cross-lane sum of the PT head dots is one joint reduction (16 instructions for 4
 // heads instead of 40).  CG = true: R was written inside this launch by another CTA (bypass L1).
+// The caller loads the row's out-list entry of this lane (my_j, -1 beyond D) -- one row ahead, so that the list load
+// of the next row is in flight while this one is being scored.
 template <int PT, bool CG>
 __device__ __forceinline__ void attention_kq_row(const float* __restrict__ xb, unsigned x_sn, const float* __restrict__ r_row,
-                                                 const int32_t* __restrict__ nbr_row, float* att_row, int D, int lane,
-                                                 float* e_s) {
+                                                 int my_j, float* att_row, int D, int lane, float* e_s) {
   constexpr int LOGP = PT == 4 ? 2 : PT == 2 ? 1 : 0;
   constexpr int G = 128;
   const int half = lane >> 4, t = lane & 15;
-  const int my_j = lane < D ? (CG ? __ldcg(nbr_row + lane) : __ldg(nbr_row + lane)) : -1;
   const int deg = __popc(__ballot_sync(0xffffffffu, my_j >= 0));
   if (deg > 0) {
     float4 rv[PT][2];
@@ -107,13 +112,9 @@ __device__ __forceinline__ void attention_kq_row(const float* __restrict__ xb, u
 // and -- read through slot_in, the position of j in the sender's out-list -- its PT attention values (one 16 B
 // load); the edge loop broadcasts them by shuffle.  K1 = true gathers rows of x (one row feeds every head, two edges
 // in flight), else the heads' rows src[(i * PT + h) * trow] of the previous level.
-template <int PT, bool K1, bool CG>
-__device__ __forceinline__ void gather_row(const float* __restrict__ xb, unsigned x_sn, const float* __restrict__ src,
-                                           unsigned trow, const float* __restrict__ att_b, const int32_t* __restrict__ nbi_row,
-                                           const int32_t* __restrict__ sli_row, int D, int lane, float4 (&acc)[PT]) {
-  const int my_i = lane < D ? (CG ? __ldcg(nbi_row + lane) : __ldg(nbi_row + lane)) : -1;
-  const int my_sl = lane < D ? (CG ? __ldcg(sli_row + lane) : __ldg(sli_row + lane)) : 0;
-  float am[PT];
+// in-edge `lane` of a receiver: A_p[i, j] for all heads sits at slot my_sl of sender my_i's softmax row
+template <int PT, bool CG>
+__device__ __forceinline__ void edge_weights(const float* __restrict__ att_b, int my_i, int my_sl, int D, float (&am)[PT]) {
   if (PT == 4) {
     const float4* q = reinterpret_cast<const float4*>(att_b + (unsigned)((my_i * D + my_sl) * PT));
     const float4 wv = my_i >= 0 ? (CG ? __ldcg(q) : __ldg(q)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -125,6 +126,12 @@ __device__ __forceinline__ void gather_row(const float* __restrict__ xb, unsigne
       am[h] = my_i >= 0 ? (CG ? __ldcg(q) : __ldg(q)) : 0.f;
     }
   }
+}
+
+// my_i: this lane's in-list entry (loaded by the caller one row ahead), am: its attention values (edge_weights).
+template <int PT, bool K1, bool CG>
+__device__ __forceinline__ void gather_row(const float* __restrict__ xb, unsigned x_sn, const float* __restrict__ src,
+                                           unsigned trow, int my_i, const float (&am)[PT], int lane, float4 (&acc)[PT]) {
   const int cnt = __popc(__ballot_sync(0xffffffffu, my_i >= 0));
 #pragma unroll
   for (int h = 0; h < PT; ++h) acc[h] = make_float4(0.f, 0.f, 0.f, 0.f);
