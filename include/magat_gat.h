@@ -213,6 +213,12 @@ typedef struct magat_gat_bwd_args {
 size_t magat_gat_bwd_partial_floats(int B, int N, int G, int F, int K, int P, int mode);
 int magat_gat_backward(const magat_gat_bwd_args* a, void* stream);
 
+/* The same call with ONE scratch buffer: a->gz, a->datt, a->rc and a->partial are ignored and carved out of `workspace`
+ * (256 B aligned, magat_gat_backward_workspace_bytes(...) bytes) -- their layouts then are no part of the caller's
+ * contract.  This is the form the host mirror uses. */
+size_t magat_gat_backward_workspace_bytes(int B, int N, int G, int F, int K, int P, int D, int mode);
+int magat_gat_backward_ws(const magat_gat_bwd_args* a, void* workspace, size_t ws_bytes, void* stream);
+
 /* ---- lazy dense attention for returnAttentionGSO (graphML.py:4623-4634, :4650) ----
  * Expands att into aij[B][P][1][N][N] (mean_heads == 0), or into the head-mean [B][1][N][N]
  * that returnAttentionGSO returns.  `out` must be zero filled by the caller. */

@@ -26,6 +26,7 @@ EXPORTS = (
     "magat_gat_small_supported", "magat_gat_forward_small", "magat_gso_from_positions",
     "magat_gat_fused_supported", "magat_gat_fused_workspace_bytes", "magat_gat_forward_fused",
     "magat_gso_scan_nonzero", "magat_gso_edge_values", "magat_gso_pack_host", "magat_gso_from_rowbits",
+    "magat_gat_backward_workspace_bytes", "magat_gat_backward_ws",
 )
 
 _i32, _i64, _ptr = C.c_int32, C.c_int64, C.c_void_p
@@ -117,6 +118,10 @@ def lib():
         L.magat_gat_bwd_partial_floats.argtypes = [C.c_int] * 7
         L.magat_gat_bwd_partial_floats.restype = C.c_size_t
         L.magat_gat_backward.argtypes = [C.POINTER(BwdArgs), _ptr]
+        L.magat_gat_backward_workspace_bytes.argtypes = [C.c_int] * 8
+        L.magat_gat_backward_workspace_bytes.restype = C.c_size_t
+        L.magat_gat_backward_ws.argtypes = [C.POINTER(BwdArgs), _ptr, C.c_size_t, _ptr]
+        L.magat_gat_backward_ws.restype = C.c_int
         L.magat_gat_attention_dense.argtypes = [_ptr, _ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ptr,
                                                 _ptr]
         for name in ("magat_gso_scan", "magat_gso_build_ell", "magat_gat_forward", "magat_gat_backward",

@@ -782,6 +782,33 @@ extern "C" size_t magat_gat_bwd_partial_floats(int B, int N, int G, int F, int K
   return m;
 }
 
+// ---- one-workspace form of the backward call: gz, datt, rc and partial are carved out of a single caller buffer ----
+static size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+extern "C" size_t magat_gat_backward_workspace_bytes(int B, int N, int G, int F, int K, int P, int D, int mode) {
+  if (B < 1 || N < 1 || G < 1 || F < 1 || K < 1 || P < 1 || D < 1) return 0;
+  const size_t rows = (size_t)B * N;
+  const size_t rcw = mode == MAGAT_MODE_KEYQUERY ? (size_t)G : 2;
+  return up256(rows * P * K * G * 4) + up256(rows * D * P * 4) + up256(rows * P * rcw * 4) +
+         up256(magat_gat_bwd_partial_floats(B, N, G, F, K, P, mode) * 4);
+}
+
+extern "C" int magat_gat_backward_ws(const magat_gat_bwd_args* a, void* workspace, size_t ws_bytes, void* stream) {
+  MAGAT_REQUIRE(a != nullptr && workspace != nullptr, MAGAT_E_BAD_ARG, "magat_gat_backward_ws: null argument");
+  MAGAT_REQUIRE(((uintptr_t)workspace % 256) == 0, MAGAT_E_ALIGN, "magat_gat_backward_ws: workspace must be 256 B aligned");
+  const size_t need = magat_gat_backward_workspace_bytes(a->B, a->N, a->G, a->F, a->K, a->P, a->D, a->mode);
+  MAGAT_REQUIRE(need != 0 && ws_bytes >= need, MAGAT_E_BAD_ARG, "magat_gat_backward_ws: workspace %zu B < %zu B", ws_bytes, need);
+  const size_t rows = (size_t)a->B * a->N;
+  const size_t rcw = a->mode == MAGAT_MODE_KEYQUERY ? (size_t)a->G : 2;
+  uint8_t* w = reinterpret_cast<uint8_t*>(workspace);
+  magat_gat_bwd_args b = *a;
+  b.gz = reinterpret_cast<float*>(w); w += up256(rows * a->P * a->K * a->G * 4);
+  b.datt = reinterpret_cast<float*>(w); w += up256(rows * a->D * a->P * 4);
+  b.rc = reinterpret_cast<float*>(w); w += up256(rows * a->P * rcw * 4);
+  b.partial = reinterpret_cast<float*>(w);
+  return magat_gat_backward(&b, stream);
+}
+
 extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
   MAGAT_REQUIRE(a != nullptr, MAGAT_E_BAD_ARG, "magat_gat_backward: null args");
   const int B = a->B, N = a->N, G = a->G, F = a->F, K = a->K, P = a->P, D = a->D;

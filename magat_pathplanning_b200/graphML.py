@@ -301,7 +301,7 @@ class _GATFunction(torch.autograd.Function):
                 y_mem = torch.empty((B, C_out, N), dtype=torch.float32, device=dev)
                 y = y_mem
             att = torch.empty((B, N, D, P), dtype=torch.float32, device=dev)
-            ain = torch.empty((B, N, P, D), dtype=torch.float32, device=dev) if K > 1 else None
+            ain = None          # (receiver-major attention copy: only the round-1 gather kernels used it)
             taps = torch.empty((B, N, P, max(K - 1, 1), G), dtype=torch.float32, device=dev) if K > 1 else None
             wprep = torch.empty(L.magat_gat_wprep_floats(G, F, K, P, meta.mode), dtype=torch.float32, device=dev)
             sproj = torch.empty((B, N, P, G if meta.mode == _cabi.MODE_KEYQUERY else 2), dtype=torch.float32,
@@ -410,10 +410,9 @@ class _GATFunction(torch.autograd.Function):
             dwb = torch.empty_like(wb_c) if need_dmix else None
             df = torch.empty_like(filt_c) if need_df else None
             db = buf(F, 1) if need_db else None
-            gz = buf(B, N, P, K, G)
-            datt = buf(B, N, D, P)
-            rc = buf(B, N, P, 2 if gm else G)
-            partial = buf(L.magat_gat_bwd_partial_floats(B, N, G, F, K, P, meta.mode))
+            nws = L.magat_gat_backward_workspace_bytes(B, N, G, F, K, P, D, meta.mode)
+            ws = torch.empty(nws + 256, dtype=torch.uint8, device=dev)         # ONE scratch allocation (gz, datt, rc, partial)
+            ws = ws[(-ws.data_ptr()) % 256:]
             a = _cabi.BwdArgs(B=B, N=N, G=G, F=F, K=K, P=P, D=D, mode=meta.mode, concat=int(meta.concat),
                               relu=int(meta.relu), path=meta.path,
                               need_dx=int(need_dx), need_dweight=int(need_dw), need_dfilter=int(need_df),
@@ -429,8 +428,8 @@ class _GATFunction(torch.autograd.Function):
                               dy=dy.data_ptr(), dy_sb=dy.stride(0), dy_sn=dy.stride(2), dy_sc=dy.stride(1),
                               dx=_p(dx), dweight=_p(dw), dmixer=_p(dmix), dweight_bias=_p(dwb),
                               dfilterWeight=_p(df), dbias=_p(db),
-                              gz=gz.data_ptr(), datt=datt.data_ptr(), rc=rc.data_ptr(), partial=partial.data_ptr())
-            _cabi.check(L.magat_gat_backward(a, _stream(dev)))
+                              gz=None, datt=None, rc=None, partial=None)
+            _cabi.check(L.magat_gat_backward_ws(a, ws.data_ptr(), nws, _stream(dev)))
         gx = dx.permute(0, 2, 1) if need_dx else None
         # KeyQuery never touches mixer / weight_bias: the reference leaves their grad = None
         return (gx, dw, dmix if (need_dmix and need[2]) else None, dwb if (need_dmix and need[3]) else None,
@@ -675,7 +674,7 @@ class _LSIGFFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             y_mem = torch.empty((B, N, F), dtype=torch.float32, device=dev)
             y = y_mem.permute(0, 2, 1)                          # the reference returns this permuted view too (:5573-5575)
-            ain = torch.empty((B, N, 1, D), dtype=torch.float32, device=dev) if K > 1 else None
+            ain = None
             taps = torch.empty((B, N, 1, max(K - 1, 1), G), dtype=torch.float32, device=dev) if K > 1 else None
             wprep = torch.empty(L.magat_gat_wprep_floats(G, F, K, 1, _cabi.MODE_GSO_VALUES), dtype=torch.float32, device=dev)
             dummy = torch.empty(4, dtype=torch.float32, device=dev)
@@ -712,9 +711,10 @@ class _LSIGFFunction(torch.autograd.Function):
             dx = buf(B, N, G) if need_dx else None
             df = torch.empty_like(filt_c) if need_df else None
             db = buf(F, 1) if need_db else None
-            gz, datt = buf(B, N, 1, K, G), buf(B, N, D, 1)
-            dummy = buf(B * N * 2 + 4)
-            partial = buf(L.magat_gat_bwd_partial_floats(B, N, G, F, K, 1, _cabi.MODE_GSO_VALUES))
+            dummy = buf(4)
+            nws = L.magat_gat_backward_workspace_bytes(B, N, G, F, K, 1, D, _cabi.MODE_GSO_VALUES)
+            ws = torch.empty(nws + 256, dtype=torch.uint8, device=dev)
+            ws = ws[(-ws.data_ptr()) % 256:]
             a = _cabi.BwdArgs(B=B, N=N, G=G, F=F, K=K, P=1, D=D, mode=_cabi.MODE_GSO_VALUES, concat=1, relu=0,
                               path=_PATH[ctx.path], need_dx=int(need_dx), need_dweight=0, need_dfilter=int(need_df),
                               need_dbias=int(need_db), need_dmixer=0, taps_valid=int(ctx.taps_valid), reserved=0,
@@ -726,8 +726,8 @@ class _LSIGFFunction(torch.autograd.Function):
                               dy=dy.data_ptr(), dy_sb=dy.stride(0), dy_sn=dy.stride(2), dy_sc=dy.stride(1),
                               dx=_p(dx), dweight=None, dmixer=None, dweight_bias=None,
                               dfilterWeight=_p(df), dbias=_p(db),
-                              gz=gz.data_ptr(), datt=datt.data_ptr(), rc=dummy.data_ptr(), partial=partial.data_ptr())
-            _cabi.check(L.magat_gat_backward(a, _stream(dev)))
+                              gz=None, datt=None, rc=None, partial=None)
+            _cabi.check(L.magat_gat_backward_ws(a, ws.data_ptr(), nws, _stream(dev)))
         return (dx.permute(0, 2, 1) if need_dx else None), df, db, None, None, None
 
 
