@@ -39,6 +39,8 @@ WORKLOADS = {
     "c2_n10": dict(B=64, N=10, width=20, G=128, K=3, P=4, concat=True, mode="KeyQuery"),
     "c1_n10": dict(B=1, N=10, width=20, G=128, K=2, P=1, concat=False, mode="KeyQuery"),
     "c5_n1000": dict(B=128, N=1000, width=200, G=128, K=3, P=4, concat=True, mode="KeyQuery"),
+    # the published bottleneck model "B-32-P4" (README.md:385-396 of the reference): 32 features, heads averaged, K = 2
+    "c3_b32p4_n100": dict(B=256, N=100, width=50, G=32, K=2, P=4, concat=False, mode="KeyQuery"),
     # the class default attention mode (graphML.py:4562) at the north-star shape
     "c4_n1000_gm": dict(B=512, N=1000, width=200, G=128, K=3, P=4, concat=True, mode="GAT_modified"),
 }
