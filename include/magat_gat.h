@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define MAGAT_ABI_VERSION 9
+#define MAGAT_ABI_VERSION 10
 
 enum {
   MAGAT_OK = 0,
@@ -140,6 +140,10 @@ typedef struct magat_gat_fwd_args {
   /* scratch (caller allocated) */
   float* wprep;               /* magat_gat_wprep_floats(...) floats */
   float* sproj;               /* KeyQuery: [B][N][P][G]; GAT_modified: [B][N][P][2] */
+  /* optional (may be NULL): the ReLU mask of y, one bit per element, for magat_gat_backward -- word [m >> 5][c] holds
+   * (y[m][c] > 0) for the 32 node rows m = 32 (m >> 5) .. + 31 (m = b * N + n) of channel c = p * F + f.
+   * magat_gat_relu_bits_words(B, N, P, F) words; written only when magat_gat_forward_relu_bits_valid(a) says so. */
+  uint32_t* relu_bits;
 } magat_gat_fwd_args;
 
 size_t magat_gat_wprep_floats(int G, int F, int K, int P, int mode);
@@ -147,6 +151,10 @@ int magat_gat_forward(const magat_gat_fwd_args* a, void* stream);
 /* How many tap planes (k = 1..) of a->taps the forward call leaves valid for these arguments (K-1 today).  Pass it on
  * as bwd.taps_valid; magat_gat_backward rebuilds the planes above it. */
 int magat_gat_forward_taps_valid(const magat_gat_fwd_args* a);
+/* 1 when magat_gat_forward fills a->relu_bits for these arguments (the tcgen05 K-tap projection runs and relu = 1);
+ * only then may the buffer be passed on as bwd.relu_bits. */
+int magat_gat_forward_relu_bits_valid(const magat_gat_fwd_args* a);
+size_t magat_gat_relu_bits_words(int B, int N, int P, int F);
 
 
 /* ---- fused forward: ONE launch from the dense GSO to y (graphML.py:4636-4667 over :1724-1827, :1180-1286, :713-823) ----
@@ -208,6 +216,9 @@ typedef struct magat_gat_bwd_args {
   float* datt;                /* [B][N][D][P] */
   float* rc;                  /* KeyQuery: [B][N][P][G]; GAT_modified: [B][N][P][2] */
   float* partial;             /* magat_gat_bwd_partial_floats(...) floats */
+  /* optional (may be NULL): the forward's bit mask of y > 0 (fwd.relu_bits, only when ..._relu_bits_valid): the two
+   * dense kernels that need relu'(y) then read 1/32 of the bytes of y */
+  const uint32_t* relu_bits;
 } magat_gat_bwd_args;
 
 size_t magat_gat_bwd_partial_floats(int B, int N, int G, int F, int K, int P, int mode);

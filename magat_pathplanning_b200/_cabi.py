@@ -12,7 +12,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmagat_gat.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 MODE_KEYQUERY, MODE_GAT_MODIFIED, MODE_GSO_VALUES = 0, 1, 2
 DT_F32, DT_F64 = 0, 1
@@ -21,6 +21,7 @@ PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
 EXPORTS = (
     "magat_abi_version", "magat_last_error", "magat_device_check", "magat_gso_scan",
     "magat_gso_build_ell", "magat_gat_wprep_floats", "magat_gat_forward", "magat_gat_forward_taps_valid",
+    "magat_gat_forward_relu_bits_valid", "magat_gat_relu_bits_words",
     "magat_gat_bwd_partial_floats", "magat_gat_backward", "magat_gat_attention_dense",
     "magat_launch_count", "magat_profile_enable", "magat_profile_collect",
     "magat_gat_small_supported", "magat_gat_forward_small", "magat_gso_from_positions",
@@ -39,7 +40,7 @@ class FwdArgs(C.Structure):
         ("nbr_out", _ptr), ("nbr_in", _ptr), ("slot_in", _ptr), ("slot_out", _ptr),
         ("weight", _ptr), ("mixer", _ptr), ("weight_bias", _ptr), ("filterWeight", _ptr), ("bias", _ptr),
         ("y", _ptr), ("y_sb", _i64), ("y_sn", _i64), ("y_sc", _i64),
-        ("att", _ptr), ("ain", _ptr), ("taps", _ptr), ("wprep", _ptr), ("sproj", _ptr),
+        ("att", _ptr), ("ain", _ptr), ("taps", _ptr), ("wprep", _ptr), ("sproj", _ptr), ("relu_bits", _ptr),
     ]
 
 
@@ -55,7 +56,7 @@ class BwdArgs(C.Structure):
         ("dy", _ptr), ("dy_sb", _i64), ("dy_sn", _i64), ("dy_sc", _i64),
         ("dx", _ptr), ("dweight", _ptr), ("dmixer", _ptr), ("dweight_bias", _ptr),
         ("dfilterWeight", _ptr), ("dbias", _ptr),
-        ("gz", _ptr), ("datt", _ptr), ("rc", _ptr), ("partial", _ptr),
+        ("gz", _ptr), ("datt", _ptr), ("rc", _ptr), ("partial", _ptr), ("relu_bits", _ptr),
     ]
 
 
@@ -115,6 +116,10 @@ def lib():
         L.magat_gat_forward.argtypes = [C.POINTER(FwdArgs), _ptr]
         L.magat_gat_forward_taps_valid.argtypes = [C.POINTER(FwdArgs)]
         L.magat_gat_forward_taps_valid.restype = C.c_int
+        L.magat_gat_forward_relu_bits_valid.argtypes = [C.POINTER(FwdArgs)]
+        L.magat_gat_forward_relu_bits_valid.restype = C.c_int
+        L.magat_gat_relu_bits_words.argtypes = [C.c_int] * 4
+        L.magat_gat_relu_bits_words.restype = C.c_size_t
         L.magat_gat_bwd_partial_floats.argtypes = [C.c_int] * 7
         L.magat_gat_bwd_partial_floats.restype = C.c_size_t
         L.magat_gat_backward.argtypes = [C.POINTER(BwdArgs), _ptr]

@@ -891,19 +891,9 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
     const int first = k == K - 1 ? 1 : 0;
     float* g0sum = (k == 1 && g0_in_dx) ? a->dx : nullptr;
     float* rc_fused = (k == 1 && fuse_softmax) ? a->rc : nullptr;
-    static const int tb_occ = getenv("MAGAT_TB_OCC") ? atoi(getenv("MAGAT_TB_OCC")) : 3;
 #define MAGAT_TB(PT) \
-  do {                                                                                                              \
-    if (tb_occ == 4)                                                                                                \
-      k_tap_bwd_v<PT, 4><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->taps, a->att, a->nbr_out, rows, N, K, D, \
-                                                     k, first, a->gz, a->datt, g0sum, rc_fused);                    \
-    else if (tb_occ == 2)                                                                                           \
-      k_tap_bwd_v<PT, 2><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->taps, a->att, a->nbr_out, rows, N, K, D, \
-                                                     k, first, a->gz, a->datt, g0sum, rc_fused);                    \
-    else                                                                                                            \
-      k_tap_bwd_v<PT, 3><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->taps, a->att, a->nbr_out, rows, N, K, D, \
-                                                     k, first, a->gz, a->datt, g0sum, rc_fused);                    \
-  } while (0)
+  k_tap_bwd_v<PT, 3><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->taps, a->att, a->nbr_out, rows, N, K, D, k, \
+                                                 first, a->gz, a->datt, g0sum, rc_fused)
     if (vec && P == 4) MAGAT_TB(4);
     else if (vec && P == 2) MAGAT_TB(2);
     else if (vec && P == 1) MAGAT_TB(1);

@@ -596,19 +596,9 @@ int run_tap_gather(const float* x, long x_sb, long x_sn, const float* att, const
 #undef MAGAT_GS
     return check_launch("k_tap_gather", st);
   }
-  static const int occ = getenv("MAGAT_GATHER_OCC") ? atoi(getenv("MAGAT_GATHER_OCC")) : 4;
 #define MAGAT_GATHER(PT) \
-  do {                                                                                                              \
-    if (occ == 3)                                                                                                   \
-      k_tap_gather_v<PT, 3><<<row_blocks, 256, 0, st>>>(x, x_sb, x_sn, att, nbr_in, slot_in, rows, N, G, K, D, k, taps, \
-                                                        ain, ain_ready);                                            \
-    else if (occ == 5)                                                                                              \
-      k_tap_gather_v<PT, 5><<<row_blocks, 256, 0, st>>>(x, x_sb, x_sn, att, nbr_in, slot_in, rows, N, G, K, D, k, taps, \
-                                                        ain, ain_ready);                                            \
-    else                                                                                                            \
-      k_tap_gather_v<PT, 4><<<row_blocks, 256, 0, st>>>(x, x_sb, x_sn, att, nbr_in, slot_in, rows, N, G, K, D, k, taps, \
-                                                        ain, ain_ready);                                            \
-  } while (0)
+  k_tap_gather_v<PT, 4><<<row_blocks, 256, 0, st>>>(x, x_sb, x_sn, att, nbr_in, slot_in, rows, N, G, K, D, k, taps, ain, \
+                                                    ain_ready)
   if (vec_ok && P == 4) MAGAT_GATHER(4);
   else if (vec_ok && P == 2) MAGAT_GATHER(2);
   else if (vec_ok && P == 1) MAGAT_GATHER(1);
@@ -666,16 +656,9 @@ static int forward_impl(const magat_gat_fwd_args* a, cudaStream_t st, bool use_t
       if ((rc = check_launch("k_node_gemm(score projection)", st))) return rc;
     }
     bool fast = vec_ok && D <= 32 && (G == 128 || G == 256);
-    static const int att_occ = getenv("MAGAT_ATT_OCC") ? atoi(getenv("MAGAT_ATT_OCC")) : 8;
 #define MAGAT_ATT(PT, GV) \
-  do {                                                                                                             \
-    if (att_occ == 8)                                                                                              \
-      k_attention_kq_v<PT, GV, 8><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj, a->nbr_out, rows, N, D, \
-                                                              a->att, so, ain_w);                                  \
-    else                                                                                                           \
-      k_attention_kq_v<PT, GV, 1><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj, a->nbr_out, rows, N, D, \
-                                                              a->att, so, ain_w);                                  \
-  } while (0)
+  k_attention_kq_v<PT, GV, 8><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj, a->nbr_out, rows, N, D, \
+                                                          a->att, so, ain_w)
     if (lean && P == 4) k_attention_kq_h<4><<<lean_grid(row_blocks), 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj, a->nbr_out, rows, N, D, a->att);
     else if (lean && P == 2) k_attention_kq_h<2><<<lean_grid(row_blocks), 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj, a->nbr_out, rows, N, D, a->att);
     else if (lean && P == 1) k_attention_kq_h<1><<<lean_grid(row_blocks), 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->sproj, a->nbr_out, rows, N, D, a->att);
@@ -748,6 +731,19 @@ extern "C" size_t magat_gat_wprep_floats(int G, int F, int K, int P, int mode) {
 extern "C" int magat_gat_forward_taps_valid(const magat_gat_fwd_args* a) {
   if (a == nullptr || a->K <= 1) return 0;
   return a->K - 1;
+}
+
+// the tcgen05 K-tap projection writes the ReLU bit mask from its epilogue; no other projection route does
+extern "C" int magat_gat_forward_relu_bits_valid(const magat_gat_fwd_args* a) {
+  if (a == nullptr || a->relu_bits == nullptr || !a->relu || a->path == MAGAT_PATH_SIMT) return 0;
+  if (((uintptr_t)a->relu_bits % 16) != 0 || ((a->P * a->F) % 4) != 0) return 0;
+  return tc_supported(a) && tap_tc_supported(a) ? 1 : 0;
+}
+
+// words of the bit mask: two 32-row groups per 64-row tile of the projection kernel
+extern "C" size_t magat_gat_relu_bits_words(int B, int N, int P, int F) {
+  const size_t rows = (size_t)B * N;
+  return ((rows + 63) / 64) * 2 * (size_t)P * F;
 }
 
 extern "C" int magat_gat_forward(const magat_gat_fwd_args* a, void* stream) {

@@ -38,11 +38,16 @@ struct TapParams {
   const float* x; long x_sb, x_sn;
   int x_hdiv; long x_hmul;               // head h reads x + (h / x_hdiv) * x_hmul (0 in the forward)
   const float* mask; long m_sb, m_sn;    // optional: x is zeroed where mask <= 0 (same head offset rule)
+  // The same mask as one bit per element (what the forward epilogue below leaves in relu_bits_out): word
+  // [m >> 5][c] holds rows 32 (m >> 5) .. + 31 of column c.  Takes precedence over `mask`: 1/32 of its bytes, no second
+  // tensor copy per stage, and the raw ring keeps its four slots.
+  const uint32_t* mask_bits; int bits_C;
   const float* u1;       // taps buffer, tap k = 1 of head p of node m at u1 + (m*P + p)*(K-1)*G
   const float* H;        // filterWeight [P][F][K*G]
   const float* bias; int relu;
   float* y; long y_sb, y_sn;     // channel stride 1
   int nout;                      // P counts weight blocks; nout consecutive blocks share one operand tile
+  uint32_t* relu_bits_out; int bits_out_C;   // optional: bit (y > 0) per output element, layout as mask_bits
   int accum;                     // y += result (the caller guarantees one weight-block group, i.e. no two CTAs ever touch
                                  // the same output row)
 };
@@ -91,8 +96,10 @@ __device__ __forceinline__ void v2_store(float* dst, long stride_rt, const float
   }
 }
 
-template <bool MASKED>
+// MASK: 0 none, 1 fp32 mask tile next to every x tile, 2 bit mask read straight from global memory
+template <int MASK>
 __global__ void __launch_bounds__(V2_THREADS, 1) k_tap_tc2(const __grid_constant__ TapParams p) {
+  constexpr bool MASKED = MASK == 1;
   constexpr int NRAW = MASKED ? 2 : 4;
   constexpr int SLOT_BYTES = V2_RAW_BYTES / NRAW;
   constexpr int TILE_BYTES = TN * SK * 4;               // 32 KB of fp32
@@ -205,11 +212,19 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_tap_tc2(const __grid_constant
                           (uint32_t)((lane & 1) * 8);
     const int c = (lane >> 1) & 7;
     const uint32_t raw_s = tc::smem_u32(raw) + (uint32_t)(lane * 16);
+    const int x_c0 = p.x_hmul ? (int)(((hg * nout) / p.x_hdiv) * p.x_hmul) : 0;
     unsigned q = 0;
     for (long tile = slot; tile < tiles; tile += nslots) {
       for (int s = 0; s < nst; ++s, ++q) {
         if ((q & 1u) != grp) continue;
         const int r = (int)(q % NRAW);
+        // bit mask of this lane's four columns: rows 0-31 and 32-63 of the tile (issued before the wait on the copy)
+        uint4 bw0 = make_uint4(~0u, ~0u, ~0u, ~0u), bw1 = bw0;
+        if (MASK == 2 && s < sps) {
+          const uint32_t* bp = p.mask_bits + (size_t)(tile * 2) * p.bits_C + x_c0 + s * SK + lane * 4;
+          bw0 = __ldg(reinterpret_cast<const uint4*>(bp));
+          bw1 = __ldg(reinterpret_cast<const uint4*>(bp + p.bits_C));
+        }
         tc::mbar_wait(&raw_full[r], (q / NRAW) & 1u);
         tc::mbar_wait(&op_empty[grp], ((q >> 1) & 1u) ^ 1u);
         const uint32_t src = raw_s + (uint32_t)(r * SLOT_BYTES);
@@ -225,6 +240,15 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_tap_tc2(const __grid_constant
               const float4 mk = tc::ld_shared_v4(src + (uint32_t)TILE_BYTES + (uint32_t)((wg + 8 * (r0 + i)) * (SK * 4)));
               v[i].x = mk.x > 0.f ? v[i].x : 0.f; v[i].y = mk.y > 0.f ? v[i].y : 0.f;
               v[i].z = mk.z > 0.f ? v[i].z : 0.f; v[i].w = mk.w > 0.f ? v[i].w : 0.f;
+            }
+          }
+          if (MASK == 2) {
+#pragma unroll
+            for (int i = 0; i < RB; ++i) {
+              const uint4& bw = (r0 + i) < 4 ? bw0 : bw1;      // row wg + 8 (r0 + i): bit wg + 8 ((r0 + i) & 3) of its word
+              const uint32_t bit = 1u << (wg + 8 * ((r0 + i) & 3));
+              v[i].x = (bw.x & bit) ? v[i].x : 0.f; v[i].y = (bw.y & bit) ? v[i].y : 0.f;
+              v[i].z = (bw.z & bit) ? v[i].z : 0.f; v[i].w = (bw.w & bit) ? v[i].w : 0.f;
             }
           }
 #pragma unroll
@@ -274,6 +298,14 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_tap_tc2(const __grid_constant
 #pragma unroll
             for (int n = 0; n < 32; ++n)
               if (n < left) v[n] += dst[(long)n * p.y_sn];
+          }
+          if (p.relu_bits_out) {
+            // ReLU mask for the backward (one word per feature and 32 nodes; bits past the last row stay 0)
+            uint32_t w = 0;
+#pragma unroll
+            for (int n = 0; n < 32; ++n) w |= (v[n] + bias > 0.f ? 1u : 0u) << n;
+            if (left < 32) w = left > 0 ? w & ((1u << left) - 1u) : 0u;
+            p.relu_bits_out[(size_t)(tile * 2 + hh) * p.bits_out_C + (hg * nout + o) * FT + f] = w;
           }
           // the usual row strides as compile-time constants: every store then carries its offset as an immediate
           // (FADD + FMNMX + STG per node instead of a 64-bit multiply-add chain -- the four epilogue warps pace the
@@ -357,6 +389,10 @@ bool tap_tc2_prepare(TapParams& tq, int x_width) {
   if (tq.y_sb != (long)tq.N * tq.y_sn) return false;
   if (tq.x_sb != (long)tq.N * tq.x_sn) return false;
   if (!tma::make_row_map(&tq.tm_x, tq.x, tq.rows, x_width, tq.x_sn, TN, SK)) return false;
+  if (tq.mask_bits) {
+    if (tq.bits_C % 4 != 0 || ((uintptr_t)tq.mask_bits % 16) != 0) return false;
+    tq.mask = nullptr;
+  }
   if (tq.mask) {
     if (tq.m_sb != (long)tq.N * tq.m_sn || !tma::make_row_map(&tq.tm_m, tq.mask, tq.rows, x_width, tq.m_sn, TN, SK)) return false;
   }
@@ -376,15 +412,17 @@ int launch_tap_tc(const TapParams& tp, cudaStream_t st, const char* what) {
   // logical width of an x row: every weight-block group reads its own 128-wide (G-wide) column window
   const int x_width = tp.x_hmul ? (int)(((tp.P - 1) / tp.x_hdiv) * tp.x_hmul) + tp.G : tp.G;
   if (!tap_tc2_prepare(tq, x_width)) return -1;
-  int rc0 = ensure_dyn_smem(KID_TAP_TC2, (const void*)k_tap_tc2<false>, V2_SMEM_BYTES, "k_tap_tc2<false>");
-  if (!rc0) rc0 = ensure_dyn_smem(KID_TAP_TC2M, (const void*)k_tap_tc2<true>, V2_SMEM_BYTES, "k_tap_tc2<true>");
+  int rc0 = ensure_dyn_smem(KID_TAP_TC2, (const void*)k_tap_tc2<0>, V2_SMEM_BYTES, "k_tap_tc2<0>");
+  if (!rc0) rc0 = ensure_dyn_smem(KID_TAP_TC2M, (const void*)k_tap_tc2<1>, V2_SMEM_BYTES, "k_tap_tc2<1>");
+  if (!rc0) rc0 = ensure_dyn_smem(KID_TAP_TC2B, (const void*)k_tap_tc2<2>, V2_SMEM_BYTES, "k_tap_tc2<2>");
   if (rc0) return rc0;
   const int ngroups = tp.P / tp.nout;
   long slots = sm_count / ngroups;
   if (slots < 1) slots = 1;
   if (slots > tiles) slots = tiles;
-  if (tp.mask) k_tap_tc2<true><<<(int)(slots * ngroups), V2_THREADS, V2_SMEM_BYTES, st>>>(tq);
-  else k_tap_tc2<false><<<(int)(slots * ngroups), V2_THREADS, V2_SMEM_BYTES, st>>>(tq);
+  if (tq.mask_bits) k_tap_tc2<2><<<(int)(slots * ngroups), V2_THREADS, V2_SMEM_BYTES, st>>>(tq);
+  else if (tq.mask) k_tap_tc2<1><<<(int)(slots * ngroups), V2_THREADS, V2_SMEM_BYTES, st>>>(tq);
+  else k_tap_tc2<0><<<(int)(slots * ngroups), V2_THREADS, V2_SMEM_BYTES, st>>>(tq);
   return check_launch(what, st);
 }
 
@@ -465,6 +503,7 @@ int gz_tc_backward(const magat_gat_bwd_args* a, float* ht, cudaStream_t st) {
   tp.x = a->dy; tp.x_sb = a->dy_sb; tp.x_sn = a->dy_sn;
   tp.x_hdiv = a->K; tp.x_hmul = a->F;
   tp.mask = a->relu ? a->y : nullptr; tp.m_sb = a->y_sb; tp.m_sn = a->y_sn;
+  if (a->relu && a->relu_bits) { tp.mask_bits = a->relu_bits; tp.bits_C = a->P * a->F; }
   tp.H = ht;
   tp.bias = nullptr; tp.relu = 0;
   tp.y = a->gz; tp.y_sn = (long)a->P * a->K * a->G; tp.y_sb = (long)a->N * tp.y_sn;
@@ -539,6 +578,7 @@ int tap_tc_forward(const magat_gat_fwd_args* a, cudaStream_t st) {
   tp.H = a->filterWeight;
   tp.bias = a->bias; tp.relu = a->relu;
   tp.y = a->y; tp.y_sb = a->y_sb; tp.y_sn = a->y_sn;
+  if (a->relu && a->relu_bits) { tp.relu_bits_out = a->relu_bits; tp.bits_out_C = a->P * a->F; }
   tp.nout = 1;
   return must_launch(launch_tap_tc(tp, st, "k_tap_tc(fused taps + projection)"), "K-tap projection");
 }

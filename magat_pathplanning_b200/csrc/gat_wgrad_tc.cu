@@ -52,6 +52,7 @@ struct WgradParams {
   Src a;                     // 128 features per node
   Src b[3];                  // NB / 128 segments of 128 features
   const float* mask_y; long my_sb, my_sn, my_zoff;   // optional: A = a * (mask_y > 0)  (dP from dY and y)
+  const uint32_t* mask_bits; int bits_C;             // the same mask, one bit per element (v2 kernel only; preferred)
   float a_scale;
   float* partial;            // [Z][nslots][128][NB]
   float* colsum_partial;     // optional [Z][nslots][128]: per-CTA column sums of the (masked, scaled) A rows
@@ -312,7 +313,8 @@ struct Wgrad2Params {
   long rows;
   int Z, NB;
   int a_zoff, b0_zoff, u_zoff, u_seg;      // column offsets: z * zoff (+ (seg - 1) * u_seg for the taps)
-  int has_mask;
+  int has_mask;                       // 0 none, 1 fp32 mask rows (tm_m), 2 bit mask (mask_bits)
+  const uint32_t* mask_bits; int bits_C;      // word [m >> 5][c]: bit m & 31 = (y[m][c] > 0), written by the forward projection
   float a_scale;
   float* partial;
   float* colsum_partial;
@@ -371,7 +373,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_wgrad_tc2(const __grid_consta
     if (tc::elect_one()) {
       const uint64_t tma_ = reinterpret_cast<uint64_t>(&p.tm_a), tmm = reinterpret_cast<uint64_t>(&p.tm_m);
       const uint64_t tmb = reinterpret_cast<uint64_t>(&p.tm_b0), tmu = reinterpret_cast<uint64_t>(&p.tm_u);
-      const uint32_t bytes = (uint32_t)V2_BOX_BYTES * (uint32_t)(nsrc + (p.has_mask ? 1 : 0));
+      const uint32_t bytes = (uint32_t)V2_BOX_BYTES * (uint32_t)(nsrc + (p.has_mask == 1 ? 1 : 0));
       unsigned q = 0;
       for (long sidx = slot; sidx < nstages; sidx += nslots, ++q) {
         const int r = (int)(q % V2_NRAW);
@@ -380,7 +382,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_wgrad_tc2(const __grid_consta
         const int m0 = (int)(sidx * V2_SN);
         tc::mbar_arrive_expect_tx(&raw_full[r], bytes);
         tc::tensor_g2s_2d(dst, tma_, z * p.a_zoff, m0, &raw_full[r]);
-        if (p.has_mask) tc::tensor_g2s_2d(dst + V2_BOX_BYTES, tmm, z * p.a_zoff, m0, &raw_full[r]);
+        if (p.has_mask == 1) tc::tensor_g2s_2d(dst + V2_BOX_BYTES, tmm, z * p.a_zoff, m0, &raw_full[r]);
         tc::tensor_g2s_2d(dst + 2 * V2_BOX_BYTES, tmb, z * p.b0_zoff, m0, &raw_full[r]);
         for (int s = 1; s < nseg; ++s)
           tc::tensor_g2s_2d(dst + (2 + s) * V2_BOX_BYTES, tmu, z * p.u_zoff + (s - 1) * p.u_seg, m0, &raw_full[r]);
@@ -400,6 +402,10 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_wgrad_tc2(const __grid_consta
     for (long sidx = slot; sidx < nstages; sidx += nslots, ++q) {
       if ((q & 1u) != grp) continue;
       const int r = (int)(q % V2_NRAW);
+      // bit mask of this lane's four A columns for the 32-row group the stage lies in (issued before the wait)
+      uint4 bw = make_uint4(0u, 0u, 0u, 0u);
+      if (p.has_mask == 2)
+        bw = __ldg(reinterpret_cast<const uint4*>(p.mask_bits + (size_t)(sidx >> 1) * p.bits_C + z * p.a_zoff + lane * 4));
       tc::mbar_wait(&raw_full[r], (q / V2_NRAW) & 1u);
       tc::mbar_wait(&op_empty[grp], ((q >> 1) & 1u) ^ 1u);
       const uint32_t src = raw_s + (uint32_t)(r * V2_RAW_SLOT);
@@ -409,7 +415,13 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_wgrad_tc2(const __grid_consta
       for (int i = 0; i < 2; ++i) {
         const uint32_t ro = (uint32_t)((wg + 8 * i) * 512);
         v[0][i] = tc::ld_shared_v4(src + ro);
-        mk[i] = p.has_mask ? tc::ld_shared_v4(src + V2_BOX_BYTES + ro) : make_float4(1.f, 1.f, 1.f, 1.f);
+        if (p.has_mask == 2) {
+          const uint32_t bit = 1u << ((int)(sidx & 1) * 16 + wg + 8 * i);
+          mk[i] = make_float4((bw.x & bit) ? 1.f : 0.f, (bw.y & bit) ? 1.f : 0.f, (bw.z & bit) ? 1.f : 0.f,
+                              (bw.w & bit) ? 1.f : 0.f);
+        } else {
+          mk[i] = p.has_mask ? tc::ld_shared_v4(src + V2_BOX_BYTES + ro) : make_float4(1.f, 1.f, 1.f, 1.f);
+        }
 #pragma unroll
         for (int s = 0; s < 3; ++s)
           v[1 + s][i] = s < nseg ? tc::ld_shared_v4(src + (uint32_t)((2 + s) * V2_BOX_BYTES) + ro)
@@ -554,8 +566,12 @@ bool wgrad2_prepare(const WgradParams& wp, Wgrad2Params& q) {
   if (a_w > wp.a.sn || b0_w > wp.b[0].sn) return false;
   if (!tma::make_row_map(&q.tm_a, wp.a.p, wp.rows, a_w, wp.a.sn, V2_SN, 128)) return false;
   if (!tma::make_row_map(&q.tm_b0, wp.b[0].p, wp.rows, b0_w, wp.b[0].sn, V2_SN, 128)) return false;
-  q.has_mask = wp.mask_y != nullptr;
-  if (q.has_mask) {
+  q.has_mask = wp.mask_bits != nullptr ? 2 : wp.mask_y != nullptr ? 1 : 0;
+  if (q.has_mask == 2) {
+    if (wp.bits_C % 4 != 0 || wp.a.zoff % 4 != 0 || ((uintptr_t)wp.mask_bits % 16) != 0) return false;
+    q.mask_bits = wp.mask_bits; q.bits_C = wp.bits_C;
+  }
+  if (q.has_mask == 1) {
     if (wp.my_sb != (long)wp.N * wp.my_sn || wp.my_zoff != wp.a.zoff || a_w > wp.my_sn) return false;
     if (!tma::make_row_map(&q.tm_m, wp.mask_y, wp.rows, a_w, wp.my_sn, V2_SN, 128)) return false;
   }
@@ -626,6 +642,7 @@ int wgrad_tc_dfilter(const magat_gat_bwd_args* a, bool with_dbias, cudaStream_t 
   wp.a = Src{a->dy, a->dy_sb, a->dy_sn, (long)a->F};
   wp.mask_y = a->relu ? a->y : nullptr;
   wp.my_sb = a->y_sb; wp.my_sn = a->y_sn; wp.my_zoff = a->F;
+  if (a->relu && a->relu_bits) { wp.mask_bits = a->relu_bits; wp.bits_C = a->P * a->F; }
   wp.a_scale = 1.f;
   wp.b[0] = Src{a->x, a->x_sb, a->x_sn, 0};
   const long tap_row = (long)a->P * (a->K - 1) * a->G;

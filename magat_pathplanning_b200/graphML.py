@@ -306,8 +306,13 @@ class _GATFunction(torch.autograd.Function):
             wprep = torch.empty(L.magat_gat_wprep_floats(G, F, K, P, meta.mode), dtype=torch.float32, device=dev)
             sproj = torch.empty((B, N, P, G if meta.mode == _cabi.MODE_KEYQUERY else 2), dtype=torch.float32,
                                 device=dev)
+            # training: the projection epilogue also leaves the ReLU mask as one bit per element, so that the dense
+            # backward kernels need not read y again
+            bits = None
+            if meta.needs_grad and meta.relu and meta.concat:
+                bits = torch.empty(L.magat_gat_relu_bits_words(B, N, P, F), dtype=torch.int32, device=dev)
             a = _cabi.FwdArgs(B=B, N=N, G=G, F=F, K=K, P=P, D=D, mode=meta.mode, concat=int(meta.concat),
-                              relu=int(meta.relu), path=meta.path, reserved=0,
+                              relu=int(meta.relu), path=meta.path, reserved=0, relu_bits=_p(bits),
                               x=xt.data_ptr(), x_sb=_sb(xt), x_sn=_sn(xt),
                               nbr_out=adj.nbr_out.data_ptr(), nbr_in=adj.nbr_in.data_ptr(),
                               slot_in=adj.slot_in.data_ptr(), slot_out=_p(adj.slot_out),
@@ -318,8 +323,10 @@ class _GATFunction(torch.autograd.Function):
                               sproj=sproj.data_ptr())
             _cabi.check(L.magat_gat_forward(a, _stream(dev)))
             ctx.taps_valid = L.magat_gat_forward_taps_valid(a)
+            if bits is not None and not L.magat_gat_forward_relu_bits_valid(a):
+                bits = None
         ctx.meta, ctx.adj = meta, adj
-        ctx.save_for_backward(xt, weight_c, mixer_c, wb_c, filt_c, y, att, taps, wprep, sproj)
+        ctx.save_for_backward(xt, weight_c, mixer_c, wb_c, filt_c, y, att, taps, wprep, sproj, bits)
         ctx.mark_non_differentiable(att)
         return y, att
 
@@ -381,7 +388,7 @@ class _GATFunction(torch.autograd.Function):
         gso.adj = adj
         ctx.taps_valid = K - 1
         ctx.meta, ctx.adj = meta, adj
-        ctx.save_for_backward(xt, weight_c, mixer_c, wb_c, filt_c, y, att, taps, wprep, sproj)
+        ctx.save_for_backward(xt, weight_c, mixer_c, wb_c, filt_c, y, att, taps, wprep, sproj, None)
         ctx.mark_non_differentiable(att)
         return y, att
 
@@ -389,7 +396,7 @@ class _GATFunction(torch.autograd.Function):
     def backward(ctx, dy, _datt):
         L = _cabi.lib()
         meta, adj = ctx.meta, ctx.adj
-        xt, weight_c, mixer_c, wb_c, filt_c, y, att, taps, wprep, sproj = ctx.saved_tensors
+        xt, weight_c, mixer_c, wb_c, filt_c, y, att, taps, wprep, sproj, bits = ctx.saved_tensors
         dev = xt.device
         B, N, G = xt.shape
         F, K, P, D = meta.F, meta.K, meta.P, adj.D
@@ -428,7 +435,7 @@ class _GATFunction(torch.autograd.Function):
                               dy=dy.data_ptr(), dy_sb=dy.stride(0), dy_sn=dy.stride(2), dy_sc=dy.stride(1),
                               dx=_p(dx), dweight=_p(dw), dmixer=_p(dmix), dweight_bias=_p(dwb),
                               dfilterWeight=_p(df), dbias=_p(db),
-                              gz=None, datt=None, rc=None, partial=None)
+                              gz=None, datt=None, rc=None, partial=None, relu_bits=_p(bits))
             _cabi.check(L.magat_gat_backward_ws(a, ws.data_ptr(), nws, _stream(dev)))
         gx = dx.permute(0, 2, 1) if need_dx else None
         # KeyQuery never touches mixer / weight_bias: the reference leaves their grad = None

@@ -37,8 +37,8 @@ def test_header_symbols_exported(built):
 
 def test_struct_sizes_match_header(built):
     # 12 x int32 + 21 x 8 bytes ; 18 x int32 + 32 x 8 bytes
-    assert ctypes.sizeof(built.FwdArgs) == 12 * 4 + 21 * 8
-    assert ctypes.sizeof(built.BwdArgs) == 18 * 4 + 32 * 8
+    assert ctypes.sizeof(built.FwdArgs) == 12 * 4 + 22 * 8
+    assert ctypes.sizeof(built.BwdArgs) == 18 * 4 + 33 * 8
     # 14 x int32 + 23 x 8 bytes
     assert ctypes.sizeof(built.FusedArgs) == 14 * 4 + 23 * 8
 

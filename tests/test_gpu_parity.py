@@ -349,6 +349,47 @@ def test_tc_path_matches_simt_at_scale(B, N, K, P):
     assert all(v < TOL for v in errs.values()), errs
 
 
+@pytest.mark.parametrize("B,N,P", [(3, 50, 2), (7, 333, 4), (2, 64, 1)])
+def test_relu_bit_mask_of_the_projection_epilogue(B, N, P):
+    """Training forward on the tcgen05 path: the K-tap projection leaves (y > 0) as one bit per element for the
+    backward (word [m >> 5][c], bit m & 31), bit-exact against the y it stored, also where the row count is no multiple
+    of 32 or 64; the backward that reads the bits gives the gradients of the one that reads y (SIMT path)."""
+    dev = torch.device("cuda:0")
+    G = F = 128
+    K = 3
+    gen = torch.Generator().manual_seed(31 + N)
+    params = orc.init_params(G, F, K, P, mode="KeyQuery", generator=gen, weight_bias_std=0.1)
+    S = orc.random_geometric_gso(B, N, generator=gen).to(dev)
+    x = torch.randn(B, G, N, generator=gen).to(dev)
+    meta = dict(G=G, F=F, K=K, P=P, concat=True, mode="KeyQuery")
+    layer = make_layer(meta, {"param." + k: v for k, v in params.items() if v is not None}, dev, path="auto")
+    layer.addGSO(S)
+    xd = x.clone().requires_grad_(True)
+    y = layer(xd)
+    node, seen = y.grad_fn, 0
+    while node is not None and "_GATFunction" not in type(node).__name__ and seen < 8:
+        node, seen = node.next_functions[0][0], seen + 1
+    bits = node.saved_tensors[-1]
+    assert bits is not None and bits.dtype == torch.int32
+    rows, C = B * N, P * F
+    words = bits.view(-1, C)[: (rows + 31) // 32].cpu().numpy().astype(np.uint32)
+    got = ((words[:, None, :] >> np.arange(32, dtype=np.uint32)[None, :, None]) & 1).reshape(-1, C)
+    want = (y.detach().permute(0, 2, 1).reshape(rows, C) > 0).cpu().numpy()
+    assert np.array_equal(got[:rows].astype(bool), want)
+    assert not got[rows:].any()                       # bits past the last row are zero
+    # gradients: bits (tcgen05 backward) against y (SIMT backward); dy kept away from the ReLU kink
+    dy = torch.randn(B, C, N, generator=gen).to(dev) * (y.detach() > 1e-3)
+    y.backward(dy)
+    ref = make_layer(meta, {"param." + k: v for k, v in params.items() if v is not None}, dev, path="simt")
+    ref.addGSO(S)
+    xr = x.clone().requires_grad_(True)
+    ref(xr).backward(dy)
+    assert rel_err(xd.grad, xr.grad) < TOL
+    for k in PARAMS:
+        if getattr(ref, k).grad is not None:
+            assert rel_err(getattr(layer, k).grad, getattr(ref, k).grad) < TOL, k
+
+
 def test_tc_path_rejects_uncovered_shape(golden):
     from magat_pathplanning_b200._cabi import MagatError
     d, meta = golden.case("kq_concat_n10")          # G = 16
