@@ -137,6 +137,65 @@ template <> struct Edge4<double> {
   }
 };
 
+// one staged element (shared-space load; the generic-address loads the compiler emitted for a
+// plain pointer into the ring were measurably slower)
+template <typename T> struct EdgeS;
+template <> struct EdgeS<float> {
+  static __device__ __forceinline__ float ld(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+  }
+};
+template <> struct EdgeS<double> {
+  static __device__ __forceinline__ double ld(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+  }
+};
+
+// R staged rows x one 128-column segment.  FULL: all R rows are there (no per-row guards around the ballots).
+// Columns past N (last segment only) read whatever follows in the ring: their bits are cut out of the row words by
+// the masks below and their column words are never stored.
+// a[k] = (lane == k) ? mask of the in-range lanes of column group k : 0 -- lane k < 4 stores word k.
+template <typename T, int R, bool FULL>
+__device__ __forceinline__ void scan_rows(uint32_t addr, uint32_t row_bytes, int nrows, uint32_t bit0,
+                                          const uint32_t (&a)[4], bool wr, uint32_t* rw, int W, uint32_t (&col)[4]) {
+  constexpr int RB = R < 8 ? R : 8;                   // rows whose loads are issued back to back
+  unsigned woff = 0;
+#pragma unroll
+  for (int r0 = 0; r0 < R; r0 += RB) {
+    if (!FULL && r0 >= nrows) break;
+    T v[RB][4];
+    uint32_t ad = addr;
+#pragma unroll
+    for (int u = 0; u < RB; ++u) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[u][k] = EdgeS<T>::ld(ad + (uint32_t)(32 * k * sizeof(T)));
+      ad += row_bytes;
+    }
+    addr = ad;
+#pragma unroll
+    for (int u = 0; u < RB; ++u) {
+      const int r = r0 + u;
+      if (FULL || r < nrows) {
+        const bool p0 = is_edge<T>(v[u][0]), p1 = is_edge<T>(v[u][1]), p2 = is_edge<T>(v[u][2]), p3 = is_edge<T>(v[u][3]);
+        const uint32_t w0 = __ballot_sync(0xffffffffu, p0), w1 = __ballot_sync(0xffffffffu, p1);
+        const uint32_t w2 = __ballot_sync(0xffffffffu, p2), w3 = __ballot_sync(0xffffffffu, p3);
+        const uint32_t bit = bit0 << r;
+        col[0] |= p0 ? bit : 0u;
+        col[1] |= p1 ? bit : 0u;
+        col[2] |= p2 ? bit : 0u;
+        col[3] |= p3 ? bit : 0u;
+        const uint32_t w = (w0 & a[0]) | (w1 & a[1]) | (w2 & a[2]) | (w3 & a[3]);
+        if (wr) rw[woff] = w;
+      }
+      woff += (unsigned)W;
+    }
+  }
+}
+
 constexpr int kScanWarps = 8;                 // consumer warps; warp 8 is the copy issuer
 constexpr int kScanRing = 192 * 1024;
 
@@ -187,13 +246,17 @@ __global__ void __launch_bounds__((kScanWarps + 1) * 32, 1) k_gso_scan_tma(const
     }
   } else {
     // ===== consumers ========================================================================
+    // Warp w owns the 128-column segments w and w + 8 of every staged row.  Lane l reads columns 32k + l of the segment
+    // (k = 0..3; conflict-free scalar shared loads): one ballot per 32 columns IS the row word, and the lane's own
+    // predicate is its bit of the transposed column word -- no nibble packing, no shuffles (the first version of this
+    // loop spent 106 instructions per row segment and paced the kernel at 56 % of the DRAM peak; this one ~30).
     int stage = 0;
     uint32_t phase = 0;
+    const uint32_t smem_s = tc::smem_u32(smem);
     for (long band = blockIdx.x; band < bands; band += gridDim.x) {
       const long b = band / W;
       const int rb = (int)(band - b * W);
       const int i0 = rb * 32;
-      // column accumulators for up to 2 segments per warp (N <= 2048 in this kernel)
       uint32_t col[2][4];
 #pragma unroll
       for (int q = 0; q < 2; ++q)
@@ -205,35 +268,25 @@ __global__ void __launch_bounds__((kScanWarps + 1) * 32, 1) k_gso_scan_tma(const
         if (nrows > R) nrows = R;
         if (nrows <= 0) break;
         tc::mbar_wait(&full[stage], phase);
-        const T* tile = reinterpret_cast<const T*>(smem + (size_t)stage * chunk_bytes);
+        const uint32_t tile_s = smem_s + (uint32_t)((size_t)stage * chunk_bytes);
+        const uint32_t bit0 = 1u << (c * R);                  // bit of the chunk's first row inside the band
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const int seg = warp + q * kScanWarps;
           if (seg >= segs) break;
-          const int j0 = seg * 128 + lane * 4;
-          const bool jin = j0 < N;
-          uint32_t nb[R], v[R];
+          const int j = seg * 128 + lane;
+          uint32_t am[4];
 #pragma unroll
-          for (int r = 0; r < R; ++r) nb[r] = (jin && r < nrows) ? Edge4<T>::nib(tile + (size_t)r * N + j0) : 0u;
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const int rr = c * R + r;                       // row inside the band
-            col[q][0] |= (nb[r] & 1u) << rr;
-            col[q][1] |= ((nb[r] >> 1) & 1u) << rr;
-            col[q][2] |= ((nb[r] >> 2) & 1u) << rr;
-            col[q][3] |= ((nb[r] >> 3) & 1u) << rr;
-            v[r] = nb[r] << (4 * (lane & 7));
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t vm = __ballot_sync(0xffffffffu, j + 32 * k < N);
+            am[k] = lane == k ? vm : 0u;
+            asm volatile("" : "+r"(am[k]));               // keep it a register value (not re-derived per row)
           }
-#pragma unroll
-          for (int o = 1; o <= 4; o <<= 1)
-#pragma unroll
-            for (int r = 0; r < R; ++r) v[r] |= __shfl_xor_sync(0xffffffffu, v[r], o);
-          const int w = seg * 4 + (lane >> 3);
-          if ((lane & 7) == 0 && w < W) {
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-              if (r < nrows) rowbits[((size_t)b * N + r_first + r) * W + w] = v[r];
-          }
+          const uint32_t addr = tile_s + (uint32_t)(j * sizeof(T));
+          uint32_t* rw = rowbits + ((size_t)b * N + r_first) * W + seg * 4 + lane;
+          const bool wr = lane < 4 && seg * 4 + lane < W;
+          if (nrows == R) scan_rows<T, R, true>(addr, (uint32_t)row_bytes, nrows, bit0, am, wr, rw, W, col[q]);
+          else scan_rows<T, R, false>(addr, (uint32_t)row_bytes, nrows, bit0, am, wr, rw, W, col[q]);
         }
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&empty[stage]);
@@ -242,13 +295,11 @@ __global__ void __launch_bounds__((kScanWarps + 1) * 32, 1) k_gso_scan_tma(const
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const int seg = warp + q * kScanWarps;
-        const int j0 = seg * 128 + lane * 4;
-        if (seg < segs && j0 < N) {
-          uint32_t* cb = colbits + ((size_t)b * N + j0) * W + rb;
-          cb[0] = col[q][0];
-          cb[W] = col[q][1];
-          cb[2 * (size_t)W] = col[q][2];
-          cb[3 * (size_t)W] = col[q][3];
+        if (seg >= segs) break;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int j = seg * 128 + 32 * k + lane;
+          if (j < N) colbits[((size_t)b * N + j) * W + rb] = col[q][k];
         }
       }
     }
@@ -630,11 +681,13 @@ extern "C" int magat_gso_scan(const void* S, int s_dtype, int B, int N, uint32_t
     if (nstages > 16) nstages = 16;
     const long bands = (long)B * W;
     const int grid = (int)(bands < sm_count ? bands : sm_count);
-    const size_t smem = (size_t)nstages * chunk_bytes + 2 * nstages * 8 + 256;
+    // + 1280: the consumers of the last column segment read up to 127 elements past a row's end (masked afterwards);
+    // for the last row of the last stage that lands behind the ring
+    const size_t smem = (size_t)nstages * chunk_bytes + 2 * nstages * 8 + 256 + 1280;
 #define MAGAT_SCAN(TT, RR)                                                                                      \
   do {                                                                                                         \
     const int kid = KID_SCAN_BASE + (sizeof(TT) == 8 ? 6 : 0) + (RR >= 32 ? 5 : RR >= 16 ? 4 : RR >= 8 ? 3 : RR >= 4 ? 2 : RR >= 2 ? 1 : 0); \
-    if (ensure_dyn_smem(kid, (const void*)k_gso_scan_tma<TT, RR>, kScanRing + 1024, "k_gso_scan_tma")) return MAGAT_E_CUDA; \
+    if (ensure_dyn_smem(kid, (const void*)k_gso_scan_tma<TT, RR>, kScanRing + 2048, "k_gso_scan_tma")) return MAGAT_E_CUDA; \
     k_gso_scan_tma<TT, RR><<<grid, (kScanWarps + 1) * 32, smem, st>>>((const TT*)S, N, W, bands, nstages, rowbits, \
                                                                       colbits);                                \
   } while (0)
