@@ -155,24 +155,24 @@ template <> struct EdgeS<double> {
   }
 };
 
-// R staged rows x one 128-column segment.  FULL: all R rows are there (no per-row guards around the ballots).
+// R staged rows x one segment of 32 KK columns.  FULL: all R rows are there (no per-row guards around the ballots).
 // Columns past N (last segment only) read whatever follows in the ring: their bits are cut out of the row words by
 // the masks below and their column words are never stored.
-// a[k] = (lane == k) ? mask of the in-range lanes of column group k : 0 -- lane k < 4 stores word k.
-template <typename T, int R, bool FULL>
+// a[k] = (lane == k) ? mask of the in-range lanes of column group k : 0 -- lane k < KK stores word k.
+template <typename T, int R, int KK, bool FULL>
 __device__ __forceinline__ void scan_rows(uint32_t addr, uint32_t row_bytes, int nrows, uint32_t bit0,
-                                          const uint32_t (&a)[4], bool wr, uint32_t* rw, int W, uint32_t (&col)[4]) {
+                                          const uint32_t (&a)[KK], bool wr, uint32_t* rw, int W, uint32_t (&col)[KK]) {
   constexpr int RB = R < 8 ? R : 8;                   // rows whose loads are issued back to back
   unsigned woff = 0;
 #pragma unroll
   for (int r0 = 0; r0 < R; r0 += RB) {
     if (!FULL && r0 >= nrows) break;
-    T v[RB][4];
+    T v[RB][KK];
     uint32_t ad = addr;
 #pragma unroll
     for (int u = 0; u < RB; ++u) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) v[u][k] = EdgeS<T>::ld(ad + (uint32_t)(32 * k * sizeof(T)));
+      for (int k = 0; k < KK; ++k) v[u][k] = EdgeS<T>::ld(ad + (uint32_t)(32 * k * sizeof(T)));
       ad += row_bytes;
     }
     addr = ad;
@@ -180,15 +180,14 @@ __device__ __forceinline__ void scan_rows(uint32_t addr, uint32_t row_bytes, int
     for (int u = 0; u < RB; ++u) {
       const int r = r0 + u;
       if (FULL || r < nrows) {
-        const bool p0 = is_edge<T>(v[u][0]), p1 = is_edge<T>(v[u][1]), p2 = is_edge<T>(v[u][2]), p3 = is_edge<T>(v[u][3]);
-        const uint32_t w0 = __ballot_sync(0xffffffffu, p0), w1 = __ballot_sync(0xffffffffu, p1);
-        const uint32_t w2 = __ballot_sync(0xffffffffu, p2), w3 = __ballot_sync(0xffffffffu, p3);
         const uint32_t bit = bit0 << r;
-        col[0] |= p0 ? bit : 0u;
-        col[1] |= p1 ? bit : 0u;
-        col[2] |= p2 ? bit : 0u;
-        col[3] |= p3 ? bit : 0u;
-        const uint32_t w = (w0 & a[0]) | (w1 & a[1]) | (w2 & a[2]) | (w3 & a[3]);
+        uint32_t w = 0;
+#pragma unroll
+        for (int k = 0; k < KK; ++k) {
+          const bool pk = is_edge<T>(v[u][k]);
+          w |= __ballot_sync(0xffffffffu, pk) & a[k];
+          col[k] |= pk ? bit : 0u;
+        }
         if (wr) rw[woff] = w;
       }
       woff += (unsigned)W;
@@ -196,10 +195,11 @@ __device__ __forceinline__ void scan_rows(uint32_t addr, uint32_t row_bytes, int
   }
 }
 
-constexpr int kScanWarps = 8;                 // consumer warps; warp 8 is the copy issuer
+constexpr int kScanWarps = 16;                // consumer warps; warp 16 is the copy issuer
 constexpr int kScanRing = 192 * 1024;
 
-template <typename T, int R>
+// KK: 32-column groups per consumer warp (2 for N <= 1024 -- sixteen warps on 64-column segments --, 4 up to N = 2048)
+template <typename T, int R, int KK>
 __global__ void __launch_bounds__((kScanWarps + 1) * 32, 1) k_gso_scan_tma(const T* __restrict__ S, int N, int W,
                                                                            long bands, int nstages,
                                                                            uint32_t* __restrict__ rowbits,
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__((kScanWarps + 1) * 32, 1) k_gso_scan_tma(const
   }
   __syncthreads();
   const int chunks_per_band = 32 / R;
-  const int segs = (N + 127) / 128;
+  const int segs = (N + 32 * KK - 1) / (32 * KK);       // <= kScanWarps
 
   if (warp == kScanWarps) {
     // ===== copy issuer ======================================================================
@@ -246,60 +246,53 @@ __global__ void __launch_bounds__((kScanWarps + 1) * 32, 1) k_gso_scan_tma(const
     }
   } else {
     // ===== consumers ========================================================================
-    // Warp w owns the 128-column segments w and w + 8 of every staged row.  Lane l reads columns 32k + l of the segment
-    // (k = 0..3; conflict-free scalar shared loads): one ballot per 32 columns IS the row word, and the lane's own
-    // predicate is its bit of the transposed column word -- no nibble packing, no shuffles (the first version of this
-    // loop spent 106 instructions per row segment and paced the kernel at 56 % of the DRAM peak; this one ~30).
+    // Warp w owns the 32 KK-column segment w of every staged row.  Lane l reads columns 32k + l of the segment
+    // (conflict-free scalar shared loads): one ballot per 32 columns IS the row word, and the lane's own predicate is
+    // its bit of the transposed column word -- no nibble packing, no shuffles (the first version of this loop spent 106
+    // instructions per 128 columns of a row and paced the kernel at 56 % of the DRAM peak; this one ~28).
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t smem_s = tc::smem_u32(smem);
+    const int seg = warp;
+    const bool active = seg < segs;
+    const int j = seg * (32 * KK) + lane;
+    uint32_t am[KK];
+#pragma unroll
+    for (int k = 0; k < KK; ++k) {
+      const uint32_t vm = __ballot_sync(0xffffffffu, j + 32 * k < N);
+      am[k] = lane == k ? vm : 0u;
+      asm volatile("" : "+r"(am[k]));                   // keep it a register value (not re-derived per row)
+    }
+    const bool wr = active && lane < KK && seg * KK + lane < W;
     for (long band = blockIdx.x; band < bands; band += gridDim.x) {
       const long b = band / W;
       const int rb = (int)(band - b * W);
       const int i0 = rb * 32;
-      uint32_t col[2][4];
+      uint32_t col[KK];
 #pragma unroll
-      for (int q = 0; q < 2; ++q)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) col[q][e] = 0u;
+      for (int k = 0; k < KK; ++k) col[k] = 0u;
       for (int c = 0; c < chunks_per_band; ++c) {
         const int r_first = i0 + c * R;
         int nrows = N - r_first;
         if (nrows > R) nrows = R;
         if (nrows <= 0) break;
         tc::mbar_wait(&full[stage], phase);
-        const uint32_t tile_s = smem_s + (uint32_t)((size_t)stage * chunk_bytes);
-        const uint32_t bit0 = 1u << (c * R);                  // bit of the chunk's first row inside the band
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int seg = warp + q * kScanWarps;
-          if (seg >= segs) break;
-          const int j = seg * 128 + lane;
-          uint32_t am[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t vm = __ballot_sync(0xffffffffu, j + 32 * k < N);
-            am[k] = lane == k ? vm : 0u;
-            asm volatile("" : "+r"(am[k]));               // keep it a register value (not re-derived per row)
-          }
-          const uint32_t addr = tile_s + (uint32_t)(j * sizeof(T));
-          uint32_t* rw = rowbits + ((size_t)b * N + r_first) * W + seg * 4 + lane;
-          const bool wr = lane < 4 && seg * 4 + lane < W;
-          if (nrows == R) scan_rows<T, R, true>(addr, (uint32_t)row_bytes, nrows, bit0, am, wr, rw, W, col[q]);
-          else scan_rows<T, R, false>(addr, (uint32_t)row_bytes, nrows, bit0, am, wr, rw, W, col[q]);
+        if (active) {
+          const uint32_t addr = smem_s + (uint32_t)((size_t)stage * chunk_bytes) + (uint32_t)(j * sizeof(T));
+          const uint32_t bit0 = 1u << (c * R);                // bit of the chunk's first row inside the band
+          uint32_t* rw = rowbits + ((size_t)b * N + r_first) * W + seg * KK + lane;
+          if (nrows == R) scan_rows<T, R, KK, true>(addr, (uint32_t)row_bytes, nrows, bit0, am, wr, rw, W, col);
+          else scan_rows<T, R, KK, false>(addr, (uint32_t)row_bytes, nrows, bit0, am, wr, rw, W, col);
         }
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&empty[stage]);
         if (++stage == nstages) { stage = 0; phase ^= 1; }
       }
+      if (active) {
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int seg = warp + q * kScanWarps;
-        if (seg >= segs) break;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int j = seg * 128 + 32 * k + lane;
-          if (j < N) colbits[((size_t)b * N + j) * W + rb] = col[q][k];
+        for (int k = 0; k < KK; ++k) {
+          const int jj = j + 32 * k;
+          if (jj < N) colbits[((size_t)b * N + jj) * W + rb] = col[k];
         }
       }
     }
@@ -684,12 +677,19 @@ extern "C" int magat_gso_scan(const void* S, int s_dtype, int B, int N, uint32_t
     // + 1280: the consumers of the last column segment read up to 127 elements past a row's end (masked afterwards);
     // for the last row of the last stage that lands behind the ring
     const size_t smem = (size_t)nstages * chunk_bytes + 2 * nstages * 8 + 256 + 1280;
-#define MAGAT_SCAN(TT, RR)                                                                                      \
+#define MAGAT_SCAN_K(TT, RR, KKV)                                                                               \
   do {                                                                                                         \
-    const int kid = KID_SCAN_BASE + (sizeof(TT) == 8 ? 6 : 0) + (RR >= 32 ? 5 : RR >= 16 ? 4 : RR >= 8 ? 3 : RR >= 4 ? 2 : RR >= 2 ? 1 : 0); \
-    if (ensure_dyn_smem(kid, (const void*)k_gso_scan_tma<TT, RR>, kScanRing + 2048, "k_gso_scan_tma")) return MAGAT_E_CUDA; \
-    k_gso_scan_tma<TT, RR><<<grid, (kScanWarps + 1) * 32, smem, st>>>((const TT*)S, N, W, bands, nstages, rowbits, \
-                                                                      colbits);                                \
+    const int kid = KID_SCAN_BASE + (KKV == 4 ? 12 : 0) + (sizeof(TT) == 8 ? 6 : 0) +                           \
+                    (RR >= 32 ? 5 : RR >= 16 ? 4 : RR >= 8 ? 3 : RR >= 4 ? 2 : RR >= 2 ? 1 : 0);              \
+    if (ensure_dyn_smem(kid, (const void*)k_gso_scan_tma<TT, RR, KKV>, kScanRing + 2048, "k_gso_scan_tma"))    \
+      return MAGAT_E_CUDA;                                                                                     \
+    k_gso_scan_tma<TT, RR, KKV><<<grid, (kScanWarps + 1) * 32, smem, st>>>((const TT*)S, N, W, bands, nstages, \
+                                                                           rowbits, colbits);                  \
+  } while (0)
+#define MAGAT_SCAN(TT, RR)             \
+  do {                                 \
+    if (N <= 1024) MAGAT_SCAN_K(TT, RR, 2); \
+    else MAGAT_SCAN_K(TT, RR, 4);      \
   } while (0)
 #define MAGAT_SCAN_R(TT)                          \
   switch (R) {                                    \
@@ -703,6 +703,7 @@ extern "C" int magat_gso_scan(const void* S, int s_dtype, int B, int N, uint32_t
     if (s_dtype == MAGAT_DT_F32) MAGAT_SCAN_R(float) else MAGAT_SCAN_R(double)
 #undef MAGAT_SCAN_R
 #undef MAGAT_SCAN
+#undef MAGAT_SCAN_K
   } else if (N % 4 == 0 && ((uintptr_t)S % 16) == 0) {
     const int segs = cdiv(N, 128);
     const long units = (long)B * W * segs;
