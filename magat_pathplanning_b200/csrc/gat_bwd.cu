@@ -276,14 +276,19 @@ __global__ void __launch_bounds__(256, MINB) k_tap_bwd_v(const float* __restrict
     }
     return;
   }
+  // Everything this row needs that does not depend on its neighbour list is requested up front, next to the list
+  // itself: the accumulators START as the row's own plane k-1 (the read of its read-modify-write) and dsum as the
+  // datt it adds to, so neither costs a serialised round trip to memory after the edge loop (nor a register).
   float am[PT], dsum[PT];
 #pragma unroll
   for (int q = 0; q < PT; ++q) { am[q] = 0.f; dsum[q] = 0.f; }
+  float* da = datt + ((size_t)row * D + lane) * PT;
   if (my_j >= 0) ldp<PT>(att + ((size_t)row * D + lane) * PT, am);
+  if (!first && lane < D) ldp<PT>(da, dsum);
   float4 u[PT], acc[PT];
 #pragma unroll
   for (int q = 0; q < PT; ++q) {
-    acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    acc[q] = *reinterpret_cast<const float4*>(gz + (((size_t)row * PT + q) * K + (k - 1)) * G + g0);
     u[q] = (k == 1) ? __ldg(reinterpret_cast<const float4*>(x + b * x_sb + (row - b * N) * x_sn + g0))
                     : __ldg(reinterpret_cast<const float4*>(taps + (((size_t)row * PT + q) * (K - 1) + (k - 2)) * G + g0));
   }
@@ -306,7 +311,7 @@ __global__ void __launch_bounds__(256, MINB) k_tap_bwd_v(const float* __restrict
         const float a = __shfl_sync(0xffffffffu, am[q], (s + w) & 31);
         float d = bdot4(u[q], gv[w][q]);
         d = warp_sum(d);
-        if (lane == s + w) dsum[q] = d;
+        if (lane == s + w) dsum[q] += d;
         bfma4(acc[q], a, gv[w][q]);
       }
     }
@@ -316,34 +321,16 @@ __global__ void __launch_bounds__(256, MINB) k_tap_bwd_v(const float* __restrict
     // kernel used (heads ascending), instead of writing P rows back and reading them again
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int q = 0; q < PT; ++q) {
-      const float4 o = *reinterpret_cast<const float4*>(gz + (((size_t)row * PT + q) * K + (k - 1)) * G + g0);
-      t.x += o.x + acc[q].x; t.y += o.y + acc[q].y; t.z += o.z + acc[q].z; t.w += o.w + acc[q].w;
-    }
+    for (int q = 0; q < PT; ++q) { t.x += acc[q].x; t.y += acc[q].y; t.z += acc[q].z; t.w += acc[q].w; }
     *reinterpret_cast<float4*>(g0sum + (size_t)row * G + g0) = t;
   } else {
 #pragma unroll
-    for (int q = 0; q < PT; ++q) {
-      float4* dst = reinterpret_cast<float4*>(gz + (((size_t)row * PT + q) * K + (k - 1)) * G + g0);
-      float4 o = *dst;
-      o.x += acc[q].x; o.y += acc[q].y; o.z += acc[q].z; o.w += acc[q].w;
-      *dst = o;
-    }
+    for (int q = 0; q < PT; ++q)
+      *reinterpret_cast<float4*>(gz + (((size_t)row * PT + q) * K + (k - 1)) * G + g0) = acc[q];
   }
   float o[PT];
 #pragma unroll
-  for (int q = 0; q < PT; ++q) o[q] = 0.f;
-  float* da = datt + ((size_t)row * D + lane) * PT;
-  if (lane < D) {
-    if (first) {
-#pragma unroll
-      for (int q = 0; q < PT; ++q) o[q] = dsum[q];
-    } else {
-      ldp<PT>(da, o);
-#pragma unroll
-      for (int q = 0; q < PT; ++q) o[q] += dsum[q];
-    }
-  }
+  for (int q = 0; q < PT; ++q) o[q] = lane < D ? dsum[q] : 0.f;
   if (rc_out == nullptr) {
     if (lane < D) stp<PT>(da, o);
     return;
@@ -378,6 +365,139 @@ __global__ void __launch_bounds__(256, MINB) k_tap_bwd_v(const float* __restrict
   }
 #pragma unroll
   for (int q = 0; q < PT; ++q) *reinterpret_cast<float4*>(rc_out + ((size_t)row * PT + q) * G + g0) = racc[q];
+}
+
+// Sum NV per-lane values over the warp at once: every step halves the number of live values and doubles the lanes
+// each has absorbed (NV - 1 + log2(32 / NV) shuffles instead of 5 NV).  Lane l ends up with the total of value
+// l >> (5 - log2 NV).
+template <int NV>
+__device__ __forceinline__ float warp_multi_sum(float (&v)[NV], int lane) {
+  int off = 16;
+#pragma unroll
+  for (int n = NV; n > 1; n >>= 1, off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float keep = hi ? v[i + n / 2] : v[i];
+      const float send = hi ? v[i] : v[i + n / 2];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+#pragma unroll
+  for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+  return v[0];
+}
+
+// The same level of the tap recursion backward, HP heads at a time (PT / HP passes over the row's edges) and FOUR edges
+// per step.  k_tap_bwd_v keeps all heads of two edges in registers: 80 registers plus an 80 B spill frame (ncu: a third
+// of its L2 traffic was local memory) at three CTAs per SM.  Half the heads need half the accumulators, so four edges
+// are in flight per step at the same register budget without spills, and the 4 x HP dot products of a step share one
+// joint reduction.
+template <int PT, int HP>
+__global__ void __launch_bounds__(256, 3) k_tap_bwd_p(const float* __restrict__ x, long x_sb, long x_sn,
+                                                      const float* __restrict__ taps, const float* __restrict__ att,
+                                                      const int32_t* __restrict__ nbr_out, long rows, int N, int K, int D,
+                                                      int k, int first, float* __restrict__ gz, float* __restrict__ datt,
+                                                      float* __restrict__ g0sum, float* __restrict__ rc_out) {
+  constexpr int G = 128, EF = 4, NV = EF * HP;
+  constexpr int SH = NV == 8 ? 2 : NV == 4 ? 3 : 4;      // lane l holds the total of value l >> SH
+  const int lane = threadIdx.x & 31;
+  const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  const long b = batch_of32(row, N);
+  const int g0 = lane * 4;
+  const int my_j = lane < D ? nbr_out[row * D + lane] : -1;
+  const int deg = __popc(__ballot_sync(0xffffffffu, my_j >= 0));
+  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);            // g0sum: head sum of g_0
+#pragma unroll 1
+  for (int h0 = 0; h0 < PT; h0 += HP) {
+    float* da = datt + ((size_t)row * D + lane) * PT + h0;
+    float am[HP], dsum[HP];
+    float4 u[HP], acc[HP];
+#pragma unroll
+    for (int q = 0; q < HP; ++q) {
+      am[q] = my_j >= 0 ? att[((size_t)row * D + lane) * PT + h0 + q] : 0.f;
+      dsum[q] = (!first && lane < D) ? da[q] : 0.f;
+      acc[q] = *reinterpret_cast<const float4*>(gz + (((size_t)row * PT + h0 + q) * K + (k - 1)) * G + g0);
+      u[q] = (k == 1) ? __ldg(reinterpret_cast<const float4*>(x + b * x_sb + (row - b * N) * x_sn + g0))
+                      : __ldg(reinterpret_cast<const float4*>(taps + (((size_t)row * PT + h0 + q) * (K - 1) + (k - 2)) * G + g0));
+    }
+    for (int s = 0; s < deg; s += EF) {
+      float4 gv[EF][HP];
+#pragma unroll
+      for (int w = 0; w < EF; ++w) {
+        const int j = __shfl_sync(0xffffffffu, my_j, (s + w) & 31);
+#pragma unroll
+        for (int q = 0; q < HP; ++q)
+          gv[w][q] = s + w < deg ? *reinterpret_cast<const float4*>(gz + ((((size_t)(b * N + j)) * PT + h0 + q) * K + k) * G + g0)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      float d[NV];
+#pragma unroll
+      for (int w = 0; w < EF; ++w)
+#pragma unroll
+        for (int q = 0; q < HP; ++q) {
+          d[w * HP + q] = bdot4(u[q], gv[w][q]);
+          bfma4(acc[q], __shfl_sync(0xffffffffu, am[q], (s + w) & 31), gv[w][q]);
+        }
+      const float tot = warp_multi_sum<NV>(d, lane);
+      // lane s + w takes the HP totals of edge w
+      const int wme = (lane - s) & (EF - 1);
+      const bool mine = lane >= s && lane < s + EF;
+#pragma unroll
+      for (int q = 0; q < HP; ++q) {
+        const float dq = __shfl_sync(0xffffffffu, tot, (wme * HP + q) << SH);
+        if (mine) dsum[q] += dq;
+      }
+    }
+    if (g0sum != nullptr) {
+#pragma unroll
+      for (int q = 0; q < HP; ++q) { t.x += acc[q].x; t.y += acc[q].y; t.z += acc[q].z; t.w += acc[q].w; }
+    } else {
+#pragma unroll
+      for (int q = 0; q < HP; ++q)
+        *reinterpret_cast<float4*>(gz + (((size_t)row * PT + h0 + q) * K + (k - 1)) * G + g0) = acc[q];
+    }
+    if (rc_out == nullptr) {
+      if (lane < D && (first || deg > 0)) {
+#pragma unroll
+        for (int q = 0; q < HP; ++q) da[q] = dsum[q];
+      }
+      continue;
+    }
+    // Last level, KeyQuery: dA of this row is complete, so its softmax backward and dR_i = sum_j de[i,j] x_j follow
+    // here (same arithmetic as k_softmax_bwd_kq_v, which then need not run).  datt <- de.
+    float de[HP];
+#pragma unroll
+    for (int q = 0; q < HP; ++q) {
+      const float o = lane < D ? dsum[q] : 0.f;
+      const float dot = warp_sum(am[q] * o);
+      de[q] = am[q] * (o - dot);
+      if (lane < D) da[q] = de[q];
+    }
+    float4 racc[HP];
+#pragma unroll
+    for (int q = 0; q < HP; ++q) racc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < deg; s += 4) {
+      float4 xv[4];
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const int j = __shfl_sync(0xffffffffu, my_j, (s + w) & 31);
+        xv[w] = (s + w < deg) ? __ldg(reinterpret_cast<const float4*>(x + b * x_sb + (long)j * x_sn + g0))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+#pragma unroll
+        for (int q = 0; q < HP; ++q) {
+          const float dd = __shfl_sync(0xffffffffu, de[q], (s + w) & 31);
+          bfma4(racc[q], s + w < deg ? dd : 0.f, xv[w]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < HP; ++q) *reinterpret_cast<float4*>(rc_out + ((size_t)row * PT + h0 + q) * G + g0) = racc[q];
+  }
+  if (g0sum != nullptr) *reinterpret_cast<float4*>(g0sum + (size_t)row * G + g0) = t;
 }
 
 // KeyQuery softmax backward + dR_i = sum_j de[i,j] x_j.  datt <- de in place.
@@ -891,12 +1011,12 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
     const int first = k == K - 1 ? 1 : 0;
     float* g0sum = (k == 1 && g0_in_dx) ? a->dx : nullptr;
     float* rc_fused = (k == 1 && fuse_softmax) ? a->rc : nullptr;
-#define MAGAT_TB(PT) \
-  k_tap_bwd_v<PT, 3><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->taps, a->att, a->nbr_out, rows, N, K, D, k, \
-                                                 first, a->gz, a->datt, g0sum, rc_fused)
-    if (vec && P == 4) MAGAT_TB(4);
-    else if (vec && P == 2) MAGAT_TB(2);
-    else if (vec && P == 1) MAGAT_TB(1);
+#define MAGAT_TB(PT, HPV) \
+  k_tap_bwd_p<PT, HPV><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->taps, a->att, a->nbr_out, rows, N, K, D, k, \
+                                                   first, a->gz, a->datt, g0sum, rc_fused)
+    if (vec && P == 4) MAGAT_TB(4, 2);
+    else if (vec && P == 2) MAGAT_TB(2, 2);
+    else if (vec && P == 1) MAGAT_TB(1, 1);
     else
       k_tap_bwd<<<row_blocks, 256, 0, st>>>(zn, a->att, a->nbr_out, rows, N, G, P, K, D, k, first, a->gz, a->datt);
 #undef MAGAT_TB
