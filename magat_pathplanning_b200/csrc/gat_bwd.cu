@@ -238,135 +238,6 @@ __device__ __forceinline__ void stp(float* p, const float* a) {
   }
 }
 
-// tap recursion backward, level k: one warp per sender row, lane l owns features 4l..4l+3 and out-slot l.
-template <int PT, int MINB>
-__global__ void __launch_bounds__(256, MINB) k_tap_bwd_v(const float* __restrict__ x, long x_sb, long x_sn,
-                                                   const float* __restrict__ taps, const float* __restrict__ att,
-                                                   const int32_t* __restrict__ nbr_out, long rows, int N, int K, int D,
-                                                   int k, int first, float* __restrict__ gz, float* __restrict__ datt,
-                                                   float* __restrict__ g0sum, float* __restrict__ rc_out) {
-  constexpr int G = 128;
-  const int lane = threadIdx.x & 31;
-  const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (row >= rows) return;
-  const long b = batch_of32(row, N);
-  const int g0 = lane * 4;
-  const int my_j = lane < D ? nbr_out[row * D + lane] : -1;
-  const int deg = __popc(__ballot_sync(0xffffffffu, my_j >= 0));
-  if (deg == 0) {
-    if (rc_out != nullptr) {                // fused softmax backward of an empty row: de = 0, dR = 0
-#pragma unroll
-      for (int q = 0; q < PT; ++q)
-        *reinterpret_cast<float4*>(rc_out + ((size_t)row * PT + q) * G + g0) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    if ((first || rc_out != nullptr) && lane < D) {
-      float z[PT];
-#pragma unroll
-      for (int q = 0; q < PT; ++q) z[q] = 0.f;
-      stp<PT>(datt + ((size_t)row * D + lane) * PT, z);
-    }
-    if (g0sum != nullptr) {                 // last level: the head sum of gU_0 is all that is left of this row
-      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int q = 0; q < PT; ++q) {
-        const float4 o = *reinterpret_cast<const float4*>(gz + (((size_t)row * PT + q) * K + (k - 1)) * G + g0);
-        t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w;
-      }
-      *reinterpret_cast<float4*>(g0sum + (size_t)row * G + g0) = t;
-    }
-    return;
-  }
-  // Everything this row needs that does not depend on its neighbour list is requested up front, next to the list
-  // itself: the accumulators START as the row's own plane k-1 (the read of its read-modify-write) and dsum as the
-  // datt it adds to, so neither costs a serialised round trip to memory after the edge loop (nor a register).
-  float am[PT], dsum[PT];
-#pragma unroll
-  for (int q = 0; q < PT; ++q) { am[q] = 0.f; dsum[q] = 0.f; }
-  float* da = datt + ((size_t)row * D + lane) * PT;
-  if (my_j >= 0) ldp<PT>(att + ((size_t)row * D + lane) * PT, am);
-  if (!first && lane < D) ldp<PT>(da, dsum);
-  float4 u[PT], acc[PT];
-#pragma unroll
-  for (int q = 0; q < PT; ++q) {
-    acc[q] = *reinterpret_cast<const float4*>(gz + (((size_t)row * PT + q) * K + (k - 1)) * G + g0);
-    u[q] = (k == 1) ? __ldg(reinterpret_cast<const float4*>(x + b * x_sb + (row - b * N) * x_sn + g0))
-                    : __ldg(reinterpret_cast<const float4*>(taps + (((size_t)row * PT + q) * (K - 1) + (k - 2)) * G + g0));
-  }
-  for (int s = 0; s < deg; s += 2) {
-    int jj[2];
-    float4 gv[2][PT];
-#pragma unroll
-    for (int w = 0; w < 2; ++w) {
-      jj[w] = __shfl_sync(0xffffffffu, my_j, (s + w) & 31);
-      if (s + w >= deg) jj[w] = -1;
-#pragma unroll
-      for (int q = 0; q < PT; ++q)
-        gv[w][q] = jj[w] >= 0 ? *reinterpret_cast<const float4*>(gz + ((((size_t)(b * N + jj[w])) * PT + q) * K + k) * G + g0)
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int w = 0; w < 2; ++w) {
-#pragma unroll
-      for (int q = 0; q < PT; ++q) {
-        const float a = __shfl_sync(0xffffffffu, am[q], (s + w) & 31);
-        float d = bdot4(u[q], gv[w][q]);
-        d = warp_sum(d);
-        if (lane == s + w) dsum[q] += d;
-        bfma4(acc[q], a, gv[w][q]);
-      }
-    }
-  }
-  if (g0sum != nullptr) {
-    // k == 1 and only dx consumes g_0 = gU_0 + A g_1: sum it over the heads here, in the order the column
-    // kernel used (heads ascending), instead of writing P rows back and reading them again
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int q = 0; q < PT; ++q) { t.x += acc[q].x; t.y += acc[q].y; t.z += acc[q].z; t.w += acc[q].w; }
-    *reinterpret_cast<float4*>(g0sum + (size_t)row * G + g0) = t;
-  } else {
-#pragma unroll
-    for (int q = 0; q < PT; ++q)
-      *reinterpret_cast<float4*>(gz + (((size_t)row * PT + q) * K + (k - 1)) * G + g0) = acc[q];
-  }
-  float o[PT];
-#pragma unroll
-  for (int q = 0; q < PT; ++q) o[q] = lane < D ? dsum[q] : 0.f;
-  if (rc_out == nullptr) {
-    if (lane < D) stp<PT>(da, o);
-    return;
-  }
-  // Last level, KeyQuery: dA of this row is complete, so its softmax backward and dR_i = sum_j de[i,j] x_j follow
-  // here (same arithmetic as k_softmax_bwd_kq_v, which then need not run).  datt <- de.
-  float de[PT];
-#pragma unroll
-  for (int q = 0; q < PT; ++q) {
-    const float dot = warp_sum(am[q] * o[q]);
-    de[q] = am[q] * (o[q] - dot);
-  }
-  if (lane < D) stp<PT>(da, de);
-  float4 racc[PT];
-#pragma unroll
-  for (int q = 0; q < PT; ++q) racc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int s = 0; s < deg; s += 4) {
-    float4 xv[4];
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const int j = __shfl_sync(0xffffffffu, my_j, (s + w) & 31);
-      xv[w] = (s + w < deg) ? __ldg(reinterpret_cast<const float4*>(x + b * x_sb + (long)j * x_sn + g0))
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int w = 0; w < 4; ++w)
-#pragma unroll
-      for (int q = 0; q < PT; ++q) {
-        const float d = __shfl_sync(0xffffffffu, de[q], (s + w) & 31);
-        bfma4(racc[q], s + w < deg ? d : 0.f, xv[w]);
-      }
-  }
-#pragma unroll
-  for (int q = 0; q < PT; ++q) *reinterpret_cast<float4*>(rc_out + ((size_t)row * PT + q) * G + g0) = racc[q];
-}
-
 // Sum NV per-lane values over the warp at once: every step halves the number of live values and doubles the lanes
 // each has absorbed (NV - 1 + log2(32 / NV) shuffles instead of 5 NV).  Lane l ends up with the total of value
 // l >> (5 - log2 NV).
@@ -388,19 +259,22 @@ __device__ __forceinline__ float warp_multi_sum(float (&v)[NV], int lane) {
   return v[0];
 }
 
-// The same level of the tap recursion backward, HP heads at a time (PT / HP passes over the row's edges) and FOUR edges
-// per step.  k_tap_bwd_v keeps all heads of two edges in registers: 80 registers plus an 80 B spill frame (ncu: a third
-// of its L2 traffic was local memory) at three CTAs per SM.  Half the heads need half the accumulators, so four edges
-// are in flight per step at the same register budget without spills, and the 4 x HP dot products of a step share one
-// joint reduction.
-template <int PT, int HP>
-__global__ void __launch_bounds__(256, 3) k_tap_bwd_p(const float* __restrict__ x, long x_sb, long x_sn,
+// Tap recursion backward, level k: one warp per sender row, lane l owns features 4l..4l+3 and out-slot l.  HP heads
+// at a time (PT / HP passes over the row's edges), EF edges per step.  (A first version kept all heads of two edges in
+// registers: 80 registers plus an 80 B spill frame -- ncu: a third of its L2 traffic was local memory -- at three CTAs
+// per SM, and reduced every (edge, head) dot product on its own: 2.33 ms for both levels at B = 512, N = 1000.)
+// Half the heads need half the accumulators -- 64 registers, four CTAs per SM -- and the EF x HP dot products of a
+// step share one joint reduction.
+// Everything a pass needs that does not depend on the neighbour list is requested up front: the accumulators START
+// as the row's own plane k-1 (the read of its read-modify-write) and dsum as the datt it adds to.
+template <int PT, int HP, int EF, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_tap_bwd_p(const float* __restrict__ x, long x_sb, long x_sn,
                                                       const float* __restrict__ taps, const float* __restrict__ att,
                                                       const int32_t* __restrict__ nbr_out, long rows, int N, int K, int D,
                                                       int k, int first, float* __restrict__ gz, float* __restrict__ datt,
                                                       float* __restrict__ g0sum, float* __restrict__ rc_out) {
-  constexpr int G = 128, EF = 4, NV = EF * HP;
-  constexpr int SH = NV == 8 ? 2 : NV == 4 ? 3 : 4;      // lane l holds the total of value l >> SH
+  constexpr int G = 128, NV = EF * HP;
+  constexpr int SH = NV == 16 ? 1 : NV == 8 ? 2 : NV == 4 ? 3 : 4;      // lane l holds the total of value l >> SH
   const int lane = threadIdx.x & 31;
   const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= rows) return;
@@ -572,7 +446,7 @@ __global__ void __launch_bounds__(256) k_col_bwd_kq_v(const float* __restrict__ 
   for (int q = 0; q < PT; ++q) de[q] = 0.f;
   if (my_i >= 0) ldp<PT>(datt + ((size_t)(b * N + my_i) * D + slot_in[row * D + lane]) * PT, de);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (g0_in_dx) {                          // k_tap_bwd_v already left sum_p g_0^p in dx
+  if (g0_in_dx) {                          // k_tap_bwd_p already left sum_p g_0^p in dx
     acc = *reinterpret_cast<const float4*>(dx + (size_t)row * G + g0);
   } else {
 #pragma unroll
@@ -1011,15 +885,17 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
     const int first = k == K - 1 ? 1 : 0;
     float* g0sum = (k == 1 && g0_in_dx) ? a->dx : nullptr;
     float* rc_fused = (k == 1 && fuse_softmax) ? a->rc : nullptr;
-#define MAGAT_TB(PT, HPV) \
-  k_tap_bwd_p<PT, HPV><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->taps, a->att, a->nbr_out, rows, N, K, D, k, \
+#define MAGAT_TBX(PT, HPV, EFV, MB) \
+  k_tap_bwd_p<PT, HPV, EFV, MB><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->taps, a->att, a->nbr_out, rows, N, K, D, k, \
                                                    first, a->gz, a->datt, g0sum, rc_fused)
-    if (vec && P == 4) MAGAT_TB(4, 2);
-    else if (vec && P == 2) MAGAT_TB(2, 2);
-    else if (vec && P == 1) MAGAT_TB(1, 1);
+    // measured at B = 512, N = 1000, P = 4 (both levels): 2 heads x 2 edges at 4 CTAs/SM 1.76 ms; 2 x 4 at 4 CTAs/SM
+    // 1.80; 2 x 4 at 3 CTAs/SM 2.08; 4 x 2 at 3 CTAs/SM 1.93; one head per pass >= 2.07
+    if (vec && P == 4) MAGAT_TBX(4, 2, 2, 4);
+    else if (vec && P == 2) MAGAT_TBX(2, 2, 2, 4);
+    else if (vec && P == 1) MAGAT_TBX(1, 1, 4, 4);
     else
       k_tap_bwd<<<row_blocks, 256, 0, st>>>(zn, a->att, a->nbr_out, rows, N, G, P, K, D, k, first, a->gz, a->datt);
-#undef MAGAT_TB
+#undef MAGAT_TBX
     if ((rc = check_launch("k_tap_bwd", st))) return rc;
   }
   const int has_datt = K > 1 ? 1 : 0;
