@@ -426,8 +426,8 @@ __global__ void __launch_bounds__(256) k_softmax_bwd_kq_v(const float* __restric
 }
 
 // KeyQuery column side: dx_j = sum_p gU_0[j] + sum_{i in in(j)} sum_p de_p[i,j] R_i^p
-template <int PT>
-__global__ void __launch_bounds__(256) k_col_bwd_kq_v(const float* __restrict__ gz, const float* __restrict__ datt,
+template <int PT, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_col_bwd_kq_v(const float* __restrict__ gz, const float* __restrict__ datt,
                                                       const float* __restrict__ sproj,
                                                       const int32_t* __restrict__ nbr_in,
                                                       const int32_t* __restrict__ slot_in, long rows, int N, int K,
@@ -930,9 +930,12 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
       if (rc > 0) return rc;
       if (rc == 0) { dx_done = 1; dxp = a->gz; }
     }
-#define MAGAT_CB(PT) \
-  k_col_bwd_kq_v<PT><<<row_blocks, 256, 0, st>>>(a->gz, a->datt, a->sproj, a->nbr_in, a->slot_in, rows, N, K, D, \
-                                                 g0_in_dx ? 1 : 0, dxp, dxp ? P / 2 : 0, a->dx)
+#define MAGAT_CBX(PT, MB) \
+  k_col_bwd_kq_v<PT, MB><<<row_blocks, 256, 0, st>>>(a->gz, a->datt, a->sproj, a->nbr_in, a->slot_in, rows, N, K, D, \
+                                                     g0_in_dx ? 1 : 0, dxp, dxp ? P / 2 : 0, a->dx)
+    // eight CTAs per SM (32 registers, the gathers consumed one by one) beat fewer, fuller warps here: 0.44 ms against
+    // 0.46 at five and 0.49 at four CTAs per SM
+#define MAGAT_CB(PT) MAGAT_CBX(PT, 8)
     if (vec && a->need_dx && P == 4) MAGAT_CB(4);
     else if (vec && a->need_dx && P == 2) MAGAT_CB(2);
     else if (vec && a->need_dx && P == 1) MAGAT_CB(1);
@@ -941,6 +944,7 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
                                                                   a->slot_in, rows, N, G, P, K, D, a->rc,
                                                                   a->need_dx ? a->dx : nullptr);
 #undef MAGAT_CB
+#undef MAGAT_CBX
     if ((rc = check_launch("k_col_bwd", st))) return rc;
     if (dx_done) {
     } else if (a->need_dx && a->path != MAGAT_PATH_SIMT && dx_tc_supported(a)) {
