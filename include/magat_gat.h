@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define MAGAT_ABI_VERSION 10
+#define MAGAT_ABI_VERSION 11
 
 enum {
   MAGAT_OK = 0,
@@ -155,6 +155,20 @@ int magat_gat_forward_taps_valid(const magat_gat_fwd_args* a);
  * only then may the buffer be passed on as bwd.relu_bits. */
 int magat_gat_forward_relu_bits_valid(const magat_gat_fwd_args* a);
 size_t magat_gat_relu_bits_words(int B, int N, int P, int F);
+
+
+/* ---- layer + linear action head in one pass (inference) ----
+ * The planner feeds the layer's output straight into actionsMLP (graphs/models/decentralplanner_GAT.py:329-334; one
+ * nn.Linear(P*F -> 5) in the published configurations) and decodes the action as argmax softmax
+ * (utils/new_simulator.py:863-869).  This call runs magat_gat_forward with the head folded into the epilogue of the K-tap
+ * projection: y (4*P*F bytes per agent) is never written.  a->y is ignored (may be NULL), a->relu / a->bias apply as usual.
+ * head_weight [A][P*F] and head_bias [A] (or NULL) are the nn.Linear parameters, A <= 8; partial is P * B*N * 8 floats of
+ * scratch (16 B aligned); logits [B*N][A]; actions_or_null [B*N] receives argmax_a (first maximum on ties, as torch.max).
+ * Covers what the tcgen05 K-tap projection covers: concatenated heads, F = 128, G a multiple of 128, K <= 3
+ * (magat_gat_actions_supported); MAGAT_E_UNSUPPORTED otherwise. */
+int magat_gat_actions_supported(const magat_gat_fwd_args* a, int A);
+int magat_gat_forward_actions(const magat_gat_fwd_args* a, const float* head_weight, const float* head_bias, int A,
+                              float* partial, float* logits, int32_t* actions_or_null, void* stream);
 
 
 /* ---- fused forward: ONE launch from the dense GSO to y (graphML.py:4636-4667 over :1724-1827, :1180-1286, :713-823) ----

@@ -7,12 +7,12 @@ the same kernels.  See DESIGN.md / INTEGRATION.md.
 """
 from .graphML import (GraphFilterBatchAttentional, graphAttentionLSIGFBatch_KeyQuery,  # noqa: F401
                       graphAttentionLSIGFBatch_modified, learnAttentionGSOBatch_KeyQuery,
-                      learnAttentionGSOBatch, build_adjacency, build_adjacency_from_positions, gat_layer,
+                      learnAttentionGSOBatch, build_adjacency, build_adjacency_from_positions, gat_layer, gat_layer_actions,
                       attention_dense, GraphFilterBatch, BatchLSIGF, pack_gso_host, build_adjacency_host,
                       build_adjacency_from_rowbits)
 from .integration import install_into_reference  # noqa: F401
 
 __all__ = ["GraphFilterBatchAttentional", "graphAttentionLSIGFBatch_KeyQuery",
            "graphAttentionLSIGFBatch_modified", "learnAttentionGSOBatch_KeyQuery", "learnAttentionGSOBatch",
-           "build_adjacency", "build_adjacency_from_positions", "gat_layer", "attention_dense", "install_into_reference",
+           "build_adjacency", "build_adjacency_from_positions", "gat_layer", "gat_layer_actions", "attention_dense", "install_into_reference",
            "GraphFilterBatch", "BatchLSIGF", "pack_gso_host", "build_adjacency_host", "build_adjacency_from_rowbits"]

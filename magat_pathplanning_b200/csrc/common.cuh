@@ -17,6 +17,16 @@ enum { KID_TC_GEMM = 0, KID_TAP_TC4, KID_TAP_TC8, KID_WGRAD, KID_SMALL, KID_TAP_
        KID_SCAN_BASE /* + 24 dtype / R / KK variants */ = 16, KID_MAX = 40 };
 int ensure_dyn_smem(int kernel_id, const void* func, size_t bytes, const char* name);
 
+// fused linear head of the K-tap projection (magat_gat_forward_actions)
+struct HeadArgs {
+  const float* w;      // [A][P*F]
+  const float* b;      // [A] or null
+  int A;
+  float* partial;      // [P][rows][8] scratch
+  float* logits;       // [rows][A]
+  int32_t* actions;    // [rows] argmax, or null
+};
+
 #define MAGAT_REQUIRE(cond, code, ...)        \
   do {                                        \
     if (!(cond)) {                            \

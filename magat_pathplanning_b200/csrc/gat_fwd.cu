@@ -572,9 +572,10 @@ int tc_split_weights(const float* src, long n, __nv_bfloat16* hi, __nv_bfloat16*
 int tc_split_weights_t(const float* W, int G, int P, __nv_bfloat16* hi, __nv_bfloat16* lo, cudaStream_t st);
 
 bool tap_tc_supported(const magat_gat_fwd_args* a);              // gat_tap_tc.cu
+bool tap_tc_supported_no_y(const magat_gat_fwd_args* a);
 bool score_tc_supported(const magat_gat_fwd_args* a);
 int score_tc_forward(const magat_gat_fwd_args* a, float* wt, cudaStream_t st);
-int tap_tc_forward(const magat_gat_fwd_args* a, cudaStream_t st);
+int tap_tc_forward(const magat_gat_fwd_args* a, cudaStream_t st, const HeadArgs* head);
 
 // one level of the tap recursion, u_k from u_{k-1} (k >= 1), for every head
 int run_tap_gather(const float* x, long x_sb, long x_sn, const float* att, const int32_t* nbr_in,
@@ -613,7 +614,7 @@ static size_t simt_wprep_floats(int G, int P, int mode) {
   return (n + 3) & ~(size_t)3;     // keeps the bf16 region behind it 16 B aligned
 }
 
-static int forward_impl(const magat_gat_fwd_args* a, cudaStream_t st, bool use_tc) {
+static int forward_impl(const magat_gat_fwd_args* a, cudaStream_t st, bool use_tc, const HeadArgs* head = nullptr) {
   const int B = a->B, N = a->N, G = a->G, F = a->F, K = a->K, P = a->P, D = a->D;
   const long rows = (long)B * N;
   const int row_blocks = cdiv(rows, 8);
@@ -709,7 +710,11 @@ static int forward_impl(const magat_gat_fwd_args* a, cudaStream_t st, bool use_t
                              ain_w ? a->ain : nullptr, ain_w ? 1 : 0, st)))
       return rc;
   // 3. per-(head, tap) projection + bias + activation + concat / head mean
-  if (fused) return tap_tc_forward(a, st);
+  if (fused) return tap_tc_forward(a, st, head);
+  if (head != nullptr) {
+    set_error("magat_gat_forward_actions: shape not covered by the tcgen05 K-tap projection");
+    return MAGAT_E_UNSUPPORTED;
+  }
   if (use_tc) return tc_tap_projection(a, h_hi, h_lo, st);
   const int per_head = a->concat ? 1 : 0;
   const ZLoad zl{a->x, a->x_sb, a->x_sn, a->taps, N, G, K, P, per_head};
@@ -745,6 +750,33 @@ extern "C" int magat_gat_forward_relu_bits_valid(const magat_gat_fwd_args* a) {
 extern "C" size_t magat_gat_relu_bits_words(int B, int N, int P, int F) {
   const size_t rows = (size_t)B * N;
   return ((rows + 63) / 64) * 2 * (size_t)P * F;
+}
+
+// the layer and the planner's linear action head in one pass (inference).  y never reaches memory.
+extern "C" int magat_gat_actions_supported(const magat_gat_fwd_args* a, int A) {
+  if (a == nullptr || A < 1 || A > 8 || a->path == MAGAT_PATH_SIMT) return 0;
+  return tc_supported(a) && tap_tc_supported_no_y(a) ? 1 : 0;
+}
+
+extern "C" int magat_gat_forward_actions(const magat_gat_fwd_args* a, const float* head_weight, const float* head_bias,
+                                         int A, float* partial, float* logits, int32_t* actions_or_null, void* stream) {
+  MAGAT_REQUIRE(a != nullptr && head_weight && partial && logits, MAGAT_E_BAD_ARG,
+                "magat_gat_forward_actions: null pointer");
+  int rc = validate_common(a->B, a->N, a->G, a->F, a->K, a->P, a->D, a->mode);
+  if (rc) return rc;
+  MAGAT_REQUIRE(a->x && a->nbr_out && a->nbr_in && a->slot_in && a->weight && a->filterWeight && a->att && a->sproj &&
+                    a->wprep,
+                MAGAT_E_BAD_ARG, "magat_gat_forward_actions: null pointer");
+  MAGAT_REQUIRE(a->K == 1 || a->taps, MAGAT_E_BAD_ARG, "magat_gat_forward_actions: taps buffer missing for K=%d", a->K);
+  MAGAT_REQUIRE(a->mode != MAGAT_MODE_GAT_MODIFIED || (a->mixer && a->weight_bias), MAGAT_E_BAD_ARG,
+                "magat_gat_forward_actions: GAT_modified needs mixer and weight_bias");
+  MAGAT_REQUIRE(magat_gat_actions_supported(a, A), MAGAT_E_UNSUPPORTED,
+                "magat_gat_forward_actions: needs concatenated heads, F = 128, G multiple of 128, K <= 3, A <= 8");
+  MAGAT_REQUIRE(((uintptr_t)partial % 16) == 0, MAGAT_E_BAD_ARG, "magat_gat_forward_actions: partial not 16 B aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin(st);
+  const HeadArgs head{head_weight, head_bias, A, partial, logits, actions_or_null};
+  return forward_impl(a, st, true, &head);
 }
 
 extern "C" int magat_gat_forward(const magat_gat_fwd_args* a, void* stream) {

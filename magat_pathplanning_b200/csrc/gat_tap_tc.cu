@@ -48,6 +48,9 @@ struct TapParams {
   float* y; long y_sb, y_sn;     // channel stride 1
   int nout;                      // P counts weight blocks; nout consecutive blocks share one operand tile
   uint32_t* relu_bits_out; int bits_out_C;   // optional: bit (y > 0) per output element, layout as mask_bits
+  // optional fused linear head (the planner's actionsMLP, decentralplanner_GAT.py:329-334): y is NOT
+  // stored; head_partial[(p * rows + m) * 8 + a] = sum_f y[m][p*F + f] * head_w[a][p*F + f]  (a < head_A <= 8)
+  const float* head_w; int head_A; float* head_partial;
   int accum;                     // y += result (the caller guarantees one weight-block group, i.e. no two CTAs ever touch
                                  // the same output row)
 };
@@ -69,7 +72,12 @@ constexpr int V2_NOP = 2;                               // operand stages (one p
 constexpr int V2_RAW_BYTES = 128 * 1024;                // raw ring: 4 slots of 32 KB, or 2 of 64 KB with a mask
 constexpr int V2_CONV_WARPS = 16, V2_GROUP = 256;
 constexpr int V2_EPI_WARP0 = 16, V2_EPI_WARPS = 4, V2_MMA_WARP = 20, V2_TMA_WARP = 21, V2_THREADS = 22 * 32;
-constexpr size_t V2_SMEM_BYTES = (size_t)V2_NOP * STAGE_BYTES + V2_RAW_BYTES + 1024 + 256;
+// linear head: a [32 nodes][128 features] fp32 tile of y (row stride 144 floats: conflict-free for both the feature-
+// major writes and the node-major 16 B reads) + the head's [8][128] weight slice
+constexpr int V2_YS_STRIDE = 144;
+constexpr int V2_HEAD_BYTES = 32 * V2_YS_STRIDE * 4 + 8 * 128 * 4;
+constexpr size_t V2_SMEM_BYTES = (size_t)V2_NOP * STAGE_BYTES + V2_RAW_BYTES + 1024 + 256 + V2_HEAD_BYTES;
+static_assert(V2_SMEM_BYTES <= 227 * 1024, "k_tap_tc2 shared memory");
 
 
 template <int STRIDE>
@@ -114,6 +122,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_tap_tc2(const __grid_constant
   uint64_t* acc_full = bars + 12;            // [2]
   uint64_t* acc_empty = bars + 14;           // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  float* ys = reinterpret_cast<float*>(raw + V2_RAW_BYTES + 1024 + 256);      // [32][V2_YS_STRIDE]
+  float* was = ys + 32 * V2_YS_STRIDE;                                        // [8][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nout = p.nout;
@@ -273,6 +283,13 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_tap_tc2(const __grid_constant
     const int qd = warp - V2_EPI_WARP0;                  // TMEM lane quarter (= warp % 4)
     const int f = qd * 32 + lane;
     const float bias = p.bias ? __ldg(p.bias + f) : 0.f;
+    const bool head = p.head_partial != nullptr;             // (nout == 1: one head per CTA)
+    if (head) {
+      const int C = p.P * FT;
+#pragma unroll
+      for (int a = 0; a < 8; ++a) was[a * 128 + f] = a < p.head_A ? __ldg(p.head_w + (size_t)a * C + hg * FT + f) : 0.f;
+      tc::named_bar_sync(1, V2_EPI_WARPS * 32);
+    }
     unsigned oc = 0;
     for (long tile = slot; tile < tiles; tile += nslots) {
       const long m0 = tile * TN;
@@ -294,6 +311,45 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_tap_tc2(const __grid_constant
           const long mrow = m0 + 32 * hh;
           float* dst = ybase + mrow * p.y_sn;
           const long left = p.rows - mrow;
+          if (head) {
+            // y of these 32 nodes goes through shared memory, feature-major in, node-major out: thread (node nn,
+            // quarter q) multiplies features 4 (q + 4 i) .. + 3, i = 0..7, with the head's weights
+            tc::named_bar_sync(1, V2_EPI_WARPS * 32);            // the previous half has been read
+#pragma unroll
+            for (int n = 0; n < 32; ++n) {
+              const float yv = v[n] + bias;
+              ys[n * V2_YS_STRIDE + f] = p.relu ? fmaxf(yv, 0.f) : yv;
+            }
+            tc::named_bar_sync(1, V2_EPI_WARPS * 32);
+            const int nn = qd * 8 + (lane >> 2), q = lane & 3;
+            float hacc[8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) hacc[a] = 0.f;
+            const uint32_t ys_s = tc::smem_u32(ys + nn * V2_YS_STRIDE + 4 * q);
+            const uint32_t wa_s = tc::smem_u32(was + 4 * q);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 y4 = tc::ld_shared_v4(ys_s + i * 64);
+#pragma unroll
+              for (int a = 0; a < 8; ++a) {
+                if (a < p.head_A) {
+                  const float4 w4 = tc::ld_shared_v4(wa_s + a * 512 + i * 64);
+                  hacc[a] = fmaf(y4.x, w4.x, fmaf(y4.y, w4.y, fmaf(y4.z, w4.z, fmaf(y4.w, w4.w, hacc[a]))));
+                }
+              }
+            }
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+              hacc[a] += __shfl_xor_sync(0xffffffffu, hacc[a], 1);
+              hacc[a] += __shfl_xor_sync(0xffffffffu, hacc[a], 2);
+            }
+            if (q == 0 && nn < left) {
+              float4* hp = reinterpret_cast<float4*>(p.head_partial + ((size_t)hg * p.rows + mrow + nn) * 8);
+              hp[0] = make_float4(hacc[0], hacc[1], hacc[2], hacc[3]);
+              hp[1] = make_float4(hacc[4], hacc[5], hacc[6], hacc[7]);
+            }
+            continue;
+          }
           if (p.accum) {
 #pragma unroll
             for (int n = 0; n < 32; ++n)
@@ -567,8 +623,43 @@ bool tap_tc_supported(const magat_gat_fwd_args* a) {
   return true;
 }
 
-// needs the taps k = 1 .. K-1 in a->taps
-int tap_tc_forward(const magat_gat_fwd_args* a, cudaStream_t st) {
+// logits[m][a] = b[a] + sum_p partial[p][m][a]; optional decode = argmax_a (softmax is monotone:
+// utils/new_simulator.py:863-869), first maximum on ties like torch.max
+__global__ void __launch_bounds__(256) k_actions_finalize(const float* __restrict__ partial, const float* __restrict__ b,
+                                                          long rows, int P, int A, float* __restrict__ logits,
+                                                          int32_t* __restrict__ actions) {
+  const long m = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= rows) return;
+  float acc[8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a) acc[a] = (b != nullptr && a < A) ? __ldg(b + a) : 0.f;
+  for (int h = 0; h < P; ++h) {
+    const float4* q = reinterpret_cast<const float4*>(partial + ((size_t)h * rows + m) * 8);
+    const float4 lo = __ldcs(q), hi = __ldcs(q + 1);
+    acc[0] += lo.x; acc[1] += lo.y; acc[2] += lo.z; acc[3] += lo.w;
+    acc[4] += hi.x; acc[5] += hi.y; acc[6] += hi.z; acc[7] += hi.w;
+  }
+  int best = 0;
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    if (a < A) {
+      logits[m * A + a] = acc[a];
+      if (acc[a] > acc[best]) best = a;
+    }
+  }
+  if (actions != nullptr) actions[m] = best;
+}
+
+// the same shapes when y is not written (linear head): its layout does not matter
+bool tap_tc_supported_no_y(const magat_gat_fwd_args* a) {
+  magat_gat_fwd_args t = *a;
+  t.y = reinterpret_cast<float*>(uintptr_t(256));
+  t.y_sc = 1; t.y_sn = (long)a->P * a->F; t.y_sb = (long)a->N * t.y_sn;
+  return tap_tc_supported(&t);
+}
+
+// needs the taps k = 1 .. K-1 in a->taps.  head != null: y is not written, the logits of the linear head are.
+int tap_tc_forward(const magat_gat_fwd_args* a, cudaStream_t st, const HeadArgs* head) {
   TapParams tp{};
   tp.rows = (long)a->B * a->N;
   tp.N = a->N; tp.G = a->G; tp.K = a->K; tp.P = a->P; tp.D = a->D;
@@ -580,6 +671,16 @@ int tap_tc_forward(const magat_gat_fwd_args* a, cudaStream_t st) {
   tp.y = a->y; tp.y_sb = a->y_sb; tp.y_sn = a->y_sn;
   if (a->relu && a->relu_bits) { tp.relu_bits_out = a->relu_bits; tp.bits_out_C = a->P * a->F; }
   tp.nout = 1;
+  if (head != nullptr) {
+    tp.head_w = head->w; tp.head_A = head->A; tp.head_partial = head->partial;
+    tp.relu_bits_out = nullptr;
+    tp.y = nullptr; tp.y_sn = (long)a->P * a->F; tp.y_sb = (long)a->N * tp.y_sn;      // never dereferenced
+    int rc = must_launch(launch_tap_tc(tp, st, "k_tap_tc(fused taps + projection + linear head)"), "K-tap projection");
+    if (rc) return rc;
+    k_actions_finalize<<<cdiv(tp.rows, 256), 256, 0, st>>>(head->partial, head->b, tp.rows, a->P, head->A, head->logits,
+                                                          head->actions);
+    return check_launch("k_actions_finalize", st);
+  }
   return must_launch(launch_tap_tc(tp, st, "k_tap_tc(fused taps + projection)"), "K-tap projection");
 }
 

@@ -601,6 +601,69 @@ def gat_layer(x, S, filterWeight, mixer, weight, weight_bias, bias, *, mode: int
     return y, SparseAttention(att.detach(), adj)
 
 
+def gat_layer_actions(x, S, filterWeight, mixer, weight, weight_bias, bias, head_weight, head_bias, *, mode: int,
+                      relu: bool = True, adjacency: Optional[Adjacency] = None, max_degree: Optional[int] = None,
+                      return_actions: bool = False):
+    """SURVEY 8f row f3 (inference): the layer with concatenated heads AND the planner's linear action head
+    (``actionsMLP`` = one ``nn.Linear(P*F, A)``, graphs/models/decentralplanner_GAT.py:221-233, :329-334) in one pass --
+    ``y`` never reaches memory.  Returns ``logits [B*N, A]`` (row = b * N + n, as ``sharedFeature_stack`` orders them)
+    and, with ``return_actions``, also ``argmax softmax`` per agent (utils/new_simulator.py:863-869) as int32 ``[B*N]``,
+    plus the sparse attention of the call."""
+    L = _cabi.lib()
+    _require_cuda(x, "x")
+    assert len(x.shape) == 3
+    P, F, E, K, G = filterWeight.shape
+    assert E == 1 and x.shape[1] == G
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in
+                                       (x, filterWeight, mixer, weight, weight_bias, bias, head_weight, head_bias)):
+        raise RuntimeError("gat_layer_actions is an inference call (nothing is kept for backward): use torch.no_grad()")
+    if x.dtype != torch.float32:
+        x = x.float()
+    kq = mode == _cabi.MODE_KEYQUERY
+    _check_params(x, filterWeight, None if kq else mixer, weight, None if kq else weight_bias, bias)
+    A = head_weight.shape[0]
+    assert tuple(head_weight.shape) == (A, P * F), "the head is nn.Linear(P*F, A) on the concatenated heads"
+    for t, name in ((head_weight, "head_weight"), (head_bias, "head_bias")):
+        if t is not None and (t.dtype != torch.float32 or t.device != x.device):
+            raise RuntimeError(f"{name}: expected a float32 tensor on {x.device}")
+    dev = x.device
+    B, _, N = x.shape
+    if adjacency is None and S is not None and not S.is_cuda:
+        adjacency = build_adjacency_host(S, dev, max_degree)
+    adj = adjacency if adjacency is not None else build_adjacency(S, max_degree)
+    assert adj.B == B and adj.N == N
+    D = adj.D
+    xt = _node_major(x.detach())
+    weight_c, filt_c = weight.detach().contiguous(), filterWeight.detach().contiguous()
+    mixer_c = None if kq or mixer is None else mixer.detach().contiguous()
+    wb_c = None if kq or weight_bias is None else weight_bias.detach().contiguous()
+    bias_c = None if bias is None else bias.detach().contiguous()
+    hw_c = head_weight.detach().contiguous()
+    hb_c = None if head_bias is None else head_bias.detach().contiguous()
+    with torch.cuda.device(dev):
+        att = torch.empty((B, N, D, P), dtype=torch.float32, device=dev)
+        taps = torch.empty((B, N, P, max(K - 1, 1), G), dtype=torch.float32, device=dev) if K > 1 else None
+        wprep = torch.empty(L.magat_gat_wprep_floats(G, F, K, P, mode), dtype=torch.float32, device=dev)
+        sproj = torch.empty((B, N, P, G if kq else 2), dtype=torch.float32, device=dev)
+        partial = torch.empty((P, B * N, 8), dtype=torch.float32, device=dev)
+        logits = torch.empty((B * N, A), dtype=torch.float32, device=dev)
+        actions = torch.empty((B * N,), dtype=torch.int32, device=dev) if return_actions else None
+        a = _cabi.FwdArgs(B=B, N=N, G=G, F=F, K=K, P=P, D=D, mode=mode, concat=1, relu=int(relu),
+                          path=_cabi.PATH_AUTO, reserved=0, x=xt.data_ptr(), x_sb=_sb(xt), x_sn=_sn(xt),
+                          nbr_out=adj.nbr_out.data_ptr(), nbr_in=adj.nbr_in.data_ptr(), slot_in=adj.slot_in.data_ptr(),
+                          slot_out=_p(adj.slot_out), weight=weight_c.data_ptr(), mixer=_p(mixer_c), weight_bias=_p(wb_c),
+                          filterWeight=filt_c.data_ptr(), bias=_p(bias_c), y=None, y_sb=N * P * F, y_sn=P * F, y_sc=1,
+                          att=att.data_ptr(), ain=None, taps=_p(taps), wprep=wprep.data_ptr(), sproj=sproj.data_ptr(),
+                          relu_bits=None)
+        if not L.magat_gat_actions_supported(a, A):
+            raise RuntimeError("gat_layer_actions: needs F = 128, G a multiple of 128, K <= 3 and at most 8 actions "
+                               "(magat_gat_actions_supported); use the layer followed by the nn.Linear otherwise")
+        _cabi.check(L.magat_gat_forward_actions(a, hw_c.data_ptr(), _p(hb_c), A, partial.data_ptr(), logits.data_ptr(),
+                                                _p(actions), _stream(dev)))
+    att_out = SparseAttention(att, adj)
+    return (logits, actions, att_out) if return_actions else (logits, att_out)
+
+
 def attention_dense(att: torch.Tensor, adj: Adjacency, mean_heads: bool = False) -> torch.Tensor:
     """Sparse attention -> dense ``aij`` [B,P,1,N,N] (or its head mean [B,1,N,N])."""
     L = _cabi.lib()
@@ -953,6 +1016,33 @@ class GraphFilterBatchAttentional(nn.Module):
         if Nin < self.N:
             y = torch.index_select(y, 2, torch.arange(Nin).to(y.device))
         return y
+
+    def forward_actions(self, x, actions_mlp, return_actions: bool = False):
+        """``actions_mlp(self(x).permute(0, 2, 1).reshape(B * N, -1))`` in one pass, for inference
+        (``torch.no_grad()``), when ``actions_mlp`` is the reference's single ``nn.Linear`` (optionally wrapped in an
+        ``nn.Sequential``; graphs/models/decentralplanner_GAT.py:221-237) and the heads are concatenated: the layer's
+        output is never written.  Anything else (more layers, dropout in training mode, head mean, a custom
+        nonlinearity, padded inputs) takes the two-step route, with the same result."""
+        lin = actions_mlp
+        if isinstance(lin, nn.Sequential):
+            mods = [m for m in lin if not (isinstance(m, nn.Dropout) and not m.training)]
+            lin = mods[0] if len(mods) == 1 else None
+        fusable = (isinstance(lin, nn.Linear) and self.concatenate and x.shape[2] == self.N
+                   and self.nonlinearity in (nn.functional.relu, torch.relu) and not torch.is_grad_enabled()
+                   and lin.in_features == self.P * self.F and lin.out_features <= 8 and self.F == 128
+                   and self.G % 128 == 0 and self.K <= 3 and self.path in ("auto", "tcgen05"))
+        if self.S is None and getattr(self, "_adj", None) is None:
+            raise RuntimeError("GraphFilterBatchAttentional.forward_actions: no GSO stored -- call addGSO(S) first")
+        if not fusable:
+            y = self.forward(x)
+            logits = actions_mlp(y.permute(0, 2, 1).reshape(y.shape[0] * y.shape[2], -1))
+            return (logits, torch.max(logits, 1)[1].int()) if return_actions else logits
+        out = gat_layer_actions(x, self.S, self.filterWeight, self.mixer, self.weight, self.weight_bias, self.bias,
+                                lin.weight, lin.bias, mode=_mode_of(self.attentionMode), relu=True,
+                                adjacency=getattr(self, "_adj", None), max_degree=getattr(self, "max_degree", None),
+                                return_actions=return_actions)
+        self._last, self._aij = out[-1], None
+        return (out[0], out[1]) if return_actions else out[0]
 
     def extra_repr(self):
         reprString = "in_features=%d, " % self.G

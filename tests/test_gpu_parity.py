@@ -590,3 +590,43 @@ def test_gso_in_host_memory_gives_the_same_adjacency_and_output(golden):
     assert rel_err(y, d["y"]) < TOL
     y.backward(d["dy"].to(dev))
     assert rel_err(x.grad, d["grad.x"]) < TOL
+
+
+@pytest.mark.parametrize("mode,B,N,K,P,A", [("KeyQuery", 5, 200, 3, 4, 5), ("GAT_modified", 3, 77, 2, 2, 5),
+                                           ("KeyQuery", 2, 64, 3, 1, 8), ("KeyQuery", 7, 333, 1, 4, 3)])
+def test_layer_with_fused_action_head(mode, B, N, K, P, A):
+    """layer + the planner's linear action head in one pass (y never written) against the ORACLE's
+    layer output pushed through the same nn.Linear on the CPU, and against the two-step route of the CUDA layer; the
+    decoded actions are argmax softmax (utils/new_simulator.py:863-869)."""
+    dev = torch.device("cuda:0")
+    G = F = 128
+    gen = torch.Generator().manual_seed(77 + N + A)
+    params = orc.init_params(G, F, K, P, mode=mode, generator=gen, weight_bias_std=0.1)
+    S = orc.random_geometric_gso(B, N, generator=gen)
+    x = torch.relu(torch.randn(B, N, G, generator=gen)).permute(0, 2, 1)
+    head = torch.nn.Linear(P * F, A)
+    with torch.no_grad():
+        head.weight.copy_(torch.randn(A, P * F, generator=gen) * 0.05)
+        head.bias.copy_(torch.randn(A, generator=gen) * 0.1)
+    y_ref, _ = orc.gat_layer_forward(x, S, params, mode=mode, concatenate=True)
+    with torch.no_grad():
+        logits_ref = head(y_ref.permute(0, 2, 1).reshape(B * N, -1))
+    meta = dict(G=G, F=F, K=K, P=P, concat=True, mode=mode)
+    layer = make_layer(meta, {"param." + k: v for k, v in params.items() if v is not None}, dev, path="auto")
+    layer.addGSO(S.to(dev))
+    head_d = torch.nn.Sequential(torch.nn.Linear(P * F, A)).to(dev)
+    head_d[0].load_state_dict(head.state_dict())
+    with torch.no_grad():
+        logits, actions = layer.forward_actions(x.to(dev), head_d, return_actions=True)
+        y2 = layer(x.to(dev))
+        logits2 = head_d(y2.permute(0, 2, 1).reshape(B * N, -1))
+    assert logits.shape == (B * N, A) and actions.shape == (B * N,) and actions.dtype == torch.int32
+    assert rel_err(logits, logits_ref) < TOL
+    assert rel_err(logits, logits2) < TOL
+    assert torch.equal(actions.long(), torch.max(logits, 1)[1])
+    # the attention of the call is kept like forward() keeps it
+    assert (torch.from_numpy(layer.aij) - orc.gat_layer_forward(x, S, params, mode=mode, concatenate=True)[1]).abs().max() < TOL
+    # with autograd on (or any shape the fused head does not take) the two-step route answers
+    xg = x.to(dev).requires_grad_(True)
+    lg = layer.forward_actions(xg, head_d)
+    assert lg.requires_grad and rel_err(lg, logits_ref) < TOL
