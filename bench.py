@@ -420,6 +420,35 @@ def main():
             fused_fwd = {"error": str(exc)[-300:]}
         layer.path, layer.fused_team = args.path, 0
 
+    # ---- inference with the planner's linear action head folded into the projection epilogue --------
+    actions_head = None
+    if w["G"] == 128 and w["concat"] and w["K"] <= 3 and args.path == "auto":
+        try:
+            head = torch.nn.Linear(w["P"] * 128, 5).to(dev)           # actionsMLP of the published configurations
+
+            def step_two():
+                with torch.no_grad():
+                    layer.addGSO(S)
+                    y = layer(x)
+                    return head(y.permute(0, 2, 1).reshape(B * N, -1))
+
+            def step_one():
+                with torch.no_grad():
+                    layer.addGSO(S)
+                    return layer.forward_actions(x, head)
+
+            ms_two = timed(step_two, args.steps, 3, dist_on)
+            ms_one = timed(step_one, args.steps, 3, dist_on)
+            err = float((step_one() - step_two()).abs().max() / step_two().abs().max())
+            actions_head = {"fused": {"ms_per_step": ms_one, "value": units / (ms_one * 1e-3), "unit": "agent-steps/s"},
+                            "layer_then_linear": {"ms_per_step": ms_two, "value": units / (ms_two * 1e-3),
+                                                  "unit": "agent-steps/s"},
+                            "max_rel_diff": err,
+                            "note": "addGSO + forward + nn.Linear(P*F, 5) under no_grad; fused = forward_actions(): the "
+                                    "layer output y (4*P*F B per agent) is never written (magat_gat_forward_actions)"}
+        except Exception as exc:
+            actions_head = {"error": str(exc)[-300:]}
+
     # ---- the same step captured in a CUDA graph (small graphs are launch-bound: ~20 launches of a few us each) ----
     # Needs a forward without host synchronisation: the list width comes from N (N <= 32) or from a max-degree promise
     # (measured once here, outside the timed region; a training set's maximum degree is known up front).
@@ -718,6 +747,7 @@ def main():
         "fwd": {"value": units / (ms_fwd * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms_fwd},
         "roofline": roofline, "train_kernels": train_kernels, "cpu_baseline": cpu_baseline, "e2e": e2e,
         "positions_input": positions, "cuda_graph": graphed, "fused_forward": fused_fwd,
+        "actions_head": actions_head,
         "gpu_launches": int(launches_per_step) * args.steps, "gpu_launches_per_step": int(launches_per_step),
         "clocks": clocks,
     }

@@ -13,7 +13,7 @@ int check_launch(const char* what, cudaStream_t st);
 void prof_begin(cudaStream_t st);
 int device_sm_count();                       // SMs of the current device (cached per device), 0 without a device
 // once per (kernel id, device): raise the dynamic shared memory limit of `func`
-enum { KID_TC_GEMM = 0, KID_TAP_TC4, KID_TAP_TC8, KID_WGRAD, KID_SMALL, KID_TAP_TC2, KID_TAP_TC2M, KID_WGRAD2, KID_FUSED, KID_TAP_TC2B,
+enum { KID_TC_GEMM = 0, KID_TAP_TC4, KID_TAP_TC8, KID_WGRAD, KID_SMALL, KID_TAP_TC2, KID_TAP_TC2M, KID_WGRAD2, KID_FUSED, KID_TAP_TC2B, KID_TAP_TC2H,
        KID_SCAN_BASE /* + 24 dtype / R / KK variants */ = 16, KID_MAX = 40 };
 int ensure_dyn_smem(int kernel_id, const void* func, size_t bytes, const char* name);
 
@@ -42,6 +42,26 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+// Sum NV per-lane values over the warp at once: every step halves the number of live values and doubles the lanes
+// each has absorbed (NV - 1 + 5 - log2 NV shuffles instead of 5 NV).  The lane's result is the sum with index
+// lane >> (5 - log2 NV).
+template <int NV>
+__device__ __forceinline__ float warp_multi_sum(float (&v)[NV], int lane) {
+  int off = 16;
+#pragma unroll
+  for (int n = NV; n > 1; n >>= 1, off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float keep = hi ? v[i + n / 2] : v[i];
+      const float send = hi ? v[i] : v[i + n / 2];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+#pragma unroll
+  for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+  return v[0];
 }
 __device__ __forceinline__ int warp_sum_i(int v) {
 #pragma unroll

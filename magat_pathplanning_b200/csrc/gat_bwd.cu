@@ -238,27 +238,6 @@ __device__ __forceinline__ void stp(float* p, const float* a) {
   }
 }
 
-// Sum NV per-lane values over the warp at once: every step halves the number of live values and doubles the lanes
-// each has absorbed (NV - 1 + log2(32 / NV) shuffles instead of 5 NV).  Lane l ends up with the total of value
-// l >> (5 - log2 NV).
-template <int NV>
-__device__ __forceinline__ float warp_multi_sum(float (&v)[NV], int lane) {
-  int off = 16;
-#pragma unroll
-  for (int n = NV; n > 1; n >>= 1, off >>= 1) {
-    const bool hi = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < n / 2; ++i) {
-      const float keep = hi ? v[i + n / 2] : v[i];
-      const float send = hi ? v[i] : v[i + n / 2];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-#pragma unroll
-  for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
-  return v[0];
-}
-
 // Tap recursion backward, level k: one warp per sender row, lane l owns features 4l..4l+3 and out-slot l.  HP heads
 // at a time (PT / HP passes over the row's edges), EF edges per step.  (A first version kept all heads of two edges in
 // registers: 80 registers plus an 80 B spill frame -- ncu: a third of its L2 traffic was local memory -- at three CTAs

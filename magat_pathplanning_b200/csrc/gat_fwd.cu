@@ -325,27 +325,6 @@ __global__ void __launch_bounds__(256, MINB) k_attention_kq_v(const float* __res
 }
 
 // ---- GAT_modified fast path (G = 128, P in {1,2,4}, D <= 32) ----------------------------------------
-// Sum NV per-lane values over the warp at once: every step halves the number of live values and doubles the lanes
-// each has absorbed (NV - 1 + 5 - log2 NV shuffles instead of 5 NV).  The lane's result is the sum with index
-// lane >> (5 - log2 NV).
-template <int NV>
-__device__ __forceinline__ float warp_multi_sum(float (&v)[NV], int lane) {
-  int off = 16;
-#pragma unroll
-  for (int n = NV; n > 1; n >>= 1, off >>= 1) {
-    const bool hi = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < n / 2; ++i) {
-      const float keep = hi ? v[i + n / 2] : v[i];
-      const float send = hi ? v[i] : v[i + n / 2];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-#pragma unroll
-  for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
-  return v[0];
-}
-
 // sproj[m][2p + t] = cvec[p][t] . x_m + dvec[p][t]: the whole "projection" of this mode is 2P dot products per node.
 // A warp keeps its slice of the 2P vectors in registers and walks over `per_warp` consecutive nodes, one 512 B row
 // load each -- the generic 64 x 64 tile GEMM spent 0.40 ms on an 8-column output.

@@ -72,10 +72,13 @@ constexpr int V2_NOP = 2;                               // operand stages (one p
 constexpr int V2_RAW_BYTES = 128 * 1024;                // raw ring: 4 slots of 32 KB, or 2 of 64 KB with a mask
 constexpr int V2_CONV_WARPS = 16, V2_GROUP = 256;
 constexpr int V2_EPI_WARP0 = 16, V2_EPI_WARPS = 4, V2_MMA_WARP = 20, V2_TMA_WARP = 21, V2_THREADS = 22 * 32;
-// linear head: a [32 nodes][128 features] fp32 tile of y (row stride 144 floats: conflict-free for both the feature-
-// major writes and the node-major 16 B reads) + the head's [8][128] weight slice
+// linear-head variant: warps 22-25 take the dot products over from the four epilogue warps (which then only drain TMEM
+// into shared memory), 16 nodes at a time through a double-buffered tile
+constexpr int V2_HEAD_WARP0 = 22, V2_HEAD_WARPS = 4, V2_THREADS_HEAD = 26 * 32;
+// linear head: two [16 nodes][128 features] fp32 tiles of y (row stride 144 floats) + the head's [8][128] weight slice
 constexpr int V2_YS_STRIDE = 144;
-constexpr int V2_HEAD_BYTES = 32 * V2_YS_STRIDE * 4 + 8 * 128 * 4;
+constexpr int V2_YS_NODES = 16;                               // nodes per hand-over
+constexpr int V2_HEAD_BYTES = 2 * V2_YS_NODES * V2_YS_STRIDE * 4 + 8 * 128 * 4;
 constexpr size_t V2_SMEM_BYTES = (size_t)V2_NOP * STAGE_BYTES + V2_RAW_BYTES + 1024 + 256 + V2_HEAD_BYTES;
 static_assert(V2_SMEM_BYTES <= 227 * 1024, "k_tap_tc2 shared memory");
 
@@ -105,8 +108,10 @@ __device__ __forceinline__ void v2_store(float* dst, long stride_rt, const float
 }
 
 // MASK: 0 none, 1 fp32 mask tile next to every x tile, 2 bit mask read straight from global memory
-template <int MASK>
-__global__ void __launch_bounds__(V2_THREADS, 1) k_tap_tc2(const __grid_constant__ TapParams p) {
+// HEAD: the epilogue feeds the linear action head instead of storing y (its own instantiation: the register
+// allocation of the other variants stays what it was)
+template <int MASK, bool HEAD = false>
+__global__ void __launch_bounds__(HEAD ? V2_THREADS_HEAD : V2_THREADS, 1) k_tap_tc2(const __grid_constant__ TapParams p) {
   constexpr bool MASKED = MASK == 1;
   constexpr int NRAW = MASKED ? 2 : 4;
   constexpr int SLOT_BYTES = V2_RAW_BYTES / NRAW;
@@ -122,8 +127,10 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_tap_tc2(const __grid_constant
   uint64_t* acc_full = bars + 12;            // [2]
   uint64_t* acc_empty = bars + 14;           // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-  float* ys = reinterpret_cast<float*>(raw + V2_RAW_BYTES + 1024 + 256);      // [32][V2_YS_STRIDE]
-  float* was = ys + 32 * V2_YS_STRIDE;                                        // [8][128]
+  uint64_t* ys_full = bars + 20;             // [2]  128 drain threads have written the tile   (HEAD only)
+  uint64_t* ys_empty = bars + 22;            // [2]  128 head threads have taken it
+  float* ys = reinterpret_cast<float*>(raw + V2_RAW_BYTES + 1024 + 256);      // [2][16][V2_YS_STRIDE] (HEAD only)
+  float* was = ys + 2 * V2_YS_NODES * V2_YS_STRIDE;                           // [8][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nout = p.nout;
@@ -148,6 +155,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_tap_tc2(const __grid_constant
     for (int a = 0; a < 2; ++a) {
       tc::mbar_init(&acc_full[a], 1);
       tc::mbar_init(&acc_empty[a], V2_EPI_WARPS * 32);
+      tc::mbar_init(&ys_full[a], V2_EPI_WARPS * 32);
+      tc::mbar_init(&ys_empty[a], V2_HEAD_WARPS * 32);
     }
     tc::fence_barrier_init();
   }
@@ -278,19 +287,50 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_tap_tc2(const __grid_constant
         if (lane == 0) tc::mbar_arrive(&raw_empty[r]);
       }
     }
+  } else if (HEAD && warp >= V2_HEAD_WARP0) {
+    // ===== linear head (nout == 1: one head per CTA) =======================================================
+    // Warp hw takes nodes 4 hw .. + 3 of every 16-node tile the epilogue warps hand over, its lane l features
+    // 4l .. 4l+3 of each.  The head's slice of every weight row sits in shared memory (zero rows past head_A).
+    const int hw = warp - V2_HEAD_WARP0;
+    const int t = hw * 32 + lane;
+    {
+      const int C = p.P * FT;
+#pragma unroll
+      for (int a = 0; a < 8; ++a) was[a * 128 + t] = a < p.head_A ? __ldg(p.head_w + (size_t)a * C + hg * FT + t) : 0.f;
+      tc::named_bar_sync(1, V2_HEAD_WARPS * 32);
+    }
+    const uint32_t was_s = tc::smem_u32(was + lane * 4);
+    unsigned part = 0;
+    for (long tile = slot; tile < tiles; tile += nslots) {
+      for (int s = 0; s < TN / V2_YS_NODES; ++s, ++part) {
+        const int buf = (int)(part & 1u);
+        tc::mbar_wait(&ys_full[buf], (part >> 1) & 1u);
+        float4 yv[4];
+        const uint32_t ys_s = tc::smem_u32(ys + (buf * V2_YS_NODES + hw * 4) * V2_YS_STRIDE + lane * 4);
+#pragma unroll
+        for (int n = 0; n < 4; ++n) yv[n] = tc::ld_shared_v4(ys_s + n * (V2_YS_STRIDE * 4));
+        // all 8 (zero padded) actions x 4 nodes = 32 dot products, straight-line, then ONE joint reduction: lane
+        // 4a + n ends up with action a of node n
+        float d[32];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+          const float4 w = tc::ld_shared_v4(was_s + a * 512);
+#pragma unroll
+          for (int n = 0; n < 4; ++n)
+            d[a * 4 + n] = fmaf(yv[n].x, w.x, fmaf(yv[n].y, w.y, fmaf(yv[n].z, w.z, yv[n].w * w.w)));
+        }
+        tc::mbar_arrive(&ys_empty[buf]);                  // every yv has been used: the tile may be overwritten
+        const float tot = warp_multi_sum<32>(d, lane);
+        const long m = tile * TN + s * V2_YS_NODES + hw * 4 + (lane & 3);
+        if (m < p.rows) p.head_partial[((size_t)hg * p.rows + m) * 8 + (lane >> 2)] = tot;
+      }
+    }
   } else if (warp < V2_MMA_WARP) {
     // ===== epilogue =======================================================================================
     const int qd = warp - V2_EPI_WARP0;                  // TMEM lane quarter (= warp % 4)
     const int f = qd * 32 + lane;
     const float bias = p.bias ? __ldg(p.bias + f) : 0.f;
-    const bool head = p.head_partial != nullptr;             // (nout == 1: one head per CTA)
-    if (head) {
-      const int C = p.P * FT;
-#pragma unroll
-      for (int a = 0; a < 8; ++a) was[a * 128 + f] = a < p.head_A ? __ldg(p.head_w + (size_t)a * C + hg * FT + f) : 0.f;
-      tc::named_bar_sync(1, V2_EPI_WARPS * 32);
-    }
-    unsigned oc = 0;
+    unsigned oc = 0, part = 0;
     for (long tile = slot; tile < tiles; tile += nslots) {
       const long m0 = tile * TN;
       for (int o = 0; o < nout; ++o, ++oc) {
@@ -311,42 +351,19 @@ __global__ void __launch_bounds__(V2_THREADS, 1) k_tap_tc2(const __grid_constant
           const long mrow = m0 + 32 * hh;
           float* dst = ybase + mrow * p.y_sn;
           const long left = p.rows - mrow;
-          if (head) {
-            // y of these 32 nodes goes through shared memory, feature-major in, node-major out: thread (node nn,
-            // quarter q) multiplies features 4 (q + 4 i) .. + 3, i = 0..7, with the head's weights
-            tc::named_bar_sync(1, V2_EPI_WARPS * 32);            // the previous half has been read
+          if (HEAD) {
+            // y goes to the head warps through shared memory, feature-major in (thread = feature), 16 nodes at a time
 #pragma unroll
-            for (int n = 0; n < 32; ++n) {
-              const float yv = v[n] + bias;
-              ys[n * V2_YS_STRIDE + f] = p.relu ? fmaxf(yv, 0.f) : yv;
-            }
-            tc::named_bar_sync(1, V2_EPI_WARPS * 32);
-            const int nn = qd * 8 + (lane >> 2), q = lane & 3;
-            float hacc[8];
+            for (int s = 0; s < 32 / V2_YS_NODES; ++s, ++part) {
+              const int buf = (int)(part & 1u);
+              tc::mbar_wait(&ys_empty[buf], ((part >> 1) & 1u) ^ 1u);
+              float* yd = ys + buf * V2_YS_NODES * V2_YS_STRIDE + f;
 #pragma unroll
-            for (int a = 0; a < 8; ++a) hacc[a] = 0.f;
-            const uint32_t ys_s = tc::smem_u32(ys + nn * V2_YS_STRIDE + 4 * q);
-            const uint32_t wa_s = tc::smem_u32(was + 4 * q);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 y4 = tc::ld_shared_v4(ys_s + i * 64);
-#pragma unroll
-              for (int a = 0; a < 8; ++a) {
-                if (a < p.head_A) {
-                  const float4 w4 = tc::ld_shared_v4(wa_s + a * 512 + i * 64);
-                  hacc[a] = fmaf(y4.x, w4.x, fmaf(y4.y, w4.y, fmaf(y4.z, w4.z, fmaf(y4.w, w4.w, hacc[a]))));
-                }
+              for (int n = 0; n < V2_YS_NODES; ++n) {
+                const float yv = v[s * V2_YS_NODES + n] + bias;
+                yd[n * V2_YS_STRIDE] = p.relu ? fmaxf(yv, 0.f) : yv;
               }
-            }
-#pragma unroll
-            for (int a = 0; a < 8; ++a) {
-              hacc[a] += __shfl_xor_sync(0xffffffffu, hacc[a], 1);
-              hacc[a] += __shfl_xor_sync(0xffffffffu, hacc[a], 2);
-            }
-            if (q == 0 && nn < left) {
-              float4* hp = reinterpret_cast<float4*>(p.head_partial + ((size_t)hg * p.rows + mrow + nn) * 8);
-              hp[0] = make_float4(hacc[0], hacc[1], hacc[2], hacc[3]);
-              hp[1] = make_float4(hacc[4], hacc[5], hacc[6], hacc[7]);
+              tc::mbar_arrive(&ys_full[buf]);
             }
             continue;
           }
@@ -471,12 +488,14 @@ int launch_tap_tc(const TapParams& tp, cudaStream_t st, const char* what) {
   int rc0 = ensure_dyn_smem(KID_TAP_TC2, (const void*)k_tap_tc2<0>, V2_SMEM_BYTES, "k_tap_tc2<0>");
   if (!rc0) rc0 = ensure_dyn_smem(KID_TAP_TC2M, (const void*)k_tap_tc2<1>, V2_SMEM_BYTES, "k_tap_tc2<1>");
   if (!rc0) rc0 = ensure_dyn_smem(KID_TAP_TC2B, (const void*)k_tap_tc2<2>, V2_SMEM_BYTES, "k_tap_tc2<2>");
+  if (!rc0) rc0 = ensure_dyn_smem(KID_TAP_TC2H, (const void*)k_tap_tc2<0, true>, V2_SMEM_BYTES, "k_tap_tc2<0, head>");
   if (rc0) return rc0;
   const int ngroups = tp.P / tp.nout;
   long slots = sm_count / ngroups;
   if (slots < 1) slots = 1;
   if (slots > tiles) slots = tiles;
-  if (tq.mask_bits) k_tap_tc2<2><<<(int)(slots * ngroups), V2_THREADS, V2_SMEM_BYTES, st>>>(tq);
+  if (tq.head_partial) k_tap_tc2<0, true><<<(int)(slots * ngroups), V2_THREADS_HEAD, V2_SMEM_BYTES, st>>>(tq);
+  else if (tq.mask_bits) k_tap_tc2<2><<<(int)(slots * ngroups), V2_THREADS, V2_SMEM_BYTES, st>>>(tq);
   else if (tq.mask) k_tap_tc2<1><<<(int)(slots * ngroups), V2_THREADS, V2_SMEM_BYTES, st>>>(tq);
   else k_tap_tc2<0><<<(int)(slots * ngroups), V2_THREADS, V2_SMEM_BYTES, st>>>(tq);
   return check_launch(what, st);

@@ -630,3 +630,39 @@ def test_layer_with_fused_action_head(mode, B, N, K, P, A):
     xg = x.to(dev).requires_grad_(True)
     lg = layer.forward_actions(xg, head_d)
     assert lg.requires_grad and rel_err(lg, logits_ref) < TOL
+
+
+def test_fused_action_head_at_the_graded_shape():
+    """B x N = 160 x 1000 (persistent CTAs wrap their rings many times; the last tile is ragged in neither 32 nor 64):
+    the fused head against the ORACLE on two instances and against the two-step route on all of them."""
+    from bench import synth_gso
+    dev = torch.device("cuda:0")
+    G = F = 128
+    B, N, K, P, A = 160, 1000, 3, 4, 5
+    gen = torch.Generator().manual_seed(909)
+    params = orc.init_params(G, F, K, P, mode="KeyQuery", generator=gen, weight_bias_std=0.1)
+    S = synth_gso(B, N, 200, dev, torch.Generator(device=dev).manual_seed(23))
+    x_mem = torch.relu(torch.randn(B, N, G, generator=gen))
+    head = torch.nn.Linear(P * F, A)
+    with torch.no_grad():
+        head.weight.copy_(torch.randn(A, P * F, generator=gen) * 0.05)
+    layer = make_layer(dict(G=G, F=F, K=K, P=P, concat=True, mode="KeyQuery"),
+                       {"param." + k: v for k, v in params.items() if v is not None}, dev, path="auto")
+    layer.addGSO(S)
+    head_d = torch.nn.Linear(P * F, A).to(dev)
+    head_d.load_state_dict(head.state_dict())
+    xd = x_mem.to(dev).permute(0, 2, 1)
+    with torch.no_grad():
+        logits, actions = layer.forward_actions(xd, head_d, return_actions=True)
+        logits2 = head_d(layer(xd).permute(0, 2, 1).reshape(B * N, -1))
+    assert rel_err(logits, logits2) < 2e-5
+    pick = [0, 159]
+    y_ref, _ = orc.gat_layer_forward(x_mem[pick].permute(0, 2, 1), S[pick].cpu(), params, mode="KeyQuery", concatenate=True)
+    with torch.no_grad():
+        ref = head(y_ref.permute(0, 2, 1).reshape(len(pick) * N, -1))
+    got = logits.view(B, N, A)[pick].reshape(-1, A)
+    assert rel_err(got, ref) < TOL
+    # decode: equal to the argmax of the reference logits wherever the top two are not within rounding of each other
+    top2 = ref.topk(2, dim=1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 1e-4 * ref.abs().max()
+    assert torch.equal(actions.view(B, N)[pick].reshape(-1).cpu().long()[clear], ref.argmax(1)[clear])
