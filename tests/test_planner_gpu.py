@@ -93,6 +93,18 @@ def test_reference_planner_forward_and_backward_through_the_cuda_layer(model_fil
     with torch.no_grad():
         our_model.addGSO(S.clone().to("cuda:0"))
         assert rel_err(our_model(x.to("cuda:0")), ref_logits) < TOL
+    # the planner's tail -- GFL, actionsMLP, argmax decode -- as ONE call on the features the planner
+    # feeds its graph layer (the fused head where the configuration allows it, layer + MLP otherwise)
+    if len(our_model.GFL) == 1 and "Skip" not in model_file:      # one graph layer (activation inside), no skip connection
+        seen = {}
+        hook = our_model.GFL[0].register_forward_pre_hook(lambda m, a: seen.__setitem__("x", a[0].detach()))
+        with torch.no_grad():
+            our_model.addGSO(S.clone().to("cuda:0"))
+            our_model(x.to("cuda:0"))
+            hook.remove()
+            logits, keys = our_model.GFL[0].forward_actions(seen["x"], our_model.actionsMLP, return_actions=True)
+        assert rel_err(logits, ref_logits) < TOL
+        assert torch.equal(keys.long().cpu(), torch.max(torch.softmax(logits.cpu(), 1), 1)[1])
 
 
 def _child(blob, x_np, S_np, q):
