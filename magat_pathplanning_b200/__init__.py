@@ -9,10 +9,12 @@ from .graphML import (GraphFilterBatchAttentional, graphAttentionLSIGFBatch_KeyQ
                       graphAttentionLSIGFBatch_modified, learnAttentionGSOBatch_KeyQuery,
                       learnAttentionGSOBatch, build_adjacency, build_adjacency_from_positions, gat_layer, gat_layer_actions,
                       attention_dense, GraphFilterBatch, BatchLSIGF, pack_gso_host, build_adjacency_host,
-                      build_adjacency_from_rowbits)
+                      build_adjacency_from_rowbits, GraphFilterBatchAttentional_Origin,
+                      graphAttentionLSIGFBatch_Origin, learnAttentionGSOBatch_origin)
 from .integration import install_into_reference  # noqa: F401
 
 __all__ = ["GraphFilterBatchAttentional", "graphAttentionLSIGFBatch_KeyQuery",
            "graphAttentionLSIGFBatch_modified", "learnAttentionGSOBatch_KeyQuery", "learnAttentionGSOBatch",
            "build_adjacency", "build_adjacency_from_positions", "gat_layer", "gat_layer_actions", "attention_dense", "install_into_reference",
-           "GraphFilterBatch", "BatchLSIGF", "pack_gso_host", "build_adjacency_host", "build_adjacency_from_rowbits"]
+           "GraphFilterBatch", "BatchLSIGF", "pack_gso_host", "build_adjacency_host", "build_adjacency_from_rowbits",
+           "GraphFilterBatchAttentional_Origin", "graphAttentionLSIGFBatch_Origin", "learnAttentionGSOBatch_origin"]

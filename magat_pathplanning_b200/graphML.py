@@ -725,6 +725,138 @@ def learnAttentionGSOBatch(x, a, W, W_b, S, negative_slope=0.2):
     return _attention_only(x, a, W, W_b, S, _cabi.MODE_GAT_MODIFIED)
 
 
+# ---- SURVEY 8f row f4 (first of the ablation modes): GAT_origin on the same kernels -----------------------------
+# learnAttentionGSOBatch_origin (graphML.py:964-1070) is the GAT_modified score WITHOUT the per-head bias on
+# z = W x and with a self loop added to the GSO (S + I, :1019) before the edge test; graphAttentionLSIGFBatch_Origin
+# (:1939-2005) filters with K SCALAR taps h[e, k] times a reshaped copy of the attention weight W (:1964-1969).  Both
+# are expressed here on the GAT_modified kernels: the effective per-head filter h[k] * W' is a differentiable torch
+# expression in front of the fused layer (autograd carries dh and the filter part of dW), the self loops are one
+# elementwise pass over S.
+
+def _origin_gso(S: torch.Tensor) -> torch.Tensor:
+    B, E, N, _ = S.shape
+    eye = torch.eye(N, dtype=torch.float32, device=S.device)
+    return S.to(torch.float32) + eye            # fp32 as the reference casts it (:1019); a -1 diagonal cancels the loop
+
+
+def _origin_filter(h: torch.Tensor, W: torch.Tensor) -> torch.Tensor:
+    P, E, F, G = W.shape
+    K = h.shape[1]
+    Wr = W.permute(0, 3, 1, 2).reshape(P, F, E, 1, G)           # the reference's own reshape (:1966-1967), kept as is
+    return h.reshape(1, 1, E, K, 1) * Wr                           # P x F x E x K x G
+
+
+def _origin_layer(x, S, h, a, W, b, concatenate, relu, path="auto", max_degree=None):
+    P, E, F, G = W.shape
+    if E != 1:
+        raise NotImplementedError("edge_features E != 1 is not supported")
+    wb0 = torch.zeros((P, E, F), dtype=torch.float32, device=W.device)
+    return gat_layer(x, _origin_gso(S), _origin_filter(h, W), a, W, wb0, b, mode=_cabi.MODE_GAT_MODIFIED,
+                     concatenate=concatenate, relu=relu, path=path, max_degree=max_degree)
+
+
+def learnAttentionGSOBatch_origin(x, a, W, S, negative_slope=0.2):
+    """graphML.py:964-1070."""
+    _check_slope(negative_slope)
+    P, E, F, G = W.shape
+    wb0 = torch.zeros((P, E, F), dtype=torch.float32, device=W.device)
+    return _attention_only(x, a, W, wb0, _origin_gso(S), _cabi.MODE_GAT_MODIFIED)
+
+
+def graphAttentionLSIGFBatch_Origin(h, x, a, W, S, b=None, negative_slope=0.2):
+    """graphML.py:1939-2005: returns (y [B,P,F,N] before the nonlinearity, aij [B,P,E,N,N])."""
+    _check_slope(negative_slope)
+    P, E, F, G = W.shape
+    B, N = x.shape[0], x.shape[2]
+    y, att = _origin_layer(x, S, h, a, W, b, True, False)
+    return y.permute(0, 2, 1).reshape(B, N, P, F).permute(0, 2, 3, 1), att.dense()
+
+
+class GraphFilterBatchAttentional_Origin(nn.Module):
+    """Mirror of the reference module of the same name (graphML.py:4175-4339): the GAT_origin ablation
+    (``--attentionMode GAT_origin``, graphs/models/decentralplanner_GAT.py:186-189).  Parameters, their order and
+    initialisation as in the reference: mixer [P,E,2F], weight [P,E,F,G], filterWeight [E,K], bias [F,1]."""
+
+    def __init__(self, G, F, K, P, E=1, bias=True, nonlinearity=nn.functional.relu, concatenate=True,
+                 attentionMode='GAT_origin'):
+        super().__init__()
+        self.G, self.F, self.K, self.P, self.E = G, F, K, P, E
+        self.S = None
+        self._last, self._aij = None, None
+        self.nonlinearity = nonlinearity
+        self.concatenate = concatenate
+        self.attentionMode = attentionMode
+        self.path = "auto"
+        self.mixer = nn.parameter.Parameter(torch.Tensor(P, E, 2 * F))
+        self.weight = nn.parameter.Parameter(torch.Tensor(P, E, F, G))
+        self.filterWeight = nn.parameter.Parameter(torch.Tensor(E, K))
+        if bias:
+            self.bias = nn.parameter.Parameter(torch.Tensor(F, 1))
+        else:
+            self.register_parameter('bias', None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        stdv = 1. / math.sqrt(self.G * self.P)
+        for p_ in (self.weight, self.mixer, self.filterWeight):
+            p_.data.uniform_(-stdv, stdv)
+        if self.bias is not None:
+            self.bias.data.uniform_(-stdv, stdv)
+
+    def addGSO(self, S):
+        assert len(S.shape) == 4
+        assert S.shape[1] == self.E
+        self.N = S.shape[2]
+        assert S.shape[3] == self.N
+        self.S = S
+
+    @property
+    def aij(self):
+        if self._aij is None and self._last is not None:
+            self._aij = self._last.dense().cpu().numpy()
+        return self._aij
+
+    @aij.setter
+    def aij(self, value):
+        self._aij = value
+
+    def returnAttentionGSO(self):
+        aij = self.aij
+        assert len(aij.shape) == 5
+        assert aij.shape[2] == self.E
+        self.N = aij.shape[3]
+        return np.mean(aij, axis=1)
+
+    def forward(self, x):
+        B, F, Nin = x.shape
+        if Nin < self.N:
+            x = torch.cat((x, torch.zeros(B, F, self.N - Nin).type(x.dtype).to(x.device)), dim=2)
+        if self.S is None:
+            raise RuntimeError("GraphFilterBatchAttentional_Origin.forward: no GSO stored -- call addGSO(S) first")
+        fused_relu = self.nonlinearity in (nn.functional.relu, torch.relu)
+        y, att = _origin_layer(x, self.S, self.filterWeight, self.mixer, self.weight, self.bias, self.concatenate,
+                               fused_relu, path=self.path, max_degree=getattr(self, "max_degree", None))
+        self._last, self._aij = att, None
+        if not fused_relu:
+            y = self.nonlinearity(y)
+        if Nin < self.N:
+            y = torch.index_select(y, 2, torch.arange(Nin).to(y.device))
+        return y
+
+    def extra_repr(self):
+        rep = "in_features=%d, out_features=%d, filter_taps=%d, attention_heads=%d, edge_features=%d, bias=%s, " % (
+            self.G, self.F, self.K, self.P, self.E, self.bias is not None)
+        rep += "attentionMode=%s, " % (self.attentionMode)
+        rep += ("GSO stored: number_nodes=%d" % self.N) if self.S is not None else "no GSO stored"
+        return rep
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_last"] = None
+        state["_aij"] = None
+        return state
+
+
 # ---- SURVEY 8f row f2: the non-attentional graph filter on the same kernels ------------------------------------
 
 class _LSIGFFunction(torch.autograd.Function):

@@ -18,7 +18,8 @@ def install_into_reference(graphml_module=None):
         raise RuntimeError("import utils.graphUtils.graphML (the reference) before installing")
     names = ("GraphFilterBatchAttentional", "graphAttentionLSIGFBatch_KeyQuery",
              "graphAttentionLSIGFBatch_modified", "learnAttentionGSOBatch_KeyQuery", "learnAttentionGSOBatch",
-             "GraphFilterBatch", "BatchLSIGF")
+             "GraphFilterBatch", "BatchLSIGF",
+             "GraphFilterBatchAttentional_Origin", "graphAttentionLSIGFBatch_Origin", "learnAttentionGSOBatch_origin")
     originals = {n: getattr(mod, n, None) for n in names}
     for n in names:
         setattr(mod, n, getattr(ours, n))

@@ -243,3 +243,43 @@ def lsigf_fwd_bwd(x, S, weight, bias, dy):
     y = lsigf_forward(xg, S, w, b)
     y.backward(dy)
     return y.detach(), {"x": xg.grad, "weight": w.grad, "bias": None if b is None else b.grad}
+
+
+# ---- the GAT_origin ablation ----------------------------------------------------------------------
+
+def origin_layer_forward(x, S, params, *, concatenate=True):
+    """GraphFilterBatchAttentional_Origin.forward (graphML.py:4284-4311) over graphAttentionLSIGFBatch_Origin
+    (:1939-2005) and learnAttentionGSOBatch_origin (:964-1070), dense.
+
+    params: mixer [P,1,2F], weight [P,1,F,G], filterWeight [1,K] (scalar taps), bias [F,1] or None.
+    Scores s[i,j] = a2.z_i + a1.z_j with z = W x (no bias), LeakyReLU 0.2; edge mask from S + I (:1019); the filter of
+    head p and tap k is h[k] times the reference's reshape of W (:1964-1969)."""
+    mixer, W, h, bias = params["mixer"], params["weight"], params["filterWeight"], params.get("bias")
+    B, G, Nin = x.shape
+    N = S.shape[2]
+    if Nin < N:
+        x = torch.cat((x, torch.zeros(B, G, N - Nin, dtype=x.dtype)), dim=2)
+    P, E, F, _ = W.shape
+    K = h.shape[1]
+    S1 = S.to(torch.float32) + torch.eye(N).reshape(1, 1, N, N)
+    z = torch.einsum("pfg,bgn->bpfn", W[:, 0], x)
+    a1, a2 = mixer[:, 0, :F], mixer[:, 0, F:]
+    s = torch.einsum("pf,bpfn->bpn", a2, z)[:, :, :, None] + torch.einsum("pf,bpfn->bpn", a1, z)[:, :, None, :]
+    e = torch.nn.functional.leaky_relu(s, 0.2)
+    mask = edge_mask(S1, x.dtype).reshape(B, 1, N, N)
+    aij = masked_row_softmax(e, mask)                                   # B x P x N x N
+    filt = h.reshape(1, 1, E, K, 1) * W.permute(0, 3, 1, 2).reshape(P, F, E, 1, G)      # P x F x E x K x G
+    u = x[:, None].expand(B, P, G, N)
+    y = torch.einsum("pfg,bpgn->bpfn", filt[:, :, 0, 0], u)
+    for k in range(1, K):
+        u = torch.matmul(u, aij)
+        y = y + torch.einsum("pfg,bpgn->bpfn", filt[:, :, 0, k], u)
+    if bias is not None:
+        y = y + bias
+    if concatenate:
+        out = torch.relu(y).permute(0, 3, 1, 2).reshape(B, N, P * F).permute(0, 2, 1)
+    else:
+        out = torch.relu(y.mean(dim=1))
+    if Nin < N:
+        out = out[:, :, :Nin]
+    return out, aij.reshape(B, P, 1, N, N)

@@ -64,6 +64,7 @@ def inputs(B, N, fov, seed):
     ("decentralplanner_GAT", dict(attentionMode="KeyQuery", nGraphFilterTaps=3, nAttentionHeads=4, AttentionConcat=True), 3, 10),
     ("decentralplanner_GAT", dict(attentionMode="KeyQuery", nGraphFilterTaps=2, nAttentionHeads=1, AttentionConcat=False), 1, 10),
     ("decentralplanner_GAT", dict(attentionMode="GAT_modified", nGraphFilterTaps=3, nAttentionHeads=4, AttentionConcat=True), 2, 24),
+    ("decentralplanner_GAT", dict(attentionMode="GAT_origin", nGraphFilterTaps=3, nAttentionHeads=4, AttentionConcat=True), 2, 12),
     ("decentralplanner_GAT_bottleneck_SkipConcat", dict(attentionMode="KeyQuery", nGraphFilterTaps=2, nAttentionHeads=4,
                                                         AttentionConcat=False, bottleneckFeature=32), 2, 16),
 ])
@@ -95,7 +96,7 @@ def test_reference_planner_forward_and_backward_through_the_cuda_layer(model_fil
         assert rel_err(our_model(x.to("cuda:0")), ref_logits) < TOL
     # the planner's tail -- GFL, actionsMLP, argmax decode -- as ONE call on the features the planner
     # feeds its graph layer (the fused head where the configuration allows it, layer + MLP otherwise)
-    if len(our_model.GFL) == 1 and "Skip" not in model_file:      # one graph layer (activation inside), no skip connection
+    if len(our_model.GFL) == 1 and "Skip" not in model_file and hasattr(our_model.GFL[0], "forward_actions"):      # one graph layer (activation inside), no skip connection
         seen = {}
         hook = our_model.GFL[0].register_forward_pre_hook(lambda m, a: seen.__setitem__("x", a[0].detach()))
         with torch.no_grad():
