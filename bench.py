@@ -599,20 +599,30 @@ def main():
         layer.addGSO(S)
         bits_chunk_bytes = cb * N * ((N + 31) // 32) * 4
         h2d_gso = nchunk * bits_chunk_bytes
-        e2e = {"value": units / (ms_e2e * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": (h2d_gso + x_h.numel() * 4) * world,
-               "d2h_bytes_per_step": 4 * world, "steps": e2e_steps,
-               "chunks": nchunk, "host_pack_threads": pack_threads, "host_placement": numa,
+        packed = {"value": units / (ms_e2e * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms_e2e,
+                  "h2d_bytes_per_step": (h2d_gso + x_h.numel() * 4) * world,
+                  "note": "the GSO's edge mask is packed on the host cores (pack_gso_host, inside the timed region), "
+                          "N^2/8 B per instance cross PCIe"}
+        dense = {"value": units / (ms_e2e_dense * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms_e2e_dense,
+                 "h2d_bytes_per_step": (S_h.numel() * S_h.element_size() + x_h.numel() * 4) * world,
+                 "note": "every chunk's dense fp32 GSO copied to the device by the copy engine and scanned there"}
+        # Which ingest route a deployment takes is decided by the host cores a rank has to itself (both read the same
+        # host memory; the copy engines need no cores): packing pays from ~6 cores per GPU up, the dense copy below
+        # that (16-core bench host: 1-2 GPUs packed, 4-8 GPUs dense).  Both are measured and reported either way.
+        from magat_pathplanning_b200.graphML import _PACK_MIN_CORES, host_cores_per_rank
+        cores_per_rank = min(host_cores_per_rank(), (os.cpu_count() or 1) // max(1, world))
+        route = "host-packed mask" if cores_per_rank >= _PACK_MIN_CORES else "dense copy"     # the layer's own policy
+        main_r, other_r = (packed, dense) if route == "host-packed mask" else (dense, packed)
+        e2e = {"value": main_r["value"], "unit": "agent-steps/s", "ms_per_step": main_r["ms_per_step"],
+               "h2d_bytes_per_step": main_r["h2d_bytes_per_step"], "d2h_bytes_per_step": 4 * world,
+               "steps": e2e_steps, "chunks": nchunk, "route": route, "host_cores_per_rank": cores_per_rank,
+               "host_pack_threads": pack_threads, "host_placement": numa,
                "host_bytes_read_per_step": S_h.numel() * S_h.element_size() * world,
-               "dense_h2d": {"value": units / (ms_e2e_dense * 1e-3), "unit": "agent-steps/s",
-                             "ms_per_step": ms_e2e_dense,
-                             "h2d_bytes_per_step": (S_h.numel() * S_h.element_size() + x_h.numel() * 4) * world,
-                             "note": "every chunk's dense fp32 GSO copied to the device (round-1 path)"},
+               "host_packed": packed, "dense_h2d": dense,
                "note": "inputs start in pinned HOST buffers every step: the dense fp32 GSO (4N^2 B per instance, as the "
-                       "reference builds it on the CPU) and x. The GSO's edge mask is packed on the host cores "
-                       "(pack_gso_host, inside the timed region) and N^2/8 B per instance cross PCIe; x is copied "
-                       "as is; the scalar loss is read back. Chunked: packing / copies of chunk c+1 overlap the "
-                       "layer call on chunk c"}
+                       "reference builds it on the CPU) and x; x is copied as is; the scalar loss is read back. "
+                       "Chunked: packing / copies of chunk c+1 overlap the layer call on chunk c. `route` names the "
+                       "GSO ingest this line reports (chosen by host cores per rank), both routes are listed"}
         del S_h, x_h, S_d, x_d
 
     # ---- the same step fed with agent positions instead of the dense GSO -------------------------

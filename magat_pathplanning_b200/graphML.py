@@ -189,8 +189,31 @@ def build_adjacency_from_rowbits(bits: torch.Tensor, device, max_degree: Optiona
         return _lists_from_masks(rowbits, colbits, stats, B, N, dev, st, max_degree)
 
 
+#: host cores a process needs to itself for the host-side packing to beat the copy engine (both read the same host
+#: memory, the copy engine needs no core; 16-core bench host: packing wins with 1-2 processes, the dense copy with 4-8)
+_PACK_MIN_CORES = 6
+
+
+def host_cores_per_rank() -> int:
+    """Cores this process may use, shared evenly with the other local ranks of a torchrun launch."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    return max(1, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
+
+
 def build_adjacency_host(S: torch.Tensor, device, max_degree: Optional[int] = None, threads: int = 0) -> Adjacency:
-    """``build_adjacency`` for a GSO in host memory: mask packed on the host cores, N^2 / 8 bytes over PCIe."""
+    """``build_adjacency`` for a GSO in host memory.  With enough host cores per process the edge mask is packed on the
+    host (N^2 / 8 bytes over PCIe); otherwise (or with ``threads < 0``) the dense tensor is copied and scanned on the
+    device, which costs no core."""
+    if threads < 0 or (threads == 0 and host_cores_per_rank() < _PACK_MIN_CORES):
+        dev = torch.device(device)
+        Sd = S.detach()
+        if Sd.dtype not in (torch.float32, torch.float64):
+            Sd = Sd.to(torch.float32)
+        with torch.cuda.device(dev):
+            return build_adjacency(Sd.to(dev, non_blocking=True), max_degree)
     return build_adjacency_from_rowbits(pack_gso_host(S, threads), device, max_degree)
 
 

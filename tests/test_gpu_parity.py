@@ -569,7 +569,8 @@ def test_layer_is_cuda_graph_capturable(N, promise):
 
 
 def test_gso_in_host_memory_gives_the_same_adjacency_and_output(golden):
-    """addGSO with a CPU tensor: the mask is packed on the host (magat_gso_pack_host), transposed on the device."""
+    """addGSO with a CPU tensor: the mask is packed on the host (magat_gso_pack_host) and transposed on the device, or --
+    with few host cores per process -- the dense tensor is copied and scanned on the device; same lists either way."""
     from magat_pathplanning_b200 import build_adjacency, build_adjacency_host
     dev = torch.device("cuda:0")
     gen = torch.Generator().manual_seed(12)
@@ -578,10 +579,13 @@ def test_gso_in_host_memory_gives_the_same_adjacency_and_output(golden):
         S[0, 0, 1, 2] = float("nan")
         S[1, 0, 2, 1] = -3e-9
         S[2, 0, 0, 1] = 5e-10
-        a, b = build_adjacency(S.to(dev)), build_adjacency_host(S, dev)
-        assert a.D == b.D
-        for k in ("nbr_out", "nbr_in", "slot_in"):
-            assert torch.equal(getattr(a, k), getattr(b, k)), (N, k)
+        a = build_adjacency(S.to(dev))
+        # threads = 2: packed on the host whatever the box; -1: the dense-copy route (few cores per process); 0: policy
+        for threads in (2, -1, 0):
+            b = build_adjacency_host(S, dev, threads=threads)
+            assert a.D == b.D
+            for k in ("nbr_out", "nbr_in", "slot_in"):
+                assert torch.equal(getattr(a, k), getattr(b, k)), (N, k, threads)
     d, meta = golden.case("kq_concat_c2")
     layer = make_layer(meta, d, dev)
     layer.addGSO(d["S"])                                   # stays on the CPU
