@@ -337,6 +337,138 @@ __global__ void __launch_bounds__(256) k_gso_from_positions(const T* __restrict_
   }
 }
 
+// The same mask through a cell list (SURVEY 8f row f1 asks for it): one CTA per instance bins its agents into square
+// cells a hair wider than the radius, and every agent tests only the agents of its 3 x 3 cells with the SAME fp64
+// predicate as above -- ~11 candidates instead of N - 1 at the reference's density.  Agent i owns row i of the
+// (zero-initialised) masks and sets its bits with plain read-modify-writes; the mask is symmetric, so colbits takes the
+// same words.  An instance whose positions are not all finite, or whose bounding box needs more than kCellMax cells,
+// takes the all-pairs loop inside the same CTA.
+constexpr int kCellMax = 4096;
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_gso_cells_from_positions(const T* __restrict__ pos, int N, int W, double thr2,
+                                                                  double cell, uint32_t* __restrict__ rowbits,
+                                                                  uint32_t* __restrict__ colbits) {
+  extern __shared__ double cell_smem[];
+  double* pos_s = cell_smem;                                        // [N][2]
+  int* cell_of = reinterpret_cast<int*>(pos_s + 2 * (size_t)N);     // [N]
+  int* ids = cell_of + N;                                           // [N] agents sorted by cell
+  int* start = ids + N;                                             // [kCellMax + 1]
+  int* fill = start + kCellMax + 1;                                 // [kCellMax]
+  __shared__ double red[4][8];
+  __shared__ int bad_s, gx_s, gy_s;
+  __shared__ double x0_s, y0_s;
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const T* pb = pos + (size_t)b * N * 2;
+  double xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+  int bad = 0;
+  for (int i = tid; i < N; i += blockDim.x) {
+    const double x = (double)pb[2 * i], y = (double)pb[2 * i + 1];
+    pos_s[2 * i] = x;
+    pos_s[2 * i + 1] = y;
+    if (!(fabs(x) < INFINITY) || !(fabs(y) < INFINITY)) bad = 1;
+    xmin = fmin(xmin, x); xmax = fmax(xmax, x); ymin = fmin(ymin, y); ymax = fmax(ymax, y);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    xmin = fmin(xmin, __shfl_xor_sync(0xffffffffu, xmin, o)); xmax = fmax(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+    ymin = fmin(ymin, __shfl_xor_sync(0xffffffffu, ymin, o)); ymax = fmax(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+    bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  if (tid == 0) bad_s = 0;
+  __syncthreads();
+  if (lane == 0) {
+    red[0][warp] = xmin; red[1][warp] = xmax; red[2][warp] = ymin; red[3][warp] = ymax;
+    if (bad) bad_s = 1;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w) {
+      red[0][0] = fmin(red[0][0], red[0][w]); red[1][0] = fmax(red[1][0], red[1][w]);
+      red[2][0] = fmin(red[2][0], red[2][w]); red[3][0] = fmax(red[3][0], red[3][w]);
+    }
+    const double nx = floor((red[1][0] - red[0][0]) / cell) + 1.0, ny = floor((red[3][0] - red[2][0]) / cell) + 1.0;
+    if (bad_s || !(nx * ny <= (double)kCellMax)) {
+      bad_s = 1;
+    } else {
+      gx_s = (int)nx; gy_s = (int)ny; x0_s = red[0][0]; y0_s = red[2][0];
+    }
+  }
+  __syncthreads();
+  uint32_t* rb = rowbits + (size_t)b * N * W;
+  uint32_t* cb = colbits + (size_t)b * N * W;
+  if (bad_s) {
+    // all pairs (NaN compares false: no edge), one warp per row
+    for (int i = warp; i < N; i += 8) {
+      const double xi = pos_s[2 * i], yi = pos_s[2 * i + 1];
+      for (int w = 0; w < W; ++w) {
+        const int j = w * 32 + lane;
+        bool e = false;
+        if (j < N && j != i) {
+          const double dx = xi - pos_s[2 * j], dy = yi - pos_s[2 * j + 1];
+          e = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < thr2;
+        }
+        const uint32_t word = __ballot_sync(0xffffffffu, e);
+        if (lane == 0) rb[(size_t)i * W + w] = word;
+        if (lane == 1) cb[(size_t)i * W + w] = word;
+      }
+    }
+    return;
+  }
+  const int gx = gx_s, gy = gy_s, ncell = gx * gy;
+  const double x0 = x0_s, y0 = y0_s;
+  for (int c = tid; c <= ncell; c += blockDim.x) start[c] = 0;
+  for (int c = tid; c < ncell; c += blockDim.x) fill[c] = 0;
+  __syncthreads();
+  for (int i = tid; i < N; i += blockDim.x) {
+    int cx = (int)floor((pos_s[2 * i] - x0) / cell), cy = (int)floor((pos_s[2 * i + 1] - y0) / cell);
+    cx = min(max(cx, 0), gx - 1);
+    cy = min(max(cy, 0), gy - 1);
+    const int c = cy * gx + cx;
+    cell_of[i] = c;
+    atomicAdd(&start[c + 1], 1);
+  }
+  __syncthreads();
+  if (warp == 0) {                                   // inclusive scan of the counts: start[c] = first slot of cell c
+    int carry = 0;
+    for (int c0 = 1; c0 <= ncell; c0 += 32) {
+      const int c = c0 + lane;
+      int v = c <= ncell ? start[c] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+      }
+      if (c <= ncell) start[c] = v + carry;
+      carry += __shfl_sync(0xffffffffu, v, 31);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < N; i += blockDim.x) {
+    const int c = cell_of[i];
+    ids[start[c] + atomicAdd(&fill[c], 1)] = i;
+  }
+  __syncthreads();
+  for (int i = tid; i < N; i += blockDim.x) {
+    const double xi = pos_s[2 * i], yi = pos_s[2 * i + 1];
+    const int c = cell_of[i], cx = c % gx, cy = c / gx;
+    uint32_t* ri = rb + (size_t)i * W;
+    uint32_t* ci = cb + (size_t)i * W;
+    for (int yy = max(cy - 1, 0); yy <= min(cy + 1, gy - 1); ++yy) {
+      const int c_lo = yy * gx + max(cx - 1, 0), c_hi = yy * gx + min(cx + 1, gx - 1);
+      for (int k = start[c_lo]; k < start[c_hi + 1]; ++k) {             // the three cells of a row are contiguous
+        const int j = ids[k];
+        if (j == i) continue;
+        const double dx = xi - pos_s[2 * j], dy = yi - pos_s[2 * j + 1];
+        if (__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) < thr2) {
+          const uint32_t word = ri[j >> 5] | (1u << (j & 31));
+          ri[j >> 5] = word;
+          ci[j >> 5] = word;
+        }
+      }
+    }
+  }
+}
+
 // stats[0] max out-degree, [1] max in-degree, [2] number of edges, [3] symmetric flag.
 __global__ void __launch_bounds__(256) k_gso_stats(const uint32_t* __restrict__ rowbits,
                                                    const uint32_t* __restrict__ colbits, long rows,
@@ -856,13 +988,32 @@ extern "C" int magat_gso_from_positions(const void* pos, int pos_dtype, int B, i
       while (sqrt(thr2) < comm_radius) thr2 = nextafter(thr2, INFINITY);
     }
   }
+  int rc;
+  // cell list when the radius makes sense as a cell size (cells a hair wider than the radius: two agents closer than
+  // the radius can then never sit two cells apart, whatever the rounding of the divisions)
+  const bool cells = comm_radius > 0.0 && comm_radius < INFINITY;
+  if (cells) {
+    const size_t words = (size_t)B * N * W;
+    cudaMemsetAsync(rowbits, 0, words * 4, st);
+    cudaMemsetAsync(colbits, 0, words * 4, st);
+    const size_t csm = (size_t)N * 2 * sizeof(double) + (size_t)N * 2 * sizeof(int) + (size_t)(2 * kCellMax + 1) * sizeof(int);
+    const double cell = comm_radius * (1.0 + 1e-9);
+    if (pos_dtype == MAGAT_DT_F32) {
+      if ((rc = ensure_dyn_smem(KID_CELLS_F32, (const void*)k_gso_cells_from_positions<float>, 128 * 1024, "k_gso_cells_from_positions"))) return rc;
+      k_gso_cells_from_positions<float><<<B, 256, csm, st>>>((const float*)pos, N, W, thr2, cell, rowbits, colbits);
+    } else {
+      if ((rc = ensure_dyn_smem(KID_CELLS_F64, (const void*)k_gso_cells_from_positions<double>, 128 * 1024, "k_gso_cells_from_positions"))) return rc;
+      k_gso_cells_from_positions<double><<<B, 256, csm, st>>>((const double*)pos, N, W, thr2, cell, rowbits, colbits);
+    }
+    if ((rc = check_launch("k_gso_from_positions(cells)", st))) return rc;
+    return launch_gso_stats(rowbits, colbits, B, N, W, stats, st);
+  }
   dim3 grid(cdiv(N, 32), B);
   if (pos_dtype == MAGAT_DT_F32)
     k_gso_from_positions<float><<<grid, 256, smem, st>>>((const float*)pos, N, W, thr2, rowbits, colbits);
   else
     k_gso_from_positions<double><<<grid, 256, smem, st>>>((const double*)pos, N, W, thr2, rowbits, colbits);
-  int rc = check_launch("k_gso_from_positions", st);
-  if (rc) return rc;
+  if ((rc = check_launch("k_gso_from_positions", st))) return rc;
   return launch_gso_stats(rowbits, colbits, B, N, W, stats, st);
 }
 

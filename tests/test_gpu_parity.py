@@ -464,6 +464,48 @@ def test_adjacency_from_positions(N, width, R, dtype):
         assert torch.equal(getattr(a, name), getattr(p_, name)), name
 
 
+@pytest.mark.parametrize("case", ["exact_radius_lattice", "huge_radius", "tiny_radius_many_cells", "nan_and_inf",
+                                  "negative_coordinates", "zero_radius", "n3000"])
+def test_adjacency_from_positions_edge_cases(case):
+    """The cell-list builder against the dense formula where cells could go wrong: pairs at exactly the radius (lattice
+    positions: d = 7 is NOT an edge, d just below is), one cell for everything, a bounding box of more cells than the
+    kernel bins (it then takes all pairs), non-finite positions (no edge, as the comparison is false), negative and large
+    coordinates, a radius of zero, and the largest N the kernel takes."""
+    from magat_pathplanning_b200 import build_adjacency, build_adjacency_from_positions
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(len(case))
+    B, N, R = 3, 200, 7.0
+    pos = torch.rand(B, N, 2, generator=gen, dtype=torch.float64) * 60
+    if case == "exact_radius_lattice":
+        pos = torch.floor(pos)                                   # integer coordinates: many pairs at distance exactly 7, 5-5-7.07...
+        pos[:, 1] = pos[:, 0] + torch.tensor([7.0, 0.0])
+        pos[:, 2] = pos[:, 0] + torch.tensor([0.0, -7.0])
+        pos[:, 3] = pos[:, 0] + torch.tensor([7.0 - 1e-12, 0.0])
+    elif case == "huge_radius":
+        R = 1e6
+    elif case == "tiny_radius_many_cells":
+        R, pos = 0.05, pos * 10                                  # 600 / 0.05 = 12000 cells per side
+        pos[:, 1] = pos[:, 0] + 0.03
+    elif case == "nan_and_inf":
+        pos[0, 5, 0] = float("nan")
+        pos[1, 7, 1] = float("inf")
+        pos[2, 9] = float("-inf")
+    elif case == "negative_coordinates":
+        pos = pos - 1e5
+        pos[:, 1] = pos[:, 0] + 6.999
+    elif case == "zero_radius":
+        R = 0.0
+    elif case == "n3000":
+        B, N = 2, 3000
+        pos = torch.rand(B, N, 2, generator=gen, dtype=torch.float64) * 340
+    S = orc.gso_from_positions(pos, R)
+    a = build_adjacency(S.to(dev))
+    p_ = build_adjacency_from_positions(pos.to(dev), R)
+    assert a.D == p_.D
+    for name in ("nbr_out", "nbr_in", "slot_in"):
+        assert torch.equal(getattr(a, name), getattr(p_, name)), name
+
+
 def test_layer_from_positions_matches_dense_gso(golden):
     from magat_pathplanning_b200 import GraphFilterBatchAttentional
     dev = torch.device("cuda:0")
