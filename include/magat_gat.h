@@ -109,7 +109,9 @@ int magat_gso_build_ell(const uint32_t* rowbits, const uint32_t* colbits, int B,
  * squareform(pdist(pos)) < commR + zero diagonal of utils/new_simulator.py:823-827 and the 4N^2-byte dense GSO that
  * then crosses PCIe.  pos: [B][N][2] fp32 or fp64 (device); the predicate is evaluated in fp64 like scipy's.  Writes the
  * same rowbits / colbits / stats as magat_gso_scan (stats zero-initialised by the caller except stats[3] = 1);
- * continue with magat_gso_build_ell.  N <= 3072. */
+ * continue with magat_gso_build_ell.  N <= 3072.  Neighbour search through a cell list (cells of the radius, 3 x 3 per
+ * agent; an instance with non-finite positions or a bounding box of more than 4096 cells is tested all pairs): the
+ * result is that of the all-pairs formula bit for bit. */
 int magat_gso_from_positions(const void* pos, int pos_dtype, int B, int N, double comm_radius,
                              uint32_t* rowbits, uint32_t* colbits, int32_t* stats, void* stream);
 
