@@ -466,6 +466,16 @@ class _GATFunction(torch.autograd.Function):
                 df, db, None, None)
 
 
+def _apply_nonlinearity(fn, y, P, F, concatenate):
+    """A custom nonlinearity sees what it sees in the reference: [B,P,F,N] before the heads are concatenated
+    (graphML.py:4656-4662), [B,F,N] after the head mean (:4665-4667).  (ReLU is fused into the kernels.)"""
+    if not concatenate:
+        return fn(y)
+    B, _, N = y.shape
+    y4 = fn(y.permute(0, 2, 1).reshape(B, N, P, F).permute(0, 2, 3, 1))
+    return y4.permute(0, 3, 1, 2).reshape(B, N, P * F).permute(0, 2, 1)
+
+
 def _mode_of(attentionMode: str) -> int:
     if 'GAT_modified' in attentionMode:          # graphML.py:4588
         return _cabi.MODE_GAT_MODIFIED
@@ -861,7 +871,7 @@ class GraphFilterBatchAttentional_Origin(nn.Module):
                                fused_relu, path=self.path, max_degree=getattr(self, "max_degree", None))
         self._last, self._aij = att, None
         if not fused_relu:
-            y = self.nonlinearity(y)
+            y = _apply_nonlinearity(self.nonlinearity, y, self.P, self.F, self.concatenate)
         if Nin < self.N:
             y = torch.index_select(y, 2, torch.arange(Nin).to(y.device))
         return y
@@ -1167,7 +1177,7 @@ class GraphFilterBatchAttentional(nn.Module):
                            max_degree=getattr(self, "max_degree", None), fused_team=getattr(self, "fused_team", 0))
         self._last, self._aij = att, None
         if not fused_relu:
-            y = self.nonlinearity(y)
+            y = _apply_nonlinearity(self.nonlinearity, y, self.P, self.F, self.concatenate)
         if Nin < self.N:
             y = torch.index_select(y, 2, torch.arange(Nin).to(y.device))
         return y

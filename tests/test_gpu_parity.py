@@ -158,6 +158,13 @@ def test_custom_nonlinearity_and_pickle(golden):
     B, P, F, N = pre.shape
     want = torch.tanh(pre).permute(0, 3, 1, 2).reshape(B, N, P * F).permute(0, 2, 1)
     assert rel_err(y, want) < TOL
+    # a nonlinearity that is NOT elementwise sees [B,P,F,N], as in the reference (graphML.py:4656): softmax over the
+    # features of each head
+    layer.nonlinearity = lambda t: torch.softmax(t, dim=2)
+    with torch.no_grad():
+        y = layer(d["x"].to(dev))
+    want = torch.softmax(pre, dim=2).permute(0, 3, 1, 2).reshape(B, N, P * F).permute(0, 2, 1)
+    assert list(y.stride()) == list(want.stride()) and rel_err(y, want) < TOL
     layer.nonlinearity = torch.nn.functional.relu
     clone = pickle.loads(pickle.dumps(layer))            # mp.spawn pickles the model (agents/...GAT.py:720-728)
     clone.addGSO(d["S"].to(dev))
