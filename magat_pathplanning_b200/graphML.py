@@ -351,6 +351,7 @@ class _GATFunction(torch.autograd.Function):
         ctx.meta, ctx.adj = meta, adj
         ctx.save_for_backward(xt, weight_c, mixer_c, wb_c, filt_c, y, att, taps, wprep, sproj, bits)
         ctx.mark_non_differentiable(att)
+        ctx.set_materialize_grads(False)       # no zero-filled gradient tensor for the attention output
         return y, att
 
     @staticmethod
@@ -413,10 +414,13 @@ class _GATFunction(torch.autograd.Function):
         ctx.meta, ctx.adj = meta, adj
         ctx.save_for_backward(xt, weight_c, mixer_c, wb_c, filt_c, y, att, taps, wprep, sproj, None)
         ctx.mark_non_differentiable(att)
+        ctx.set_materialize_grads(False)       # no zero-filled gradient tensor for the attention output
         return y, att
 
     @staticmethod
     def backward(ctx, dy, _datt):
+        if dy is None:                                   # y took no part in the loss
+            return (None,) * 8
         L = _cabi.lib()
         meta, adj = ctx.meta, ctx.adj
         xt, weight_c, mixer_c, wb_c, filt_c, y, att, taps, wprep, sproj, bits = ctx.saved_tensors
