@@ -648,7 +648,6 @@ def main():
             x_h2 = torch.empty(x_mem.shape, dtype=x_mem.dtype, pin_memory=True)
             pos_h.copy_(pos)
             x_h2.copy_(x_mem)
-            pos_d, x_d2 = torch.empty_like(pos), torch.empty_like(x_mem)
         except Exception as exc:                      # an extra, never a reason to lose the contract line
             pos_ok, pos_err = 0, str(exc)[-200:]
         if dist_on:
@@ -672,19 +671,46 @@ def main():
                     layer.addGSOFromPositions(pos, COMM_RADIUS)
                     return layer(x)
 
+            # end to end like the dense-GSO step: the batch crosses PCIe in chunks on a copy stream while the previous
+            # chunk is being processed (two device buffers); gradients accumulate over the chunks
+            # (few chunks: every layer call synchronises once on the degree statistics, which stalls the pipeline)
+            pn = 4 if B % 4 == 0 and B >= 256 else 1
+            pcb = B // pn
+            pos_dc = [torch.empty((pcb,) + tuple(pos.shape[1:]), dtype=pos.dtype, device=dev) for _ in range(2)]
+            x_dc = [torch.empty((pcb,) + tuple(x_mem.shape[1:]), dtype=x_mem.dtype, device=dev) for _ in range(2)]
+            pos_copy = torch.cuda.Stream(device=dev)
+
             def step_e2e_pos():
-                pos_d.copy_(pos_h, non_blocking=True)
-                x_d2.copy_(x_h2, non_blocking=True)
+                main = torch.cuda.current_stream(dev)
                 for p in params:
                     p.grad = None
-                xg = x_d2.permute(0, 2, 1).requires_grad_(True)
-                layer.addGSOFromPositions(pos_d, COMM_RADIUS)
-                y = layer(xg)
-                loss = (y * dy).sum()
-                loss.backward()
+                loss_acc = torch.zeros((), device=dev)
+                ready, done = [None] * pn, [None] * pn
+
+                def prepare(c):
+                    with torch.cuda.stream(pos_copy):
+                        if c >= 2:
+                            pos_copy.wait_event(done[c - 2])
+                        else:
+                            pos_copy.wait_stream(main)
+                        pos_dc[c % 2].copy_(pos_h[c * pcb:(c + 1) * pcb], non_blocking=True)
+                        x_dc[c % 2].copy_(x_h2[c * pcb:(c + 1) * pcb], non_blocking=True)
+                        ready[c] = pos_copy.record_event()
+                prepare(0)
+                for c in range(pn):
+                    if c + 1 < pn:
+                        prepare(c + 1)
+                    main.wait_event(ready[c])
+                    layer.addGSOFromPositions(pos_dc[c % 2], COMM_RADIUS)
+                    xg = x_dc[c % 2].permute(0, 2, 1).requires_grad_(True)
+                    y = layer(xg)
+                    loss = (y * dy[c * pcb:(c + 1) * pcb]).sum()
+                    loss.backward()
+                    loss_acc += loss.detach()
+                    done[c] = main.record_event()
                 if dist_on:
                     allreduce_gradients(params)
-                return float(loss.item())
+                return float(loss_acc.item())
             ms_tp = timed(step_train_pos, max(2, args.steps // 2), 2, dist_on)
             ms_fp = timed(step_fwd_pos, max(2, args.steps // 2), 2, dist_on)
             ms_ep = timed(step_e2e_pos, max(2, min(args.steps, 5)), 1, dist_on)
@@ -697,7 +723,7 @@ def main():
                          "note": "addGSOFromPositions(pos [B,N,2], commR): neighbour lists built on the device from "
                                  "positions (utils/new_simulator.py:823-827); no N x N GSO exists or crosses PCIe; "
                                  "all ranks, max over ranks, gradient all-reduce included"}
-            del pos_h, x_h2, pos_d, x_d2
+            del pos_h, x_h2, pos_dc, x_dc
             layer.addGSO(S)
         else:
             positions = {"error": pos_err or "set-up failed on another rank"}
