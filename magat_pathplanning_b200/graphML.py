@@ -97,6 +97,14 @@ class Adjacency:
         self.nbr_out, self.nbr_in, self.slot_in, self.slot_out = nbr_out, nbr_in, slot_in, slot_out
         self.stats = stats          # device int32 {max out-degree, max in-degree, edges, symmetric} of the scan, or None
 
+    def record_stream(self, stream):
+        """The lists were built on another stream (e.g. by a worker thread preparing the next chunk): tell the caching
+        allocator that ``stream`` uses them too."""
+        for t in (self.nbr_out, self.nbr_in, self.slot_in, self.slot_out, self.stats):
+            if t is not None:
+                t.record_stream(stream)
+        return self
+
     def check_degree(self):
         """Synchronising check of a ``max_degree`` promise: raises when a neighbour list did not fit its D slots."""
         if self.stats is not None:
