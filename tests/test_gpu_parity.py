@@ -719,3 +719,36 @@ def test_fused_action_head_at_the_graded_shape():
     top2 = ref.topk(2, dim=1).values
     clear = (top2[:, 0] - top2[:, 1]) > 1e-4 * ref.abs().max()
     assert torch.equal(actions.view(B, N)[pick].reshape(-1).cpu().long()[clear], ref.argmax(1)[clear])
+
+
+@pytest.mark.parametrize("mode,K,P", [("KeyQuery", 3, 4), ("KeyQuery", 2, 1), ("GAT_modified", 2, 4)])
+def test_head_mean_at_the_tensor_core_shapes(mode, K, P):
+    """Heads averaged (the reference's CLI default) with G = F = 128: routed through the concat path's tcgen05 kernels
+    plus elementwise mean / ReLU.  Forward, output layout (contiguous [B,F,N], graphML.py:4665-4667) and every gradient
+    against the oracle."""
+    dev = torch.device("cuda:0")
+    G = F = 128
+    B, N = 6, 300
+    gen = torch.Generator().manual_seed(555 + K + P)
+    params = orc.init_params(G, F, K, P, mode=mode, generator=gen, weight_bias_std=0.1)
+    S = orc.random_geometric_gso(B, N, generator=gen)
+    x = torch.relu(torch.randn(B, N, G, generator=gen)).permute(0, 2, 1)
+    dy = torch.randn(B, F, N, generator=gen)
+    _, _, pre = orc.gat_layer_forward(x, S, params, mode=mode, concatenate=False, return_pre=True)
+    dy = dy * (pre.mean(dim=1).abs() > 1e-3)
+    y_ref, aij_ref, g_ref = orc.gat_layer_fwd_bwd(x, S, params, dy, mode=mode, concatenate=False)
+    layer = make_layer(dict(G=G, F=F, K=K, P=P, concat=False, mode=mode),
+                       {"param." + k: v for k, v in params.items() if v is not None}, dev, path="auto")
+    layer.addGSO(S.to(dev))
+    xd = x.to(dev).requires_grad_(True)
+    y = layer(xd)
+    assert y.shape == (B, F, N) and y.is_contiguous()
+    assert rel_err(y, y_ref) < TOL
+    assert (torch.from_numpy(layer.aij) - aij_ref).abs().max() < TOL
+    y.backward(dy.to(dev))
+    assert rel_err(xd.grad, g_ref["x"]) < TOL
+    for k in PARAMS:
+        if g_ref[k] is not None:
+            assert rel_err(getattr(layer, k).grad, g_ref[k]) < TOL, k
+        else:
+            assert getattr(layer, k).grad is None, k
