@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define MAGAT_ABI_VERSION 11
+#define MAGAT_ABI_VERSION 12
 
 enum {
   MAGAT_OK = 0,
@@ -158,6 +158,14 @@ int magat_gat_forward_taps_valid(const magat_gat_fwd_args* a);
 int magat_gat_forward_relu_bits_valid(const magat_gat_fwd_args* a);
 size_t magat_gat_relu_bits_words(int B, int N, int P, int F);
 
+
+/* ---- heads averaged on top of the concat layout (graphML.py:4665-4667: y = act(mean_p y_p), contiguous [B][F][N]) ----
+ * ycat / dycat: [B*N][P*F] (what magat_gat_forward writes with concat = 1, relu = 0, unit channel stride); y, dy: contiguous
+ * [B][F][N].  forward: y = act(mean over heads); backward: dycat[.][p*F + f] = dy * act'(y) / P for every head.
+ * F a multiple of 32. */
+int magat_head_mean_forward(const float* ycat, int B, int N, int P, int F, int relu, float* y, void* stream);
+int magat_head_mean_backward(const float* dy, const float* y, int B, int N, int P, int F, int relu, float* dycat,
+                             void* stream);
 
 /* ---- layer + linear action head in one pass (inference) ----
  * The planner feeds the layer's output straight into actionsMLP (graphs/models/decentralplanner_GAT.py:329-334; one

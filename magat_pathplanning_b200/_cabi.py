@@ -12,7 +12,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmagat_gat.so")
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 MODE_KEYQUERY, MODE_GAT_MODIFIED, MODE_GSO_VALUES = 0, 1, 2
 DT_F32, DT_F64 = 0, 1
@@ -22,7 +22,7 @@ EXPORTS = (
     "magat_abi_version", "magat_last_error", "magat_device_check", "magat_gso_scan",
     "magat_gso_build_ell", "magat_gat_wprep_floats", "magat_gat_forward", "magat_gat_forward_taps_valid",
     "magat_gat_forward_relu_bits_valid", "magat_gat_relu_bits_words",
-    "magat_gat_actions_supported", "magat_gat_forward_actions",
+    "magat_gat_actions_supported", "magat_gat_forward_actions", "magat_head_mean_forward", "magat_head_mean_backward",
     "magat_gat_bwd_partial_floats", "magat_gat_backward", "magat_gat_attention_dense",
     "magat_launch_count", "magat_profile_enable", "magat_profile_collect",
     "magat_gat_small_supported", "magat_gat_forward_small", "magat_gso_from_positions",
@@ -121,6 +121,10 @@ def lib():
         L.magat_gat_forward_relu_bits_valid.restype = C.c_int
         L.magat_gat_relu_bits_words.argtypes = [C.c_int] * 4
         L.magat_gat_relu_bits_words.restype = C.c_size_t
+        L.magat_head_mean_forward.argtypes = [_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ptr, _ptr]
+        L.magat_head_mean_forward.restype = C.c_int
+        L.magat_head_mean_backward.argtypes = [_ptr, _ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ptr, _ptr]
+        L.magat_head_mean_backward.restype = C.c_int
         L.magat_gat_actions_supported.argtypes = [C.POINTER(FwdArgs), C.c_int]
         L.magat_gat_actions_supported.restype = C.c_int
         L.magat_gat_forward_actions.argtypes = [C.POINTER(FwdArgs), _ptr, _ptr, C.c_int, _ptr, _ptr, _ptr, _ptr]

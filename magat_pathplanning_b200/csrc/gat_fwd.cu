@@ -731,6 +731,61 @@ extern "C" size_t magat_gat_relu_bits_words(int B, int N, int P, int F) {
   return ((rows + 63) / 64) * 2 * (size_t)P * F;
 }
 
+// ---- heads averaged on top of the concat path (graphML.py:4665-4667) ------------------------------------------------
+// y[b][f][n] = act((1/P) sum_p ycat[b*N + n][p*F + f]) as a contiguous [B][F][N] tensor: 32 x 32 tiles, read along f,
+// transposed through shared memory, written along n.
+__global__ void __launch_bounds__(256) k_head_mean_fwd(const float* __restrict__ ycat, int N, int P, int F, int relu,
+                                                       float* __restrict__ y) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, n0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;            // 32 x 8
+  const float inv = 1.f / (float)P;
+  for (int r = ty; r < 32; r += 8) {
+    const int n = n0 + r;
+    float s = 0.f;
+    if (n < N) {
+      const float* src = ycat + ((size_t)b * N + n) * ((size_t)P * F) + f0 + tx;
+      for (int p = 0; p < P; ++p) s += __ldcs(src + (size_t)p * F);
+      s *= inv;
+      if (relu) s = fmaxf(s, 0.f);
+    }
+    tile[r][tx] = s;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int n = n0 + tx;
+    if (n < N) y[((size_t)b * F + f0 + r) * N + n] = tile[tx][r];
+  }
+}
+
+// dycat[b*N + n][p*F + f] = dy[b][f][n] * (relu ? y[b][f][n] > 0 : 1) / P for every head p
+__global__ void __launch_bounds__(256) k_head_mean_bwd(const float* __restrict__ dy, const float* __restrict__ y, int N,
+                                                       int P, int F, int relu, float* __restrict__ dycat) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, n0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float inv = 1.f / (float)P;
+  for (int r = ty; r < 32; r += 8) {
+    const int n = n0 + tx;
+    float g = 0.f;
+    if (n < N) {
+      const size_t i = ((size_t)b * F + f0 + r) * N + n;
+      g = dy[i] * inv;
+      if (relu && !(y[i] > 0.f)) g = 0.f;
+    }
+    tile[r][tx] = g;                                                 // [f][n]
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int n = n0 + r;
+    if (n < N) {
+      const float g = tile[tx][r];
+      float* dst = dycat + ((size_t)b * N + n) * ((size_t)P * F) + f0 + tx;
+      for (int p = 0; p < P; ++p) __stcs(dst + (size_t)p * F, g);
+    }
+  }
+}
+
 // the layer and the planner's linear action head in one pass (inference).  y never reaches memory.
 extern "C" int magat_gat_actions_supported(const magat_gat_fwd_args* a, int A) {
   if (a == nullptr || A < 1 || A > 8 || a->path == MAGAT_PATH_SIMT) return 0;
@@ -756,6 +811,27 @@ extern "C" int magat_gat_forward_actions(const magat_gat_fwd_args* a, const floa
   prof_begin(st);
   const HeadArgs head{head_weight, head_bias, A, partial, logits, actions_or_null};
   return forward_impl(a, st, true, &head);
+}
+
+extern "C" int magat_head_mean_forward(const float* ycat, int B, int N, int P, int F, int relu, float* y, void* stream) {
+  MAGAT_REQUIRE(ycat && y, MAGAT_E_BAD_ARG, "magat_head_mean_forward: null pointer");
+  MAGAT_REQUIRE(B >= 1 && B <= 65535 && N >= 1 && P >= 1 && F >= 32 && F % 32 == 0, MAGAT_E_BAD_ARG,
+                "magat_head_mean_forward: B=%d N=%d P=%d F=%d (F must be a multiple of 32)", B, N, P, F);
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin(st);
+  k_head_mean_fwd<<<dim3(cdiv(N, 32), F / 32, B), 256, 0, st>>>(ycat, N, P, F, relu, y);
+  return check_launch("k_head_mean_fwd", st);
+}
+
+extern "C" int magat_head_mean_backward(const float* dy, const float* y, int B, int N, int P, int F, int relu,
+                                        float* dycat, void* stream) {
+  MAGAT_REQUIRE(dy && y && dycat, MAGAT_E_BAD_ARG, "magat_head_mean_backward: null pointer");
+  MAGAT_REQUIRE(B >= 1 && B <= 65535 && N >= 1 && P >= 1 && F >= 32 && F % 32 == 0, MAGAT_E_BAD_ARG,
+                "magat_head_mean_backward: B=%d N=%d P=%d F=%d (F must be a multiple of 32)", B, N, P, F);
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin(st);
+  k_head_mean_bwd<<<dim3(cdiv(N, 32), F / 32, B), 256, 0, st>>>(dy, y, N, P, F, relu, dycat);
+  return check_launch("k_head_mean_bwd", st);
 }
 
 extern "C" int magat_gat_forward(const magat_gat_fwd_args* a, void* stream) {
