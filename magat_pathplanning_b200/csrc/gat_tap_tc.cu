@@ -556,6 +556,7 @@ __global__ void __launch_bounds__(256) k_transpose_h(const float* __restrict__ H
 
 bool gz_tc_supported(const magat_gat_bwd_args* a) {
   if (!a->concat || a->G != FT || a->F % SK != 0 || a->F > ACC_COL0 || a->P * a->K > 64) return false;
+  if ((long)a->K * a->F > ACC_COL0 || (a->K > 1 && a->F != SK)) return false;     // the K blocks of a head sit side by side in TMEM
   if (a->dy_sc != 1 || (a->dy_sn % 4) || (a->dy_sb % 4) || ((uintptr_t)a->dy % 16)) return false;
   if (a->relu && (a->y_sc != 1 || (a->y_sn % 4) || (a->y_sb % 4) || ((uintptr_t)a->y % 16))) return false;
   if (((uintptr_t)a->gz % 16) != 0) return false;

@@ -236,6 +236,9 @@ def test_tc_path_golden(golden, name):
     ("GAT_modified", True, 128, 128, 3, 4, 4, 100),
     ("GAT_modified", False, 64, 128, 2, 3, 5, 77),
     ("KeyQuery", True, 256, 256, 2, 1, 2, 50),
+    ("KeyQuery", True, 128, 128, 4, 2, 2, 60),          # K = 4: more tap blocks than fit TMEM next to the accumulators
+    ("GAT_modified", True, 128, 128, 4, 4, 2, 40),
+    ("KeyQuery", True, 128, 128, 3, 3, 2, 70),          # P = 3: none of the {1, 2, 4}-head sparse kernels
 ])
 def test_tc_path_oracle(mode, concat, G, F, K, P, B, N):
     """Forward AND backward of the tcgen05 path (both attention modes) against the CPU oracle."""
