@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define MAGAT_ABI_VERSION 12
+#define MAGAT_ABI_VERSION 13
 
 enum {
   MAGAT_OK = 0,
@@ -99,6 +99,11 @@ int magat_gso_edge_values(const void* S, int s_dtype, const int32_t* nbr_out, in
  * with magat_gso_build_ell.  threads <= 0: one per hardware thread. */
 int magat_gso_pack_host(const void* S_host, int s_dtype, long rows, int N, uint32_t* rowbits_host, int threads);
 int magat_gso_from_rowbits(const uint32_t* rowbits, int B, int N, uint32_t* colbits, int32_t* stats, void* stream);
+
+/* GAT_origin (graphML.py:964-1070) tests the edges of S + I (:1019): after magat_gso_scan, sets bit (i, i) of both masks to
+ * |float(S_ii) + 1| > 1e-9 and recomputes stats.  Then magat_gso_build_ell as usual. */
+int magat_gso_self_loops(const void* S, int s_dtype, int B, int N, uint32_t* rowbits, uint32_t* colbits, int32_t* stats,
+                         void* stream);
 
 /* Bit masks -> padded neighbour lists of width D (D >= max(stats[0], stats[1]), D >= 1). */
 int magat_gso_build_ell(const uint32_t* rowbits, const uint32_t* colbits, int B, int N, int D,

@@ -12,7 +12,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmagat_gat.so")
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 MODE_KEYQUERY, MODE_GAT_MODIFIED, MODE_GSO_VALUES = 0, 1, 2
 DT_F32, DT_F64 = 0, 1
@@ -23,6 +23,7 @@ EXPORTS = (
     "magat_gso_build_ell", "magat_gat_wprep_floats", "magat_gat_forward", "magat_gat_forward_taps_valid",
     "magat_gat_forward_relu_bits_valid", "magat_gat_relu_bits_words",
     "magat_gat_actions_supported", "magat_gat_forward_actions", "magat_head_mean_forward", "magat_head_mean_backward",
+    "magat_gso_self_loops",
     "magat_gat_bwd_partial_floats", "magat_gat_backward", "magat_gat_attention_dense",
     "magat_launch_count", "magat_profile_enable", "magat_profile_collect",
     "magat_gat_small_supported", "magat_gat_forward_small", "magat_gso_from_positions",
@@ -108,6 +109,8 @@ def lib():
         L.magat_gso_pack_host.argtypes = [_ptr, C.c_int, C.c_long, C.c_int, _ptr, C.c_int]
         L.magat_gso_pack_host.restype = C.c_int
         L.magat_gso_from_rowbits.argtypes = [_ptr, C.c_int, C.c_int, _ptr, _ptr, _ptr]
+        L.magat_gso_self_loops.argtypes = [_ptr, C.c_int, C.c_int, C.c_int, _ptr, _ptr, _ptr, _ptr]
+        L.magat_gso_self_loops.restype = C.c_int
         L.magat_gso_from_rowbits.restype = C.c_int
         L.magat_gso_build_ell.argtypes = [_ptr, _ptr, C.c_int, C.c_int, C.c_int, _ptr, _ptr, _ptr, _ptr, _ptr]
         L.magat_gso_from_positions.argtypes = [_ptr, C.c_int, C.c_int, C.c_int, C.c_double, _ptr, _ptr, _ptr, _ptr]

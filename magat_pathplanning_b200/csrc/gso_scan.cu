@@ -1017,6 +1017,44 @@ extern "C" int magat_gso_from_positions(const void* pos, int pos_dtype, int B, i
   return launch_gso_stats(rowbits, colbits, B, N, W, stats, st);
 }
 
+// GAT_origin's edge test runs on S + I (graphML.py:1019): off the diagonal nothing changes, on it the bit becomes
+// |float(S_ii) + 1| > 1e-9 (a -1 cancels the loop).  Fixes bit i of row / column word i in place.
+template <typename T>
+__global__ void __launch_bounds__(256) k_gso_self_loops(const T* __restrict__ S, long rows, int N, int W,
+                                                        uint32_t* __restrict__ rowbits, uint32_t* __restrict__ colbits) {
+  const long m = (long)blockIdx.x * blockDim.x + threadIdx.x;            // m = b * N + i
+  if (m >= rows) return;
+  const int i = (int)(m % N);
+  const float d = (float)S[(size_t)m * N + i] + 1.0f;
+  const bool e = fabsf(d) > 1e-9f;
+  const uint32_t bit = 1u << (i & 31);
+  const size_t w = (size_t)m * W + (i >> 5);
+  rowbits[w] = e ? (rowbits[w] | bit) : (rowbits[w] & ~bit);
+  colbits[w] = e ? (colbits[w] | bit) : (colbits[w] & ~bit);
+}
+
+extern "C" int magat_gso_self_loops(const void* S, int s_dtype, int B, int N, uint32_t* rowbits, uint32_t* colbits,
+                                    int32_t* stats, void* stream) {
+  MAGAT_REQUIRE(S && rowbits && colbits && stats, MAGAT_E_BAD_ARG, "magat_gso_self_loops: null pointer");
+  MAGAT_REQUIRE(B >= 1 && N >= 1, MAGAT_E_BAD_ARG, "magat_gso_self_loops: B=%d N=%d", B, N);
+  MAGAT_REQUIRE(s_dtype == MAGAT_DT_F32 || s_dtype == MAGAT_DT_F64, MAGAT_E_BAD_ARG,
+                "magat_gso_self_loops: GSO dtype must be fp32 or fp64");
+  cudaStream_t st = (cudaStream_t)stream;
+  prof_begin(st);
+  const int W = (N + 31) / 32;
+  const long rows = (long)B * N;
+  if (s_dtype == MAGAT_DT_F32)
+    k_gso_self_loops<float><<<cdiv(rows, 256), 256, 0, st>>>((const float*)S, rows, N, W, rowbits, colbits);
+  else
+    k_gso_self_loops<double><<<cdiv(rows, 256), 256, 0, st>>>((const double*)S, rows, N, W, rowbits, colbits);
+  int rc = check_launch("k_gso_self_loops", st);
+  if (rc) return rc;
+  // the degree statistics of the scan are stale now: {0, 0, 0, 1} again, then recount
+  static const int32_t init[4] = {0, 0, 0, 1};
+  cudaMemcpyAsync(stats, init, sizeof(init), cudaMemcpyHostToDevice, st);
+  return launch_gso_stats(rowbits, colbits, B, N, W, stats, st);
+}
+
 extern "C" int magat_gat_attention_dense(const float* att, const int32_t* nbr_out, int B, int N,
                                          int D, int P, int mean_heads, float* out, void* stream) {
   MAGAT_REQUIRE(att && nbr_out && out, MAGAT_E_BAD_ARG, "magat_gat_attention_dense: null pointer");

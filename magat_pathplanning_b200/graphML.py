@@ -128,7 +128,7 @@ def _stats_init(dev):
 
 
 def build_adjacency(S: torch.Tensor, max_degree: Optional[int] = None, nonzero: bool = False,
-                    with_slot_out: bool = False) -> Adjacency:
+                    with_slot_out: bool = False, self_loops: bool = False) -> Adjacency:
     """[B,1,N,N] dense GSO -> neighbour lists.  Only ``|S| > 1e-9`` matters (graphML.py:1274-1276):
     NaN is "no edge", negative weights are edges.  S is read once, by one kernel.
 
@@ -155,8 +155,11 @@ def build_adjacency(S: torch.Tensor, max_degree: Optional[int] = None, nonzero: 
         colbits = torch.empty((B, N, W), dtype=torch.int32, device=dev)
         stats = _stats_init(dev)
         scan = L.magat_gso_scan_nonzero if nonzero else L.magat_gso_scan    # nonzero: BatchLSIGF's "S itself" predicate
-        _cabi.check(scan(S.data_ptr(), _cabi.DT_F32 if S.dtype == torch.float32 else _cabi.DT_F64,
-                         B, N, rowbits.data_ptr(), colbits.data_ptr(), stats.data_ptr(), st))
+        dt = _cabi.DT_F32 if S.dtype == torch.float32 else _cabi.DT_F64
+        _cabi.check(scan(S.data_ptr(), dt, B, N, rowbits.data_ptr(), colbits.data_ptr(), stats.data_ptr(), st))
+        if self_loops:          # GAT_origin: the edges of S + I (graphML.py:1019)
+            _cabi.check(L.magat_gso_self_loops(S.data_ptr(), dt, B, N, rowbits.data_ptr(), colbits.data_ptr(),
+                                               stats.data_ptr(), st))
         return _lists_from_masks(rowbits, colbits, stats, B, N, dev, st, max_degree, with_slot_out)
 
 
@@ -838,8 +841,15 @@ def _origin_layer(x, S, h, a, W, b, concatenate, relu, path="auto", max_degree=N
     if E != 1:
         raise NotImplementedError("edge_features E != 1 is not supported")
     wb0 = torch.zeros((P, E, F), dtype=torch.float32, device=W.device)
-    return gat_layer(x, _origin_gso(S), _origin_filter(h, W), a, W, wb0, b, mode=_cabi.MODE_GAT_MODIFIED,
-                     concatenate=concatenate, relu=relu, path=path, max_degree=max_degree)
+    _require_cuda(S, "the GSO")
+    if S.shape[2] <= _SMALL_N_MAX and S.shape[0] <= _SMALL_B:
+        # the simulator's shape: S + I is a handful of kilobytes and the single-launch small-graph kernel takes it dense
+        return gat_layer(x, _origin_gso(S), _origin_filter(h, W), a, W, wb0, b, mode=_cabi.MODE_GAT_MODIFIED,
+                         concatenate=concatenate, relu=relu, path=path, max_degree=max_degree)
+    adj = build_adjacency(S, max_degree, self_loops=True)       # the edges of S + I without materialising it
+    return gat_layer(x, None, _origin_filter(h, W), a, W, wb0, b, mode=_cabi.MODE_GAT_MODIFIED,
+                     concatenate=concatenate, relu=relu, path="auto" if path == "fused" else path, adjacency=adj,
+                     max_degree=max_degree)
 
 
 def learnAttentionGSOBatch_origin(x, a, W, S, negative_slope=0.2):
@@ -847,7 +857,7 @@ def learnAttentionGSOBatch_origin(x, a, W, S, negative_slope=0.2):
     _check_slope(negative_slope)
     P, E, F, G = W.shape
     wb0 = torch.zeros((P, E, F), dtype=torch.float32, device=W.device)
-    return _attention_only(x, a, W, wb0, _origin_gso(S), _cabi.MODE_GAT_MODIFIED)
+    return _attention_only(x, a, W, wb0, _origin_gso(S), _cabi.MODE_GAT_MODIFIED)     # (functional: S + I as a tensor)
 
 
 def graphAttentionLSIGFBatch_Origin(h, x, a, W, S, b=None, negative_slope=0.2):

@@ -118,3 +118,40 @@ def test_functionals_and_rebinding():
     y_cat = torch.relu(y).permute(0, 3, 1, 2).reshape(B, N, P * F).permute(0, 2, 1)
     assert rel_err(y_cat, d["y"]) < TOL
     assert float((aij.cpu() - d["aij"]).abs().max()) < TOL and float((aij2.cpu() - d["aij"]).abs().max()) < TOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("s_dtype", [torch.float32, torch.float64])
+def test_cuda_matches_oracle_larger_with_self_loop_bits(s_dtype):
+    """Beyond the simulator's shape the self loops are set as bits on the scanned mask (magat_gso_self_loops) instead of
+    materialising S + I: forward, attention and every gradient against the oracle, with diagonals that cancel the loop
+    (-1), keep it (anything else, NaN excepted) and an isolated agent whose only edge is its loop."""
+    from magat_pathplanning_b200.graphML import GraphFilterBatchAttentional_Origin as Ours
+    dev = torch.device("cuda:0")
+    G = F = 128
+    K, P, B, N = 3, 4, 6, 100
+    gen = torch.Generator().manual_seed(99)
+    S = orc.random_geometric_gso(B, N, generator=gen).to(s_dtype)
+    S[:, 0, 3, 3] = -1.0                 # S + I = 0: no self loop for agent 3
+    S[:, 0, 4, 4] = 0.5
+    S[0, 0, 5, 5] = float("nan")         # NaN + 1 is NaN: no edge
+    S[:, 0, 7, :] = 0.0                  # agent 7 sends to nobody but itself
+    layer = Ours(G, F, K, P, 1, True, concatenate=True)
+    with torch.no_grad():
+        layer.filterWeight.copy_(torch.randn(1, K, generator=gen))
+    params = {k: getattr(layer, k).detach().clone().requires_grad_(True) for k in PARAMS}
+    x = torch.relu(torch.randn(B, N, G, generator=gen)).permute(0, 2, 1)
+    xr = x.clone().requires_grad_(True)
+    y_ref, aij_ref = orc.origin_layer_forward(xr, S, params, concatenate=True)
+    dy = torch.randn(y_ref.shape, generator=gen) * (y_ref.detach() > 1e-3)
+    y_ref.backward(dy)
+    layer = layer.to(dev)
+    layer.addGSO(S.to(dev))
+    xd = x.to(dev).requires_grad_(True)
+    y = layer(xd)
+    assert rel_err(y, y_ref) < TOL
+    assert float((torch.from_numpy(layer.aij) - aij_ref.detach()).abs().max()) < TOL
+    y.backward(dy.to(dev))
+    assert rel_err(xd.grad, xr.grad) < TOL
+    for k in PARAMS:
+        assert rel_err(getattr(layer, k).grad, params[k].grad) < TOL, k
