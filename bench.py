@@ -41,6 +41,8 @@ WORKLOADS = {
     "c5_n1000": dict(B=128, N=1000, width=200, G=128, K=3, P=4, concat=True, mode="KeyQuery"),
     # the published bottleneck model "B-32-P4" (README.md:385-396 of the reference): 32 features, heads averaged, K = 2
     "c3_b32p4_n100": dict(B=256, N=100, width=50, G=32, K=2, P=4, concat=False, mode="KeyQuery"),
+    # the same model at scale (the reference's generalisation runs go to 1000 agents)
+    "c4_b32p4_n1000": dict(B=512, N=1000, width=200, G=32, K=2, P=4, concat=False, mode="KeyQuery"),
     # heads AVERAGED (the CLI default: no --AttentionConcat in any script of the reference, main.py:113-115) at scale
     "c4_n1000_mean": dict(B=512, N=1000, width=200, G=128, K=3, P=4, concat=False, mode="KeyQuery"),
     "c4_n1000_mean_k2": dict(B=512, N=1000, width=200, G=128, K=2, P=4, concat=False, mode="KeyQuery"),

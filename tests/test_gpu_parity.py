@@ -755,3 +755,47 @@ def test_head_mean_at_the_tensor_core_shapes(mode, K, P):
             assert rel_err(getattr(layer, k).grad, g_ref[k]) < TOL, k
         else:
             assert getattr(layer, k).grad is None, k
+
+
+@pytest.mark.parametrize("mode,concat,G,F,K,P", [("KeyQuery", False, 32, 32, 2, 4), ("KeyQuery", True, 64, 64, 3, 4),
+                                                 ("GAT_modified", True, 32, 64, 3, 2), ("GAT_modified", False, 48, 128, 2, 1),
+                                                 ("KeyQuery", True, 16, 16, 1, 3)])
+def test_narrow_layers_zero_padded_onto_the_128_feature_kernels(mode, concat, G, F, K, P):
+    """From 32768 node rows on, layers with fewer than 128 features run zero padded on the 128-feature kernels
+    (graphML.py::_padded_layer): forward, layout, attention and every gradient against the oracle -- padding must not
+    show anywhere."""
+    from magat_pathplanning_b200 import graphML as ours
+    dev = torch.device("cuda:0")
+    B, N = 4, 150
+    gen = torch.Generator().manual_seed(321 + G + F)
+    params = orc.init_params(G, F, K, P, mode=mode, generator=gen, weight_bias_std=0.1)
+    S = orc.random_geometric_gso(B, N, generator=gen)
+    x = torch.relu(torch.randn(B, N, G, generator=gen)).permute(0, 2, 1)
+    _, _, pre = orc.gat_layer_forward(x, S, params, mode=mode, concatenate=concat, return_pre=True)
+    pre_out = pre.reshape(B, P * F, N) if concat else pre.mean(dim=1)
+    dy = torch.randn(pre_out.shape, generator=gen) * (pre_out.abs() > 1e-3)
+    y_ref, aij_ref, g_ref = orc.gat_layer_fwd_bwd(x, S, params, dy, mode=mode, concatenate=concat)
+    layer = make_layer(dict(G=G, F=F, K=K, P=P, concat=concat, mode=mode),
+                       {"param." + k: v for k, v in params.items() if v is not None}, dev, path="auto")
+    old = ours._PAD_MIN_ROWS
+    ours._PAD_MIN_ROWS = 1                       # (the test batch is small: force the route)
+    try:
+        layer.addGSO(S.to(dev))
+        xd = x.to(dev).requires_grad_(True)
+        y = layer(xd)
+        assert y.shape == y_ref.shape and list(y.stride()) == list(y_ref.stride())
+        assert rel_err(y, y_ref) < TOL
+        assert (torch.from_numpy(layer.aij) - aij_ref).abs().max() < TOL
+        y.backward(dy.to(dev))
+    finally:
+        ours._PAD_MIN_ROWS = old
+    assert rel_err(xd.grad, g_ref["x"]) < TOL
+    gmax = max(float(v.abs().max()) for v in g_ref.values() if v is not None)
+    for k in PARAMS:
+        if g_ref[k] is None:
+            assert getattr(layer, k).grad is None, k
+        elif float(g_ref[k].abs().max()) < 1e-6 * gmax:
+            assert float(getattr(layer, k).grad.abs().max()) < 1e-5 * gmax, k
+        else:
+            assert tuple(getattr(layer, k).grad.shape) == tuple(g_ref[k].shape)
+            assert rel_err(getattr(layer, k).grad, g_ref[k]) < TOL, k
