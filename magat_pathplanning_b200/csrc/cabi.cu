@@ -48,7 +48,7 @@ void prof_begin(cudaStream_t st) {
 
 // ---- per-device caches (one process may drive several devices) -----------------------------------
 static std::atomic<int> g_sm_count[64];
-static std::atomic<unsigned long long> g_attr_done[32];     // [kernel id] -> bit per device
+static std::atomic<unsigned long long> g_attr_done[KID_MAX];     // [kernel id] -> bit per device
 
 static int current_device() {
   int dev = 0;
@@ -70,6 +70,10 @@ int device_sm_count() {
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: do it once per (kernel, device)
 int ensure_dyn_smem(int kernel_id, const void* func, size_t bytes, const char* name) {
+  if (kernel_id < 0 || kernel_id >= KID_MAX) {
+    set_error("ensure_dyn_smem(%s): kernel id %d outside [0, %d)", name, kernel_id, (int)KID_MAX);
+    return MAGAT_E_CUDA;
+  }
   const int dev = current_device();
   const unsigned long long bit = 1ull << dev;
   if (g_attr_done[kernel_id].load(std::memory_order_acquire) & bit) return MAGAT_OK;

@@ -14,7 +14,7 @@ void prof_begin(cudaStream_t st);
 int device_sm_count();                       // SMs of the current device (cached per device), 0 without a device
 // once per (kernel id, device): raise the dynamic shared memory limit of `func`
 enum { KID_TC_GEMM = 0, KID_TAP_TC4, KID_TAP_TC8, KID_WGRAD, KID_SMALL, KID_TAP_TC2, KID_TAP_TC2M, KID_WGRAD2, KID_FUSED, KID_TAP_TC2B, KID_TAP_TC2H, KID_CELLS_F32, KID_CELLS_F64,
-       KID_SCAN_BASE /* + 24 dtype / R / KK variants */ = 16, KID_MAX = 40 };
+       KID_SCAN_BASE /* + 48 dtype / R / KK / predicate variants */ = 16, KID_MAX = 72 };
 int ensure_dyn_smem(int kernel_id, const void* func, size_t bytes, const char* name);
 
 // fused linear head of the K-tap projection (magat_gat_forward_actions)

@@ -159,7 +159,7 @@ template <> struct EdgeS<double> {
 // Columns past N (last segment only) read whatever follows in the ring: their bits are cut out of the row words by
 // the masks below and their column words are never stored.
 // a[k] = (lane == k) ? mask of the in-range lanes of column group k : 0 -- lane k < KK stores word k.
-template <typename T, int R, int KK, bool FULL>
+template <typename T, int R, int KK, bool FULL, bool NZ>
 __device__ __forceinline__ void scan_rows(uint32_t addr, uint32_t row_bytes, int nrows, uint32_t bit0,
                                           const uint32_t (&a)[KK], bool wr, uint32_t* rw, int W, uint32_t (&col)[KK]) {
   constexpr int RB = R < 8 ? R : 8;                   // rows whose loads are issued back to back
@@ -184,7 +184,7 @@ __device__ __forceinline__ void scan_rows(uint32_t addr, uint32_t row_bytes, int
         uint32_t w = 0;
 #pragma unroll
         for (int k = 0; k < KK; ++k) {
-          const bool pk = is_edge<T>(v[u][k]);
+          const bool pk = NZ ? (v[u][k] != T(0)) : is_edge<T>(v[u][k]);
           w |= __ballot_sync(0xffffffffu, pk) & a[k];
           col[k] |= pk ? bit : 0u;
         }
@@ -199,7 +199,8 @@ constexpr int kScanWarps = 16;                // consumer warps; warp 16 is the 
 constexpr int kScanRing = 192 * 1024;
 
 // KK: 32-column groups per consumer warp (2 for N <= 1024 -- sixteen warps on 64-column segments --, 4 up to N = 2048)
-template <typename T, int R, int KK>
+// NZ: the non-attentional filter's predicate (every entry that is not exactly zero, NaN included) instead of |s| > 1e-9
+template <typename T, int R, int KK, bool NZ>
 __global__ void __launch_bounds__((kScanWarps + 1) * 32, 1) k_gso_scan_tma(const T* __restrict__ S, int N, int W,
                                                                            long bands, int nstages,
                                                                            uint32_t* __restrict__ rowbits,
@@ -281,8 +282,8 @@ __global__ void __launch_bounds__((kScanWarps + 1) * 32, 1) k_gso_scan_tma(const
           const uint32_t addr = smem_s + (uint32_t)((size_t)stage * chunk_bytes) + (uint32_t)(j * sizeof(T));
           const uint32_t bit0 = 1u << (c * R);                // bit of the chunk's first row inside the band
           uint32_t* rw = rowbits + ((size_t)b * N + r_first) * W + seg * KK + lane;
-          if (nrows == R) scan_rows<T, R, KK, true>(addr, (uint32_t)row_bytes, nrows, bit0, am, wr, rw, W, col);
-          else scan_rows<T, R, KK, false>(addr, (uint32_t)row_bytes, nrows, bit0, am, wr, rw, W, col);
+          if (nrows == R) scan_rows<T, R, KK, true, NZ>(addr, (uint32_t)row_bytes, nrows, bit0, am, wr, rw, W, col);
+          else scan_rows<T, R, KK, false, NZ>(addr, (uint32_t)row_bytes, nrows, bit0, am, wr, rw, W, col);
         }
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&empty[stage]);
@@ -785,8 +786,9 @@ static int launch_gso_stats(const uint32_t* rowbits, const uint32_t* colbits, in
   return check_launch("k_gso_stats", st);
 }
 
-extern "C" int magat_gso_scan(const void* S, int s_dtype, int B, int N, uint32_t* rowbits,
-                              uint32_t* colbits, int32_t* stats, void* stream) {
+// nz: the non-attentional filter's predicate (entry != 0, NaN included) instead of |entry| > 1e-9
+static int gso_scan_impl(const void* S, int s_dtype, int B, int N, uint32_t* rowbits, uint32_t* colbits, int32_t* stats,
+                         void* stream, bool nz) {
   MAGAT_REQUIRE(S && rowbits && colbits && stats, MAGAT_E_BAD_ARG, "magat_gso_scan: null pointer");
   MAGAT_REQUIRE(B >= 1 && N >= 1, MAGAT_E_BAD_ARG, "magat_gso_scan: B=%d N=%d", B, N);
   MAGAT_REQUIRE(B <= 65535, MAGAT_E_BAD_ARG, "magat_gso_scan: B=%d exceeds 65535", B);
@@ -811,12 +813,19 @@ extern "C" int magat_gso_scan(const void* S, int s_dtype, int B, int N, uint32_t
     const size_t smem = (size_t)nstages * chunk_bytes + 2 * nstages * 8 + 256 + 1280;
 #define MAGAT_SCAN_K(TT, RR, KKV)                                                                               \
   do {                                                                                                         \
-    const int kid = KID_SCAN_BASE + (KKV == 4 ? 12 : 0) + (sizeof(TT) == 8 ? 6 : 0) +                           \
+    const int kid = KID_SCAN_BASE + (nz ? 24 : 0) + (KKV == 4 ? 12 : 0) + (sizeof(TT) == 8 ? 6 : 0) +           \
                     (RR >= 32 ? 5 : RR >= 16 ? 4 : RR >= 8 ? 3 : RR >= 4 ? 2 : RR >= 2 ? 1 : 0);              \
-    if (ensure_dyn_smem(kid, (const void*)k_gso_scan_tma<TT, RR, KKV>, kScanRing + 2048, "k_gso_scan_tma"))    \
-      return MAGAT_E_CUDA;                                                                                     \
-    k_gso_scan_tma<TT, RR, KKV><<<grid, (kScanWarps + 1) * 32, smem, st>>>((const TT*)S, N, W, bands, nstages, \
-                                                                           rowbits, colbits);                  \
+    if (nz) {                                                                                                  \
+      if (ensure_dyn_smem(kid, (const void*)k_gso_scan_tma<TT, RR, KKV, true>, kScanRing + 2048, "k_gso_scan_tma")) \
+        return MAGAT_E_CUDA;                                                                                   \
+      k_gso_scan_tma<TT, RR, KKV, true><<<grid, (kScanWarps + 1) * 32, smem, st>>>((const TT*)S, N, W, bands,  \
+                                                                                   nstages, rowbits, colbits); \
+    } else {                                                                                                   \
+      if (ensure_dyn_smem(kid, (const void*)k_gso_scan_tma<TT, RR, KKV, false>, kScanRing + 2048, "k_gso_scan_tma")) \
+        return MAGAT_E_CUDA;                                                                                   \
+      k_gso_scan_tma<TT, RR, KKV, false><<<grid, (kScanWarps + 1) * 32, smem, st>>>((const TT*)S, N, W, bands, \
+                                                                                    nstages, rowbits, colbits); \
+    }                                                                                                          \
   } while (0)
 #define MAGAT_SCAN(TT, RR)             \
   do {                                 \
@@ -836,7 +845,7 @@ extern "C" int magat_gso_scan(const void* S, int s_dtype, int B, int N, uint32_t
 #undef MAGAT_SCAN_R
 #undef MAGAT_SCAN
 #undef MAGAT_SCAN_K
-  } else if (N % 4 == 0 && ((uintptr_t)S % 16) == 0) {
+  } else if (!nz && N % 4 == 0 && ((uintptr_t)S % 16) == 0) {
     const int segs = cdiv(N, 128);
     const long units = (long)B * W * segs;
     const int blocks = cdiv(units, 8);
@@ -846,14 +855,22 @@ extern "C" int magat_gso_scan(const void* S, int s_dtype, int B, int N, uint32_t
       k_gso_scan_v4<double><<<blocks, 256, 0, st>>>((const double*)S, N, W, segs, units, rowbits, colbits);
   } else {
     dim3 grid(cdiv(W, 8), B);
-    if (s_dtype == MAGAT_DT_F32)
-      k_gso_scan<float><<<grid, 256, 0, st>>>((const float*)S, N, W, rowbits, colbits);
-    else
-      k_gso_scan<double><<<grid, 256, 0, st>>>((const double*)S, N, W, rowbits, colbits);
+    if (s_dtype == MAGAT_DT_F32) {
+      if (nz) k_gso_scan<float, true><<<grid, 256, 0, st>>>((const float*)S, N, W, rowbits, colbits);
+      else k_gso_scan<float><<<grid, 256, 0, st>>>((const float*)S, N, W, rowbits, colbits);
+    } else {
+      if (nz) k_gso_scan<double, true><<<grid, 256, 0, st>>>((const double*)S, N, W, rowbits, colbits);
+      else k_gso_scan<double><<<grid, 256, 0, st>>>((const double*)S, N, W, rowbits, colbits);
+    }
   }
-  int rc = check_launch("k_gso_scan", (cudaStream_t)stream);
+  int rc = check_launch(nz ? "k_gso_scan(nonzero)" : "k_gso_scan", (cudaStream_t)stream);
   if (rc) return rc;
   return launch_gso_stats(rowbits, colbits, B, N, W, stats, st);
+}
+
+extern "C" int magat_gso_scan(const void* S, int s_dtype, int B, int N, uint32_t* rowbits,
+                              uint32_t* colbits, int32_t* stats, void* stream) {
+  return gso_scan_impl(S, s_dtype, B, N, rowbits, colbits, stats, stream, false);
 }
 
 // att[b][i][s][0] = (float) S[b][i][nbr_out[b][i][s]], 0 beyond the degree: the "attention" of the non-attentional
@@ -906,19 +923,7 @@ extern "C" int magat_gso_from_rowbits(const uint32_t* rowbits, int B, int N, uin
 
 extern "C" int magat_gso_scan_nonzero(const void* S, int s_dtype, int B, int N, uint32_t* rowbits, uint32_t* colbits,
                                       int32_t* stats, void* stream) {
-  MAGAT_REQUIRE(S && rowbits && colbits && stats, MAGAT_E_BAD_ARG, "magat_gso_scan_nonzero: null pointer");
-  MAGAT_REQUIRE(B >= 1 && N >= 1 && B <= 65535, MAGAT_E_BAD_ARG, "magat_gso_scan_nonzero: B=%d N=%d", B, N);
-  MAGAT_REQUIRE(s_dtype == MAGAT_DT_F32 || s_dtype == MAGAT_DT_F64, MAGAT_E_BAD_ARG,
-                "magat_gso_scan_nonzero: GSO dtype must be fp32 or fp64");
-  cudaStream_t st = (cudaStream_t)stream;
-  prof_begin(st);
-  const int W = (N + 31) / 32;
-  dim3 grid(cdiv(W, 8), B);
-  if (s_dtype == MAGAT_DT_F32) k_gso_scan<float, true><<<grid, 256, 0, st>>>((const float*)S, N, W, rowbits, colbits);
-  else k_gso_scan<double, true><<<grid, 256, 0, st>>>((const double*)S, N, W, rowbits, colbits);
-  int rc = check_launch("k_gso_scan(nonzero)", st);
-  if (rc) return rc;
-  return launch_gso_stats(rowbits, colbits, B, N, W, stats, st);
+  return gso_scan_impl(S, s_dtype, B, N, rowbits, colbits, stats, stream, true);
 }
 
 extern "C" int magat_gso_edge_values(const void* S, int s_dtype, const int32_t* nbr_out, int B, int N, int D, float* att,
