@@ -395,6 +395,61 @@ __global__ void __launch_bounds__(256) k_attention_gm_v(const float* __restrict_
   }
 }
 
+// The same attention with lane = (slot, head): 32 / PT out-slots x PT heads per chunk, so a row of degree <= 8 (P = 4) is
+// one pass: one gathered score per lane, the max and the sum over the slots are xor-shuffles over the upper lane bits
+// for all heads at once (6 shuffles instead of 40), one coalesced store.  Grid-stride, the next row's list entry of the
+// lane loaded one iteration ahead.  No receiver-major copy (the lean gathers do not read one).
+template <int PT>
+__global__ void __launch_bounds__(256) k_attention_gm_h(const float* __restrict__ sproj,
+                                                        const int32_t* __restrict__ nbr_out, long rows, int N, int D,
+                                                        float* __restrict__ att) {
+  constexpr int LOGP = PT == 4 ? 2 : PT == 2 ? 1 : 0;
+  constexpr int SPC = 32 / PT, NC = 32 / SPC;
+  const int lane = threadIdx.x & 31;
+  const int sl = lane >> LOGP, hd = lane & (PT - 1);
+  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  int nj[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) nj[c] = (c * SPC + sl < D) ? __ldg(nbr_out + row * D + c * SPC + sl) : -1;
+  for (; row < rows; row += nwarps) {
+    int j[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) j[c] = nj[c];
+    const long nxt = row + nwarps;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) nj[c] = (nxt < rows && c * SPC + sl < D) ? __ldg(nbr_out + nxt * D + c * SPC + sl) : -1;
+    const long b = batch_of32(row, N);
+    const float si = __ldg(sproj + ((size_t)row * PT + hd) * 2 + 1);
+    float e[NC];
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      e[c] = -INFINITY;
+      if (c * SPC < D && j[c] >= 0) {
+        const float v = si + __ldg(sproj + ((size_t)(b * N + j[c]) * PT + hd) * 2 + 0);
+        e[c] = v > 0.f ? v : kLeaky * v;
+      }
+      m = fmaxf(m, e[c]);
+    }
+#pragma unroll
+    for (int o = PT; o < 32; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      e[c] = (c * SPC < D && j[c] >= 0) ? expf(e[c] - m) : 0.f;
+      sum += e[c];
+    }
+#pragma unroll
+    for (int o = PT; o < 32; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    float* dst = att + (size_t)row * D * PT;
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+      if (c * SPC + sl < D) dst[c * SPC * PT + lane] = j[c] >= 0 ? e[c] / sum : 0.f;
+  }
+}
+
 // ---- lean sparse kernels (G = 128, D <= 32, P in {1,2,4}): the warp-level routines of gat_sparse.cuh, one row per warp ----
 // Attention: half a warp per edge, joint head reduction, softmax through shared memory; no receiver-major copy.
 template <int PT, int MINB>
@@ -670,10 +725,15 @@ static int forward_impl(const magat_gat_fwd_args* a, cudaStream_t st, bool use_t
 #undef MAGAT_GMX
       if ((rc = check_launch("k_gm_mixer", st))) return rc;
 #define MAGAT_GMA(PT) k_attention_gm_v<PT><<<row_blocks, 256, 0, st>>>(a->sproj, a->nbr_out, rows, N, D, a->att, so, ain_w)
-      if (P == 4) MAGAT_GMA(4);
+#define MAGAT_GMH(PT) k_attention_gm_h<PT><<<lean_grid(row_blocks), 256, 0, st>>>(a->sproj, a->nbr_out, rows, N, D, a->att)
+      if (so == nullptr && P == 4) MAGAT_GMH(4);
+      else if (so == nullptr && P == 2) MAGAT_GMH(2);
+      else if (so == nullptr && P == 1) MAGAT_GMH(1);
+      else if (P == 4) MAGAT_GMA(4);
       else if (P == 2) MAGAT_GMA(2);
       else MAGAT_GMA(1);
 #undef MAGAT_GMA
+#undef MAGAT_GMH
     } else {
       dim3 grid(cdiv(rows, 64), cdiv(2l * P, 64), 1);
       k_node_gemm<<<grid, 256, 0, st>>>(rows, 2 * P, G, xl, GmCLoad{cvec, G}, GmEpi{a->sproj, dvec, 2 * P});
