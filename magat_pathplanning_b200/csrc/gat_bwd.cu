@@ -494,6 +494,8 @@ __global__ void __launch_bounds__(256) k_softmax_bwd_gm_v(const float* __restric
 }
 
 // column side: rc[row][p][0] = sum_{i in in(row)} ds[i,row]; dx_row = sum_p gU_0 + sum_p (c_p cvec[p][0] + r_p cvec[p][1])
+// Grid-stride over the rows with the next row's in-list entries loaded one iteration ahead; the P column sums share one
+// joint warp reduction.
 template <int PT>
 __global__ void __launch_bounds__(256) k_col_bwd_gm_v(const float* __restrict__ gz, const float* __restrict__ datt,
                                                       const float* __restrict__ cvec,
@@ -502,39 +504,53 @@ __global__ void __launch_bounds__(256) k_col_bwd_gm_v(const float* __restrict__ 
                                                       int D, int g0_in_dx, float* __restrict__ rc,
                                                       float* __restrict__ dx) {
   constexpr int G = 128;
+  constexpr int SH = PT == 4 ? 3 : PT == 2 ? 4 : 5;           // warp_multi_sum<PT>: lane l holds value l >> SH
   const int lane = threadIdx.x & 31;
-  const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= rows) return;
-  const long b = batch_of32(row, N);
   const int g0 = lane * 4;
-  const int my_i = lane < D ? nbr_in[row * D + lane] : -1;
-  float ds[PT], c[PT], r[PT];
-#pragma unroll
-  for (int q = 0; q < PT; ++q) ds[q] = 0.f;
-  if (my_i >= 0) ldp<PT>(datt + ((size_t)(b * N + my_i) * D + slot_in[row * D + lane]) * PT, ds);
+  float4 cv[PT][2];                                            // the 2 P projection vectors of this lane's features
 #pragma unroll
   for (int q = 0; q < PT; ++q) {
-    c[q] = warp_sum(ds[q]);
-    r[q] = rc[((size_t)row * PT + q) * 2 + 1];
-    if (lane == 0) rc[((size_t)row * PT + q) * 2 + 0] = c[q];
+    cv[q][0] = __ldg(reinterpret_cast<const float4*>(cvec + ((size_t)q * 2 + 0) * G + g0));
+    cv[q][1] = __ldg(reinterpret_cast<const float4*>(cvec + ((size_t)q * 2 + 1) * G + g0));
   }
-  if (dx == nullptr) return;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (g0_in_dx) {
-    acc = *reinterpret_cast<const float4*>(dx + (size_t)row * G + g0);
-  } else {
+  int n_i = lane < D ? __ldg(nbr_in + row * D + lane) : -1;
+  int n_s = lane < D ? __ldg(slot_in + row * D + lane) : 0;
+  for (; row < rows; row += nwarps) {
+    const int my_i = n_i, my_s = n_s;
+    const long nxt = row + nwarps;
+    n_i = (nxt < rows && lane < D) ? __ldg(nbr_in + nxt * D + lane) : -1;
+    n_s = (nxt < rows && lane < D) ? __ldg(slot_in + nxt * D + lane) : 0;
+    const long b = batch_of32(row, N);
+    float ds[PT];
+#pragma unroll
+    for (int q = 0; q < PT; ++q) ds[q] = 0.f;
+    if (my_i >= 0) ldp<PT>(datt + ((size_t)(b * N + my_i) * D + my_s) * PT, ds);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (dx != nullptr) {                                       // requested before the reduction below needs it
+      if (g0_in_dx) {
+        acc = *reinterpret_cast<const float4*>(dx + (size_t)row * G + g0);
+      } else {
+#pragma unroll
+        for (int q = 0; q < PT; ++q) {
+          const float4 v = *reinterpret_cast<const float4*>(gz + (((size_t)row * PT + q) * K + 0) * G + g0);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+      }
+    }
+    float rq = lane < PT ? rc[((size_t)row * PT + lane) * 2 + 1] : 0.f;
+    const float tot = warp_multi_sum<PT>(ds, lane);
+    if ((lane & ((1 << SH) - 1)) == 0) rc[((size_t)row * PT + (lane >> SH)) * 2 + 0] = tot;
+    if (dx == nullptr) continue;
 #pragma unroll
     for (int q = 0; q < PT; ++q) {
-      const float4 v = *reinterpret_cast<const float4*>(gz + (((size_t)row * PT + q) * K + 0) * G + g0);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      bfma4(acc, __shfl_sync(0xffffffffu, tot, q << SH), cv[q][0]);
+      bfma4(acc, __shfl_sync(0xffffffffu, rq, q), cv[q][1]);
     }
+    *reinterpret_cast<float4*>(dx + (size_t)row * G + g0) = acc;
   }
-#pragma unroll
-  for (int q = 0; q < PT; ++q) {
-    bfma4(acc, c[q], __ldg(reinterpret_cast<const float4*>(cvec + ((size_t)q * 2 + 0) * G + g0)));
-    bfma4(acc, r[q], __ldg(reinterpret_cast<const float4*>(cvec + ((size_t)q * 2 + 1) * G + g0)));
-  }
-  *reinterpret_cast<float4*>(dx + (size_t)row * G + g0) = acc;
 }
 
 // dc[n][g] = sum_m rc[m][n] x[m][g] (g < G) and dc[n][G] = sum_m rc[m][n], n = 2p + t.  Every warp walks a contiguous
@@ -954,8 +970,9 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
       else MAGAT_GSB(1);
 #undef MAGAT_GSB
       if ((rc = check_launch("k_softmax_bwd", st))) return rc;
+      const int col_grid = row_blocks < sm_count_or_default() * 48 ? row_blocks : sm_count_or_default() * 48;
 #define MAGAT_GCB(PT) \
-  k_col_bwd_gm_v<PT><<<row_blocks, 256, 0, st>>>(a->gz, a->datt, cvec, a->nbr_in, a->slot_in, rows, N, K, D, \
+  k_col_bwd_gm_v<PT><<<col_grid, 256, 0, st>>>(a->gz, a->datt, cvec, a->nbr_in, a->slot_in, rows, N, K, D, \
                                                  g0_in_dx ? 1 : 0, a->rc, a->need_dx ? a->dx : nullptr)
       if (P == 4) MAGAT_GCB(4);
       else if (P == 2) MAGAT_GCB(2);
