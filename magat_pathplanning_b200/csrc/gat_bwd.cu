@@ -251,7 +251,8 @@ __global__ void __launch_bounds__(256, MINB) k_tap_bwd_p(const float* __restrict
                                                       const float* __restrict__ taps, const float* __restrict__ att,
                                                       const int32_t* __restrict__ nbr_out, long rows, int N, int K, int D,
                                                       int k, int first, float* __restrict__ gz, float* __restrict__ datt,
-                                                      float* __restrict__ g0sum, float* __restrict__ rc_out) {
+                                                      float* __restrict__ g0sum, float* __restrict__ rc_out,
+                                                      const float* __restrict__ gm_sproj, float* __restrict__ gm_rc) {
   constexpr int G = 128, NV = EF * HP;
   constexpr int SH = NV == 16 ? 1 : NV == 8 ? 2 : NV == 4 ? 3 : 4;      // lane l holds the total of value l >> SH
   const int lane = threadIdx.x & 31;
@@ -310,6 +311,25 @@ __global__ void __launch_bounds__(256, MINB) k_tap_bwd_p(const float* __restrict
 #pragma unroll
       for (int q = 0; q < HP; ++q)
         *reinterpret_cast<float4*>(gz + (((size_t)row * PT + h0 + q) * K + (k - 1)) * G + g0) = acc[q];
+    }
+    if (gm_rc != nullptr) {
+      // Last level, GAT_modified: dA of this row is complete, so its softmax + LeakyReLU backward follows here (same
+      // arithmetic as k_softmax_bwd_gm_v, which then need not run): datt <- ds, rc[row][p][1] = sum_j ds[i,j].
+#pragma unroll
+      for (int q = 0; q < HP; ++q) {
+        const float o = lane < D ? dsum[q] : 0.f;
+        const float dot = warp_sum(am[q] * o);
+        float de = am[q] * (o - dot);
+        if (my_j >= 0) {
+          const float sr = gm_sproj[((size_t)row * PT + h0 + q) * 2 + 1] +
+                           gm_sproj[((size_t)(b * N + my_j) * PT + h0 + q) * 2 + 0];
+          de *= sr > 0.f ? 1.f : kLeaky;
+        }
+        const float rsum = warp_sum(de);
+        if (lane == 0) gm_rc[((size_t)row * PT + h0 + q) * 2 + 1] = rsum;
+        if (lane < D) da[q] = de;
+      }
+      continue;
     }
     if (rc_out == nullptr) {
       if (lane < D && (first || deg > 0)) {
@@ -568,15 +588,30 @@ __global__ void __launch_bounds__(256) k_gm_dcvec_v(const float* __restrict__ x,
   float cs[NV];
 #pragma unroll
   for (int n = 0; n < NV; ++n) { acc[n] = make_float4(0.f, 0.f, 0.f, 0.f); cs[n] = 0.f; }
-  for (long m = m0 + warp; m < m1; m += 8) {
-    const long b = batch_of32(m, N);
-    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + b * x_sb + (m - b * N) * x_sn + lane * 4));
+  // four rows per step and warp: their loads are issued together (with one row in flight per warp the kernel streamed
+  // x at 1.7 TB/s)
+  for (long mq = m0 + warp; mq < m1; mq += 32) {
+    float4 xv[4];
+    float w[4];
 #pragma unroll
-    for (int n = 0; n < NV; ++n) {
-      const float w = __ldg(rc + (size_t)m * NV + n);
-      bfma4(acc[n], w, xv);
-      cs[n] += w;                          // identical in every lane; lane 0 reports it
+    for (int u = 0; u < 4; ++u) {
+      const long m = mq + 8 * u;
+      xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      w[u] = 0.f;
+      if (m < m1) {
+        const long b = batch_of32(m, N);
+        xv[u] = __ldg(reinterpret_cast<const float4*>(x + b * x_sb + (m - b * N) * x_sn + lane * 4));
+        if (lane < NV) w[u] = __ldg(rc + (size_t)m * NV + lane);          // lane n keeps rc[m][n]
+      }
     }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int n = 0; n < NV; ++n) {
+        const float wn = __shfl_sync(0xffffffffu, w[u], n);
+        bfma4(acc[n], wn, xv[u]);
+        cs[n] += wn;                       // identical in every lane; lane 0 reports it
+      }
   }
 #pragma unroll
   for (int n = 0; n < NV; ++n) {
@@ -876,13 +911,15 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
   const bool g0_in_dx = vec && (!gm || gm_vec) && K > 1 && a->need_dx;
   // ... and the row softmax backward (+ dR) rides on the same last level
   const bool fuse_softmax = vec && !gm && !plain && K > 1;
+  const bool fuse_softmax_gm = gm_vec && K > 1;
   for (int k = K - 1; k >= 1; --k) {
     const int first = k == K - 1 ? 1 : 0;
     float* g0sum = (k == 1 && g0_in_dx) ? a->dx : nullptr;
     float* rc_fused = (k == 1 && fuse_softmax) ? a->rc : nullptr;
+    float* gm_rc = (k == 1 && fuse_softmax_gm) ? a->rc : nullptr;
 #define MAGAT_TBX(PT, HPV, EFV, MB) \
   k_tap_bwd_p<PT, HPV, EFV, MB><<<row_blocks, 256, 0, st>>>(a->x, a->x_sb, a->x_sn, a->taps, a->att, a->nbr_out, rows, N, K, D, k, \
-                                                   first, a->gz, a->datt, g0sum, rc_fused)
+                                                   first, a->gz, a->datt, g0sum, rc_fused, a->sproj, gm_rc)
     // measured at B = 512, N = 1000, P = 4 (both levels): 2 heads x 2 edges at 4 CTAs/SM 1.76 ms; 2 x 4 at 4 CTAs/SM
     // 1.80; 2 x 4 at 3 CTAs/SM 2.08; 4 x 2 at 3 CTAs/SM 1.93; one head per pass >= 2.07
     if (vec && P == 4) MAGAT_TBX(4, 2, 2, 4);
@@ -965,11 +1002,13 @@ extern "C" int magat_gat_backward(const magat_gat_bwd_args* a, void* stream) {
     if (gm_vec) {
 #define MAGAT_GSB(PT) \
   k_softmax_bwd_gm_v<PT><<<row_blocks, 256, 0, st>>>(a->sproj, a->att, a->nbr_out, rows, N, D, has_datt, a->datt, a->rc)
-      if (P == 4) MAGAT_GSB(4);
+      if (fuse_softmax_gm) {
+        // done by the last level of the recursion
+      } else if (P == 4) MAGAT_GSB(4);
       else if (P == 2) MAGAT_GSB(2);
       else MAGAT_GSB(1);
 #undef MAGAT_GSB
-      if ((rc = check_launch("k_softmax_bwd", st))) return rc;
+      if (!fuse_softmax_gm && (rc = check_launch("k_softmax_bwd", st))) return rc;
       const int col_grid = row_blocks < sm_count_or_default() * 48 ? row_blocks : sm_count_or_default() * 48;
 #define MAGAT_GCB(PT) \
   k_col_bwd_gm_v<PT><<<col_grid, 256, 0, st>>>(a->gz, a->datt, cvec, a->nbr_in, a->slot_in, rows, N, K, D, \
