@@ -342,14 +342,22 @@ __global__ void __launch_bounds__(256) k_gm_mixer_v(const float* __restrict__ x,
   const int mine = lane >> SH;                                   // output this lane ends up holding
   const float dv = __ldg(dvec + mine);
   const long m_end = min(rows, (w + 1) * per_warp);
-  for (long m = w * per_warp; m < m_end; ++m) {
-    const long b = batch_of32(m, N);
-    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + b * x_sb + (m - b * N) * x_sn + lane * 4));
-    float d[NV];
+  for (long m0 = w * per_warp; m0 < m_end; m0 += 4) {          // four row loads in flight per warp
+    float4 xv[4];
 #pragma unroll
-    for (int n = 0; n < NV; ++n) d[n] = dot4(c[n], xv);
-    const float tot = warp_multi_sum<NV>(d, lane);
-    if ((lane & ((1 << SH) - 1)) == 0) sproj[(size_t)m * NV + mine] = tot + dv;
+    for (int u = 0; u < 4; ++u) {
+      const long m = m0 + u < m_end ? m0 + u : m_end - 1;
+      const long b = batch_of32(m, N);
+      xv[u] = __ldg(reinterpret_cast<const float4*>(x + b * x_sb + (m - b * N) * x_sn + lane * 4));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float d[NV];
+#pragma unroll
+      for (int n = 0; n < NV; ++n) d[n] = dot4(c[n], xv[u]);
+      const float tot = warp_multi_sum<NV>(d, lane);
+      if (m0 + u < m_end && (lane & ((1 << SH) - 1)) == 0) sproj[(size_t)(m0 + u) * NV + mine] = tot + dv;
+    }
   }
 }
 
