@@ -648,7 +648,8 @@ def gat_layer(x, S, filterWeight, mixer, weight, weight_bias, bias, *, mode: int
             and B_ * N_ >= _PAD_MIN_ROWS and (mode != _cabi.MODE_KEYQUERY or F == G)):
         return _padded_layer(x, S, filterWeight, mixer, weight, weight_bias, bias, mode, concatenate, relu, adjacency,
                              max_degree, fused_team)
-    if not concatenate and path in ("auto", "tcgen05", "fused") and F == 128 and G % 128 == 0 and K <= 3:
+    if (not concatenate and path in ("auto", "tcgen05", "fused") and F == 128 and G % 128 == 0 and K <= 3
+            and B_ * N_ >= _MEAN_VIA_CONCAT_MIN_ROWS):
         # Heads AVERAGED (the reference's CLI default, main.py:113-115) at the tensor-core shapes: the per-head outputs
         # come from the concat path (tcgen05 projections forward and backward -- its weights do not fit TMEM for a
         # fused head sum); the mean over the heads, the ReLU and the reference's contiguous [B,F,N] layout
@@ -757,6 +758,10 @@ def gat_layer_actions(x, S, filterWeight, mixer, weight, weight_bias, bias, head
     att_out = SparseAttention(att, adj)
     return (logits, actions, att_out) if return_actions else (logits, att_out)
 
+
+#: heads averaged: from this many node rows on the per-head outputs come from the concat path (below, the two extra
+#: launches of the head mean cost more than the generic backward kernels do)
+_MEAN_VIA_CONCAT_MIN_ROWS = 2048
 
 #: from this many node rows (B * N) on, layers with fewer than 128 features are zero padded onto the 128-feature kernels
 _PAD_MIN_ROWS = 32768
