@@ -13,6 +13,7 @@ import torch  # noqa: E402
 
 from oracle import gat_oracle as orc  # noqa: E402
 from magat_pathplanning_b200 import GraphFilterBatchAttentional  # noqa: E402
+from magat_pathplanning_b200 import graphML as ours  # noqa: E402
 
 PARAMS = ("mixer", "weight_bias", "filterWeight", "bias", "weight")
 
